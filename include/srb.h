@@ -1,0 +1,132 @@
+/*
+ * srb.h -- C ABI of libsrb.so, the sm_100a kernels behind speech_resynth_b200.
+ *
+ * The reference (misternasty/speech_resynth) is pure Python and has no FFI; every entry point below replaces a
+ * PyTorch call site of the reference's unit-to-speech path (file:line relative to /root/reference, "HF:" =
+ * transformers/models/fastspeech2_conformer/modeling_fastspeech2_conformer.py).  INTEGRATION.md shows the ctypes
+ * binding a maintainer would add on the reference side.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers borrowed from the caller (torch owns the memory); nothing is allocated;
+ *   - `stream` is a cudaStream_t passed as void*; launches are asynchronous and CUDA-graph capturable;
+ *   - return value 0 = success, negative = error (srb_last_error() gives the text); nothing throws;
+ *   - activations are channel-last: (batch, rows, channels) with explicit element strides, bf16 unless noted;
+ *   - "packed" weights are bf16 [n][k] with k contiguous, k ordered (tap, channel) and the channel count padded to
+ *     a multiple of the K block the op uses (see speech_resynth_b200/packing.py for the exact recipe);
+ *   - `lengths` is int32[batch]: number of valid (non-pad) rows per utterance.
+ */
+#ifndef SRB_H_
+#define SRB_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRB_VERSION 100
+
+int srb_version(void);
+const char* srb_last_error(void);
+/* compute capability major*10+minor of the current device, or negative error */
+int srb_device_arch(void);
+
+/* ---- unit embedding gather: nn.Embedding forward, src/flow_matching/models.py:50-52,154 ----------------------
+ * out[m, :] = table[ids[m], :]  (fp32 rows, bit exact).  ids int64 in [0, vocab]; dim % 4 == 0. */
+int srb_embed_gather(const float* table, const int64_t* ids, float* out, int64_t m, int32_t vocab_rows, int32_t dim,
+                     void* stream);
+
+/* valid-frame count per utterance: mask = input_ids.ne(0) (models.py:152); lengths[b] = sum(mask[b]) */
+int srb_unit_lengths(const int64_t* ids, int32_t* lengths, int32_t batch, int32_t frames, void* stream);
+
+/* ---- time conditioning table: models.py:47-49,179 + norm.py:42 --------------------------------------------
+ * For each ODE time t_s (s < nfe): c = SiLU(Linear([t, sin(2*pi*t*w), cos(2*pi*t*w)])) and, for each of the
+ * n_norm AdaptiveRMSNorm layers, g[s][j][:] = sqrt(H) * (W_j c + 1).  All fp32, H = 256.
+ * four_w[128], lin_w[256*257], lin_b[256], gamma_w[n_norm][256*256] -> time_emb[nfe][256], g[nfe][n_norm][256]. */
+int srb_time_cond_table(const float* times, int32_t nfe, const float* four_w, const float* lin_w, const float* lin_b,
+                        const float* gamma_w, int32_t n_norm, float* time_emb, float* g, void* stream);
+
+/* rotary table: transformer.py:56-63.  cos/sin[(pos, f)] for pos < rows, f < 64 (fp32, freq = pos * inv_freq[f]) */
+int srb_rotary_table(const float* inv_freq, int32_t rows, float* cos_out, float* sin_out, void* stream);
+
+/* noise truncation + bf16 copy: models.py:168-170.  xt (fp32, in place) = clamp(xt, -tv, tv) when tv > 0;
+ * xt_bf16 = bf16(xt).  n = batch*frames*80 */
+int srb_prior_prepare(float* xt, void* xt_bf16, int64_t n, float truncation, void* stream);
+
+/* ---- ODE loop body ------------------------------------------------------------------------------------------
+ * to_embed: x0 = xt @ W[:, :80]^T + cond_proj       (models.py:175-176; cond_proj = hoisted cond part + bias, fp32)
+ *   xt_bf16 (B, N, 80) bf16; w_packed [256][128]; cond_proj, x0: (B, N, 256) fp32 */
+int srb_cfm_embed(const void* xt_bf16, const void* w_packed, const float* cond_proj, float* x0, int32_t batch,
+                  int32_t frames, void* stream);
+
+/* ConvPositionEmbed + residual (transformer.py:84-96, models.py:177) fused with the first AdaptiveRMSNorm
+ * (norm.py:41-43):  x = gelu(dwconv31(mask(x0)) + b) * mask + x0 ;  xn = bf16(x / max(|x|,1e-12) * g) * mask
+ *   dw_w [256][31] fp32, dw_b[256], g[256] (= sqrt(H)(gamma+1) for this step) */
+int srb_cfm_posconv_norm(const float* x0, const float* dw_w, const float* dw_b, const float* g, const int32_t* lengths,
+                         float* x, void* xn_bf16, int32_t batch, int32_t frames, void* stream);
+
+/* to_qkv + rotary on q,k (transformer.py:109-113): qkv (B, N, 768) bf16 = rope(xn @ Wqkv^T) */
+int srb_cfm_qkv_rope(const void* xn_bf16, const void* w_packed, const float* rot_cos, const float* rot_sin,
+                     void* qkv_bf16, int32_t batch, int32_t frames, void* stream);
+
+/* key-padding-masked softmax attention, 2 heads x 128 (transformer.py:115-127): o (B, N, 256) bf16 */
+int srb_cfm_attention(const void* qkv_bf16, const int32_t* lengths, void* o_bf16, int32_t batch, int32_t frames,
+                      void* stream);
+
+/* to_out + residual (transformer.py:129-130,203) fused with the following AdaptiveRMSNorm:
+ *   x += o @ Wout^T ; xn = bf16(adanorm(x, g)) * mask */
+int srb_cfm_attn_out_norm(const void* o_bf16, const void* w_packed, const float* g, const int32_t* lengths, float* x,
+                          void* xn_bf16, int32_t batch, int32_t frames, void* stream);
+
+/* FeedForward conv1 (k=3) + SIGLU + pad mask (fastspeech/modules.py:58-69):
+ *   h (B, N, 896) bf16 = mask * silu(gate) * value, (value | gate) = conv1(xn) + b.
+ *   w_packed [1792][768] with rows permuted so every 256-row block holds 128 value rows then their 128 gate rows;
+ *   bias_packed[1792] in the same row order. */
+int srb_cfm_ffn_glu(const void* xn_bf16, const void* w_packed, const float* bias_packed, const int32_t* lengths,
+                    void* h_bf16, int32_t batch, int32_t frames, void* stream);
+
+/* FeedForward conv2 (k=3) + bias + residual (fastspeech/modules.py:71-73, transformer.py:206) fused with the NEXT
+ * norm: norm_mode 1 = AdaptiveRMSNorm with g (next layer), 2 = final nn.RMSNorm (transformer.py:208; g = weight,
+ * eps = FLT_EPSILON).  x += conv2(h) + b ; xn = bf16(norm(x)) * mask */
+int srb_cfm_ffn_out_norm(const void* h_bf16, const void* w_packed, const float* bias, const float* g, int32_t norm_mode,
+                         const int32_t* lengths, float* x, void* xn_bf16, int32_t batch, int32_t frames, void* stream);
+
+/* to_pred + Euler update (models.py:183-184), and on the last step the de-normalisation and pad fill
+ * (models.py:186-187): xt += dt * (xn @ Wpred^T); xt_bf16 = bf16(xt);
+ * if mel != NULL: mel = xt*std + mean, pad rows = log(1e-5) (fp32 and bf16 copies) */
+int srb_cfm_pred_euler(const void* xn_bf16, const void* w_packed, float dt, float* xt, void* xt_bf16, float* mel,
+                       void* mel_bf16, float std, float mean, float pad_value, const int32_t* lengths, int32_t batch,
+                       int32_t frames, void* stream);
+
+/* ---- HiFi-GAN generator (HF:1308-1367, 1451-1491) ------------------------------------------------------------
+ * "same"-padded dilated Conv1d as an implicit GEMM with a fused epilogue:
+ *   y = (sum_i conv_{k_i, dil_i}(x_i) + bias + sum_j res_j) * scale ; out_raw = bf16(y) ; out_act = bf16(lrelu(y, slope))
+ * n_src = 1 for conv_pre / resblock convs; n_src = 3 fuses the last conv2 of the three MRF resblocks, their
+ * residuals and the /3 mean (HF:1475-1478) into one launch.  Any of res*, out_raw, out_act may be NULL.
+ * x_i: (B, L, c_in) bf16 contiguous; outputs/residuals (B, L, c_out) bf16 contiguous. */
+int srb_hifigan_conv(const void* x0, const void* x1, const void* x2, int32_t n_src, const int32_t* kernel,
+                     const int32_t* dilation, const void* w_packed, const float* bias, const void* res0,
+                     const void* res1, const void* res2, void* out_raw, void* out_act, int32_t batch, int32_t rows,
+                     int32_t c_in, int32_t c_out, float scale, float slope, void* stream);
+
+/* ConvTranspose1d (HF:1392-1402,1473) in polyphase form: for phase r < stride, output rows q*stride + r are a
+ * 2-3 tap conv of the input.  x (B, L_in, c_in) bf16 (already leaky-relu'ed by its producer);
+ * out rows L_out = (L_in-1)*stride - 2*pad + k; writes raw and lrelu(slope) copies. */
+int srb_hifigan_upsample(const void* x, const void* w_packed, const float* bias, void* out_raw, void* out_act,
+                         int32_t batch, int32_t rows_in, int32_t c_in, int32_t c_out, int32_t kernel, int32_t stride,
+                         float slope, void* stream);
+
+/* conv_post (16 -> 1, k = 7) + tanh (HF:1480-1482); x is the leaky_relu(0.01)'ed stage-5 output (B, L, 16) bf16;
+ * w[7][16] fp32 (tap-major), wav (B, L) fp32 */
+int srb_hifigan_post(const void* x_act, const float* w, float bias, float* wav, int32_t batch, int32_t rows,
+                     void* stream);
+
+/* length-aware copy-out replacing the per-utterance crop loop (models.py:252-256):
+ * dst[offsets[b] + i] = wav[b, i] for i < 320*len_b + 80 */
+int srb_crop_concat(const float* wav, const int32_t* lengths, const int64_t* offsets, float* dst, int32_t batch,
+                    int32_t rows, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRB_H_ */

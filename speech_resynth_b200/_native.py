@@ -1,0 +1,109 @@
+"""ctypes binding of libsrb.so (the C ABI declared in include/srb.h).
+
+There is no fallback: if the shared library is missing or was not built for the GPU in use, importing the
+compute path raises.  torch is used only to own device memory and to name the current stream.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int32, c_int64, c_void_p
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsrb.so")
+
+_P = c_void_p
+_I = c_int32
+_L = c_int64
+_F = c_float
+
+# name -> argument ctypes (everything returns int except srb_last_error)
+_PROTOTYPES = {
+    "srb_version": [],
+    "srb_device_arch": [],
+    "srb_embed_gather": [_P, _P, _P, _L, _I, _I, _P],
+    "srb_unit_lengths": [_P, _P, _I, _I, _P],
+    "srb_time_cond_table": [_P, _I, _P, _P, _P, _P, _I, _P, _P, _P],
+    "srb_rotary_table": [_P, _I, _P, _P, _P],
+    "srb_prior_prepare": [_P, _P, _L, _F, _P],
+    "srb_cfm_embed": [_P, _P, _P, _P, _I, _I, _P],
+    "srb_cfm_posconv_norm": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P],
+    "srb_cfm_qkv_rope": [_P, _P, _P, _P, _P, _I, _I, _P],
+    "srb_cfm_attention": [_P, _P, _P, _I, _I, _P],
+    "srb_cfm_attn_out_norm": [_P, _P, _P, _P, _P, _P, _I, _I, _P],
+    "srb_cfm_ffn_glu": [_P, _P, _P, _P, _P, _I, _I, _P],
+    "srb_cfm_ffn_out_norm": [_P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _P],
+    "srb_cfm_pred_euler": [_P, _P, _F, _P, _P, _P, _P, _F, _F, _F, _P, _I, _I, _P],
+    "srb_hifigan_conv": [_P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _P],
+    "srb_hifigan_upsample": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P],
+    "srb_hifigan_post": [_P, _P, _F, _P, _I, _I, _P],
+    "srb_crop_concat": [_P, _P, _P, _P, _I, _I, _P],
+}
+
+EXPORTED_SYMBOLS = tuple(_PROTOTYPES) + ("srb_last_error",)
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+_lib: Optional[ctypes.CDLL] = None
+launch_count = 0  # kernels launched through this binding (bench.py reports it as gpu_launches)
+
+
+def load() -> ctypes.CDLL:
+    """Load libsrb.so and declare prototypes.  Raises NativeLibraryError when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeLibraryError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(speech_resynth_b200 has no CPU or PyTorch fallback)"
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in _PROTOTYPES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = c_int32
+    lib.srb_last_error.argtypes = []
+    lib.srb_last_error.restype = c_char_p
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().srb_last_error().decode("utf-8", "replace")
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "native ops take contiguous CUDA tensors"
+    return t.data_ptr()
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name: str, *args) -> None:
+    """Invoke an entry point on the current torch stream; non-zero status -> RuntimeError with the C-side text."""
+    global launch_count
+    lib = load()
+    rc = getattr(lib, name)(*args, stream_ptr())
+    if rc != 0:
+        raise RuntimeError(f"{name} failed ({rc}): {last_error()}")
+    launch_count += 1
+
+
+def require_blackwell() -> None:
+    lib = load()
+    if not torch.cuda.is_available():
+        raise NativeLibraryError("speech_resynth_b200 needs a CUDA device (sm_100a); none is visible")
+    arch = lib.srb_device_arch()
+    if arch != 100:
+        raise NativeLibraryError(f"libsrb.so is built for sm_100a only; current device reports sm_{arch}")

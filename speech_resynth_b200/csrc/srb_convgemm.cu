@@ -1,0 +1,502 @@
+// Host side of the implicit-GEMM core: tensor-map construction, tile bookkeeping, dispatch over the
+// (BN, KB, epilogue) instantiations, and the C-ABI ops that are thin descriptions on top of it.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cudaTypedefs.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/srb.h"
+#include "srb_common.h"
+#include "srb_convgemm.cuh"
+
+namespace srb {
+
+// ----------------------------------------------------------------------------------------- error plumbing
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return 0;
+  set_error("%s: %s", what, cudaGetErrorString(e));
+  return -1;
+}
+int num_sms() {
+  static int sms[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (sms[dev] == 0) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+  return sms[dev];
+}
+
+// ----------------------------------------------------------------------------------------- tensor maps
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+static CUtensorMapSwizzle swizzle_for(int kb) {
+  return kb == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kb == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+// activation view (batch, rows, channels) bf16 -> 3-D map, box = (kb channels, 128 rows, 1)
+static int make_act_map(CUtensorMap* m, const void* ptr, int channels, int rows, int batch, long long row_stride,
+                        long long batch_stride, int kb) {
+  auto enc = get_encode();
+  SRB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  SRB_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "activation pointer not 16-byte aligned");
+  SRB_REQUIRE((row_stride * 2) % 16 == 0 && (batch_stride * 2) % 16 == 0, "activation strides must be multiples of 16 bytes");
+  cuuint64_t dims[3] = {(cuuint64_t)channels, (cuuint64_t)rows, (cuuint64_t)batch};
+  cuuint64_t strides[2] = {(cuuint64_t)row_stride * 2, (cuuint64_t)batch_stride * 2};
+  cuuint32_t box[3] = {(cuuint32_t)kb, (cuuint32_t)kTileM, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(kb), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SRB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activation) failed: %d (C=%d rows=%d B=%d rs=%lld bs=%lld kb=%d)",
+              (int)r, channels, rows, batch, row_stride, batch_stride, kb);
+  return 0;
+}
+
+// packed weight [n_total][k_total] bf16 -> 2-D map, box = (kb, bn)
+static int make_weight_map(CUtensorMap* m, const void* ptr, int k_total, int n_total, int kb, int bn) {
+  auto enc = get_encode();
+  SRB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  SRB_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "weight pointer not 16-byte aligned");
+  SRB_REQUIRE((k_total * 2) % 16 == 0, "weight row pitch must be a multiple of 16 bytes");
+  cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)n_total};
+  cuuint64_t strides[1] = {(cuuint64_t)k_total * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kb, (cuuint32_t)bn};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(kb), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SRB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weight) failed: %d (K=%d N=%d kb=%d bn=%d)", (int)r, k_total,
+              n_total, kb, bn);
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------------- generic description
+struct ActView {
+  const void* ptr = nullptr;
+  int channels = 0, rows = 0, batch = 0;
+  long long row_stride = 0, batch_stride = 0;
+};
+
+struct ConvGemmDesc {
+  ActView src[kMaxSrc];
+  int n_src = 1;
+  const void* weight = nullptr;
+  int n_total = 0;
+  int block_n = 0, block_k = 0;
+  int channels = 0;                         // input channels per tap (same for every source)
+  int n_groups = 1;
+  int group_tap_begin[kMaxGroups + 1] = {0};
+  int group_rows[kMaxGroups] = {0};
+  int group_row_add[kMaxGroups] = {0};
+  int row_mul = 1;
+  int tap_src[kMaxTaps] = {0};
+  int tap_shift[kMaxTaps] = {0};
+  int batch = 0;
+  int epilogue = EPI_GENERIC;
+  ConvGemmParams epi;                       // only the epilogue-operand fields are read from here
+};
+
+template <int BN, int KB, int EPI>
+static int launch_inst(ConvGemmParams& p, int total_tiles, cudaStream_t stream) {
+  using L = StageLayout<BN, KB>;
+  auto kernel = convgemm_kernel<BN, KB, EPI>;
+  const int budget = L::stage_bytes >= 40 * 1024 ? 200 * 1024 : (L::stage_bytes >= 16 * 1024 ? 100 * 1024 : 44 * 1024);
+  int stages = budget / L::stage_bytes;
+  stages = stages < 2 ? 2 : (stages > 8 ? 8 : stages);
+  p.stages = stages;
+  const int smem = stages * L::stage_bytes + 1024 + 8 * (2 * stages + 4) + 16;
+  static int configured_smem[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (configured_smem[dev & 63] < smem) {
+    SRB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured_smem[dev & 63] = smem;
+  }
+  static int blocks_per_sm[64] = {0};
+  if (blocks_per_sm[dev & 63] == 0) {
+    int occ = 0;
+    SRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 192, smem));
+    const int tmem_limit = 512 / TmemCols<BN>::total;
+    occ = occ < 1 ? 1 : occ;
+    blocks_per_sm[dev & 63] = occ < tmem_limit ? occ : tmem_limit;
+  }
+  int grid = num_sms() * blocks_per_sm[dev & 63];
+  if (grid > total_tiles) grid = total_tiles;
+  if (grid < 1) return 0;
+  kernel<<<grid, 192, smem, stream>>>(p, total_tiles);
+  return after_launch("convgemm_kernel");
+}
+
+static int launch_convgemm(const ConvGemmDesc& d, cudaStream_t stream) {
+  ConvGemmParams p = d.epi;
+  const int bn = d.block_n, kb = d.block_k;
+  SRB_REQUIRE(d.n_total % bn == 0, "n_total %d not a multiple of block_n %d", d.n_total, bn);
+  SRB_REQUIRE(d.n_groups >= 1 && d.n_groups <= kMaxGroups, "bad group count %d", d.n_groups);
+  const int n_taps = d.group_tap_begin[d.n_groups];
+  SRB_REQUIRE(n_taps >= 1 && n_taps <= kMaxTaps, "bad tap count %d", n_taps);
+  p.batch = d.batch;
+  p.kchunks = (d.channels + kb - 1) / kb;
+  p.n_groups = d.n_groups;
+  p.n_tiles = d.n_total / bn;
+  p.row_mul = d.row_mul;
+  int tiles = 0;
+  for (int g = 0; g < kMaxGroups; ++g) {
+    p.tile_begin[g] = tiles;
+    if (g < d.n_groups) {
+      p.m_tiles[g] = (d.group_rows[g] + kTileM - 1) / kTileM;
+      p.group_rows[g] = d.group_rows[g];
+      p.group_row_add[g] = d.group_row_add[g];
+      tiles += d.batch * p.m_tiles[g] * p.n_tiles;
+    } else {
+      p.m_tiles[g] = 1;
+      p.group_rows[g] = 0;
+      p.group_row_add[g] = 0;
+    }
+    p.group_tap_begin[g] = d.group_tap_begin[g < d.n_groups ? g : d.n_groups];
+  }
+  p.tile_begin[kMaxGroups] = tiles;
+  p.group_tap_begin[kMaxGroups] = n_taps;
+  for (int g = d.n_groups; g <= kMaxGroups; ++g) p.group_tap_begin[g] = n_taps;
+  for (int t = 0; t < kMaxTaps; ++t) {
+    p.tap_shift[t] = (short)(t < n_taps ? d.tap_shift[t] : 0);
+    p.tap_src[t] = (signed char)(t < n_taps ? d.tap_src[t] : 0);
+  }
+  const int k_total = n_taps * p.kchunks * kb;
+  for (int s = 0; s < kMaxSrc; ++s) {
+    const ActView& a = d.src[s < d.n_src ? s : 0];
+    int rc = make_act_map(&p.tmA[s], a.ptr, a.channels, a.rows, a.batch, a.row_stride, a.batch_stride, kb);
+    if (rc) return rc;
+  }
+  int rc = make_weight_map(&p.tmW, d.weight, k_total, d.n_total, kb, bn);
+  if (rc) return rc;
+  if (tiles == 0) return 0;
+
+#define SRB_DISPATCH(BN_, KB_, EPI_) \
+  if (bn == BN_ && kb == KB_ && d.epilogue == EPI_) return launch_inst<BN_, KB_, EPI_>(p, tiles, stream);
+  SRB_DISPATCH(256, 64, EPI_GENERIC)
+  SRB_DISPATCH(128, 64, EPI_GENERIC)
+  SRB_DISPATCH(64, 64, EPI_GENERIC)
+  SRB_DISPATCH(32, 64, EPI_GENERIC)
+  SRB_DISPATCH(32, 32, EPI_GENERIC)
+  SRB_DISPATCH(16, 32, EPI_GENERIC)
+  SRB_DISPATCH(16, 16, EPI_GENERIC)
+  SRB_DISPATCH(256, 64, EPI_GLU)
+  SRB_DISPATCH(256, 64, EPI_RESNORM)
+  SRB_DISPATCH(256, 64, EPI_QKV_ROPE)
+  SRB_DISPATCH(80, 64, EPI_EULER)
+#undef SRB_DISPATCH
+  set_error("no convgemm instantiation for block_n=%d block_k=%d epilogue=%d", bn, kb, d.epilogue);
+  return -4;
+}
+
+static ConvGemmParams empty_epi() {
+  ConvGemmParams e;
+  memset(&e, 0, sizeof(e));
+  e.scale = 1.f;
+  e.slope = 1.f;
+  return e;
+}
+
+static ActView act(const void* ptr, int batch, int rows, int channels) {
+  ActView a;
+  a.ptr = ptr;
+  a.channels = channels;
+  a.rows = rows;
+  a.batch = batch;
+  a.row_stride = channels;
+  a.batch_stride = (long long)rows * channels;
+  return a;
+}
+
+static void same_conv_taps(ConvGemmDesc& d, int src, int kernel, int dilation, int& ntap) {
+  for (int j = 0; j < kernel; ++j) {
+    d.tap_src[ntap] = src;
+    d.tap_shift[ntap] = (j - (kernel - 1) / 2) * dilation;
+    ++ntap;
+  }
+}
+
+// channel block the vocoder uses for a given input width
+static int block_k_for(int c_in) { return c_in >= 64 ? 64 : (c_in >= 32 ? 32 : 16); }
+
+}  // namespace srb
+
+using namespace srb;
+
+extern "C" {
+
+int srb_version(void) { return SRB_VERSION; }
+const char* srb_last_error(void) { return g_err; }
+
+int srb_device_arch(void) {
+  int dev = 0, major = 0, minor = 0;
+  SRB_CUDA(cudaGetDevice(&dev));
+  SRB_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  SRB_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  return major * 10 + minor;
+}
+
+int srb_cfm_embed(const void* xt_bf16, const void* w_packed, const float* cond_proj, float* x0, int32_t batch,
+                  int32_t frames, void* stream) {
+  ConvGemmDesc d;
+  d.src[0] = act(xt_bf16, batch, frames, 80);
+  d.weight = w_packed;
+  d.n_total = 256;
+  d.block_n = 256;
+  d.block_k = 64;
+  d.channels = 80;
+  d.group_tap_begin[1] = 1;
+  d.group_rows[0] = frames;
+  d.batch = batch;
+  d.epilogue = EPI_RESNORM;
+  d.epi = empty_epi();
+  d.epi.norm_mode = 0;
+  d.epi.res[0] = cond_proj;
+  d.epi.res_row_stride = 256;
+  d.epi.res_batch_stride = (long long)frames * 256;
+  d.epi.out1 = x0;
+  d.epi.out_row_stride = 256;
+  d.epi.out_batch_stride = (long long)frames * 256;
+  return launch_convgemm(d, (cudaStream_t)stream);
+}
+
+int srb_cfm_qkv_rope(const void* xn_bf16, const void* w_packed, const float* rot_cos, const float* rot_sin,
+                     void* qkv_bf16, int32_t batch, int32_t frames, void* stream) {
+  ConvGemmDesc d;
+  d.src[0] = act(xn_bf16, batch, frames, 256);
+  d.weight = w_packed;
+  d.n_total = 768;
+  d.block_n = 256;
+  d.block_k = 64;
+  d.channels = 256;
+  d.group_tap_begin[1] = 1;
+  d.group_rows[0] = frames;
+  d.batch = batch;
+  d.epilogue = EPI_QKV_ROPE;
+  d.epi = empty_epi();
+  d.epi.vec0 = rot_cos;
+  d.epi.vec1 = rot_sin;
+  d.epi.out0 = qkv_bf16;
+  d.epi.out_row_stride = 768;
+  d.epi.out_batch_stride = (long long)frames * 768;
+  return launch_convgemm(d, (cudaStream_t)stream);
+}
+
+int srb_cfm_attn_out_norm(const void* o_bf16, const void* w_packed, const float* g, const int32_t* lengths, float* x,
+                          void* xn_bf16, int32_t batch, int32_t frames, void* stream) {
+  ConvGemmDesc d;
+  d.src[0] = act(o_bf16, batch, frames, 256);
+  d.weight = w_packed;
+  d.n_total = 256;
+  d.block_n = 256;
+  d.block_k = 64;
+  d.channels = 256;
+  d.group_tap_begin[1] = 1;
+  d.group_rows[0] = frames;
+  d.batch = batch;
+  d.epilogue = EPI_RESNORM;
+  d.epi = empty_epi();
+  d.epi.norm_mode = 1;
+  d.epi.vec0 = g;
+  d.epi.lengths = lengths;
+  d.epi.res[0] = x;
+  d.epi.res_row_stride = 256;
+  d.epi.res_batch_stride = (long long)frames * 256;
+  d.epi.out1 = x;
+  d.epi.out0 = xn_bf16;
+  d.epi.out_row_stride = 256;
+  d.epi.out_batch_stride = (long long)frames * 256;
+  return launch_convgemm(d, (cudaStream_t)stream);
+}
+
+int srb_cfm_ffn_glu(const void* xn_bf16, const void* w_packed, const float* bias_packed, const int32_t* lengths,
+                    void* h_bf16, int32_t batch, int32_t frames, void* stream) {
+  SRB_REQUIRE(lengths != nullptr, "srb_cfm_ffn_glu: lengths required");
+  ConvGemmDesc d;
+  d.src[0] = act(xn_bf16, batch, frames, 256);
+  d.weight = w_packed;
+  d.n_total = 1792;
+  d.block_n = 256;
+  d.block_k = 64;
+  d.channels = 256;
+  int ntap = 0;
+  same_conv_taps(d, 0, 3, 1, ntap);
+  d.group_tap_begin[1] = ntap;
+  d.group_rows[0] = frames;
+  d.batch = batch;
+  d.epilogue = EPI_GLU;
+  d.epi = empty_epi();
+  d.epi.bias = bias_packed;
+  d.epi.lengths = lengths;
+  d.epi.out0 = h_bf16;
+  d.epi.out_row_stride = 896;
+  d.epi.out_batch_stride = (long long)frames * 896;
+  return launch_convgemm(d, (cudaStream_t)stream);
+}
+
+int srb_cfm_ffn_out_norm(const void* h_bf16, const void* w_packed, const float* bias, const float* g, int32_t norm_mode,
+                         const int32_t* lengths, float* x, void* xn_bf16, int32_t batch, int32_t frames, void* stream) {
+  SRB_REQUIRE(norm_mode == 1 || norm_mode == 2, "srb_cfm_ffn_out_norm: norm_mode must be 1 or 2");
+  ConvGemmDesc d;
+  d.src[0] = act(h_bf16, batch, frames, 896);
+  d.weight = w_packed;
+  d.n_total = 256;
+  d.block_n = 256;
+  d.block_k = 64;
+  d.channels = 896;
+  int ntap = 0;
+  same_conv_taps(d, 0, 3, 1, ntap);
+  d.group_tap_begin[1] = ntap;
+  d.group_rows[0] = frames;
+  d.batch = batch;
+  d.epilogue = EPI_RESNORM;
+  d.epi = empty_epi();
+  d.epi.norm_mode = norm_mode;
+  d.epi.bias = bias;
+  d.epi.vec0 = g;
+  d.epi.lengths = lengths;
+  d.epi.res[0] = x;
+  d.epi.res_row_stride = 256;
+  d.epi.res_batch_stride = (long long)frames * 256;
+  d.epi.out1 = x;
+  d.epi.out0 = xn_bf16;
+  d.epi.out_row_stride = 256;
+  d.epi.out_batch_stride = (long long)frames * 256;
+  return launch_convgemm(d, (cudaStream_t)stream);
+}
+
+int srb_cfm_pred_euler(const void* xn_bf16, const void* w_packed, float dt, float* xt, void* xt_bf16, float* mel,
+                       void* mel_bf16, float std, float mean, float pad_value, const int32_t* lengths, int32_t batch,
+                       int32_t frames, void* stream) {
+  SRB_REQUIRE((mel == nullptr) == (mel_bf16 == nullptr), "srb_cfm_pred_euler: mel and mel_bf16 go together");
+  ConvGemmDesc d;
+  d.src[0] = act(xn_bf16, batch, frames, 256);
+  d.weight = w_packed;
+  d.n_total = 80;
+  d.block_n = 80;
+  d.block_k = 64;
+  d.channels = 256;
+  d.group_tap_begin[1] = 1;
+  d.group_rows[0] = frames;
+  d.batch = batch;
+  d.epilogue = EPI_EULER;
+  d.epi = empty_epi();
+  d.epi.lengths = lengths;
+  d.epi.out1 = xt;
+  d.epi.out0 = xt_bf16;
+  d.epi.out_row_stride = 80;
+  d.epi.out_batch_stride = (long long)frames * 80;
+  d.epi.f0 = dt;
+  d.epi.f1 = std;
+  d.epi.f2 = mean;
+  d.epi.f3 = pad_value;
+  d.epi.aux0 = mel;
+  d.epi.aux1 = mel_bf16;
+  return launch_convgemm(d, (cudaStream_t)stream);
+}
+
+int srb_hifigan_conv(const void* x0, const void* x1, const void* x2, int32_t n_src, const int32_t* kernel,
+                     const int32_t* dilation, const void* w_packed, const float* bias, const void* res0,
+                     const void* res1, const void* res2, void* out_raw, void* out_act, int32_t batch, int32_t rows,
+                     int32_t c_in, int32_t c_out, float scale, float slope, void* stream) {
+  SRB_REQUIRE(n_src >= 1 && n_src <= 3, "srb_hifigan_conv: n_src must be 1..3");
+  const void* xs[3] = {x0, x1, x2};
+  ConvGemmDesc d;
+  d.n_src = n_src;
+  int ntap = 0;
+  for (int s = 0; s < n_src; ++s) {
+    SRB_REQUIRE(xs[s] != nullptr, "srb_hifigan_conv: source %d is NULL", s);
+    SRB_REQUIRE(kernel[s] % 2 == 1 && ntap + kernel[s] <= kMaxTaps, "srb_hifigan_conv: bad kernel size");
+    d.src[s] = act(xs[s], batch, rows, c_in);
+    same_conv_taps(d, s, kernel[s], dilation[s], ntap);
+  }
+  d.weight = w_packed;
+  d.n_total = c_out;
+  d.block_n = c_out > 256 ? 256 : c_out;
+  d.block_k = block_k_for(c_in);
+  d.channels = c_in;
+  d.group_tap_begin[1] = ntap;
+  d.group_rows[0] = rows;
+  d.batch = batch;
+  d.epilogue = EPI_GENERIC;
+  d.epi = empty_epi();
+  d.epi.bias = bias;
+  d.epi.res[0] = res0;
+  d.epi.res[1] = res1;
+  d.epi.res[2] = res2;
+  d.epi.res_row_stride = c_out;
+  d.epi.res_batch_stride = (long long)rows * c_out;
+  d.epi.out1 = out_raw;
+  d.epi.out0 = out_act;
+  d.epi.out_row_stride = c_out;
+  d.epi.out_batch_stride = (long long)rows * c_out;
+  d.epi.scale = scale;
+  d.epi.slope = slope;
+  return launch_convgemm(d, (cudaStream_t)stream);
+}
+
+int srb_hifigan_upsample(const void* x, const void* w_packed, const float* bias, void* out_raw, void* out_act,
+                         int32_t batch, int32_t rows_in, int32_t c_in, int32_t c_out, int32_t kernel, int32_t stride,
+                         float slope, void* stream) {
+  SRB_REQUIRE(stride >= 1 && stride <= kMaxGroups, "srb_hifigan_upsample: stride %d unsupported", stride);
+  const int pad = (kernel - stride) / 2;
+  const int rows_out = (rows_in - 1) * stride - 2 * pad + kernel;
+  ConvGemmDesc d;
+  d.src[0] = act(x, batch, rows_in, c_in);
+  d.weight = w_packed;
+  d.n_total = c_out;
+  d.block_n = c_out > 256 ? 256 : c_out;
+  d.block_k = block_k_for(c_in);
+  d.channels = c_in;
+  d.n_groups = stride;
+  d.row_mul = stride;
+  int ntap = 0;
+  for (int r = 0; r < stride; ++r) {
+    // out[q*stride + r] = sum_m W[:, :, j0 + m*stride]^T x[q + c_r - m],  j0 = (r+pad) % stride, c_r = (r+pad) / stride
+    const int j0 = (r + pad) % stride, c_r = (r + pad) / stride;
+    d.group_tap_begin[r] = ntap;
+    for (int j = j0, m = 0; j < kernel; j += stride, ++m) {
+      SRB_REQUIRE(ntap < kMaxTaps, "srb_hifigan_upsample: too many taps");
+      d.tap_src[ntap] = 0;
+      d.tap_shift[ntap] = c_r - m;
+      ++ntap;
+    }
+    d.group_rows[r] = rows_out > r ? (rows_out - r + stride - 1) / stride : 0;
+    d.group_row_add[r] = r;
+  }
+  d.group_tap_begin[stride] = ntap;
+  d.batch = batch;
+  d.epilogue = EPI_GENERIC;
+  d.epi = empty_epi();
+  d.epi.bias = bias;
+  d.epi.out1 = out_raw;
+  d.epi.out0 = out_act;
+  d.epi.out_row_stride = c_out;
+  d.epi.out_batch_stride = (long long)rows_out * c_out;
+  d.epi.res_row_stride = c_out;
+  d.epi.res_batch_stride = (long long)rows_out * c_out;
+  d.epi.slope = slope;
+  return launch_convgemm(d, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,501 @@
+// Implicit-GEMM conv1d / linear core for sm_100a: TMA -> swizzled smem -> tcgen05.mma (accumulators in TMEM)
+// -> fused epilogue straight from TMEM.  One kernel template serves every dense op of the path:
+//   Linear (1 tap), k=3 FFN convs, dilated HiFi-GAN convs (k = 3/7/11), conv_pre (k = 7), the fused MRF tail
+//   (21 taps over 3 source tensors) and the polyphase transposed convs (one tap group per output phase).
+//
+// GEMM view:  D[128 rows (time) x BN (out channels)] += A[128 x KB] * W[BN x KB]^T  per K step, where the A box
+// of a tap is the activation tile shifted by the tap's time offset (3-D tensor map (channels, rows, batch); TMA
+// zero-fills rows outside [0, rows) which is exactly the conv's zero padding and also isolates utterances).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue
+// (thread <-> accumulator row / TMEM lane).  smem ring of `stages` {A, W} slots; two TMEM accumulator buffers so
+// the epilogue of tile i overlaps the MMAs of tile i+1; persistent over tiles.
+#pragma once
+#include <cuda.h>
+#include "srb_ptx.cuh"
+
+namespace srb {
+
+constexpr int kMaxTaps = 32;
+constexpr int kMaxGroups = 5;
+constexpr int kMaxSrc = 3;
+constexpr int kTileM = 128;
+
+enum Epilogue : int { EPI_GENERIC = 0, EPI_GLU = 1, EPI_RESNORM = 2, EPI_QKV_ROPE = 3, EPI_EULER = 4 };
+
+struct ConvGemmParams {
+  CUtensorMap tmA[kMaxSrc];
+  CUtensorMap tmW;
+  // problem
+  int batch, kchunks, n_groups, n_tiles;          // n_tiles = n_total / BN
+  int m_tiles[kMaxGroups];                        // row tiles per batch, per group
+  int tile_begin[kMaxGroups + 1];                 // prefix sum of batch*m_tiles*n_tiles
+  int group_tap_begin[kMaxGroups + 1];
+  int group_rows[kMaxGroups];                     // valid output rows q per batch
+  int group_row_add[kMaxGroups];                  // output row = q*row_mul + row_add
+  int row_mul;
+  short tap_shift[kMaxTaps];
+  signed char tap_src[kMaxTaps];
+  int stages;
+  // epilogue operands
+  const float* bias;
+  void* out0;                                     // bf16 "activated"/normalised output
+  void* out1;                                     // raw output (bf16 for GENERIC, fp32 for RESNORM/EULER)
+  long long out_row_stride, out_batch_stride;     // elements
+  const void* res[3];
+  long long res_row_stride, res_batch_stride;
+  const int* lengths;
+  const float* vec0;
+  const float* vec1;
+  float scale, slope;
+  int norm_mode;                                  // RESNORM: 0 none, 1 adaptive (L2), 2 rms
+  float f0, f1, f2, f3;                           // EULER: dt, std, mean, pad
+  void* aux0;                                     // EULER: mel fp32 (or null)
+  void* aux1;                                     // EULER: mel bf16
+};
+
+template <int BN>
+struct TmemCols {
+  static constexpr int buf = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+  static constexpr int total = 2 * buf;
+};
+
+template <int BN, int KB>
+struct StageLayout {
+  static constexpr int a_bytes = kTileM * KB * 2;
+  static constexpr int w_bytes_raw = BN * KB * 2;
+  static constexpr int w_bytes = (w_bytes_raw + 1023) & ~1023;
+  static constexpr int stage_bytes = a_bytes + w_bytes;
+};
+
+struct TileCoord {
+  int group, b, m, n;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const ConvGemmParams& p, int tile) {
+  TileCoord c;
+  int g = 0;
+#pragma unroll
+  for (int i = 1; i < kMaxGroups; ++i)
+    if (i < p.n_groups && tile >= p.tile_begin[i]) g = i;
+  int local = tile - p.tile_begin[g];
+  c.group = g;
+  c.n = local % p.n_tiles;
+  int rest = local / p.n_tiles;
+  c.m = rest % p.m_tiles[g];
+  c.b = rest / p.m_tiles[g];
+  return c;
+}
+
+// ---------------------------------------------------------------------------------------------- epilogues
+// Every epilogue runs with thread <-> one accumulator row; `tacc` is the TMEM address of (lane base, column 0)
+// of this tile's accumulator buffer.  All 32 lanes of a warp must execute the tcgen05.ld/st (sync.aligned).
+
+template <int BN>
+__device__ __forceinline__ void epi_generic(const ConvGemmParams& p, uint32_t tacc, const TileCoord& tc, int q) {
+  constexpr int CW = BN < 32 ? BN : 32;
+  const bool valid = q < p.group_rows[tc.group];
+  const long long orow = (long long)q * p.row_mul + p.group_row_add[tc.group];
+  const long long obase = (long long)tc.b * p.out_batch_stride + orow * p.out_row_stride + (long long)tc.n * BN;
+  const long long rbase = (long long)tc.b * p.res_batch_stride + orow * p.res_row_stride + (long long)tc.n * BN;
+#pragma unroll 1
+  for (int c0 = 0; c0 < BN; c0 += CW) {
+    float y[CW];
+    if constexpr (CW == 32) {
+      uint32_t v[32];
+      tmem_ld32(tacc + c0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) y[j] = __uint_as_float(v[j]);
+    } else {
+      uint32_t v[16];
+      tmem_ld16(tacc + c0, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) y[j] = __uint_as_float(v[j]);
+    }
+    if (valid) {
+      if (p.bias) {
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + tc.n * BN + c0);
+#pragma unroll
+        for (int j = 0; j < CW / 4; ++j) {
+          float4 bb = __ldg(b4 + j);
+          y[4 * j + 0] += bb.x; y[4 * j + 1] += bb.y; y[4 * j + 2] += bb.z; y[4 * j + 3] += bb.w;
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        if (p.res[r]) {
+          const uint4* r4 = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.res[r]) + rbase + c0);
+#pragma unroll
+          for (int j = 0; j < CW / 8; ++j) {
+            uint4 u = __ldg(r4 + j);
+            y[8 * j + 0] += bf16_lo(u.x); y[8 * j + 1] += bf16_hi(u.x);
+            y[8 * j + 2] += bf16_lo(u.y); y[8 * j + 3] += bf16_hi(u.y);
+            y[8 * j + 4] += bf16_lo(u.z); y[8 * j + 5] += bf16_hi(u.z);
+            y[8 * j + 6] += bf16_lo(u.w); y[8 * j + 7] += bf16_hi(u.w);
+          }
+        }
+      }
+      const float sc = p.scale;
+#pragma unroll
+      for (int j = 0; j < CW; ++j) y[j] *= sc;
+      if (p.out1) {
+        uint4* o4 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out1) + obase + c0);
+#pragma unroll
+        for (int j = 0; j < CW / 8; ++j)
+          o4[j] = make_uint4(pack_bf16(y[8 * j], y[8 * j + 1]), pack_bf16(y[8 * j + 2], y[8 * j + 3]),
+                             pack_bf16(y[8 * j + 4], y[8 * j + 5]), pack_bf16(y[8 * j + 6], y[8 * j + 7]));
+      }
+      if (p.out0) {
+        const float sl = p.slope;
+        uint4* o4 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out0) + obase + c0);
+#pragma unroll
+        for (int j = 0; j < CW / 8; ++j)
+          o4[j] = make_uint4(pack_bf16(lrelu(y[8 * j], sl), lrelu(y[8 * j + 1], sl)),
+                             pack_bf16(lrelu(y[8 * j + 2], sl), lrelu(y[8 * j + 3], sl)),
+                             pack_bf16(lrelu(y[8 * j + 4], sl), lrelu(y[8 * j + 5], sl)),
+                             pack_bf16(lrelu(y[8 * j + 6], sl), lrelu(y[8 * j + 7], sl)));
+      }
+    }
+  }
+}
+
+// FFN conv1 tile = [128 value columns | 128 gate columns] -> 128 outputs  (fastspeech/modules.py:27-30, 62-69)
+__device__ __forceinline__ void epi_glu(const ConvGemmParams& p, uint32_t tacc, const TileCoord& tc, int q) {
+  const bool valid = q < p.group_rows[0];
+  const bool keep = valid && q < p.lengths[tc.b];
+  __nv_bfloat16* out = static_cast<__nv_bfloat16*>(p.out0) + (long long)tc.b * p.out_batch_stride +
+                       (long long)q * p.out_row_stride + tc.n * 128;
+  const float* bias = p.bias + tc.n * 256;
+#pragma unroll 1
+  for (int c0 = 0; c0 < 128; c0 += 32) {
+    uint32_t v[32], g[32];
+    tmem_ld32(tacc + c0, v);
+    tmem_ld32(tacc + 128 + c0, g);
+    tmem_ld_wait();
+    if (valid) {
+      uint32_t o[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float h0 = 0.f, h1 = 0.f;
+        if (keep) {
+          float v0 = __uint_as_float(v[2 * j]) + __ldg(bias + c0 + 2 * j);
+          float v1 = __uint_as_float(v[2 * j + 1]) + __ldg(bias + c0 + 2 * j + 1);
+          float g0 = __uint_as_float(g[2 * j]) + __ldg(bias + 128 + c0 + 2 * j);
+          float g1 = __uint_as_float(g[2 * j + 1]) + __ldg(bias + 128 + c0 + 2 * j + 1);
+          h0 = silu(g0) * v0;
+          h1 = silu(g1) * v1;
+        }
+        o[j] = pack_bf16(h0, h1);
+      }
+      uint4* o4 = reinterpret_cast<uint4*>(out + c0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o4[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+    }
+  }
+}
+
+// y = acc + bias + residual (fp32 stream, in place allowed); x_out = y; xn = bf16(norm(y) * g) with pad rows zeroed.
+// The full 256-wide row lives in this thread's TMEM lane, so the row reduction needs no communication.
+__device__ __forceinline__ void epi_resnorm(const ConvGemmParams& p, uint32_t tacc, const TileCoord& tc, int q) {
+  const bool valid = q < p.group_rows[0];
+  const long long off = (long long)tc.b * p.out_batch_stride + (long long)q * p.out_row_stride;
+  const float* res = static_cast<const float*>(p.res[0]) + (long long)tc.b * p.res_batch_stride + (long long)q * p.res_row_stride;
+  float* xout = static_cast<float*>(p.out1) + off;
+  float sumsq = 0.f;
+#pragma unroll 1
+  for (int c0 = 0; c0 < 256; c0 += 32) {
+    uint32_t v[32];
+    tmem_ld32(tacc + c0, v);
+    tmem_ld_wait();
+    if (valid) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 r = *reinterpret_cast<const float4*>(res + c0 + 4 * j);
+        float4 y;
+        y.x = __uint_as_float(v[4 * j + 0]) + r.x;
+        y.y = __uint_as_float(v[4 * j + 1]) + r.y;
+        y.z = __uint_as_float(v[4 * j + 2]) + r.z;
+        y.w = __uint_as_float(v[4 * j + 3]) + r.w;
+        if (p.bias) {
+          float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + 4 * j));
+          y.x += bb.x; y.y += bb.y; y.z += bb.z; y.w += bb.w;
+        }
+        sumsq += y.x * y.x + y.y * y.y + y.z * y.z + y.w * y.w;
+        *reinterpret_cast<float4*>(xout + c0 + 4 * j) = y;
+        v[4 * j + 0] = __float_as_uint(y.x); v[4 * j + 1] = __float_as_uint(y.y);
+        v[4 * j + 2] = __float_as_uint(y.z); v[4 * j + 3] = __float_as_uint(y.w);
+      }
+    }
+    if (p.norm_mode != 0) tmem_st32(tacc + c0, v);  // stash y for the second pass
+  }
+  if (p.norm_mode == 0) return;
+  tmem_st_wait();
+  float inv;
+  if (p.norm_mode == 1) inv = 1.f / fmaxf(sqrtf(sumsq), 1e-12f);           // F.normalize (norm.py:41)
+  else inv = rsqrtf(sumsq * (1.f / 256.f) + 1.1920928955078125e-07f);      // nn.RMSNorm eps = finfo(fp32).eps
+  const bool keep = valid && (p.lengths == nullptr || q < p.lengths[tc.b]);
+  __nv_bfloat16* xn = static_cast<__nv_bfloat16*>(p.out0) + off;
+#pragma unroll 1
+  for (int c0 = 0; c0 < 256; c0 += 32) {
+    uint32_t v[32];
+    tmem_ld32(tacc + c0, v);
+    tmem_ld_wait();
+    if (valid) {
+      uint32_t o[16];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 g = __ldg(reinterpret_cast<const float4*>(p.vec0 + c0 + 4 * j));
+        // select (not multiply) so a non-finite pad row can never leak into the conv taps of valid frames
+        o[2 * j] = keep ? pack_bf16(__uint_as_float(v[4 * j]) * inv * g.x, __uint_as_float(v[4 * j + 1]) * inv * g.y) : 0u;
+        o[2 * j + 1] = keep ? pack_bf16(__uint_as_float(v[4 * j + 2]) * inv * g.z, __uint_as_float(v[4 * j + 3]) * inv * g.w) : 0u;
+      }
+      uint4* o4 = reinterpret_cast<uint4*>(xn + c0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o4[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+    }
+  }
+}
+
+// to_qkv tile n: 0 = q (2 heads x 128), 1 = k, 2 = v.  Rotary (transformer.py:66-73) on q,k:
+// out[i] = t[i] cos - t[i+64] sin ; out[i+64] = t[i+64] cos + t[i] sin, angle = pos * inv_freq[i], i < 64.
+__device__ __forceinline__ void epi_qkv_rope(const ConvGemmParams& p, uint32_t tacc, const TileCoord& tc, int q) {
+  const bool valid = q < p.group_rows[0];
+  __nv_bfloat16* out = static_cast<__nv_bfloat16*>(p.out0) + (long long)tc.b * p.out_batch_stride +
+                       (long long)q * p.out_row_stride + tc.n * 256;
+  if (tc.n == 2) {
+#pragma unroll 1
+    for (int c0 = 0; c0 < 256; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tacc + c0, v);
+      tmem_ld_wait();
+      if (valid) {
+        uint4* o4 = reinterpret_cast<uint4*>(out + c0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          o4[j] = make_uint4(pack_bf16(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1])),
+                             pack_bf16(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
+                             pack_bf16(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
+                             pack_bf16(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
+      }
+    }
+    return;
+  }
+  const float* cs = p.vec0 + (long long)(valid ? q : 0) * 64;
+  const float* sn = p.vec1 + (long long)(valid ? q : 0) * 64;
+#pragma unroll 1
+  for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll 1
+    for (int f0 = 0; f0 < 64; f0 += 32) {
+      uint32_t lo[32], hi[32];
+      tmem_ld32(tacc + hh * 128 + f0, lo);
+      tmem_ld32(tacc + hh * 128 + 64 + f0, hi);
+      tmem_ld_wait();
+      if (valid) {
+        uint32_t olo[16], ohi[16];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 c = __ldg(reinterpret_cast<const float4*>(cs + f0 + 4 * j));
+          float4 s = __ldg(reinterpret_cast<const float4*>(sn + f0 + 4 * j));
+          float a0 = __uint_as_float(lo[4 * j]), a1 = __uint_as_float(lo[4 * j + 1]);
+          float a2 = __uint_as_float(lo[4 * j + 2]), a3 = __uint_as_float(lo[4 * j + 3]);
+          float b0 = __uint_as_float(hi[4 * j]), b1 = __uint_as_float(hi[4 * j + 1]);
+          float b2 = __uint_as_float(hi[4 * j + 2]), b3 = __uint_as_float(hi[4 * j + 3]);
+          olo[2 * j] = pack_bf16(a0 * c.x - b0 * s.x, a1 * c.y - b1 * s.y);
+          olo[2 * j + 1] = pack_bf16(a2 * c.z - b2 * s.z, a3 * c.w - b3 * s.w);
+          ohi[2 * j] = pack_bf16(b0 * c.x + a0 * s.x, b1 * c.y + a1 * s.y);
+          ohi[2 * j + 1] = pack_bf16(b2 * c.z + a2 * s.z, b3 * c.w + a3 * s.w);
+        }
+        uint4* l4 = reinterpret_cast<uint4*>(out + hh * 128 + f0);
+        uint4* h4 = reinterpret_cast<uint4*>(out + hh * 128 + 64 + f0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          l4[j] = make_uint4(olo[4 * j], olo[4 * j + 1], olo[4 * j + 2], olo[4 * j + 3]);
+          h4[j] = make_uint4(ohi[4 * j], ohi[4 * j + 1], ohi[4 * j + 2], ohi[4 * j + 3]);
+        }
+      }
+    }
+  }
+}
+
+template <int N>
+__device__ __forceinline__ void euler_chunk(const uint32_t (&v)[N], int c0, float* xt, __nv_bfloat16* xtb, float* mel,
+                                            __nv_bfloat16* melb, long long off, bool is_pad, float dt, float sd,
+                                            float mean, float padv) {
+#pragma unroll
+  for (int j = 0; j < N; j += 4) {
+    float4 x = *reinterpret_cast<const float4*>(xt + c0 + j);
+    x.x += dt * __uint_as_float(v[j]);
+    x.y += dt * __uint_as_float(v[j + 1]);
+    x.z += dt * __uint_as_float(v[j + 2]);
+    x.w += dt * __uint_as_float(v[j + 3]);
+    *reinterpret_cast<float4*>(xt + c0 + j) = x;
+    *reinterpret_cast<uint2*>(xtb + c0 + j) = make_uint2(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w));
+    if (mel) {
+      float4 m;
+      m.x = is_pad ? padv : x.x * sd + mean;
+      m.y = is_pad ? padv : x.y * sd + mean;
+      m.z = is_pad ? padv : x.z * sd + mean;
+      m.w = is_pad ? padv : x.w * sd + mean;
+      *reinterpret_cast<float4*>(mel + off + c0 + j) = m;
+      *reinterpret_cast<uint2*>(melb + off + c0 + j) = make_uint2(pack_bf16(m.x, m.y), pack_bf16(m.z, m.w));
+    }
+  }
+}
+
+// to_pred (N = 80) + Euler step in fp32 (models.py:183-184); last step also de-normalises and fills pads (:186-187)
+__device__ __forceinline__ void epi_euler(const ConvGemmParams& p, uint32_t tacc, const TileCoord& tc, int q) {
+  const bool valid = q < p.group_rows[0];
+  const long long off = (long long)tc.b * p.out_batch_stride + (long long)q * p.out_row_stride;
+  float* xt = static_cast<float*>(p.out1) + off;
+  __nv_bfloat16* xtb = static_cast<__nv_bfloat16*>(p.out0) + off;
+  float* mel = static_cast<float*>(p.aux0);
+  __nv_bfloat16* melb = static_cast<__nv_bfloat16*>(p.aux1);
+  const bool is_pad = valid && p.lengths != nullptr && q >= p.lengths[tc.b];
+  const float dt = p.f0, sd = p.f1, mean = p.f2, padv = p.f3;
+  {
+    uint32_t v[32];
+    tmem_ld32(tacc, v);
+    tmem_ld_wait();
+    if (valid) euler_chunk<32>(v, 0, xt, xtb, mel, melb, off, is_pad, dt, sd, mean, padv);
+    tmem_ld32(tacc + 32, v);
+    tmem_ld_wait();
+    if (valid) euler_chunk<32>(v, 32, xt, xtb, mel, melb, off, is_pad, dt, sd, mean, padv);
+  }
+  {
+    uint32_t v[16];
+    tmem_ld16(tacc + 64, v);
+    tmem_ld_wait();
+    if (valid) euler_chunk<16>(v, 64, xt, xtb, mel, melb, off, is_pad, dt, sd, mean, padv);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- kernel
+template <int BN, int KB, int EPI>
+__global__ void __launch_bounds__(192) convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
+  using L = StageLayout<BN, KB>;
+  constexpr int SW = KB * 2;
+  constexpr int TBUF = TmemCols<BN>::buf;
+  constexpr int TCOLS = TmemCols<BN>::total;
+  constexpr uint32_t IDESC = umma_idesc_bf16(kTileM, BN);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int stages = p.stages;
+  const uint32_t bar_base = smem_base + stages * L::stage_bytes;  // 8-byte aligned (stage_bytes % 1024 == 0)
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (stages + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * stages + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * stages + 2 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * stages + 4);
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 4);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&p.tmW);
+    tma_prefetch_desc(&p.tmA[0]);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TCOLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(p, tile);
+        const int t0 = tc.m * kTileM;
+        const int tap0 = p.group_tap_begin[tc.group];
+        const int ntap = p.group_tap_begin[tc.group + 1] - tap0;
+        int wk = tap0 * p.kchunks * KB;
+        for (int t = 0; t < ntap; ++t) {
+          const int src = p.tap_src[tap0 + t];
+          const int row = t0 + p.tap_shift[tap0 + t];
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            mbar_expect_tx(full_bar(stage), L::a_bytes + L::w_bytes_raw);
+            const uint32_t a_dst = smem_base + stage * L::stage_bytes;
+            tma_load_3d(a_dst, &p.tmA[src], full_bar(stage), kc * KB, row, tc.b);
+            tma_load_2d(a_dst + L::a_bytes, &p.tmW, full_bar(stage), wk, tc.n * BN);
+            wk += KB;
+            if (++stage == stages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const TileCoord tc = decode_tile(p, tile);
+        const int nk = (p.group_tap_begin[tc.group + 1] - p.group_tap_begin[tc.group]) * p.kchunks;
+        const int buf = it & 1;
+        const uint32_t bphase = (it >> 1) & 1;
+        mbar_wait(tempty_bar(buf), bphase ^ 1u);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + buf * TBUF;
+        for (int ks = 0; ks < nk; ++ks) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + stage * L::stage_bytes;
+          const uint64_t adesc = umma_smem_desc<SW>(a_addr);
+          const uint64_t wdesc = umma_smem_desc<SW>(a_addr + L::a_bytes);
+#pragma unroll
+          for (int k = 0; k < KB / 16; ++k)
+            umma_bf16(tacc, adesc + 2 * k, wdesc + 2 * k, IDESC, (ks | k) != 0 ? 1u : 0u);
+          umma_commit(empty_bar(stage));
+          if (++stage == stages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(buf));
+      }
+    }
+    __syncwarp();
+  } else {
+    const int lane_base = (warp & 3) * 32;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const TileCoord tc = decode_tile(p, tile);
+      const int buf = it & 1;
+      const uint32_t bphase = (it >> 1) & 1;
+      mbar_wait(tfull_bar(buf), bphase);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + (static_cast<uint32_t>(lane_base) << 16) + buf * TBUF;
+      const int q = tc.m * kTileM + lane_base + lane;
+      if constexpr (EPI == EPI_GENERIC) epi_generic<BN>(p, tacc, tc, q);
+      else if constexpr (EPI == EPI_GLU) epi_glu(p, tacc, tc, q);
+      else if constexpr (EPI == EPI_RESNORM) epi_resnorm(p, tacc, tc, q);
+      else if constexpr (EPI == EPI_QKV_ROPE) epi_qkv_rope(p, tacc, tc, q);
+      else epi_euler(p, tacc, tc, q);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(buf));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TCOLS);
+}
+
+}  // namespace srb

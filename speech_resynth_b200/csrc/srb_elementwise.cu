@@ -1,0 +1,279 @@
+// HBM-bound pieces of the path: embedding gather, conditioning tables, depthwise positional conv, prior
+// preparation, the 16->1 output conv + tanh and the length-aware copy-out.  CUDA-core kernels, vectorised and
+// coalesced; none of them is GEMM shaped.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "../../include/srb.h"
+#include "srb_common.h"
+#include "srb_ptx.cuh"
+
+namespace srb {
+
+// ------------------------------------------------------------------------------------------ embedding gather
+// One warp per output row; 16-byte loads/stores; the table (<= 6 MB) stays L2 resident.  models.py:154
+__global__ void __launch_bounds__(256) embed_gather_kernel(const float4* __restrict__ table, const int64_t* __restrict__ ids,
+                                                           float4* __restrict__ out, long long m, int vocab_rows,
+                                                           int dim4) {
+  const int lane = threadIdx.x & 31;
+  const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < m; row += warps) {
+    long long id = ids[row];
+    id = id < 0 ? 0 : (id >= vocab_rows ? vocab_rows - 1 : id);
+    const float4* src = table + id * dim4;
+    float4* dst = out + row * dim4;
+    for (int c = lane; c < dim4; c += 32) {
+      float4 v = __ldg(src + c);
+      __stcs(dst + c, v);  // streaming store: written once, read by later kernels from L2/HBM
+    }
+  }
+}
+
+__global__ void unit_lengths_kernel(const int64_t* __restrict__ ids, int* __restrict__ lengths, int frames) {
+  const int b = blockIdx.x;
+  int cnt = 0;
+  for (int t = threadIdx.x; t < frames; t += blockDim.x) cnt += ids[(long long)b * frames + t] != 0;
+  __shared__ int s[32];
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tot = 0;
+    for (int w = 0; w < (blockDim.x + 31) / 32; ++w) tot += s[w];
+    lengths[b] = tot;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ time conditioning
+// One block (256 threads) per ODE step.  fourier_embed.py:37-40, models.py:47-49, norm.py:42.
+__global__ void __launch_bounds__(256) time_cond_kernel(const float* __restrict__ times, const float* __restrict__ four_w,
+                                                        const float* __restrict__ lin_w, const float* __restrict__ lin_b,
+                                                        const float* __restrict__ gamma_w, int n_norm,
+                                                        float* __restrict__ time_emb, float* __restrict__ g) {
+  __shared__ float four[257];
+  __shared__ float c[256];
+  const int s = blockIdx.x, tid = threadIdx.x;
+  const float t = times[s];
+  if (tid == 0) four[0] = t;
+  if (tid < 128) {
+    // freqs = ((t * w) * 2) * pi, evaluated in that order in fp32 (fourier_embed.py:38)
+    float f = __fmul_rn(__fmul_rn(__fmul_rn(t, four_w[tid]), 2.0f), 3.14159265358979323846f);
+    four[1 + tid] = sinf(f);
+    four[129 + tid] = cosf(f);
+  }
+  __syncthreads();
+  float acc = lin_b[tid];
+  const float* wrow = lin_w + (long long)tid * 257;
+  for (int k = 0; k < 257; ++k) acc = fmaf(wrow[k], four[k], acc);
+  const float ce = acc / (1.f + expf(-acc));  // SiLU
+  c[tid] = ce;
+  time_emb[(long long)s * 256 + tid] = ce;
+  __syncthreads();
+  for (int j = 0; j < n_norm; ++j) {
+    const float* w = gamma_w + ((long long)j * 256 + tid) * 256;
+    float a = 0.f;
+    for (int k = 0; k < 256; ++k) a = fmaf(w[k], c[k], a);
+    g[((long long)s * n_norm + j) * 256 + tid] = 16.0f * (a + 1.0f);  // sqrt(256) * (gamma + 1)
+  }
+}
+
+__global__ void rotary_table_kernel(const float* __restrict__ inv_freq, int rows, float* __restrict__ cs,
+                                    float* __restrict__ sn) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * 64) return;
+  const int pos = i >> 6, f = i & 63;
+  const float a = __fmul_rn((float)pos, inv_freq[f]);  // transformer.py:61
+  cs[i] = cosf(a);
+  sn[i] = sinf(a);
+}
+
+__global__ void prior_prepare_kernel(float4* __restrict__ xt, uint2* __restrict__ xtb, long long n4, float tv) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 v = xt[i];
+    if (tv > 0.f) {
+      v.x = fminf(fmaxf(v.x, -tv), tv);
+      v.y = fminf(fmaxf(v.y, -tv), tv);
+      v.z = fminf(fmaxf(v.z, -tv), tv);
+      v.w = fminf(fmaxf(v.w, -tv), tv);
+      xt[i] = v;
+    }
+    xtb[i] = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+  }
+}
+
+// ------------------------------------------------------------------------------------------ positional conv
+// x = gelu(dwconv31(mask(x0)) + b) * mask + x0, then the first AdaptiveRMSNorm.  Block = 256 threads (one per
+// channel) x ROWS consecutive frames of one utterance; each thread keeps its channel's 31-tap window in registers.
+template <int ROWS>
+__global__ void __launch_bounds__(256) posconv_norm_kernel(const float* __restrict__ x0, const float* __restrict__ dw_w,
+                                                           const float* __restrict__ dw_b, const float* __restrict__ g,
+                                                           const int* __restrict__ lengths, float* __restrict__ x,
+                                                           __nv_bfloat16* __restrict__ xn, int frames) {
+  constexpr int K = 31, HALO = 15;
+  const int b = blockIdx.y, t0 = blockIdx.x * ROWS, c = threadIdx.x;
+  const int len = lengths[b];
+  const float* xb = x0 + (long long)b * frames * 256;
+  float w[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) w[j] = __ldg(dw_w + c * K + j);
+  const float bias = __ldg(dw_b + c);
+  const float gc = __ldg(g + c);
+  float win[ROWS + 2 * HALO];
+#pragma unroll
+  for (int i = 0; i < ROWS + 2 * HALO; ++i) {
+    const int t = t0 - HALO + i;
+    win[i] = (t >= 0 && t < len && t < frames) ? __ldg(xb + (long long)t * 256 + c) : 0.f;
+  }
+  __shared__ float red[ROWS][8];
+  float xv[ROWS];
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    const int t = t0 + r;
+    float acc = bias;
+#pragma unroll
+    for (int j = 0; j < K; ++j) acc = fmaf(w[j], win[r + j], acc);
+    float y = 0.5f * acc * (1.f + erff(acc * 0.70710678118654752440f));  // exact GELU (transformer.py:81)
+    const bool in = t < frames;
+    if (t >= len) y = 0.f;
+    const float orig = in ? __ldg(xb + (long long)t * 256 + c) : 0.f;  // residual uses the unmasked x0
+    const float v = y + orig;
+    xv[r] = v;
+    float sq = v * v;
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    if ((c & 31) == 0) red[r][c >> 5] = sq;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    const int t = t0 + r;
+    if (t >= frames) break;
+    float tot = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) tot += red[r][wv];
+    const float inv = 1.f / fmaxf(sqrtf(tot), 1e-12f);
+    const long long o = ((long long)b * frames + t) * 256 + c;
+    x[o] = xv[r];
+    xn[o] = (t < len) ? __float2bfloat16_rn(xv[r] * inv * gc) : __float2bfloat16_rn(0.f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ conv_post + tanh
+// wav[b, t] = tanh(bias + sum_{j<7, c<16} w[j][c] * x[b, t + j - 3, c]);  x already leaky_relu(0.01)'ed.  HF:1480-1482
+__global__ void __launch_bounds__(256) post_tanh_kernel(const uint4* __restrict__ x, const float* __restrict__ w, float bias,
+                                                        float* __restrict__ wav, int rows) {
+  __shared__ uint4 tile[(256 + 6) * 2];
+  __shared__ float ws[7 * 16];
+  const int b = blockIdx.y, t0 = blockIdx.x * 256;
+  if (threadIdx.x < 112) ws[threadIdx.x] = w[threadIdx.x];
+  const uint4* xb = x + (long long)b * rows * 2;
+  for (int i = threadIdx.x; i < (256 + 6) * 2; i += 256) {
+    const int t = t0 - 3 + (i >> 1);
+    tile[i] = (t >= 0 && t < rows) ? __ldg(xb + (long long)t * 2 + (i & 1)) : make_uint4(0, 0, 0, 0);
+  }
+  __syncthreads();
+  const int t = t0 + threadIdx.x;
+  if (t >= rows) return;
+  float acc = bias;
+#pragma unroll
+  for (int j = 0; j < 7; ++j) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const uint4 u = tile[(threadIdx.x + j) * 2 + h];
+      const float* wj = ws + j * 16 + h * 8;
+      acc = fmaf(bf16_lo(u.x), wj[0], acc); acc = fmaf(bf16_hi(u.x), wj[1], acc);
+      acc = fmaf(bf16_lo(u.y), wj[2], acc); acc = fmaf(bf16_hi(u.y), wj[3], acc);
+      acc = fmaf(bf16_lo(u.z), wj[4], acc); acc = fmaf(bf16_hi(u.z), wj[5], acc);
+      acc = fmaf(bf16_lo(u.w), wj[6], acc); acc = fmaf(bf16_hi(u.w), wj[7], acc);
+    }
+  }
+  wav[(long long)b * rows + t] = tanhf(acc);
+}
+
+__global__ void crop_concat_kernel(const float* __restrict__ wav, const int* __restrict__ lengths,
+                                   const int64_t* __restrict__ offsets, float* __restrict__ dst, int rows) {
+  const int b = blockIdx.y;
+  const int n = 320 * lengths[b] + 80;  // models.py:211-221
+  const float* src = wav + (long long)b * rows;
+  float* d = dst + offsets[b];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n && i < rows; i += gridDim.x * blockDim.x) d[i] = src[i];
+}
+
+}  // namespace srb
+
+using namespace srb;
+
+extern "C" {
+
+int srb_embed_gather(const float* table, const int64_t* ids, float* out, int64_t m, int32_t vocab_rows, int32_t dim,
+                     void* stream) {
+  SRB_REQUIRE(dim % 4 == 0, "srb_embed_gather: dim must be a multiple of 4");
+  SRB_REQUIRE(((uintptr_t)table & 15) == 0 && ((uintptr_t)out & 15) == 0, "srb_embed_gather: pointers must be 16-byte aligned");
+  if (m <= 0) return 0;
+  long long blocks = (m + 7) / 8;
+  const long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  embed_gather_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4*>(table), ids, reinterpret_cast<float4*>(out), m, vocab_rows, dim / 4);
+  return after_launch("embed_gather_kernel");
+}
+
+int srb_unit_lengths(const int64_t* ids, int32_t* lengths, int32_t batch, int32_t frames, void* stream) {
+  if (batch <= 0) return 0;
+  unit_lengths_kernel<<<batch, 256, 0, (cudaStream_t)stream>>>(ids, lengths, frames);
+  return after_launch("unit_lengths_kernel");
+}
+
+int srb_time_cond_table(const float* times, int32_t nfe, const float* four_w, const float* lin_w, const float* lin_b,
+                        const float* gamma_w, int32_t n_norm, float* time_emb, float* g, void* stream) {
+  if (nfe <= 0) return 0;
+  time_cond_kernel<<<nfe, 256, 0, (cudaStream_t)stream>>>(times, four_w, lin_w, lin_b, gamma_w, n_norm, time_emb, g);
+  return after_launch("time_cond_kernel");
+}
+
+int srb_rotary_table(const float* inv_freq, int32_t rows, float* cos_out, float* sin_out, void* stream) {
+  if (rows <= 0) return 0;
+  const int n = rows * 64;
+  rotary_table_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(inv_freq, rows, cos_out, sin_out);
+  return after_launch("rotary_table_kernel");
+}
+
+int srb_prior_prepare(float* xt, void* xt_bf16, int64_t n, float truncation, void* stream) {
+  SRB_REQUIRE(n % 4 == 0, "srb_prior_prepare: element count must be a multiple of 4");
+  if (n <= 0) return 0;
+  long long blocks = (n / 4 + 255) / 256;
+  const long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  prior_prepare_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float4*>(xt),
+                                                                            reinterpret_cast<uint2*>(xt_bf16), n / 4,
+                                                                            truncation);
+  return after_launch("prior_prepare_kernel");
+}
+
+int srb_cfm_posconv_norm(const float* x0, const float* dw_w, const float* dw_b, const float* g, const int32_t* lengths,
+                         float* x, void* xn_bf16, int32_t batch, int32_t frames, void* stream) {
+  if (batch <= 0 || frames <= 0) return 0;
+  constexpr int ROWS = 16;
+  dim3 grid((frames + ROWS - 1) / ROWS, batch);
+  posconv_norm_kernel<ROWS><<<grid, 256, 0, (cudaStream_t)stream>>>(x0, dw_w, dw_b, g, lengths, x,
+                                                                     static_cast<__nv_bfloat16*>(xn_bf16), frames);
+  return after_launch("posconv_norm_kernel");
+}
+
+int srb_hifigan_post(const void* x_act, const float* w, float bias, float* wav, int32_t batch, int32_t rows,
+                     void* stream) {
+  if (batch <= 0 || rows <= 0) return 0;
+  dim3 grid((rows + 255) / 256, batch);
+  post_tanh_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(static_cast<const uint4*>(x_act), w, bias, wav, rows);
+  return after_launch("post_tanh_kernel");
+}
+
+int srb_crop_concat(const float* wav, const int32_t* lengths, const int64_t* offsets, float* dst, int32_t batch,
+                    int32_t rows, void* stream) {
+  if (batch <= 0) return 0;
+  dim3 grid((rows + 1023) / 1024, batch);
+  crop_concat_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(wav, lengths, offsets, dst, rows);
+  return after_launch("crop_concat_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,167 @@
+"""Load-time repacking of the reference state-dict into the layouts the sm_100a kernels consume.
+
+Runs once per model (``.cuda()`` / first call).  GEMM operands become bf16 ``[n][k]`` matrices with ``k`` ordered
+(tap, channel) so a conv tap is a contiguous K slab; everything read by CUDA-core epilogues stays fp32.
+Shapes/keys: SURVEY.md section 8(b).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List
+
+import torch
+
+UPSAMPLE_RATES = (5, 4, 4, 2, 2)
+UPSAMPLE_KERNELS = (10, 9, 8, 4, 4)
+RESBLOCK_KERNELS = (3, 7, 11)
+RESBLOCK_DILATIONS = (1, 3, 5)
+
+
+def block_k_for(c_in: int) -> int:
+    """K block (channels per TMA box) the conv-GEMM core uses for an input width (mirrors srb_convgemm.cu)."""
+    return 64 if c_in >= 64 else (32 if c_in >= 32 else 16)
+
+
+def pack_conv_weight(w: torch.Tensor, block_k: int) -> torch.Tensor:
+    """Conv1d weight (C_out, C_in, k) -> bf16 [C_out][k * C_in_pad], k-major then channel, channels zero-padded."""
+    c_out, c_in, k = w.shape
+    c_pad = (c_in + block_k - 1) // block_k * block_k
+    p = torch.zeros(c_out, k, c_pad, dtype=torch.float32, device=w.device)
+    p[:, :, :c_in] = w.float().permute(0, 2, 1)
+    return p.reshape(c_out, k * c_pad).to(torch.bfloat16).contiguous()
+
+
+def pack_upsampler_weight(w: torch.Tensor, stride: int) -> torch.Tensor:
+    """ConvTranspose1d weight (C_in, C_out, k) -> polyphase bf16 [C_out][k * C_in].
+
+    Phase r (output rows q*stride + r) uses taps j = j0 + m*stride, j0 = (r + pad) % stride, in increasing m
+    (the kernel reads input row q + (r + pad)//stride - m for tap m); phases are concatenated along K.
+    """
+    c_in, c_out, k = w.shape
+    pad = (k - stride) // 2
+    cols: List[torch.Tensor] = []
+    for r in range(stride):
+        j0 = (r + pad) % stride
+        for j in range(j0, k, stride):
+            cols.append(w[:, :, j].float().t())  # (C_out, C_in)
+    return torch.cat(cols, dim=1).to(torch.bfloat16).contiguous()
+
+
+@dataclass
+class PackedCFM:
+    cond_table: torch.Tensor          # (vocab+1, 256) fp32 : E @ W_embed[:, 80:]^T + b_embed (hoisted, loop invariant)
+    emb_table: torch.Tensor           # (vocab+1, 768) fp32 : raw embedding (API parity / duration predictor)
+    w_embed: torch.Tensor             # bf16 [256][128]  (xt part of to_embed, K padded 80 -> 128)
+    dw_w: torch.Tensor                # fp32 [256][31]
+    dw_b: torch.Tensor
+    four_w: torch.Tensor
+    lin_w: torch.Tensor
+    lin_b: torch.Tensor
+    gamma_w: torch.Tensor             # fp32 [2*depth][256][256]
+    inv_freq: torch.Tensor
+    w_qkv: List[torch.Tensor] = field(default_factory=list)
+    w_out: List[torch.Tensor] = field(default_factory=list)
+    w_ff1: List[torch.Tensor] = field(default_factory=list)   # bf16 [1792][768], value/gate rows interleaved per 256 block
+    b_ff1: List[torch.Tensor] = field(default_factory=list)
+    w_ff2: List[torch.Tensor] = field(default_factory=list)   # bf16 [256][2688]
+    b_ff2: List[torch.Tensor] = field(default_factory=list)
+    final_norm_w: torch.Tensor = None
+    w_pred: torch.Tensor = None       # bf16 [80][256]
+
+
+@dataclass
+class PackedVocoder:
+    w_pre: torch.Tensor               # bf16 [512][7*128]
+    b_pre: torch.Tensor
+    w_up: List[torch.Tensor] = field(default_factory=list)
+    b_up: List[torch.Tensor] = field(default_factory=list)
+    # [stage][resblock j][pair q] -> (w1, b1, w2, b2); for q == 2 the conv2 lives in w_tail instead
+    w_c1: List[List[List[torch.Tensor]]] = field(default_factory=list)
+    b_c1: List[List[List[torch.Tensor]]] = field(default_factory=list)
+    w_c2: List[List[List[torch.Tensor]]] = field(default_factory=list)
+    b_c2: List[List[List[torch.Tensor]]] = field(default_factory=list)
+    w_tail: List[torch.Tensor] = field(default_factory=list)  # bf16 [C][(3+7+11)*C]: last conv2 of the 3 resblocks
+    b_tail: List[torch.Tensor] = field(default_factory=list)  # fp32 [C] = sum of their biases
+    w_post: torch.Tensor = None       # fp32 [7][16]
+    b_post: float = 0.0
+
+
+def glu_row_permutation(inter: int = 896, device=None) -> torch.Tensor:
+    """Row order of the packed conv1 weight: per 256-row tile, 128 value rows then the matching 128 gate rows
+    (SIGLU: value = first half of the channels, gate = second half; fastspeech/modules.py:29)."""
+    idx = []
+    for t in range(inter // 128):
+        idx.append(torch.arange(t * 128, (t + 1) * 128))
+        idx.append(torch.arange(inter + t * 128, inter + (t + 1) * 128))
+    return torch.cat(idx).to(device)
+
+
+def pack_cfm(sd: Dict[str, torch.Tensor], device, depth: int = 4, dim_in: int = 80) -> PackedCFM:
+    f = lambda k: sd[k].detach().to(device=device, dtype=torch.float32)
+    w_emb = f("model.to_embed.weight")
+    emb = f("model.to_cond_emb.weight").contiguous()
+    hidden = w_emb.shape[0]
+    inter = sd["model.transformer.layers.0.4.conv2.weight"].shape[1]
+    # hoisted loop-invariant conditioning projection, in fp64 then rounded once to fp32
+    cond_table = (emb.double() @ w_emb[:, dim_in:].double().t() + f("model.to_embed.bias").double()).float().contiguous()
+    w_x = torch.zeros(hidden, 128, dtype=torch.float32, device=device)
+    w_x[:, :dim_in] = w_emb[:, :dim_in]
+    gam = []
+    for i in range(depth):
+        gam.append(f(f"model.transformer.layers.{i}.1.to_weight.weight"))
+        gam.append(f(f"model.transformer.layers.{i}.3.to_weight.weight"))
+    p = PackedCFM(
+        cond_table=cond_table,
+        emb_table=emb,
+        w_embed=w_x.to(torch.bfloat16).contiguous(),
+        dw_w=f("model.conv_embed.dw_conv1d.0.weight").reshape(hidden, -1).contiguous(),
+        dw_b=f("model.conv_embed.dw_conv1d.0.bias").contiguous(),
+        four_w=f("model.time_cond_mlp.0.weights").contiguous(),
+        lin_w=f("model.time_cond_mlp.1.weight").contiguous(),
+        lin_b=f("model.time_cond_mlp.1.bias").contiguous(),
+        gamma_w=torch.stack(gam).contiguous(),
+        inv_freq=f("model.transformer.rotary_emb.inv_freq").contiguous(),
+        final_norm_w=f("model.transformer.final_norm.weight").contiguous(),
+        w_pred=f("model.to_pred.weight").to(torch.bfloat16).contiguous(),
+    )
+    perm = glu_row_permutation(inter, device)
+    for i in range(depth):
+        pre = f"model.transformer.layers.{i}."
+        p.w_qkv.append(f(pre + "2.to_qkv.weight").to(torch.bfloat16).contiguous())
+        p.w_out.append(f(pre + "2.to_out.weight").to(torch.bfloat16).contiguous())
+        w1 = f(pre + "4.conv1.weight")[perm]
+        p.w_ff1.append(pack_conv_weight(w1, 64))
+        p.b_ff1.append(f(pre + "4.conv1.bias")[perm].contiguous())
+        p.w_ff2.append(pack_conv_weight(f(pre + "4.conv2.weight"), 64))
+        p.b_ff2.append(f(pre + "4.conv2.bias").contiguous())
+    return p
+
+
+def pack_vocoder(sd: Dict[str, torch.Tensor], device) -> PackedVocoder:
+    f = lambda k: sd[k].detach().to(device=device, dtype=torch.float32)
+    v = PackedVocoder(w_pre=pack_conv_weight(f("vocoder.conv_pre.weight"), 64), b_pre=f("vocoder.conv_pre.bias").contiguous())
+    c = 512
+    for i, (s, k) in enumerate(zip(UPSAMPLE_RATES, UPSAMPLE_KERNELS)):
+        v.w_up.append(pack_upsampler_weight(f(f"vocoder.upsampler.{i}.weight"), s))
+        v.b_up.append(f(f"vocoder.upsampler.{i}.bias").contiguous())
+        c //= 2
+        bk = block_k_for(c)
+        w1s, b1s, w2s, b2s, tails, tail_b = [], [], [], [], [], None
+        for j in range(len(RESBLOCK_KERNELS)):
+            pre = f"vocoder.resblocks.{i * 3 + j}."
+            w1s.append([pack_conv_weight(f(pre + f"convs1.{q}.weight"), bk) for q in range(3)])
+            b1s.append([f(pre + f"convs1.{q}.bias").contiguous() for q in range(3)])
+            w2s.append([pack_conv_weight(f(pre + f"convs2.{q}.weight"), bk) for q in range(2)])
+            b2s.append([f(pre + f"convs2.{q}.bias").contiguous() for q in range(2)])
+            tails.append(pack_conv_weight(f(pre + "convs2.2.weight"), bk))
+            tb = f(pre + "convs2.2.bias")
+            tail_b = tb if tail_b is None else tail_b + tb
+        v.w_c1.append(w1s)
+        v.b_c1.append(b1s)
+        v.w_c2.append(w2s)
+        v.b_c2.append(b2s)
+        v.w_tail.append(torch.cat(tails, dim=1).contiguous())
+        v.b_tail.append(tail_b.contiguous())
+    v.w_post = f("vocoder.conv_post.weight")[0].t().contiguous()  # (7, 16)
+    v.b_post = float(sd["vocoder.conv_post.bias"].detach().float().reshape(-1)[0])
+    return v

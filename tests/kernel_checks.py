@@ -1,0 +1,414 @@
+"""Per-kernel parity checks: each function runs one C-ABI op on cuda:0 and compares it with the CPU oracle
+(oracle/cfm_hifigan_oracle.py) or, for the generic conv core, with a plain torch fp32 conv of the same bf16-rounded
+operands.  Used by tests/test_gpu_kernels.py (pytest -m gpu) and tools/gpu_check.py (prints every result).
+
+Tolerances (relative L2 unless noted):
+  * integer / gather work: bit exact;
+  * fp32 CUDA-core kernels: 1e-5;
+  * bf16 tensor-core kernels (fp32 accumulate, one bf16 rounding of the output): 6e-3  (bf16 eps = 7.8e-3, the
+    rounding error of a single store is <= 3.9e-3 relative per element).
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Dict, List, Tuple
+
+import torch
+import torch.nn.functional as F
+
+from oracle import cfm_hifigan_oracle as oracle
+from speech_resynth_b200 import _native as nat
+from speech_resynth_b200 import packing, synthetic
+from speech_resynth_b200.engine import _i32
+
+P = nat.ptr
+DEV = "cuda:0"
+BF16_TOL = 6e-3
+F32_TOL = 1e-5
+
+CHECKS: Dict[str, Callable[[], Tuple[float, float]]] = {}
+
+
+def check(fn):
+    CHECKS[fn.__name__] = fn
+    return fn
+
+
+def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def bf(x: torch.Tensor) -> torch.Tensor:
+    """round to bf16 and back (what the kernels see)"""
+    return x.to(torch.bfloat16).float()
+
+
+_SD = None
+
+
+def sd():
+    global _SD
+    if _SD is None:
+        _SD = synthetic.make_state_dict(0)
+    return _SD
+
+
+def g(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+# ------------------------------------------------------------------------------------------------ small ops
+@check
+def gather_bit_exact():
+    table = sd()["model.to_cond_emb.weight"]
+    ids = synthetic.make_units(4, 33, seed=21, lengths=[33, 20, 1, 7])
+    out = torch.empty(4, 33, 768, device=DEV)
+    nat.call("srb_embed_gather", P(table.to(DEV)), P(ids.to(DEV)), P(out), ids.numel(), 2001, 768)
+    exact = torch.equal(out.cpu(), oracle.embed_gather(table, ids))
+    return (0.0 if exact else 1.0), 0.0
+
+
+@check
+def unit_lengths_exact():
+    ids = synthetic.make_units(5, 300, seed=3, lengths=[300, 1, 299, 128, 57])
+    out = torch.empty(5, dtype=torch.int32, device=DEV)
+    nat.call("srb_unit_lengths", P(ids.to(DEV)), P(out), 5, 300)
+    return (0.0 if out.cpu().tolist() == [300, 1, 299, 128, 57] else 1.0), 0.0
+
+
+@check
+def time_cond_table():
+    s = sd()
+    times = oracle.ode_times(0.1)
+    pk = packing.pack_cfm(s, DEV)
+    nfe = len(times)
+    temb = torch.empty(nfe, 256, device=DEV)
+    gt = torch.empty(nfe, 8, 256, device=DEV)
+    t_dev = times.to(DEV)
+    nat.call("srb_time_cond_table", P(t_dev), nfe, P(pk.four_w), P(pk.lin_w), P(pk.lin_b), P(pk.gamma_w), 8, P(temb), P(gt))
+    torch.cuda.synchronize()
+    s64 = oracle.to_dtype(s, torch.float64)
+    ref_t = torch.stack([oracle.time_embedding(s64, t.double()) for t in times])
+    ref_g = []
+    for t_row in ref_t:
+        rows = []
+        for i in range(4):
+            for j in (1, 3):
+                rows.append(16.0 * (F.linear(t_row, s64[f"model.transformer.layers.{i}.{j}.to_weight.weight"]) + 1.0))
+        ref_g.append(torch.stack(rows))
+    e1 = rel_l2(temb, ref_t)
+    e2 = rel_l2(gt, torch.stack(ref_g))
+    return max(e1, e2), 2e-5
+
+
+@check
+def rotary_table():
+    inv = sd()["model.transformer.rotary_emb.inv_freq"]
+    cs = torch.empty(1500, 64, device=DEV)
+    sn = torch.empty(1500, 64, device=DEV)
+    nat.call("srb_rotary_table", P(inv.to(DEV)), 1500, P(cs), P(sn))
+    ang = torch.arange(1500).float()[:, None] * inv[None, :]   # fp32 product, as the reference
+    err = max(float((cs.cpu() - ang.double().cos()).abs().max()), float((sn.cpu() - ang.double().sin()).abs().max()))
+    return err, 2e-6   # absolute
+
+
+@check
+def prior_prepare():
+    x = torch.randn(2, 37, 80, generator=g(1))
+    xt = x.clone().to(DEV)
+    xb = torch.empty(2, 37, 80, dtype=torch.bfloat16, device=DEV)
+    nat.call("srb_prior_prepare", P(xt), P(xb), x.numel(), 1.0)
+    ref = x.clamp(-1, 1)
+    ok = torch.equal(xt.cpu(), ref) and torch.equal(xb.cpu(), ref.to(torch.bfloat16))
+    return (0.0 if ok else 1.0), 0.0
+
+
+# ------------------------------------------------------------------------------------------------ conv-GEMM core
+def _conv_case(c_in, c_out, k, dil, batch=2, rows=300, with_res=True, seed=0):
+    gen = g(seed)
+    x = bf(torch.randn(batch, rows, c_in, generator=gen))
+    w = bf(torch.randn(c_out, c_in, k, generator=gen) / math.sqrt(c_in * k))
+    bias = torch.randn(c_out, generator=gen)
+    res = bf(torch.randn(batch, rows, c_out, generator=gen)) if with_res else None
+    y = F.conv1d(x.transpose(1, 2).double(), w.double(), bias.double(), dilation=dil, padding=(k - 1) // 2 * dil).transpose(1, 2)
+    if with_res:
+        y = y + res.double()
+    y = y * 0.5
+    wp = packing.pack_conv_weight(w.to(DEV), packing.block_k_for(c_in))
+    out_raw = torch.full((batch, rows, c_out), float("nan"), dtype=torch.bfloat16, device=DEV)
+    out_act = torch.full_like(out_raw, float("nan"))
+    xd = x.to(DEV).to(torch.bfloat16).contiguous()
+    rd = res.to(DEV).to(torch.bfloat16).contiguous() if with_res else None
+    nat.call("srb_hifigan_conv", P(xd), None, None, 1, _i32([k]), _i32([dil]), P(wp), P(bias.to(DEV)), P(rd), None, None,
+             P(out_raw), P(out_act), batch, rows, c_in, c_out, 0.5, 0.1)
+    torch.cuda.synchronize()
+    e1 = rel_l2(out_raw.float(), y)
+    e2 = rel_l2(out_act.float(), F.leaky_relu(y, 0.1))
+    return max(e1, e2), BF16_TOL
+
+
+def _make_conv_check(name, *args, **kw):
+    def fn():
+        return _conv_case(*args, **kw)
+
+    fn.__name__ = name
+    CHECKS[name] = fn
+
+
+# every (block_n, block_k) instantiation the vocoder uses, at the real kernel sizes / dilations
+_make_conv_check("conv_c256_k3_d1", 256, 256, 3, 1)
+_make_conv_check("conv_c256_k11_d5", 256, 256, 11, 5, rows=400)
+_make_conv_check("conv_c128_k7_d3", 128, 128, 7, 3)
+_make_conv_check("conv_c64_k11_d1", 64, 64, 11, 1)
+_make_conv_check("conv_c32_k7_d5", 32, 32, 7, 5)
+_make_conv_check("conv_c16_k3_d3", 16, 16, 3, 3)
+_make_conv_check("conv_c16_k11_d5", 16, 16, 11, 5, rows=1000, batch=3)
+_make_conv_check("conv_pre_80_512_k7", 80, 512, 7, 1, with_res=False, rows=130)
+_make_conv_check("conv_rows_lt_tile", 64, 64, 3, 1, rows=17, batch=1)
+
+
+@check
+def conv_mrf_tail_fused():
+    """three sources (k = 3, 7, 11) accumulated in one launch + three residuals + mean + leaky_relu"""
+    gen = g(5)
+    c, rows, batch = 64, 333, 2
+    xs = [bf(torch.randn(batch, rows, c, generator=gen)) for _ in range(3)]
+    ws = [bf(torch.randn(c, c, k, generator=gen) / math.sqrt(c * k)) for k in (3, 7, 11)]
+    bs = [torch.randn(c, generator=gen) for _ in range(3)]
+    rs = [bf(torch.randn(batch, rows, c, generator=gen)) for _ in range(3)]
+    y = 0
+    for x, w, b_, r, k in zip(xs, ws, bs, rs, (3, 7, 11)):
+        y = y + F.conv1d(x.transpose(1, 2).double(), w.double(), b_.double(), padding=k // 2).transpose(1, 2) + r.double()
+    y = y / 3
+    wp = torch.cat([packing.pack_conv_weight(w.to(DEV), 64) for w in ws], dim=1).contiguous()
+    out = torch.empty(batch, rows, c, dtype=torch.bfloat16, device=DEV)
+    d16 = lambda t: t.to(DEV).to(torch.bfloat16).contiguous()
+    xd, rd = [d16(x) for x in xs], [d16(r) for r in rs]
+    nat.call("srb_hifigan_conv", P(xd[0]), P(xd[1]), P(xd[2]), 3, _i32([3, 7, 11]), _i32([1, 1, 1]), P(wp),
+             P(sum(bs).to(DEV)), P(rd[0]), P(rd[1]), P(rd[2]), None, P(out), batch, rows, c, c, 1.0 / 3.0, 0.01)
+    torch.cuda.synchronize()
+    return rel_l2(out.float(), F.leaky_relu(y, 0.01)), BF16_TOL
+
+
+def _upsample_case(c_in, k, s, rows_in=77, batch=2, seed=0):
+    gen = g(seed)
+    c_out = c_in // 2
+    x = bf(torch.randn(batch, rows_in, c_in, generator=gen))
+    w = bf(torch.randn(c_in, c_out, k, generator=gen) / math.sqrt(c_in * k / s))
+    bias = torch.randn(c_out, generator=gen)
+    pad = (k - s) // 2
+    with torch.backends.mkldnn.flags(enabled=False):
+        y = F.conv_transpose1d(x.transpose(1, 2).double(), w.double(), bias.double(), stride=s, padding=pad).transpose(1, 2)
+    rows_out = y.shape[1]
+    wp = packing.pack_upsampler_weight(w.to(DEV), s)
+    out_raw = torch.full((batch, rows_out, c_out), float("nan"), dtype=torch.bfloat16, device=DEV)
+    out_act = torch.full_like(out_raw, float("nan"))
+    xd = x.to(DEV).to(torch.bfloat16).contiguous()
+    nat.call("srb_hifigan_upsample", P(xd), P(wp), P(bias.to(DEV)), P(out_raw), P(out_act), batch, rows_in, c_in, c_out, k, s, 0.1)
+    torch.cuda.synchronize()
+    e1 = rel_l2(out_raw.float(), y)
+    e2 = rel_l2(out_act.float(), F.leaky_relu(y, 0.1))
+    return max(e1, e2), BF16_TOL
+
+
+for _i, (_c, _k, _s) in enumerate(zip((512, 256, 128, 64, 32), packing.UPSAMPLE_KERNELS, packing.UPSAMPLE_RATES)):
+    def _fn(c=_c, k=_k, s=_s, i=_i):
+        return _upsample_case(c, k, s, rows_in=77 + 60 * i)
+    CHECKS[f"upsample_stage{_i}_c{_c}_k{_k}_s{_s}"] = _fn
+
+
+@check
+def post_tanh():
+    gen = g(9)
+    x = bf(torch.randn(2, 1000, 16, generator=gen))
+    w = torch.randn(1, 16, 7, generator=gen) / 10
+    b = 0.05
+    y = torch.tanh(F.conv1d(x.transpose(1, 2).double(), w.double(), torch.tensor([b]).double(), padding=3)).squeeze(1)
+    wav = torch.empty(2, 1000, device=DEV)
+    nat.call("srb_hifigan_post", P(x.to(DEV).to(torch.bfloat16).contiguous()), P(w[0].t().contiguous().to(DEV)), b, P(wav), 2, 1000)
+    return rel_l2(wav, y), F32_TOL
+
+
+# ------------------------------------------------------------------------------------------------ transformer ops
+def _cfm_inputs(batch=2, frames=150, lengths=(150, 97)):
+    ids = synthetic.make_units(batch, frames, seed=7, lengths=list(lengths))
+    mask = ids.ne(0)
+    L = torch.tensor(lengths, dtype=torch.int32, device=DEV)
+    return ids, mask, L
+
+
+@check
+def cfm_embed():
+    s = sd()
+    pk = packing.pack_cfm(s, DEV)
+    ids, mask, L = _cfm_inputs()
+    b, n = ids.shape
+    xt = bf(torch.randn(b, n, 80, generator=g(2)))
+    cond = torch.empty(b * n, 256, device=DEV)
+    nat.call("srb_embed_gather", P(pk.cond_table), P(ids.to(DEV)), P(cond), b * n, 2001, 256)
+    x0 = torch.empty(b * n, 256, device=DEV)
+    nat.call("srb_cfm_embed", P(xt.to(DEV).to(torch.bfloat16).contiguous()), P(pk.w_embed), P(cond), P(x0), b, n)
+    s64 = oracle.to_dtype(s, torch.float64)
+    w = s64["model.to_embed.weight"].clone()
+    w[:, :80] = bf(s["model.to_embed.weight"][:, :80]).double()  # the xt part of the weight is bf16 in the kernel
+    hs = oracle.embed_gather(s64["model.to_cond_emb.weight"], ids)
+    ref = F.linear(torch.cat([xt.double(), hs], dim=-1), w, s64["model.to_embed.bias"])
+    return rel_l2(x0.view(b, n, 256), ref), 1e-5
+
+
+@check
+def cfm_posconv_norm():
+    s = sd()
+    pk = packing.pack_cfm(s, DEV)
+    ids, mask, L = _cfm_inputs()
+    b, n = ids.shape
+    x0 = torch.randn(b, n, 256, generator=g(3))
+    gvec = 16.0 * (1.0 + 0.1 * torch.randn(256, generator=g(4)))
+    x = torch.empty(b, n, 256, device=DEV)
+    xn = torch.empty(b, n, 256, dtype=torch.bfloat16, device=DEV)
+    nat.call("srb_cfm_posconv_norm", P(x0.to(DEV)), P(pk.dw_w), P(pk.dw_b), P(gvec.to(DEV)), P(L), P(x), P(xn), b, n)
+    s64 = oracle.to_dtype(s, torch.float64)
+    ref_x = oracle.conv_pos_embed(s64, x0.double(), mask) + x0.double()
+    ref_n = ref_x / ref_x.norm(dim=-1, keepdim=True).clamp_min(1e-12) * gvec.double()
+    ref_n = ref_n * mask[..., None]
+    e1 = rel_l2(x.cpu()[mask], ref_x[mask])
+    e2 = rel_l2(xn.float(), ref_n)
+    return max(e1, e2 / 400), 1e-5   # xn carries one bf16 rounding (4e-3): scaled so both share a bound
+
+
+@check
+def cfm_qkv_rope():
+    s = sd()
+    pk = packing.pack_cfm(s, DEV)
+    b, n = 2, 150
+    xn = bf(torch.randn(b, n, 256, generator=g(5)))
+    sampler_cs = torch.empty(1024, 64, device=DEV)
+    sampler_sn = torch.empty(1024, 64, device=DEV)
+    nat.call("srb_rotary_table", P(pk.inv_freq), 1024, P(sampler_cs), P(sampler_sn))
+    qkv = torch.empty(b, n, 768, dtype=torch.bfloat16, device=DEV)
+    nat.call("srb_cfm_qkv_rope", P(xn.to(DEV).to(torch.bfloat16).contiguous()), P(pk.w_qkv[1]), P(sampler_cs), P(sampler_sn), P(qkv), b, n)
+    w = bf(s["model.transformer.layers.1.2.to_qkv.weight"]).double()
+    r = F.linear(xn.double(), w)
+    q, k, v = r.chunk(3, dim=-1)
+    rot = oracle.rotary_table(s["model.transformer.rotary_emb.inv_freq"], n).double()
+    hd = lambda z: z.reshape(b, n, 2, 128).permute(0, 2, 1, 3)
+    un = lambda z: z.permute(0, 2, 1, 3).reshape(b, n, 256)
+    q, k = un(oracle.apply_rotary(rot, hd(q))), un(oracle.apply_rotary(rot, hd(k)))
+    return rel_l2(qkv.float(), torch.cat([q, k, v], dim=-1)), BF16_TOL
+
+
+@check
+def cfm_attention():
+    b, n, lengths = 3, 200, (200, 131, 64)
+    L = torch.tensor(lengths, dtype=torch.int32, device=DEV)
+    qkv = bf(torch.randn(b, n, 768, generator=g(6)))
+    o = torch.empty(b, n, 256, dtype=torch.bfloat16, device=DEV)
+    nat.call("srb_cfm_attention", P(qkv.to(DEV).to(torch.bfloat16).contiguous()), P(L), P(o), b, n)
+    q, k, v = (z.reshape(b, n, 2, 128).permute(0, 2, 1, 3).double() for z in qkv.chunk(3, dim=-1))
+    mask = torch.arange(n)[None, :] < torch.tensor(lengths)[:, None]
+    sc = torch.einsum("bhid,bhjd->bhij", q, k) / math.sqrt(128)
+    sc = sc.masked_fill(~mask[:, None, None, :], float("-inf"))
+    ref = torch.einsum("bhij,bhjd->bhid", sc.softmax(-1), v).permute(0, 2, 1, 3).reshape(b, n, 256)
+    return rel_l2(o.float(), ref), 1e-2   # P is rounded to bf16 before P.V (as in any flash kernel) + bf16 store
+
+
+@check
+def cfm_attn_out_norm():
+    s = sd()
+    pk = packing.pack_cfm(s, DEV)
+    ids, mask, L = _cfm_inputs()
+    b, n = ids.shape
+    o = bf(torch.randn(b, n, 256, generator=g(7)))
+    x = torch.randn(b, n, 256, generator=g(8))
+    gvec = 16.0 * (1.0 + 0.1 * torch.randn(256, generator=g(4)))
+    xd = x.clone().to(DEV)
+    xn = torch.empty(b, n, 256, dtype=torch.bfloat16, device=DEV)
+    nat.call("srb_cfm_attn_out_norm", P(o.to(DEV).to(torch.bfloat16).contiguous()), P(pk.w_out[2]), P(gvec.to(DEV)), P(L), P(xd), P(xn), b, n)
+    w = bf(s["model.transformer.layers.2.2.to_out.weight"]).double()
+    ref_x = F.linear(o.double(), w) + x.double()
+    ref_n = ref_x / ref_x.norm(dim=-1, keepdim=True).clamp_min(1e-12) * gvec.double() * mask[..., None]
+    e1 = rel_l2(xd, ref_x)
+    e2 = rel_l2(xn.float(), ref_n)
+    return max(e1 * 400, e2), BF16_TOL   # x is fp32 (bound 1.5e-5), xn carries the bf16 rounding
+
+
+@check
+def cfm_ffn_glu():
+    s = sd()
+    pk = packing.pack_cfm(s, DEV)
+    ids, mask, L = _cfm_inputs()
+    b, n = ids.shape
+    xn = bf(torch.randn(b, n, 256, generator=g(9))) * mask[..., None]
+    h = torch.empty(b, n, 896, dtype=torch.bfloat16, device=DEV)
+    nat.call("srb_cfm_ffn_glu", P(xn.to(DEV).to(torch.bfloat16).contiguous()), P(pk.w_ff1[0]), P(pk.b_ff1[0]), P(L), P(h), b, n)
+    w = bf(s["model.transformer.layers.0.4.conv1.weight"]).double()
+    y = F.conv1d(xn.double().transpose(1, 2), w, s["model.transformer.layers.0.4.conv1.bias"].double(), padding=1)
+    val, gate = y.chunk(2, dim=1)
+    ref = (F.silu(gate) * val).transpose(1, 2) * mask[..., None]
+    return rel_l2(h.float(), ref), BF16_TOL
+
+
+@check
+def cfm_ffn_out_norm():
+    s = sd()
+    pk = packing.pack_cfm(s, DEV)
+    ids, mask, L = _cfm_inputs()
+    b, n = ids.shape
+    h = bf(torch.randn(b, n, 896, generator=g(10))) * mask[..., None]
+    x = torch.randn(b, n, 256, generator=g(11))
+    worst = 0.0
+    for mode in (1, 2):
+        gvec = 16.0 * (1.0 + 0.1 * torch.randn(256, generator=g(4))) if mode == 1 else s["model.transformer.final_norm.weight"]
+        xd = x.clone().to(DEV)
+        xn = torch.empty(b, n, 256, dtype=torch.bfloat16, device=DEV)
+        nat.call("srb_cfm_ffn_out_norm", P(h.to(DEV).to(torch.bfloat16).contiguous()), P(pk.w_ff2[3]), P(pk.b_ff2[3]),
+                 P(gvec.to(DEV)), mode, P(L), P(xd), P(xn), b, n)
+        w = bf(s["model.transformer.layers.3.4.conv2.weight"]).double()
+        ref_x = F.conv1d(h.double().transpose(1, 2), w, s["model.transformer.layers.3.4.conv2.bias"].double(), padding=1).transpose(1, 2) + x.double()
+        if mode == 1:
+            ref_n = ref_x / ref_x.norm(dim=-1, keepdim=True).clamp_min(1e-12) * gvec.double()
+        else:
+            ref_n = ref_x * torch.rsqrt(ref_x.pow(2).mean(-1, keepdim=True) + torch.finfo(torch.float32).eps) * gvec.double()
+        ref_n = ref_n * mask[..., None]
+        worst = max(worst, rel_l2(xd, ref_x) * 400, rel_l2(xn.float(), ref_n))
+    return worst, BF16_TOL
+
+
+@check
+def cfm_pred_euler():
+    s = sd()
+    pk = packing.pack_cfm(s, DEV)
+    ids, mask, L = _cfm_inputs()
+    b, n = ids.shape
+    xn = bf(torch.randn(b, n, 256, generator=g(12)))
+    xt = torch.randn(b, n, 80, generator=g(13))
+    xtd = xt.clone().to(DEV)
+    xtb = torch.empty(b, n, 80, dtype=torch.bfloat16, device=DEV)
+    mel = torch.empty(b, n, 80, device=DEV)
+    melb = torch.empty(b, n, 80, dtype=torch.bfloat16, device=DEV)
+    pv = oracle.pad_value()
+    nat.call("srb_cfm_pred_euler", P(xn.to(DEV).to(torch.bfloat16).contiguous()), P(pk.w_pred), 0.0625, P(xtd), P(xtb),
+             P(mel), P(melb), 2.2615, -5.8843, pv, P(L), b, n)
+    w = bf(s["model.to_pred.weight"]).double()
+    ref_xt = xt.double() + F.linear(xn.double(), w) * 0.0625
+    ref_mel = ref_xt * 2.2615 + (-5.8843)
+    pad_ok = bool((mel.cpu()[~mask] == pv).all())
+    e = max(rel_l2(xtd, ref_xt), rel_l2(mel.cpu()[mask], ref_mel[mask]), rel_l2(xtb.float(), ref_xt) / 400,
+            rel_l2(melb.float().cpu()[mask], ref_mel[mask]) / 400)
+    return (e if pad_ok else 1.0), 2e-5
+
+
+def run_all(verbose: bool = True) -> List[Tuple[str, float, float, str]]:
+    results = []
+    for name, fn in CHECKS.items():
+        try:
+            err, tol = fn()
+            torch.cuda.synchronize()
+            status = "ok" if (err <= tol and err == err) else "FAIL"
+        except Exception as exc:  # noqa: BLE001 - report and continue
+            err, tol, status = float("nan"), float("nan"), f"ERROR {type(exc).__name__}: {str(exc)[:200]}"
+        results.append((name, err, tol, status))
+        if verbose:
+            print(f"{name:40s} err={err:.3e} tol={tol:.1e} {status}", flush=True)
+    return results

@@ -1,0 +1,146 @@
+"""End-to-end parity of the drop-in API on the GPU against (a) the committed golden vectors minted from the live
+reference and (b) the CPU oracle run on the same inputs.
+
+Stated tolerances (relative L2; bf16 tensor-core compute with fp32 accumulation, fp32 ODE state):
+  mel (valid frames, normalised units (mel - mean) / std)  <= 1.0e-2
+  waveform                                                 <= 3.0e-2
+SURVEY.md section 8(c) measured the reference's own bf16-autocast-vs-fp32 deviation at 7.5e-4 (mel, raw units) and
+3.0e-3 (waveform) on a short utterance; the raw-unit mel bound below (5e-3) is the survey's proposed figure.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cfm_hifigan_oracle as oracle
+from speech_resynth_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+
+MEAN, STD = -5.8843, 2.2615
+MEL_TOL_NORM, MEL_TOL_RAW, WAV_TOL = 1.0e-2, 5.0e-3, 3.0e-2
+
+
+def rel_l2(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+@pytest.fixture(scope="module")
+def decoder(state_dict):
+    import speech_resynth_b200 as srb
+
+    m = srb.ConditionalFlowMatchingWithHifiGan(srb.reference_config()).eval()
+    m.load_state_dict(state_dict, strict=True)
+    return m.cuda()
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name + ".npz")), json.load(open(os.path.join(golden_dir, "MANIFEST.json")))["cases"][name]
+
+
+@pytest.mark.parametrize("name", ["resynth_b2_n40", "resynth_b1_n64_dt01", "resynth_b3_n150"])
+def test_resynthesis_matches_reference_golden(decoder, golden_dir, name):
+    z, info = _load(golden_dir, name)
+    ids = torch.from_numpy(z["ids"]).cuda()
+    x0 = torch.from_numpy(z["x0"]).cuda()
+    dt, tv = info["dt"], info["truncation"]
+    wav, lengths, mel = decoder.engine().resynthesize(ids, dt, tv, noise=x0)
+    torch.cuda.synchronize()
+    ref_mel = torch.from_numpy(z["mel"])
+    valid = ids.ne(0).cpu()
+    mel = mel.cpu()
+    assert torch.equal(lengths.cpu().long(), valid.sum(1))
+    # pads carry the exact float32 pad constant, like the reference (models.py:187)
+    assert bool((mel[~valid] == oracle.pad_value()).all())
+    assert rel_l2(mel[valid], ref_mel[valid]) <= MEL_TOL_RAW
+    assert rel_l2((mel[valid] - MEAN) / STD, (ref_mel[valid] - MEAN) / STD) <= MEL_TOL_NORM
+    ref_wavs = np.split(z["wav_flat"], np.cumsum(z["wav_lengths"])[:-1])
+    for b, ref_w in enumerate(ref_wavs):
+        n = len(ref_w)
+        assert n == 320 * int(valid[b].sum()) + 80
+        assert rel_l2(wav[b, :n], torch.from_numpy(ref_w)) <= WAV_TOL
+
+
+def test_public_call_shapes_and_seeding(decoder, golden_dir):
+    """decoder(ids, dt, tv) -> list of (1, 320 len + 80) tensors; same seed => same output (the prior is drawn with
+    the reference's own torch.randn call, models.py:168)."""
+    z, info = _load(golden_dir, "resynth_b2_n40")
+    ids = torch.from_numpy(z["ids"]).cuda()
+    torch.manual_seed(3)
+    a = decoder(ids, 0.0625, 1.0)
+    torch.manual_seed(3)
+    b = decoder(ids, 0.0625, 1.0)
+    assert [tuple(w.shape) for w in a] == [(1, n) for n in info["wav_lengths"]]
+    assert all(w.dtype == torch.float32 and w.is_cuda for w in a)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+    assert all(bool(torch.isfinite(w).all()) for w in a)
+
+
+def test_sample_matches_oracle_on_fresh_inputs(decoder, state_dict):
+    """model.sample against the CPU oracle on inputs that are not in the golden set (ragged batch, NFE 8)."""
+    ids = synthetic.make_units(4, 96, seed=31, lengths=[96, 50, 7, 1])
+    x0 = torch.randn(4, 96, 80, generator=torch.Generator().manual_seed(5))
+    mel = decoder.engine().sample(ids.cuda(), 0.125, 1.0, noise=x0.cuda()).cpu()
+    ref = oracle.sample(state_dict, ids, x0, 0.125, 1.0)
+    valid = ids.ne(0)
+    assert bool((mel[~valid] == oracle.pad_value()).all())
+    assert rel_l2((mel[valid] - MEAN) / STD, (ref[valid] - MEAN) / STD) <= MEL_TOL_NORM
+
+
+def test_vocoder_matches_reference_golden(decoder, golden_dir):
+    z, _ = _load(golden_dir, "vocoder_b2_t30")
+    wav = decoder.vocoder(torch.from_numpy(z["mel"]).cuda())
+    assert wav.shape == (2, 320 * 30 + 80)
+    assert rel_l2(wav, torch.from_numpy(z["wav"])) <= WAV_TOL
+
+
+def test_velocity_field_matches_reference_golden(decoder, golden_dir, state_dict):
+    """One Euler step from the golden xt with dt = 1: xt_new - xt is the velocity the reference computed."""
+    z, _ = _load(golden_dir, "velocity_b2_n40")
+    ids = torch.from_numpy(z["ids"])
+    xt = torch.from_numpy(z["xt"])
+    sampler = decoder.model.sampler()
+    ws = sampler.workspace(2, 40)
+    ws["ids"].copy_(ids)
+    ws["xt"].copy_(xt)
+    times = torch.tensor([float(z["t"])], dtype=torch.float32)
+    g = sampler.cond_table(times)
+    sampler.prepare(ws, None)
+    sampler.step(ws, g[0], 1.0, last=False)
+    torch.cuda.synchronize()
+    v = (ws["xt"].cpu() - xt)
+    valid = ids.ne(0)
+    assert rel_l2(v[valid], torch.from_numpy(z["v"])[valid]) <= 1.5e-2
+
+
+def test_gather_matches_reference_fingerprint(decoder, golden_dir):
+    import hashlib
+
+    z, info = _load(golden_dir, "gather_b4_n33")
+    emb = decoder.model.embed_units(torch.from_numpy(z["ids"]).cuda()).cpu()
+    assert hashlib.sha256(emb.numpy().tobytes()).hexdigest() == info["sha256"]
+
+
+def test_full_size_properties(decoder):
+    """Config-2-sized call (64 x 500 frames, NFE 16): size-independent properties instead of an oracle run.
+    Batch-composition independence: an utterance synthesised inside the big batch equals the same utterance
+    (same prior) synthesised in a batch of its own padded length, up to bf16 noise."""
+    b, n = 64, 500
+    lengths = [n] * (b - 3) + [400, 123, 1]
+    ids = synthetic.make_units(b, n, seed=77, lengths=lengths).cuda()
+    x0 = torch.randn(b, n, 80, generator=torch.Generator().manual_seed(9)).cuda()
+    wav, lens, mel = decoder.engine().resynthesize(ids, 0.0625, 1.0, noise=x0)
+    wav, mel = wav.clone(), mel.clone()
+    assert lens.cpu().tolist() == lengths
+    assert bool(torch.isfinite(wav).all()) and float(wav.abs().max()) <= 1.0
+    valid = ids.ne(0)
+    assert bool((mel[~valid] == oracle.pad_value()).all())
+    sub = [0, b - 3, b - 2]
+    wav2, _, mel2 = decoder.engine().resynthesize(ids[sub], 0.0625, 1.0, noise=x0[sub])
+    for j, i in enumerate(sub):
+        m = valid[i]
+        assert rel_l2(mel2[j][m], mel[i][m]) <= 1e-3
+    assert rel_l2(wav2[0], wav[0]) <= 1e-2
