@@ -52,6 +52,9 @@ class NativeLibraryError(RuntimeError):
 
 _lib: Optional[ctypes.CDLL] = None
 launch_count = 0  # kernels launched through this binding (bench.py reports it as gpu_launches)
+# when set to a list, every call appends (name, shape_tag, start_event, end_event): per-op device timing for
+# bench.py's roofline line and tools/profile_ops.py (never enabled on the product path)
+profile_log: Optional[list] = None
 
 
 def load() -> ctypes.CDLL:
@@ -90,13 +93,20 @@ def stream_ptr() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
-def call(name: str, *args) -> None:
-    """Invoke an entry point on the current torch stream; non-zero status -> RuntimeError with the C-side text."""
+def call(name: str, *args, flops: float = 0.0, nbytes: float = 0.0) -> None:
+    """Invoke an entry point on the current torch stream; non-zero status -> RuntimeError with the C-side text.
+    `flops` / `nbytes` are the op's algorithmic work (used only by the profiling log)."""
     global launch_count
     lib = load()
+    if profile_log is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     rc = getattr(lib, name)(*args, stream_ptr())
     if rc != 0:
         raise RuntimeError(f"{name} failed ({rc}): {last_error()}")
+    if profile_log is not None:
+        ev1.record()
+        profile_log.append((name, tuple(a for a in args if isinstance(a, int) and 0 <= a < (1 << 24)), ev0, ev1, flops, nbytes))
     launch_count += 1
 
 

@@ -93,7 +93,7 @@ class CFMSampler:
         b, n = ws["ids"].shape
         nat.call("srb_unit_lengths", P(ws["ids"]), P(ws["lengths"]), b, n)
         nat.call("srb_embed_gather", P(self.w.cond_table), P(ws["ids"]), P(ws["cond"]), b * n,
-                 self.w.cond_table.shape[0], 256)
+                 self.w.cond_table.shape[0], 256, nbytes=b * n * (2 * 256 * 4 + 8))
         tv = float(truncation) if truncation is not None else 0.0
         nat.call("srb_prior_prepare", P(ws["xt"]), P(ws["xt_b"]), b * n * 80, tv)
 
@@ -102,23 +102,28 @@ class CFMSampler:
         b, n = ws["ids"].shape
         w, L = self.w, ws["lengths"]
         cs, sn = self.rotary(n)
-        nat.call("srb_cfm_embed", P(ws["xt_b"]), P(w.w_embed), P(ws["cond"]), P(ws["x0"]), b, n)
-        nat.call("srb_cfm_posconv_norm", P(ws["x0"]), P(w.dw_w), P(w.dw_b), P(g_step[0]), P(L), P(ws["x"]), P(ws["xn"]), b, n)
+        m = b * n
+        nat.call("srb_cfm_embed", P(ws["xt_b"]), P(w.w_embed), P(ws["cond"]), P(ws["x0"]), b, n, flops=2.0 * m * 80 * 256)
+        nat.call("srb_cfm_posconv_norm", P(ws["x0"]), P(w.dw_w), P(w.dw_b), P(g_step[0]), P(L), P(ws["x"]), P(ws["xn"]), b, n,
+                 flops=2.0 * m * 31 * 256, nbytes=m * 256 * (4 + 4 + 2))
         for i in range(self.depth):
-            nat.call("srb_cfm_qkv_rope", P(ws["xn"]), P(w.w_qkv[i]), P(cs), P(sn), P(ws["qkv"]), b, n)
-            nat.call("srb_cfm_attention", P(ws["qkv"]), P(L), P(ws["o"]), b, n)
-            nat.call("srb_cfm_attn_out_norm", P(ws["o"]), P(w.w_out[i]), P(g_step[2 * i + 1]), P(L), P(ws["x"]), P(ws["xn"]), b, n)
-            nat.call("srb_cfm_ffn_glu", P(ws["xn"]), P(w.w_ff1[i]), P(w.b_ff1[i]), P(L), P(ws["h"]), b, n)
+            nat.call("srb_cfm_qkv_rope", P(ws["xn"]), P(w.w_qkv[i]), P(cs), P(sn), P(ws["qkv"]), b, n,
+                     flops=2.0 * m * 256 * 768)
+            nat.call("srb_cfm_attention", P(ws["qkv"]), P(L), P(ws["o"]), b, n, flops=4.0 * m * n * 256)
+            nat.call("srb_cfm_attn_out_norm", P(ws["o"]), P(w.w_out[i]), P(g_step[2 * i + 1]), P(L), P(ws["x"]), P(ws["xn"]), b, n,
+                     flops=2.0 * m * 256 * 256)
+            nat.call("srb_cfm_ffn_glu", P(ws["xn"]), P(w.w_ff1[i]), P(w.b_ff1[i]), P(L), P(ws["h"]), b, n,
+                     flops=2.0 * m * 768 * 1792)
             if i + 1 < self.depth:
                 g_next, mode = g_step[2 * i + 2], 1
             else:
                 g_next, mode = w.final_norm_w, 2
             nat.call("srb_cfm_ffn_out_norm", P(ws["h"]), P(w.w_ff2[i]), P(w.b_ff2[i]), P(g_next), mode, P(L), P(ws["x"]),
-                     P(ws["xn"]), b, n)
+                     P(ws["xn"]), b, n, flops=2.0 * m * 2688 * 256)
         mel = P(ws["mel"]) if last else None
         mel_b = P(ws["mel_b"]) if last else None
         nat.call("srb_cfm_pred_euler", P(ws["xn"]), P(w.w_pred), float(dt), P(ws["xt"]), P(ws["xt_b"]), mel, mel_b,
-                 self.std, self.mean, pad_value_f32(), P(L), b, n)
+                 self.std, self.mean, pad_value_f32(), P(L), b, n, flops=2.0 * m * 256 * 80)
 
     def run(self, ws: Dict[str, torch.Tensor], dt: float, truncation: Optional[float]) -> None:
         """ids and the prior sample must already be in ws['ids'] / ws['xt']; result lands in ws['mel'], ws['mel_b']."""
@@ -170,7 +175,7 @@ class HifiGanGenerator:
         dil1 = _i32([1])
         # conv_pre (HF:1470); its only consumer is leaky_relu -> upsampler, so only the activated copy is stored
         nat.call("srb_hifigan_conv", P(mel_b), None, None, 1, one, dil1, P(w.w_pre), P(w.b_pre), None, None, None, None,
-                 P(ws["pre"]), b, t, 80, 512, 1.0, self.slope)
+                 P(ws["pre"]), b, t, 80, 512, 1.0, self.slope, flops=2.0 * b * t * 7 * 80 * 512)
         x_act, rows_in, c_in = ws["pre"], t, 512
         n_stage = len(UPSAMPLE_RATES)
         for i, (k, s) in enumerate(zip(UPSAMPLE_KERNELS, UPSAMPLE_RATES)):
@@ -178,19 +183,20 @@ class HifiGanGenerator:
             rows, c = st["rows"], st["c"]
             # upsampler (HF:1472-1473): raw copy = residual of the three resblocks, activated copy = their input
             nat.call("srb_hifigan_upsample", P(x_act), P(w.w_up[i]), P(w.b_up[i]), P(st["u_raw"]), P(st["u_act"]), b,
-                     rows_in, c_in, c, k, s, self.slope)
+                     rows_in, c_in, c, k, s, self.slope, flops=2.0 * b * rows_in * k * c_in * c)
             for j, rk in enumerate(RESBLOCK_KERNELS):
                 kk = _i32([rk])
                 xr, xa = st["u_raw"], st["u_act"]
                 for q, dil in enumerate(RESBLOCK_DILATIONS):
                     # conv1 with dilation (HF:1361-1363), output only needed activated
                     nat.call("srb_hifigan_conv", P(xa), None, None, 1, kk, _i32([dil]), P(w.w_c1[i][j][q]),
-                             P(w.b_c1[i][j][q]), None, None, None, None, P(st["t"][j]), b, rows, c, c, 1.0, self.slope)
+                             P(w.b_c1[i][j][q]), None, None, None, None, P(st["t"][j]), b, rows, c, c, 1.0, self.slope,
+                             flops=2.0 * b * rows * rk * c * c)
                     if q < 2:
                         # conv2 + residual (HF:1364-1366): raw (next residual) and activated (next conv1 input)
                         nat.call("srb_hifigan_conv", P(st["t"][j]), None, None, 1, kk, dil1, P(w.w_c2[i][j][q]),
                                  P(w.b_c2[i][j][q]), P(xr), None, None, P(st["xr"][j]), P(st["xa"][j]), b, rows, c, c,
-                                 1.0, self.slope)
+                                 1.0, self.slope, flops=2.0 * b * rows * rk * c * c)
                         xr, xa = st["xr"][j], st["xa"][j]
                 if j == 0:
                     res = [xr]
@@ -201,9 +207,10 @@ class HifiGanGenerator:
             slope_next = self.slope if i + 1 < n_stage else 0.01
             nat.call("srb_hifigan_conv", P(st["t"][0]), P(st["t"][1]), P(st["t"][2]), 3, _i32(list(RESBLOCK_KERNELS)),
                      _i32([1, 1, 1]), P(w.w_tail[i]), P(w.b_tail[i]), P(res[0]), P(res[1]), P(res[2]), None, P(st["out"]),
-                     b, rows, c, c, 1.0 / 3.0, slope_next)
+                     b, rows, c, c, 1.0 / 3.0, slope_next, flops=2.0 * b * rows * sum(RESBLOCK_KERNELS) * c * c)
             x_act, rows_in, c_in = st["out"], rows, c
-        nat.call("srb_hifigan_post", P(x_act), P(w.w_post), w.b_post, P(ws["wav"]), b, rows_in)
+        nat.call("srb_hifigan_post", P(x_act), P(w.w_post), w.b_post, P(ws["wav"]), b, rows_in,
+                 flops=2.0 * b * rows_in * 7 * 16, nbytes=b * rows_in * (16 * 2 + 4))
         return ws["wav"]
 
 
