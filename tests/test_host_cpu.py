@@ -1,0 +1,201 @@
+"""CPU: host-side logic -- drop-in API surface (config / state-dict / save-load), weight packing layouts, the
+bucketing + sharding plan (incl. a world_size-2 gloo run), and the C-ABI library's exported symbols."""
+import ctypes
+import os
+import re
+import tempfile
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import speech_resynth_b200 as srb
+from speech_resynth_b200 import _native, packing, sharding, synthetic
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ------------------------------------------------------------------------------------------------ drop-in API
+@pytest.fixture(scope="module")
+def model(state_dict):
+    m = srb.ConditionalFlowMatchingWithHifiGan(srb.reference_config()).eval()
+    m.load_state_dict(state_dict, strict=True)
+    return m
+
+
+def test_state_dict_keys_and_shapes_match_the_reference_checkpoint_layout(model, state_dict):
+    sd = model.state_dict()
+    assert set(sd) == set(state_dict) and len(sd) == 239
+    assert all(sd[k].shape == state_dict[k].shape for k in sd)
+    assert "model.time_cond_mlp.0.weights" in sd and "model.transformer.rotary_emb.inv_freq" in sd  # persistent buffers
+
+
+def test_constructor_initialisation_follows_the_reference():
+    m = srb.ConditionalFlowMatchingWithHifiGan(srb.reference_config())
+    assert float(m.model.transformer.layers[0][1].to_weight.weight.abs().sum()) == 0.0      # norm.py:35
+    assert float(m.model.to_cond_emb.weight[0].abs().sum()) == 0.0                           # padding_idx row
+    inv = m.model.transformer.rotary_emb.inv_freq
+    assert torch.allclose(inv, 1.0 / (10000 ** (torch.arange(0, 128, 2).float() / 128)))
+    assert m.model.transformer.layers[0][0] is None                                          # no U-Net skip combiner
+
+
+def test_save_pretrained_from_pretrained_round_trip(model, state_dict):
+    with tempfile.TemporaryDirectory() as d:
+        model.save_pretrained(d)
+        assert sorted(os.listdir(d)) == ["config.json", "model.safetensors"]
+        again = srb.ConditionalFlowMatchingWithHifiGan.from_pretrained(d)
+        assert all(torch.equal(v, state_dict[k]) for k, v in again.state_dict().items())
+        assert again.config.model_config.hidden_size == 256 and again.config.vocoder_config.upsample_rates == [5, 4, 4, 2, 2]
+        model.model.save_pretrained(os.path.join(d, "cfm"))
+        model.vocoder.save_pretrained(os.path.join(d, "voc"))
+        joined = srb.ConditionalFlowMatchingWithHifiGan.load_pretrained(os.path.join(d, "cfm"), os.path.join(d, "voc"))
+        assert all(torch.equal(v, state_dict[k]) for k, v in joined.state_dict().items())
+
+
+def test_waveform_length_rule(model):
+    assert model._get_waveform_lengths(torch.tensor([1, 25, 500])).tolist() == [400, 8080, 160080]
+
+
+def test_no_cpu_fallback(model):
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_native.NativeLibraryError):
+        model(torch.ones(1, 8, dtype=torch.long))
+    with pytest.raises(RuntimeError):
+        model.model.conv_embed(torch.zeros(1, 4, 256))   # parameter containers have no PyTorch forward
+
+
+def test_unsupported_variants_are_rejected():
+    cfg = srb.ConditionalFlowMatchingConfig(predict_duration=True)
+    with pytest.raises(NotImplementedError):
+        srb.ConditionalFlowMatchingModel(cfg)
+
+
+# ------------------------------------------------------------------------------------------------ packing
+def test_conv_weight_packing_is_tap_major_with_channel_padding():
+    w = torch.randn(6, 80, 7)
+    p = packing.pack_conv_weight(w, 64).float()
+    assert p.shape == (6, 7 * 128)
+    p = p.view(6, 7, 128)
+    assert torch.equal(p[:, :, :80], w.permute(0, 2, 1).to(torch.bfloat16).float()) and float(p[:, :, 80:].abs().sum()) == 0.0
+
+
+def test_glu_row_permutation_pairs_value_and_gate_rows():
+    perm = packing.glu_row_permutation(896)
+    assert sorted(perm.tolist()) == list(range(1792))
+    for t in range(7):
+        blk = perm[t * 256:(t + 1) * 256]
+        assert blk[:128].tolist() == list(range(t * 128, (t + 1) * 128))
+        assert blk[128:].tolist() == list(range(896 + t * 128, 896 + (t + 1) * 128))
+
+
+@pytest.mark.parametrize("k,s", list(zip(packing.UPSAMPLE_KERNELS, packing.UPSAMPLE_RATES)))
+def test_polyphase_packing_reproduces_conv_transpose(k, s):
+    """emulate the kernel's gather form from the packed matrix and compare with F.conv_transpose1d (fp64 operands
+    rounded to bf16 first, so the packed bf16 weights are exact)"""
+    g = torch.Generator().manual_seed(k * 10 + s)
+    c_in, c_out, lin = 8, 4, 19
+    w = torch.randn(c_in, c_out, k, generator=g).to(torch.bfloat16).float()
+    x = torch.randn(1, lin, c_in, generator=g)
+    pad = (k - s) // 2
+    ref = F.conv_transpose1d(x.transpose(1, 2).double(), w.double(), None, stride=s, padding=pad).transpose(1, 2)[0]
+    wp = packing.pack_upsampler_weight(w, s).double()          # (c_out, k * c_in), phases concatenated along K
+    lout = ref.shape[0]
+    out = torch.zeros(lout, c_out, dtype=torch.float64)
+    col = 0
+    for r in range(s):
+        j0, c_r = (r + pad) % s, (r + pad) // s
+        for m, _ in enumerate(range(j0, k, s)):
+            wt = wp[:, col:col + c_in]
+            col += c_in
+            for q in range((lout - r + s - 1) // s):
+                src = q + c_r - m
+                if 0 <= src < lin:
+                    out[q * s + r] += wt @ x[0, src].double()
+    assert col == k * c_in
+    assert float((out - ref).abs().max()) <= 1e-12
+
+
+# ------------------------------------------------------------------------------------------------ sharding
+def test_buckets_partition_and_pad_like_pad_sequence():
+    g = torch.Generator().manual_seed(11)
+    lengths = torch.randint(100, 1001, (300,), generator=g).tolist()
+    buckets = sharding.bucket_by_length(lengths, granularity=64, max_batch=32)
+    seen = sorted(i for b in buckets for i in b.indices)
+    assert seen == list(range(300))
+    for b in buckets:
+        ls = [lengths[i] for i in b.indices]
+        assert b.frames == max(ls) and b.batch <= 32
+        assert len({(n + 63) // 64 for n in ls}) == 1
+    plan = sharding.assign_buckets(buckets, 8)
+    assert sorted(j for r in plan for j in r) == list(range(len(buckets)))
+    loads = [sum(buckets[j].batch * sharding.utterance_cost(buckets[j].frames, 16) for j in r) for r in plan]
+    assert max(loads) / (sum(loads) / 8) < 1.15
+
+
+def test_empty_utterance_is_rejected():
+    with pytest.raises(ValueError):
+        sharding.bucket_by_length([5, 0, 3])
+
+
+def _fake_synth(ids):
+    # deterministic stand-in for the decoder: waveform i = (sum of its ids) ramp of the reference's output length
+    out = []
+    for row in ids:
+        n = int(row.ne(0).sum())
+        out.append((torch.arange(320 * n + 80, dtype=torch.float32) * 1e-3 + float(row.sum())).unsqueeze(0))
+    return out
+
+
+def test_single_rank_sharded_call_restores_caller_order():
+    units = [torch.randint(1, 2001, (n,)) for n in (7, 300, 64, 65, 1)]
+    outs = sharding.resynthesize_sharded(units, _fake_synth, granularity=64)
+    for u, w in zip(units, outs):
+        assert tuple(w.shape) == (1, 320 * u.numel() + 80) and float(w[0, 0]) == float(u.sum())
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(5)
+    units = [torch.randint(1, 2001, (int(n),), generator=g) for n in torch.randint(1, 200, (23,), generator=g)]
+    outs = sharding.resynthesize_sharded(units, _fake_synth, rank=rank, world=world, granularity=32, max_batch=4)
+    if rank == 0:
+        ok = all(tuple(w.shape) == (1, 320 * u.numel() + 80) and float(w[0, 0]) == float(u.sum())
+                 and float(w[0, -1]) == pytest.approx(float(u.sum()) + (320 * u.numel() + 79) * 1e-3, rel=1e-6)
+                 for u, w in zip(units, outs))
+        q.put(ok)
+    else:
+        assert outs is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_gather():
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert ok
+
+
+# ------------------------------------------------------------------------------------------------ C ABI
+def test_library_exports_every_symbol_declared_in_the_header():
+    header = open(os.path.join(ROOT, "include", "srb.h")).read()
+    declared = set(re.findall(r"\b(srb_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_native.EXPORTED_SYMBOLS)
+    if not os.path.exists(_native.LIB_PATH):
+        pytest.skip("libsrb.so not built (run __graft_entry__.build())")
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.srb_version() == 100

@@ -1,0 +1,127 @@
+"""CPU: the oracle restatement against the golden vectors minted from the live reference (tests/golden/*.npz),
+its internal consistency (polyphase form, float64 anchor), and -- when /root/reference is mounted -- directly
+against the live reference classes."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cfm_hifigan_oracle as oracle
+from oracle import ref_loader
+from speech_resynth_b200 import synthetic
+
+
+def rel_l2(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def _golden(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name + ".npz")), json.load(open(os.path.join(golden_dir, "MANIFEST.json")))
+
+
+def test_weight_recipe_is_stable(state_dict, golden_dir):
+    man = json.load(open(os.path.join(golden_dir, "MANIFEST.json")))
+    assert len(state_dict) == 239
+    assert abs(synthetic.state_dict_checksum(state_dict) - man["weights_checksum"]) <= 1e-6 * man["weights_checksum"]
+    assert float(state_dict["model.to_cond_emb.weight"][0].abs().sum()) == 0.0
+    assert sum(v.numel() for k, v in state_dict.items() if k.startswith("vocoder.") and k not in ("vocoder.mean", "vocoder.scale")) == 12_977_473
+
+
+def test_pad_value_is_the_float32_log():
+    assert oracle.pad_value() == -11.512925148010254
+
+
+@pytest.mark.parametrize("name", ["resynth_b2_n40", "resynth_b1_n64_dt01"])
+def test_oracle_resynthesis_matches_reference_golden(state_dict, golden_dir, name):
+    z, man = _golden(golden_dir, name)
+    info = man["cases"][name]
+    ids, x0 = torch.from_numpy(z["ids"]), torch.from_numpy(z["x0"])
+    mel = oracle.sample(state_dict, ids, x0, info["dt"], info["truncation"])
+    valid = ids.ne(0)
+    assert rel_l2(mel[valid], torch.from_numpy(z["mel"])[valid]) <= 1e-5
+    assert bool((mel[~valid] == oracle.pad_value()).all())
+    wavs = oracle.resynthesize(state_dict, ids, x0, info["dt"], info["truncation"])
+    assert [w.shape[-1] for w in wavs] == info["wav_lengths"] == [320 * int(n) + 80 for n in valid.sum(1)]
+    ref = np.split(z["wav_flat"], np.cumsum(z["wav_lengths"])[:-1])
+    for w, r in zip(wavs, ref):
+        assert tuple(w.shape) == (1, len(r))
+        assert rel_l2(w[0], torch.from_numpy(r)) <= 1e-4
+
+
+def test_oracle_vocoder_and_polyphase_match_reference_golden(state_dict, golden_dir):
+    z, _ = _golden(golden_dir, "vocoder_b2_t30")
+    mel = torch.from_numpy(z["mel"])
+    ref = torch.from_numpy(z["wav"])
+    assert rel_l2(oracle.hifigan(state_dict, mel), ref) <= 1e-5
+    sd64 = oracle.to_dtype(state_dict, torch.float64)
+    assert rel_l2(oracle.hifigan(sd64, mel.double(), polyphase=True), ref) <= 1e-5
+
+
+def test_oracle_velocity_and_time_embedding_match_reference_golden(state_dict, golden_dir):
+    z, _ = _golden(golden_dir, "velocity_b2_n40")
+    ids, xt = torch.from_numpy(z["ids"]), torch.from_numpy(z["xt"])
+    t = torch.tensor(float(z["t"]))
+    mask = ids.ne(0)
+    v = oracle.velocity(state_dict, xt, oracle.embed_gather(state_dict["model.to_cond_emb.weight"], ids), mask, t)
+    assert rel_l2(v[mask], torch.from_numpy(z["v"])[mask]) <= 1e-5
+    assert rel_l2(oracle.time_embedding(state_dict, t), torch.from_numpy(z["time_emb"])) <= 1e-6
+
+
+def test_oracle_gather_fingerprint(state_dict, golden_dir):
+    z, man = _golden(golden_dir, "gather_b4_n33")
+    emb = oracle.embed_gather(state_dict["model.to_cond_emb.weight"], torch.from_numpy(z["ids"]))
+    assert hashlib.sha256(emb.numpy().tobytes()).hexdigest() == man["cases"]["gather_b4_n33"]["sha256"]
+
+
+def test_polyphase_transposed_conv_edge_cases():
+    """phase/tap bookkeeping of the polyphase form for every up-sampler geometry, tiny and ragged lengths"""
+    g = torch.Generator().manual_seed(0)
+    for k, s in zip(oracle.UPSAMPLE_KERNELS, oracle.UPSAMPLE_RATES):
+        for lin in (1, 2, 3, 17):
+            x = torch.randn(2, 6, lin, generator=g, dtype=torch.float64)
+            w = torch.randn(6, 4, k, generator=g, dtype=torch.float64)
+            b = torch.randn(4, generator=g, dtype=torch.float64)
+            ref = torch.nn.functional.conv_transpose1d(x, w, b, stride=s, padding=(k - s) // 2)
+            got = oracle.conv_transpose1d_polyphase(x, w, b, s, (k - s) // 2)
+            assert got.shape == ref.shape and rel_l2(got, ref) <= 1e-12
+
+
+def test_waveform_lengths_and_flop_model():
+    assert oracle.waveform_lengths(torch.tensor([1, 25, 500])).tolist() == [400, 8080, 160080]
+    assert oracle.vocoder_flops(500) == 160_305_440_256      # SURVEY.md section 8(a) row V*
+    assert oracle.vocoder_flops(250) == 80_190_240_256
+    assert oracle.transformer_flops(500, 16, hoisted=False) == 16 * 500 * 21_151_232
+
+
+def test_ode_time_grid_matches_torch_arange_semantics():
+    assert len(oracle.ode_times(0.0625)) == 16 and len(oracle.ode_times(0.1)) == 10
+    assert float(oracle.ode_times(0.1)[3]) == float(torch.arange(0, 1, 0.1)[3]) != 0.3
+
+
+def test_batch_composition_independence_of_valid_frames(state_dict):
+    """an utterance's valid mel frames do not depend on what it is batched with (masks isolate utterances)"""
+    ids = synthetic.make_units(2, 24, seed=3, lengths=[24, 9])
+    x0 = torch.randn(2, 24, 80, generator=torch.Generator().manual_seed(2))
+    sd64 = oracle.to_dtype(state_dict, torch.float64)
+    both = oracle.sample(sd64, ids, x0.double(), 0.5, 1.0)
+    alone = oracle.sample(sd64, ids[1:, :9], x0[1:, :9].double(), 0.5, 1.0)
+    assert rel_l2(both[1, :9], alone[0]) <= 1e-10
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference is only mounted in the build container")
+def test_oracle_against_live_reference(state_dict):
+    ref = ref_loader.build_reference_model(state_dict)
+    ids = synthetic.make_units(2, 20, seed=17, lengths=[20, 11])
+    with torch.backends.mkldnn.flags(enabled=False):   # see DESIGN.md: oneDNN fp32 deconvolution defect
+        torch.manual_seed(4)
+        with torch.inference_mode():
+            ref_wavs = ref(ids, 0.25, 1.0)
+        torch.manual_seed(4)
+        x0 = torch.randn(2, 20, 80)
+        wavs = oracle.resynthesize(state_dict, ids, x0, 0.25, 1.0)
+    for a, r in zip(wavs, ref_wavs):
+        assert a.shape == r.shape and rel_l2(a, r) <= 1e-5
