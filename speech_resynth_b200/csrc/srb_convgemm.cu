@@ -124,7 +124,8 @@ static int launch_inst(ConvGemmParams& p, int total_tiles, cudaStream_t stream) 
   int stages = budget / L::stage_bytes;
   stages = stages < 2 ? 2 : (stages > 8 ? 8 : stages);
   p.stages = stages;
-  const int smem = stages * L::stage_bytes + 1024 + 8 * (2 * stages + 4) + 16;
+  constexpr int threads = 64 + 32 * EpiWarps<BN, EPI>::value;
+  const int smem = stages * L::stage_bytes + 1024 + 8 * (2 * stages + 4) + 16 + 1024;  // + [2][128] fp32 scratch
   static int configured_smem[64] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -134,16 +135,23 @@ static int launch_inst(ConvGemmParams& p, int total_tiles, cudaStream_t stream) 
   }
   static int blocks_per_sm[64] = {0};
   if (blocks_per_sm[dev & 63] == 0) {
-    int occ = 0;
-    SRB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 192, smem));
-    const int tmem_limit = 512 / TmemCols<BN>::total;
-    occ = occ < 1 ? 1 : occ;
-    blocks_per_sm[dev & 63] = occ < tmem_limit ? occ : tmem_limit;
+    // resident CTAs per SM: shared memory, registers, threads and -- unknown to the occupancy API -- the 512 TMEM
+    // columns every CTA carves its accumulators from
+    cudaFuncAttributes fa;
+    SRB_CUDA(cudaFuncGetAttributes(&fa, kernel));
+    int occ = 232448 / (smem + 1024);
+    const int by_regs = 65536 / (((fa.numRegs + 7) & ~7) * threads);
+    const int by_threads = 2048 / threads;
+    const int by_tmem = 512 / TmemCols<BN>::total;
+    occ = occ < by_regs ? occ : by_regs;
+    occ = occ < by_threads ? occ : by_threads;
+    occ = occ < by_tmem ? occ : by_tmem;
+    blocks_per_sm[dev & 63] = occ < 1 ? 1 : occ;
   }
   int grid = num_sms() * blocks_per_sm[dev & 63];
   if (grid > total_tiles) grid = total_tiles;
   if (grid < 1) return 0;
-  kernel<<<grid, 192, smem, stream>>>(p, total_tiles);
+  kernel<<<grid, threads, smem, stream>>>(p, total_tiles);
   return after_launch("convgemm_kernel");
 }
 

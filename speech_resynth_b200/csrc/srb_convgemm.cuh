@@ -88,32 +88,53 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvGemmParams& p, int ti
 }
 
 // ---------------------------------------------------------------------------------------------- epilogues
-// Every epilogue runs with thread <-> one accumulator row; `tacc` is the TMEM address of (lane base, column 0)
-// of this tile's accumulator buffer.  All 32 lanes of a warp must execute the tcgen05.ld/st (sync.aligned).
+// Thread <-> one accumulator row (TMEM lane).  The epilogue is the throughput limiter of these kernels when it is
+// under-populated (one warp per SM sub-partition cannot hide TMEM / global latency), so wide tiles use EIGHT
+// epilogue warps: warps sharing a TMEM lane quarter split the columns in two halves (`half`, `nhalf`).
+// `tacc` is the TMEM address of (lane base, column 0) of this tile's accumulator buffer.  All 32 lanes of a warp
+// execute every tcgen05.ld/st (sync.aligned); global loads that do not depend on the accumulator are issued
+// before the TMEM wait so their latency overlaps it.
 
-template <int BN>
-__device__ __forceinline__ void epi_generic(const ConvGemmParams& p, uint32_t tacc, const TileCoord& tc, int q) {
+template <int N>
+__device__ __forceinline__ void tmem_ld_f(uint32_t taddr, float (&y)[N]) {
+  static_assert(N == 32 || N == 16, "chunk width");
+  if constexpr (N == 32) {
+    uint32_t v[32];
+    tmem_ld32(taddr, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) y[j] = __uint_as_float(v[j]);
+  } else {
+    uint32_t v[16];
+    tmem_ld16(taddr, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) y[j] = __uint_as_float(v[j]);
+  }
+}
+
+template <int BN, int NHALF>
+__device__ __forceinline__ void epi_generic(const ConvGemmParams& p, uint32_t tacc, const TileCoord& tc, int q, int half) {
   constexpr int CW = BN < 32 ? BN : 32;
+  constexpr int COLS = BN / NHALF;
   const bool valid = q < p.group_rows[tc.group];
   const long long orow = (long long)q * p.row_mul + p.group_row_add[tc.group];
   const long long obase = (long long)tc.b * p.out_batch_stride + orow * p.out_row_stride + (long long)tc.n * BN;
   const long long rbase = (long long)tc.b * p.res_batch_stride + orow * p.res_row_stride + (long long)tc.n * BN;
+  const float sc = p.scale, sl = p.slope;
 #pragma unroll 1
-  for (int c0 = 0; c0 < BN; c0 += CW) {
-    float y[CW];
-    if constexpr (CW == 32) {
-      uint32_t v[32];
-      tmem_ld32(tacc + c0, v);
-      tmem_ld_wait();
+  for (int c0 = half * COLS; c0 < (half + 1) * COLS; c0 += CW) {
+    uint4 rv[3][CW / 8];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) y[j] = __uint_as_float(v[j]);
-    } else {
-      uint32_t v[16];
-      tmem_ld16(tacc + c0, v);
-      tmem_ld_wait();
+    for (int r = 0; r < 3; ++r) {
+      if (valid && p.res[r]) {
+        const uint4* r4 = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.res[r]) + rbase + c0);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) y[j] = __uint_as_float(v[j]);
+        for (int j = 0; j < CW / 8; ++j) rv[r][j] = __ldg(r4 + j);
+      }
     }
+    float y[CW];
+    tmem_ld_f<CW>(tacc + c0, y);
     if (valid) {
       if (p.bias) {
         const float4* b4 = reinterpret_cast<const float4*>(p.bias + tc.n * BN + c0);
@@ -126,10 +147,9 @@ __device__ __forceinline__ void epi_generic(const ConvGemmParams& p, uint32_t ta
 #pragma unroll
       for (int r = 0; r < 3; ++r) {
         if (p.res[r]) {
-          const uint4* r4 = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.res[r]) + rbase + c0);
 #pragma unroll
           for (int j = 0; j < CW / 8; ++j) {
-            uint4 u = __ldg(r4 + j);
+            const uint4 u = rv[r][j];
             y[8 * j + 0] += bf16_lo(u.x); y[8 * j + 1] += bf16_hi(u.x);
             y[8 * j + 2] += bf16_lo(u.y); y[8 * j + 3] += bf16_hi(u.y);
             y[8 * j + 4] += bf16_lo(u.z); y[8 * j + 5] += bf16_hi(u.z);
@@ -137,7 +157,6 @@ __device__ __forceinline__ void epi_generic(const ConvGemmParams& p, uint32_t ta
           }
         }
       }
-      const float sc = p.scale;
 #pragma unroll
       for (int j = 0; j < CW; ++j) y[j] *= sc;
       if (p.out1) {
@@ -148,7 +167,6 @@ __device__ __forceinline__ void epi_generic(const ConvGemmParams& p, uint32_t ta
                              pack_bf16(y[8 * j + 4], y[8 * j + 5]), pack_bf16(y[8 * j + 6], y[8 * j + 7]));
       }
       if (p.out0) {
-        const float sl = p.slope;
         uint4* o4 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out0) + obase + c0);
 #pragma unroll
         for (int j = 0; j < CW / 8; ++j)
@@ -162,14 +180,16 @@ __device__ __forceinline__ void epi_generic(const ConvGemmParams& p, uint32_t ta
 }
 
 // FFN conv1 tile = [128 value columns | 128 gate columns] -> 128 outputs  (fastspeech/modules.py:27-30, 62-69)
-__device__ __forceinline__ void epi_glu(const ConvGemmParams& p, uint32_t tacc, const TileCoord& tc, int q) {
+template <int NHALF>
+__device__ __forceinline__ void epi_glu(const ConvGemmParams& p, uint32_t tacc, const TileCoord& tc, int q, int half) {
+  constexpr int COLS = 128 / NHALF;
   const bool valid = q < p.group_rows[0];
   const bool keep = valid && q < p.lengths[tc.b];
   __nv_bfloat16* out = static_cast<__nv_bfloat16*>(p.out0) + (long long)tc.b * p.out_batch_stride +
                        (long long)q * p.out_row_stride + tc.n * 128;
   const float* bias = p.bias + tc.n * 256;
 #pragma unroll 1
-  for (int c0 = 0; c0 < 128; c0 += 32) {
+  for (int c0 = half * COLS; c0 < (half + 1) * COLS; c0 += 32) {
     uint32_t v[32], g[32];
     tmem_ld32(tacc + c0, v);
     tmem_ld32(tacc + 128 + c0, g);
@@ -177,17 +197,15 @@ __device__ __forceinline__ void epi_glu(const ConvGemmParams& p, uint32_t tacc, 
     if (valid) {
       uint32_t o[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float h0 = 0.f, h1 = 0.f;
-        if (keep) {
-          float v0 = __uint_as_float(v[2 * j]) + __ldg(bias + c0 + 2 * j);
-          float v1 = __uint_as_float(v[2 * j + 1]) + __ldg(bias + c0 + 2 * j + 1);
-          float g0 = __uint_as_float(g[2 * j]) + __ldg(bias + 128 + c0 + 2 * j);
-          float g1 = __uint_as_float(g[2 * j + 1]) + __ldg(bias + 128 + c0 + 2 * j + 1);
-          h0 = silu(g0) * v0;
-          h1 = silu(g1) * v1;
-        }
-        o[j] = pack_bf16(h0, h1);
+      for (int j = 0; j < 8; ++j) {
+        const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + c0) + j);
+        const float4 bg = __ldg(reinterpret_cast<const float4*>(bias + 128 + c0) + j);
+        const float h0 = silu_fast(__uint_as_float(g[4 * j + 0]) + bg.x) * (__uint_as_float(v[4 * j + 0]) + bv.x);
+        const float h1 = silu_fast(__uint_as_float(g[4 * j + 1]) + bg.y) * (__uint_as_float(v[4 * j + 1]) + bv.y);
+        const float h2 = silu_fast(__uint_as_float(g[4 * j + 2]) + bg.z) * (__uint_as_float(v[4 * j + 2]) + bv.z);
+        const float h3 = silu_fast(__uint_as_float(g[4 * j + 3]) + bg.w) * (__uint_as_float(v[4 * j + 3]) + bv.w);
+        o[2 * j] = keep ? pack_bf16(h0, h1) : 0u;       // pads are zeroed before conv2 (fastspeech/modules.py:69)
+        o[2 * j + 1] = keep ? pack_bf16(h2, h3) : 0u;
       }
       uint4* o4 = reinterpret_cast<uint4*>(out + c0);
 #pragma unroll
@@ -197,29 +215,48 @@ __device__ __forceinline__ void epi_glu(const ConvGemmParams& p, uint32_t tacc, 
 }
 
 // y = acc + bias + residual (fp32 stream, in place allowed); x_out = y; xn = bf16(norm(y) * g) with pad rows zeroed.
-// The full 256-wide row lives in this thread's TMEM lane, so the row reduction needs no communication.
-__device__ __forceinline__ void epi_resnorm(const ConvGemmParams& p, uint32_t tacc, const TileCoord& tc, int q) {
+// A row's 256 columns live in ONE TMEM lane; with two column halves per lane quarter the two warps exchange their
+// partial sums of squares through `red` (smem, [2][128] floats) and a 64-thread named barrier.
+// 64-thread named barrier shared by the two epilogue warps of one TMEM lane quarter (ids 1-4, immediates so that
+// ptxas accounts for them; id 0 is __syncthreads)
+__device__ __forceinline__ void pair_barrier(int quarter) {
+  switch (quarter) {
+    case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+    case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+    case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+    default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+  }
+}
+
+template <int NHALF>
+__device__ __forceinline__ void epi_resnorm(const ConvGemmParams& p, uint32_t tacc, const TileCoord& tc, int q, int half,
+                                            float* red, int row_in_tile, int quarter) {
+  constexpr int COLS = 256 / NHALF;
   const bool valid = q < p.group_rows[0];
   const long long off = (long long)tc.b * p.out_batch_stride + (long long)q * p.out_row_stride;
   const float* res = static_cast<const float*>(p.res[0]) + (long long)tc.b * p.res_batch_stride + (long long)q * p.res_row_stride;
   float* xout = static_cast<float*>(p.out1) + off;
   float sumsq = 0.f;
 #pragma unroll 1
-  for (int c0 = 0; c0 < 256; c0 += 32) {
+  for (int c0 = half * COLS; c0 < (half + 1) * COLS; c0 += 32) {
+    float4 r[8];
+    if (valid) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = *reinterpret_cast<const float4*>(res + c0 + 4 * j);
+    }
     uint32_t v[32];
     tmem_ld32(tacc + c0, v);
     tmem_ld_wait();
     if (valid) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float4 r = *reinterpret_cast<const float4*>(res + c0 + 4 * j);
         float4 y;
-        y.x = __uint_as_float(v[4 * j + 0]) + r.x;
-        y.y = __uint_as_float(v[4 * j + 1]) + r.y;
-        y.z = __uint_as_float(v[4 * j + 2]) + r.z;
-        y.w = __uint_as_float(v[4 * j + 3]) + r.w;
+        y.x = __uint_as_float(v[4 * j + 0]) + r[j].x;
+        y.y = __uint_as_float(v[4 * j + 1]) + r[j].y;
+        y.z = __uint_as_float(v[4 * j + 2]) + r[j].z;
+        y.w = __uint_as_float(v[4 * j + 3]) + r[j].w;
         if (p.bias) {
-          float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + 4 * j));
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + 4 * j));
           y.x += bb.x; y.y += bb.y; y.z += bb.z; y.w += bb.w;
         }
         sumsq += y.x * y.x + y.y * y.y + y.z * y.z + y.w * y.w;
@@ -232,13 +269,18 @@ __device__ __forceinline__ void epi_resnorm(const ConvGemmParams& p, uint32_t ta
   }
   if (p.norm_mode == 0) return;
   tmem_st_wait();
+  if constexpr (NHALF == 2) {
+    red[half * 128 + row_in_tile] = sumsq;
+    pair_barrier(quarter);
+    sumsq += red[(half ^ 1) * 128 + row_in_tile];
+  }
   float inv;
   if (p.norm_mode == 1) inv = 1.f / fmaxf(sqrtf(sumsq), 1e-12f);           // F.normalize (norm.py:41)
   else inv = rsqrtf(sumsq * (1.f / 256.f) + 1.1920928955078125e-07f);      // nn.RMSNorm eps = finfo(fp32).eps
   const bool keep = valid && (p.lengths == nullptr || q < p.lengths[tc.b]);
   __nv_bfloat16* xn = static_cast<__nv_bfloat16*>(p.out0) + off;
 #pragma unroll 1
-  for (int c0 = 0; c0 < 256; c0 += 32) {
+  for (int c0 = half * COLS; c0 < (half + 1) * COLS; c0 += 32) {
     uint32_t v[32];
     tmem_ld32(tacc + c0, v);
     tmem_ld_wait();
@@ -246,7 +288,7 @@ __device__ __forceinline__ void epi_resnorm(const ConvGemmParams& p, uint32_t ta
       uint32_t o[16];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float4 g = __ldg(reinterpret_cast<const float4*>(p.vec0 + c0 + 4 * j));
+        const float4 g = __ldg(reinterpret_cast<const float4*>(p.vec0 + c0 + 4 * j));
         // select (not multiply) so a non-finite pad row can never leak into the conv taps of valid frames
         o[2 * j] = keep ? pack_bf16(__uint_as_float(v[4 * j]) * inv * g.x, __uint_as_float(v[4 * j + 1]) * inv * g.y) : 0u;
         o[2 * j + 1] = keep ? pack_bf16(__uint_as_float(v[4 * j + 2]) * inv * g.z, __uint_as_float(v[4 * j + 3]) * inv * g.w) : 0u;
@@ -256,17 +298,23 @@ __device__ __forceinline__ void epi_resnorm(const ConvGemmParams& p, uint32_t ta
       for (int j = 0; j < 4; ++j) o4[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
     }
   }
+  if constexpr (NHALF == 2) {
+    // the pair must not overwrite `red` for the next tile before both have read it
+    pair_barrier(quarter);
+  }
 }
 
 // to_qkv tile n: 0 = q (2 heads x 128), 1 = k, 2 = v.  Rotary (transformer.py:66-73) on q,k:
 // out[i] = t[i] cos - t[i+64] sin ; out[i+64] = t[i+64] cos + t[i] sin, angle = pos * inv_freq[i], i < 64.
-__device__ __forceinline__ void epi_qkv_rope(const ConvGemmParams& p, uint32_t tacc, const TileCoord& tc, int q) {
+template <int NHALF>
+__device__ __forceinline__ void epi_qkv_rope(const ConvGemmParams& p, uint32_t tacc, const TileCoord& tc, int q, int half) {
   const bool valid = q < p.group_rows[0];
   __nv_bfloat16* out = static_cast<__nv_bfloat16*>(p.out0) + (long long)tc.b * p.out_batch_stride +
                        (long long)q * p.out_row_stride + tc.n * 256;
+  constexpr int HEADS_PER = 2 / NHALF;
   if (tc.n == 2) {
 #pragma unroll 1
-    for (int c0 = 0; c0 < 256; c0 += 32) {
+    for (int c0 = half * 128 * HEADS_PER; c0 < (half + 1) * 128 * HEADS_PER; c0 += 32) {
       uint32_t v[32];
       tmem_ld32(tacc + c0, v);
       tmem_ld_wait();
@@ -285,7 +333,7 @@ __device__ __forceinline__ void epi_qkv_rope(const ConvGemmParams& p, uint32_t t
   const float* cs = p.vec0 + (long long)(valid ? q : 0) * 64;
   const float* sn = p.vec1 + (long long)(valid ? q : 0) * 64;
 #pragma unroll 1
-  for (int hh = 0; hh < 2; ++hh) {
+  for (int hh = half * HEADS_PER; hh < (half + 1) * HEADS_PER; ++hh) {
 #pragma unroll 1
     for (int f0 = 0; f0 < 64; f0 += 32) {
       uint32_t lo[32], hi[32];
@@ -296,12 +344,12 @@ __device__ __forceinline__ void epi_qkv_rope(const ConvGemmParams& p, uint32_t t
         uint32_t olo[16], ohi[16];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          float4 c = __ldg(reinterpret_cast<const float4*>(cs + f0 + 4 * j));
-          float4 s = __ldg(reinterpret_cast<const float4*>(sn + f0 + 4 * j));
-          float a0 = __uint_as_float(lo[4 * j]), a1 = __uint_as_float(lo[4 * j + 1]);
-          float a2 = __uint_as_float(lo[4 * j + 2]), a3 = __uint_as_float(lo[4 * j + 3]);
-          float b0 = __uint_as_float(hi[4 * j]), b1 = __uint_as_float(hi[4 * j + 1]);
-          float b2 = __uint_as_float(hi[4 * j + 2]), b3 = __uint_as_float(hi[4 * j + 3]);
+          const float4 c = __ldg(reinterpret_cast<const float4*>(cs + f0 + 4 * j));
+          const float4 s = __ldg(reinterpret_cast<const float4*>(sn + f0 + 4 * j));
+          const float a0 = __uint_as_float(lo[4 * j]), a1 = __uint_as_float(lo[4 * j + 1]);
+          const float a2 = __uint_as_float(lo[4 * j + 2]), a3 = __uint_as_float(lo[4 * j + 3]);
+          const float b0 = __uint_as_float(hi[4 * j]), b1 = __uint_as_float(hi[4 * j + 1]);
+          const float b2 = __uint_as_float(hi[4 * j + 2]), b3 = __uint_as_float(hi[4 * j + 3]);
           olo[2 * j] = pack_bf16(a0 * c.x - b0 * s.x, a1 * c.y - b1 * s.y);
           olo[2 * j + 1] = pack_bf16(a2 * c.z - b2 * s.z, a3 * c.w - b3 * s.w);
           ohi[2 * j] = pack_bf16(b0 * c.x + a0 * s.x, b1 * c.y + a1 * s.y);
@@ -372,12 +420,21 @@ __device__ __forceinline__ void epi_euler(const ConvGemmParams& p, uint32_t tacc
 }
 
 // ---------------------------------------------------------------------------------------------- kernel
+template <int BN, int EPI>
+struct EpiWarps {
+  // eight epilogue warps (two column halves per TMEM lane quarter) for the wide tiles, four otherwise
+  static constexpr int value = (BN >= 128 && EPI != EPI_EULER) ? 8 : 4;
+};
+
 template <int BN, int KB, int EPI>
-__global__ void __launch_bounds__(192) convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
+__global__ void __launch_bounds__(64 + 32 * EpiWarps<BN, EPI>::value)
+convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
   using L = StageLayout<BN, KB>;
   constexpr int SW = KB * 2;
   constexpr int TBUF = TmemCols<BN>::buf;
   constexpr int TCOLS = TmemCols<BN>::total;
+  constexpr int EW = EpiWarps<BN, EPI>::value;
+  constexpr int NHALF = EW / 4;
   constexpr uint32_t IDESC = umma_idesc_bf16(kTileM, BN);
 
   extern __shared__ uint8_t smem_raw[];
@@ -390,6 +447,7 @@ __global__ void __launch_bounds__(192) convgemm_kernel(const __grid_constant__ C
   auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * stages + 2 + b); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * stages + 4);
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  float* red = reinterpret_cast<float*>(smem_gen + (bar_base - smem_base) + 8 * (2 * stages + 4) + 16);  // [2][128]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -401,7 +459,7 @@ __global__ void __launch_bounds__(192) convgemm_kernel(const __grid_constant__ C
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);
-      mbar_init(tempty_bar(b), 4);
+      mbar_init(tempty_bar(b), EW);
     }
     fence_barrier_init();
     tma_prefetch_desc(&p.tmW);
@@ -472,7 +530,9 @@ __global__ void __launch_bounds__(192) convgemm_kernel(const __grid_constant__ C
     }
     __syncwarp();
   } else {
-    const int lane_base = (warp & 3) * 32;
+    const int quarter = warp & 3;               // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;           // column half (0 when EW == 4)
+    const int lane_base = quarter * 32;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const TileCoord tc = decode_tile(p, tile);
@@ -482,10 +542,10 @@ __global__ void __launch_bounds__(192) convgemm_kernel(const __grid_constant__ C
       tc_fence_after();
       const uint32_t tacc = tmem_base + (static_cast<uint32_t>(lane_base) << 16) + buf * TBUF;
       const int q = tc.m * kTileM + lane_base + lane;
-      if constexpr (EPI == EPI_GENERIC) epi_generic<BN>(p, tacc, tc, q);
-      else if constexpr (EPI == EPI_GLU) epi_glu(p, tacc, tc, q);
-      else if constexpr (EPI == EPI_RESNORM) epi_resnorm(p, tacc, tc, q);
-      else if constexpr (EPI == EPI_QKV_ROPE) epi_qkv_rope(p, tacc, tc, q);
+      if constexpr (EPI == EPI_GENERIC) epi_generic<BN, NHALF>(p, tacc, tc, q, half);
+      else if constexpr (EPI == EPI_GLU) epi_glu<NHALF>(p, tacc, tc, q, half);
+      else if constexpr (EPI == EPI_RESNORM) epi_resnorm<NHALF>(p, tacc, tc, q, half, red, lane_base + lane, quarter);
+      else if constexpr (EPI == EPI_QKV_ROPE) epi_qkv_rope<NHALF>(p, tacc, tc, q, half);
       else epi_euler(p, tacc, tc, q);
       tc_fence_before();
       __syncwarp();

@@ -173,5 +173,7 @@ __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u 
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
 __device__ __forceinline__ float lrelu(float x, float slope) { return x > 0.f ? x : x * slope; }
 __device__ __forceinline__ float silu(float x) { return x / (1.f + __expf(-x)); }
+// MUFU.EX2 + MUFU.RCP form (relative error ~2 ulp of fp32; the result is rounded to bf16 right after)
+__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.f + __expf(-x)); }
 
 }  // namespace srb
