@@ -116,6 +116,14 @@ int srb_hifigan_upsample(const void* x, const void* w_packed, const float* bias,
                          int32_t batch, int32_t rows_in, int32_t c_in, int32_t c_out, int32_t kernel, int32_t stride,
                          float slope, void* stream);
 
+/* Whole multi-receptive-field stage for the narrow stages (channels = 16 or 32), fused in one kernel:
+ *   out_act = leaky_relu((resblock_3(u) + resblock_7(u) + resblock_11(u)) / 3, slope_next)      (HF:1359-1367, 1475-1480)
+ * 18 convolutions with every intermediate kept in shared memory / TMEM.  u_raw, out_act: (B, L, C) bf16.
+ * w_packed: all 18 conv weights in tcgen05 operand layout (speech_resynth_b200/packing.py:pack_mrf_weights),
+ * bias: fp32 [18][C], conv order (resblock 3/7/11) x (pair 0..2) x (convs1, convs2). */
+int srb_hifigan_mrf_fused(const void* u_raw, const void* w_packed, const float* bias, void* out_act, int32_t batch,
+                          int32_t rows, int32_t channels, float slope, float slope_next, void* stream);
+
 /* conv_post (16 -> 1, k = 7) + tanh (HF:1480-1482); x is the leaky_relu(0.01)'ed stage-5 output (B, L, 16) bf16;
  * w[7][16] fp32 (tap-major), wav (B, L) fp32 */
 int srb_hifigan_post(const void* x_act, const float* w, float bias, float* wav, int32_t batch, int32_t rows,

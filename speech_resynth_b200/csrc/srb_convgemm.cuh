@@ -95,24 +95,6 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvGemmParams& p, int ti
 // execute every tcgen05.ld/st (sync.aligned); global loads that do not depend on the accumulator are issued
 // before the TMEM wait so their latency overlaps it.
 
-template <int N>
-__device__ __forceinline__ void tmem_ld_f(uint32_t taddr, float (&y)[N]) {
-  static_assert(N == 32 || N == 16, "chunk width");
-  if constexpr (N == 32) {
-    uint32_t v[32];
-    tmem_ld32(taddr, v);
-    tmem_ld_wait();
-#pragma unroll
-    for (int j = 0; j < 32; ++j) y[j] = __uint_as_float(v[j]);
-  } else {
-    uint32_t v[16];
-    tmem_ld16(taddr, v);
-    tmem_ld_wait();
-#pragma unroll
-    for (int j = 0; j < 16; ++j) y[j] = __uint_as_float(v[j]);
-  }
-}
-
 template <int BN, int NHALF>
 __device__ __forceinline__ void epi_generic(const ConvGemmParams& p, uint32_t tacc, const TileCoord& tc, int q, int half) {
   constexpr int CW = BN < 32 ? BN : 32;

@@ -1,0 +1,444 @@
+// Fused multi-receptive-field stage of the HiFi-GAN generator for the narrow stages (C = 16, 32):
+//   out = leaky_relu( (resblock_3(u) + resblock_7(u) + resblock_11(u)) / 3 , slope_next )        HF:1308-1367, 1475-1480
+// One CTA owns a window of R consecutive time rows of one utterance (R - 120 output rows + the 60-row receptive
+// halo of the k = 11 resblock on each side) and runs all 18 convolutions on it without touching HBM:
+//   * activations live in shared memory as tcgen05 K-major operands in the un-swizzled "interleaved" layout
+//     [channel chunk of 8][row][8 x bf16]: rows are 16 bytes apart, so a conv tap is just the same buffer with the
+//     descriptor start address moved by (tap shift) x 16 bytes -- no im2col, no reload;
+//   * the raw residual stream x of the running resblock lives in TMEM as an fp32 accumulator that the conv2 MMAs
+//     add into (it is initialised with u through an identity-matrix MMA), so residual adds are free and exact;
+//   * epilogue warps turn accumulators into the next conv's operand (bias + leaky_relu + zero outside [0, L) +
+//     bf16) and write it back to shared memory; two teams of four warps alternate over the 128-row M tiles so the
+//     tensor core works on tile m+1 while tile m is being post-processed;
+//   * per-tile mbarriers order MMA issue against the epilogue (a conv on tile m needs tiles m-1..m+1 of its input);
+//   * weights stream through a double buffer with cp.async.bulk, pre-packed on the host in operand layout.
+// HBM traffic: u read once (+ halo), out written once; everything else stays on chip.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "../../include/srb.h"
+#include "srb_common.h"
+#include "srb_ptx.cuh"
+
+namespace srb {
+
+struct MrfParams {
+  const __nv_bfloat16* u;    // (B, L, C) raw up-sampler output
+  __nv_bfloat16* out;        // (B, L, C)
+  const __nv_bfloat16* w;    // packed weights, conv order (resblock j, pair q, conv1 then conv2), operand layout
+  const float* bias;         // [18][C]
+  int batch, rows, tiles_per_b, total_tiles;
+  float slope, slope_next;
+};
+
+constexpr int kMrfHalo = 60;    // 6 * (11 - 1): receptive half-width of the k = 11 resblock
+constexpr int kMrfGuard = 32;   // zeroed rows on both sides of every operand buffer (largest tap shift is 25)
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+// un-swizzled K-major operand: 8-row groups 128 B apart (SBO), 16-byte K chunks `chunk_stride` bytes apart (LBO)
+// (layout and the legality of row-granular start addresses verified on B200 by tools/probes/umma_probe.cu)
+__device__ __forceinline__ uint64_t desc_interleaved(uint32_t addr, uint32_t chunk_stride) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((chunk_stride >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>(128 >> 4) << 32;
+  d |= 1ull << 46;
+  return d;
+}
+
+__host__ __device__ constexpr int mrf_kernel_size(int j) { return j == 0 ? 3 : (j == 1 ? 7 : 11); }
+__host__ __device__ constexpr int mrf_dilation(int q) { return q == 0 ? 1 : (q == 1 ? 3 : 5); }
+// tap offset (in taps) of conv (j, q, which) inside the packed weight / its tap count is mrf_kernel_size(j)
+__host__ __device__ constexpr int mrf_conv_tap_begin(int j, int q, int which) {
+  int base = 0;
+  for (int jj = 0; jj < j; ++jj) base += 6 * mrf_kernel_size(jj);
+  return base + (2 * q + which) * mrf_kernel_size(j);
+}
+
+template <int C, int R>
+struct MrfLayout {
+  static constexpr int NM = R / 128;
+  static constexpr int RP = R + 2 * kMrfGuard;
+  static constexpr int CH = C / 8;
+  static constexpr int buf_bytes = CH * RP * 16;
+  static constexpr int tap_bytes = C * C * 2;
+  static constexpr int wbuf_bytes = 11 * tap_bytes;
+  static constexpr int off_u = 0;
+  static constexpr int off_a = buf_bytes;
+  static constexpr int off_t = 2 * buf_bytes;
+  static constexpr int off_w = 3 * buf_bytes;
+  static constexpr int off_ident = off_w + 2 * wbuf_bytes;
+  static constexpr int off_bias = off_ident + tap_bytes;
+  static constexpr int off_bar = off_bias + 18 * C * 4;
+  static constexpr int n_bars = NM + 4 + 1;
+  static constexpr int off_cnt = off_bar + 8 * n_bars;     // uint32 written[NM]: monotonic arrival counters
+  static constexpr int off_tmem = off_cnt + 4 * ((NM + 3) & ~3);
+  static constexpr int total = off_tmem + 16;
+  static constexpr int tout = R - 2 * kMrfHalo;
+};
+
+// epilogue teams of four warps (one per TMEM lane quarter); team t post-processes the M tiles m = t (mod NTEAMS).
+// Every (conv, tile) step is a latency chain (mbarrier wake-up, TMEM load, smem store, proxy fence, arrive), so the
+// number of teams -- not arithmetic -- sets the epilogue rate.
+// The MMA side is issue-bound too (measured: ~200 instructions of descriptor/predicate bookkeeping per (conv, tile)
+// step on one thread), so NI issuer warps share the M tiles (issuer i owns tiles m = i (mod NI)); M tiles are
+// independent accumulators, so no ordering between issuers is needed beyond the per-tile barriers.
+template <int C>
+struct MrfTeams {
+  static constexpr int value = C == 16 ? 4 : 3;          // epilogue teams
+#ifdef SRB_MRF_ISSUERS
+  static constexpr int issuers = SRB_MRF_ISSUERS;
+#else
+  static constexpr int issuers = C == 16 ? 4 : 3;        // MMA issuer warps
+#endif
+  static constexpr int threads = 32 * (1 + issuers) + 128 * value;
+};
+
+template <int C, int R>
+__global__ void __launch_bounds__(MrfTeams<C>::threads, 1) mrf_fused_kernel(const MrfParams p) {
+  using L = MrfLayout<C, R>;
+  constexpr int NM = L::NM, RP = L::RP, CH = L::CH, KS = C / 16, G = kMrfGuard;
+  constexpr int NTEAMS = MrfTeams<C>::value, EPI_THREADS = 128 * NTEAMS, NI = MrfTeams<C>::issuers;
+  constexpr uint32_t IDESC = umma_idesc_bf16(128, C);
+  constexpr uint32_t TCOLS = 512;
+
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t s_u = sbase + L::off_u, s_a = sbase + L::off_a, s_t = sbase + L::off_t;
+  const uint32_t s_w = sbase + L::off_w, s_ident = sbase + L::off_ident;
+  float* bias_s = reinterpret_cast<float*>(smem + L::off_bias);
+  const uint32_t bar0 = sbase + L::off_bar;
+  auto acc_ready = [&](int m) { return bar0 + 8u * m; };
+  // "operand tile m has been (re)written" is signalled with MONOTONIC COUNTERS (4 warp arrivals per event), not
+  // mbarrier phases: several issuers wait on a neighbour tile's events, a fast neighbour can run two events ahead
+  // of a slow waiter at resblock / window boundaries, and a parity wait would then alias (and deadlock).
+  const uint32_t cnt0 = sbase + L::off_cnt;
+  auto written_cnt = [&](int m) { return cnt0 + 4u * m; };
+  auto w_full = [&](int b) { return bar0 + 8u * (NM + b); };
+  auto w_free = [&](int b) { return bar0 + 8u * (NM + 2 + b); };
+  const uint32_t u_ready = bar0 + 8u * (NM + 4);
+  const uint32_t tmem_slot = sbase + L::off_tmem;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // ---- one-time setup: barriers, TMEM, zero guards, identity operand, biases
+  if (tid == 0) {
+    for (int m = 0; m < NM; ++m) {
+      mbar_init(acc_ready(m), 1);
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(written_cnt(m)), "r"(0u) : "memory");
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(w_full(b), 1);
+      mbar_init(w_free(b), NI);
+    }
+    mbar_init(u_ready, 4 * NTEAMS);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TCOLS);
+    tmem_relinquish();
+  }
+  {
+    // zero all three operand buffers once (guards stay zero forever; interiors are rewritten per tile)
+    uint4* z = reinterpret_cast<uint4*>(smem);
+    for (int i = tid; i < 3 * L::buf_bytes / 16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+    // identity weight in operand layout: element (n, k) at chunk (k/8), row n, lane k%8
+    __nv_bfloat16* id = reinterpret_cast<__nv_bfloat16*>(smem + L::off_ident);
+    for (int i = tid; i < C * C; i += blockDim.x) {
+      const int ch = i / (C * 8), n = (i / 8) % C, e = i % 8;
+      id[i] = __float2bfloat16_rn((ch * 8 + e) == n ? 1.f : 0.f);
+    }
+    for (int i = tid; i < 18 * C; i += blockDim.x) bias_s[i] = p.bias[i];
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + L::off_tmem);
+  const uint32_t t_dt = tmem_base, t_dx = tmem_base + NM * C, t_f = tmem_base + 2 * NM * C;
+
+  if (warp == 0) {
+    // ================= weight producer =================
+    if (lane == 0) {
+      uint32_t n_loaded = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        for (int j = 0; j < 3; ++j) {
+          const int k = mrf_kernel_size(j);
+          for (int cc = 0; cc < 6; ++cc, ++n_loaded) {
+            const int buf = n_loaded & 1;
+            const uint32_t ph = (n_loaded >> 1) & 1;
+            mbar_wait(w_free(buf), ph ^ 1u);
+            const uint32_t bytes = k * L::tap_bytes;
+            mbar_expect_tx(w_full(buf), bytes);
+            const int tap0 = mrf_conv_tap_begin(j, cc >> 1, cc & 1);
+            bulk_g2s(s_w + buf * L::wbuf_bytes, p.w + (size_t)tap0 * C * C, bytes, w_full(buf));
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp <= NI) {
+    // ================= MMA issuers =================
+    if (lane == 0) {
+      const int mi = warp - 1;   // this issuer owns tiles m = mi (mod NI)
+      uint32_t n_conv = 0;       // convs issued so far (selects weight buffer / phase)
+      uint32_t n_tiles_done = 0;
+      // event e of tile m is complete once 4 * (e + 1) warp arrivals have been counted
+      auto wait_written = [&](int m, uint32_t e) {
+        const uint32_t target = 4u * (e + 1u);
+        uint32_t spins = 0, v;
+        do {
+          asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(written_cnt(m)) : "memory");
+          if (++spins > (1u << 26)) __trap();
+        } while (v < target);
+      };
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++n_tiles_done) {
+        mbar_wait(u_ready, n_tiles_done & 1);
+        tc_fence_after();
+        // events on a tile per window: per resblock 7 (E0 operand init, then conv1/conv2 of 3 pairs) => 21
+        uint32_t ev = n_tiles_done * 21u;
+        for (int j = 0; j < 3; ++j) {
+          const int k = mrf_kernel_size(j);
+          for (int cc = 0; cc < 6; ++cc, ++n_conv, ++ev) {
+            // this conv consumes the operand produced by written-event `ev`
+            const int which = cc & 1, q = cc >> 1;
+            const int dil = which == 0 ? mrf_dilation(q) : 1;
+            const uint32_t src = which == 0 ? s_a : s_t;
+            const int buf = n_conv & 1;
+            mbar_wait(w_full(buf), (n_conv >> 1) & 1);
+            const uint32_t wb = s_w + buf * L::wbuf_bytes;
+            // descriptors advance in 16-byte units: one row = +1, one K slice (two 8-channel chunks) = +2*RP / +2*C
+            const uint64_t a_desc0 = desc_interleaved(src, RP * 16);
+            const uint64_t u_desc0 = desc_interleaved(s_u, RP * 16);
+            const uint64_t w_desc0 = desc_interleaved(wb, C * 16);
+            const uint64_t i_desc0 = desc_interleaved(s_ident, C * 16);
+            for (int m = mi; m < NM; m += NI) {
+              if (m > 0) wait_written(m - 1, ev);
+              wait_written(m, ev);
+              if (m + 1 < NM) wait_written(m + 1, ev);
+              tc_fence_after();
+              const uint32_t dacc = (which == 0 ? t_dt : t_dx) + m * C;
+              if (cc == 0) {
+                // x := u (identity MMA) for this resblock, before the first conv2 accumulates into it
+#pragma unroll
+                for (int s = 0; s < KS; ++s)
+                  umma_bf16(t_dx + m * C, u_desc0 + (uint64_t)(m * 128 + G + s * 2 * RP), i_desc0 + (uint64_t)(s * 2 * C),
+                            IDESC, s != 0 ? 1u : 0u);
+              }
+              uint64_t a_desc = a_desc0 + (uint64_t)(m * 128 + G - ((k - 1) / 2) * dil);
+              uint64_t w_desc = w_desc0;
+              for (int t = 0; t < k; ++t) {
+#pragma unroll
+                for (int s = 0; s < KS; ++s)
+                  umma_bf16(dacc, a_desc + (uint64_t)(s * 2 * RP), w_desc + (uint64_t)(s * 2 * C), IDESC,
+                            (which == 1 || t != 0 || s != 0) ? 1u : 0u);
+                a_desc += (uint64_t)dil;
+                w_desc += (uint64_t)(L::tap_bytes >> 4);
+              }
+              umma_commit(acc_ready(m));
+            }
+            umma_commit(w_free(buf));
+          }
+          ++ev;  // the 7th event of the resblock (epilogue of its last conv) is waited for at the next cc == 0
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================= epilogue / operand-builder warps =================
+    const int ew = warp - 1 - NI;
+    const int team = ew >> 2;             // tiles m = team (mod NTEAMS)
+    const int quarter = warp & 3;         // TMEM lane quarter
+    const int etid = tid - 32 * (1 + NI);
+    auto signal_written = [&](int m) {
+      asm volatile("red.release.cta.shared.add.u32 [%0], %1;" ::"r"(written_cnt(m)), "r"(1u) : "memory");
+    };
+    uint32_t n_tiles_done = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++n_tiles_done) {
+      const int b = tile / p.tiles_per_b;
+      const int t0 = (tile % p.tiles_per_b) * L::tout - kMrfHalo;     // global row of window row 0
+      const __nv_bfloat16* ub = p.u + (size_t)b * p.rows * C;
+      // ---- load the raw window into the U operand buffer (rows outside [0, L) are zero)
+      for (int i = etid; i < R * CH; i += EPI_THREADS) {
+        const int row = i / CH, ch = i % CH;
+        const int gr = t0 + row;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (gr >= 0 && gr < p.rows) v = __ldg(reinterpret_cast<const uint4*>(ub + (size_t)gr * C) + ch);
+        *reinterpret_cast<uint4*>(smem + L::off_u + ch * RP * 16 + (row + G) * 16) = v;
+      }
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");   // every epilogue warp finished writing U
+      if (lane == 0) mbar_arrive(u_ready);
+
+      uint32_t acc_ev = n_tiles_done * 18u;   // events on acc_ready[m]: one per conv
+
+      for (int j = 0; j < 3; ++j) {
+        // ---- E0: A = leaky_relu(U) for my tiles
+        for (int m = team; m < NM; m += NTEAMS) {
+          const int row = m * 128 + quarter * 32 + lane;
+#pragma unroll
+          for (int ch = 0; ch < CH; ++ch) {
+            const uint4 v = *reinterpret_cast<const uint4*>(smem + L::off_u + ch * RP * 16 + (row + G) * 16);
+            uint4 o;
+            o.x = pack_bf16(lrelu(bf16_lo(v.x), p.slope), lrelu(bf16_hi(v.x), p.slope));
+            o.y = pack_bf16(lrelu(bf16_lo(v.y), p.slope), lrelu(bf16_hi(v.y), p.slope));
+            o.z = pack_bf16(lrelu(bf16_lo(v.z), p.slope), lrelu(bf16_hi(v.z), p.slope));
+            o.w = pack_bf16(lrelu(bf16_lo(v.w), p.slope), lrelu(bf16_hi(v.w), p.slope));
+            *reinterpret_cast<uint4*>(smem + L::off_a + ch * RP * 16 + (row + G) * 16) = o;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) signal_written(m);
+        }
+
+        float bsum[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) bsum[c] = 0.f;
+        for (int cc = 0; cc < 6; ++cc, ++acc_ev) {
+          const int which = cc & 1, q = cc >> 1;
+          const float* bias = bias_s + (j * 6 + cc) * C;
+          if (which == 1) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) bsum[c] += bias[c];
+          }
+          for (int m = team; m < NM; m += NTEAMS) {
+            const int row = m * 128 + quarter * 32 + lane;
+            const int gr = t0 + row;
+            const bool inside = gr >= 0 && gr < p.rows;
+            mbar_wait(acc_ready(m), acc_ev & 1);
+            tc_fence_after();
+            const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+            float y[C];
+            if (which == 0) {
+              // conv1 -> T = leaky_relu(acc + b1), zero outside the utterance (the next conv zero-pads there)
+              tmem_ld_f<C>(t_dt + m * C + lane_addr, y);
+#pragma unroll
+              for (int ch = 0; ch < CH; ++ch) {
+                uint32_t o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float a0 = lrelu(y[ch * 8 + 2 * e] + bias[ch * 8 + 2 * e], p.slope);
+                  const float a1 = lrelu(y[ch * 8 + 2 * e + 1] + bias[ch * 8 + 2 * e + 1], p.slope);
+                  o[e] = inside ? pack_bf16(a0, a1) : 0u;
+                }
+                *reinterpret_cast<uint4*>(smem + L::off_t + ch * RP * 16 + (row + G) * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+              }
+              fence_proxy_async_smem();
+            } else if (q < 2) {
+              // conv2 of pairs 0,1: x = acc (u + all conv2 so far) + their biases; A = leaky_relu(x)
+              tmem_ld_f<C>(t_dx + m * C + lane_addr, y);
+#pragma unroll
+              for (int ch = 0; ch < CH; ++ch) {
+                uint32_t o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float a0 = lrelu(y[ch * 8 + 2 * e] + bsum[ch * 8 + 2 * e], p.slope);
+                  const float a1 = lrelu(y[ch * 8 + 2 * e + 1] + bsum[ch * 8 + 2 * e + 1], p.slope);
+                  o[e] = inside ? pack_bf16(a0, a1) : 0u;
+                }
+                *reinterpret_cast<uint4*>(smem + L::off_a + ch * RP * 16 + (row + G) * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+              }
+              fence_proxy_async_smem();
+            } else {
+              // last conv2 of resblock j: x_final = acc + biases; F (+)= x_final; after the third resblock write out
+              tmem_ld_f<C>(t_dx + m * C + lane_addr, y);
+#pragma unroll
+              for (int c = 0; c < C; ++c) y[c] += bsum[c];
+              if (j > 0) {
+                float f[C];
+                tmem_ld_f<C>(t_f + m * C + lane_addr, f);
+#pragma unroll
+                for (int c = 0; c < C; ++c) y[c] += f[c];
+              }
+              if (j < 2) {
+                if constexpr (C == 32) {
+                  uint32_t v[32];
+#pragma unroll
+                  for (int c = 0; c < 32; ++c) v[c] = __float_as_uint(y[c]);
+                  tmem_st32(t_f + m * C + lane_addr, v);
+                } else {
+                  uint32_t v[16];
+#pragma unroll
+                  for (int c = 0; c < 16; ++c) v[c] = __float_as_uint(y[c]);
+                  tmem_st16(t_f + m * C + lane_addr, v);
+                }
+                tmem_st_wait();
+              } else if (inside && row >= kMrfHalo && row < kMrfHalo + L::tout) {
+                __nv_bfloat16* ob = p.out + ((size_t)b * p.rows + gr) * C;
+#pragma unroll
+                for (int ch = 0; ch < CH; ++ch) {
+                  uint32_t o[4];
+#pragma unroll
+                  for (int e = 0; e < 4; ++e)
+                    o[e] = pack_bf16(lrelu(y[ch * 8 + 2 * e] * (1.f / 3.f), p.slope_next),
+                                     lrelu(y[ch * 8 + 2 * e + 1] * (1.f / 3.f), p.slope_next));
+                  reinterpret_cast<uint4*>(ob)[ch] = make_uint4(o[0], o[1], o[2], o[3]);
+                }
+              }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) signal_written(m);
+          }
+        }
+      }
+      // all eight warps must be done reading U / writing before the next window overwrites the buffers
+      asm volatile("bar.sync 2, %0;" ::"n"(EPI_THREADS) : "memory");
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TCOLS);
+}
+
+template <int C, int R>
+static int launch_mrf(const MrfParams& p0, cudaStream_t stream) {
+  using L = MrfLayout<C, R>;
+  MrfParams p = p0;
+  p.tiles_per_b = (p.rows + L::tout - 1) / L::tout;
+  p.total_tiles = p.tiles_per_b * p.batch;
+  auto kernel = mrf_fused_kernel<C, R>;
+  static bool configured[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!configured[dev & 63]) {
+    SRB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total));
+    configured[dev & 63] = true;
+  }
+  int grid = num_sms();
+  if (grid > p.total_tiles) grid = p.total_tiles;
+  if (grid < 1) return 0;
+  kernel<<<grid, MrfTeams<C>::threads, L::total, stream>>>(p);
+  return after_launch("mrf_fused_kernel");
+}
+
+}  // namespace srb
+
+using namespace srb;
+
+extern "C" int srb_hifigan_mrf_fused(const void* u_raw, const void* w_packed, const float* bias, void* out_act,
+                                     int32_t batch, int32_t rows, int32_t channels, float slope, float slope_next,
+                                     void* stream) {
+  MrfParams p;
+  p.u = static_cast<const __nv_bfloat16*>(u_raw);
+  p.out = static_cast<__nv_bfloat16*>(out_act);
+  p.w = static_cast<const __nv_bfloat16*>(w_packed);
+  p.bias = bias;
+  p.batch = batch;
+  p.rows = rows;
+  p.tiles_per_b = 0;
+  p.total_tiles = 0;
+  p.slope = slope;
+  p.slope_next = slope_next;
+  if (batch <= 0 || rows <= 0) return 0;
+  if (channels == 16) return launch_mrf<16, 1280>(p, (cudaStream_t)stream);
+  if (channels == 32) return launch_mrf<32, 640>(p, (cudaStream_t)stream);
+  set_error("srb_hifigan_mrf_fused: channels must be 16 or 32 (got %d)", channels);
+  return -2;
+}

@@ -137,6 +137,34 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
       : "memory");
 }
 
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+        "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+
+// load + wait + reinterpret as float, N = 16 or 32 columns
+template <int N>
+__device__ __forceinline__ void tmem_ld_f(uint32_t taddr, float (&y)[N]) {
+  static_assert(N == 32 || N == 16, "chunk width");
+  if constexpr (N == 32) {
+    uint32_t v[32];
+    tmem_ld32(taddr, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) y[j] = __uint_as_float(v[j]);
+  } else {
+    uint32_t v[16];
+    tmem_ld16(taddr, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) y[j] = __uint_as_float(v[j]);
+  }
+}
+
 // ------------------------------------------------------------------ UMMA descriptors
 // Shared-memory matrix descriptor, K-major operand, rows of SWIZZLE_BYTES (128/64/32) bytes written by a TMA
 // box whose inner extent is exactly one swizzle row.  8-row groups are SWIZZLE_BYTES*8 bytes apart (SBO).

@@ -146,9 +146,10 @@ def waveform_rows(frames: int) -> int:
 class HifiGanGenerator:
     """mel (B, T, 80) bf16 -> waveform (B, 320 T + 80) fp32 (kernels: srb_hifigan_*)."""
 
-    def __init__(self, packed: PackedVocoder, slope: float = 0.1):
+    def __init__(self, packed: PackedVocoder, slope: float = 0.1, fuse_mrf: bool = True):
         self.w = packed
         self.slope = float(slope)
+        self.fuse_mrf = fuse_mrf
         self.device = packed.w_pre.device
 
     def workspace(self, batch: int, frames: int) -> Dict[str, object]:
@@ -181,9 +182,18 @@ class HifiGanGenerator:
         for i, (k, s) in enumerate(zip(UPSAMPLE_KERNELS, UPSAMPLE_RATES)):
             st = ws["stages"][i]
             rows, c = st["rows"], st["c"]
+            fused = self.fuse_mrf and i in w.w_mrf
             # upsampler (HF:1472-1473): raw copy = residual of the three resblocks, activated copy = their input
-            nat.call("srb_hifigan_upsample", P(x_act), P(w.w_up[i]), P(w.b_up[i]), P(st["u_raw"]), P(st["u_act"]), b,
-                     rows_in, c_in, c, k, s, self.slope, flops=2.0 * b * rows_in * k * c_in * c)
+            nat.call("srb_hifigan_upsample", P(x_act), P(w.w_up[i]), P(w.b_up[i]), P(st["u_raw"]),
+                     None if fused else P(st["u_act"]), b, rows_in, c_in, c, k, s, self.slope,
+                     flops=2.0 * b * rows_in * k * c_in * c)
+            if fused:
+                # narrow stages: the whole MRF block (18 convs + residuals + mean + next leaky_relu) in one kernel
+                slope_next = self.slope if i + 1 < n_stage else 0.01
+                nat.call("srb_hifigan_mrf_fused", P(st["u_raw"]), P(w.w_mrf[i]), P(w.b_mrf[i]), P(st["out"]), b, rows, c,
+                         self.slope, slope_next, flops=252.0 * c * c * b * rows)
+                x_act, rows_in, c_in = st["out"], rows, c
+                continue
             for j, rk in enumerate(RESBLOCK_KERNELS):
                 kk = _i32([rk])
                 xr, xa = st["u_raw"], st["u_act"]

@@ -15,6 +15,7 @@ UPSAMPLE_RATES = (5, 4, 4, 2, 2)
 UPSAMPLE_KERNELS = (10, 9, 8, 4, 4)
 RESBLOCK_KERNELS = (3, 7, 11)
 RESBLOCK_DILATIONS = (1, 3, 5)
+FUSED_MRF_CHANNELS = (16, 32)     # stages whose whole MRF block runs in srb_hifigan_mrf_fused
 
 
 def block_k_for(c_in: int) -> int:
@@ -45,6 +46,27 @@ def pack_upsampler_weight(w: torch.Tensor, stride: int) -> torch.Tensor:
         for j in range(j0, k, stride):
             cols.append(w[:, :, j].float().t())  # (C_out, C_in)
     return torch.cat(cols, dim=1).to(torch.bfloat16).contiguous()
+
+
+def pack_operand_taps(w: torch.Tensor) -> torch.Tensor:
+    """Conv1d weight (C_out, C_in, k) -> bf16 [k][C_in/8][C_out][8]: per tap the B operand of the fused-MRF kernel
+    in the un-swizzled K-major layout (16-byte K chunks, rows 16 bytes apart)."""
+    c_out, c_in, k = w.shape
+    t = w.float().permute(2, 1, 0).reshape(k, c_in // 8, 8, c_out).permute(0, 1, 3, 2)
+    return t.to(torch.bfloat16).contiguous()
+
+
+def pack_mrf_weights(sd: Dict[str, torch.Tensor], stage: int, device):
+    """All 18 convs of one stage's three resblocks, in the order the fused kernel walks them:
+    (resblock k=3,7,11) x (pair 0..2) x (convs1, convs2).  Returns (weights bf16 flat, bias fp32 [18][C])."""
+    ws, bs = [], []
+    for j in range(3):
+        pre = f"vocoder.resblocks.{stage * 3 + j}."
+        for q in range(3):
+            for name in ("convs1", "convs2"):
+                ws.append(pack_operand_taps(sd[pre + f"{name}.{q}.weight"].detach().to(device)).reshape(-1))
+                bs.append(sd[pre + f"{name}.{q}.bias"].detach().to(device=device, dtype=torch.float32))
+    return torch.cat(ws).contiguous(), torch.stack(bs).contiguous()
 
 
 @dataclass
@@ -82,6 +104,8 @@ class PackedVocoder:
     b_c2: List[List[List[torch.Tensor]]] = field(default_factory=list)
     w_tail: List[torch.Tensor] = field(default_factory=list)  # bf16 [C][(3+7+11)*C]: last conv2 of the 3 resblocks
     b_tail: List[torch.Tensor] = field(default_factory=list)  # fp32 [C] = sum of their biases
+    w_mrf: Dict[int, torch.Tensor] = field(default_factory=dict)   # stage -> fused-MRF operand-layout weights
+    b_mrf: Dict[int, torch.Tensor] = field(default_factory=dict)   # stage -> fp32 [18][C]
     w_post: torch.Tensor = None       # fp32 [7][16]
     b_post: float = 0.0
 
@@ -162,6 +186,8 @@ def pack_vocoder(sd: Dict[str, torch.Tensor], device) -> PackedVocoder:
         v.b_c2.append(b2s)
         v.w_tail.append(torch.cat(tails, dim=1).contiguous())
         v.b_tail.append(tail_b.contiguous())
+        if c in FUSED_MRF_CHANNELS:
+            v.w_mrf[i], v.b_mrf[i] = pack_mrf_weights(sd, i, device)
     v.w_post = f("vocoder.conv_post.weight")[0].t().contiguous()  # (7, 16)
     v.b_post = float(sd["vocoder.conv_post.bias"].detach().float().reshape(-1)[0])
     return v

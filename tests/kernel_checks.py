@@ -21,12 +21,44 @@ from speech_resynth_b200 import _native as nat
 from speech_resynth_b200 import packing, synthetic
 from speech_resynth_b200.engine import _i32
 
-P = nat.ptr
 DEV = "cuda:0"
+_KEEP: list = []
+
+
+def P(t):
+    """device pointer of `t`, keeping the tensor alive until the check ends: the launches are asynchronous and an
+    expression like P(x.to(DEV)) would otherwise free (and let the allocator recycle) the buffer before the kernel
+    has even been enqueued"""
+    if t is None:
+        return None
+    _KEEP.append(t)
+    return nat.ptr(t)
 BF16_TOL = 6e-3
 F32_TOL = 1e-5
 
-CHECKS: Dict[str, Callable[[], Tuple[float, float]]] = {}
+
+
+def _guarded(fn):
+    def run():
+        _KEEP.clear()
+        try:
+            res = fn()
+            torch.cuda.synchronize()
+            return res
+        finally:
+            torch.cuda.synchronize()
+            _KEEP.clear()
+
+    run.__name__ = fn.__name__
+    return run
+
+
+class _Registry(dict):
+    def __setitem__(self, key, fn):
+        super().__setitem__(key, _guarded(fn))
+
+
+CHECKS = _Registry()
 
 
 def check(fn):
@@ -216,6 +248,47 @@ for _i, (_c, _k, _s) in enumerate(zip((512, 256, 128, 64, 32), packing.UPSAMPLE_
     def _fn(c=_c, k=_k, s=_s, i=_i):
         return _upsample_case(c, k, s, rows_in=77 + 60 * i)
     CHECKS[f"upsample_stage{_i}_c{_c}_k{_k}_s{_s}"] = _fn
+
+
+def _mrf_case(c, rows, batch=2, seed=0):
+    """whole fused MRF stage vs a float64 evaluation of HF:1359-1367,1475-1480 on the same bf16-rounded weights"""
+    gen = g(seed)
+    u = bf(torch.randn(batch, rows, c, generator=gen))
+    ws, bs, ref_sum = [], [], 0
+    for j, k in enumerate((3, 7, 11)):
+        x = u.double().transpose(1, 2)
+        for q, dil in enumerate((1, 3, 5)):
+            w1 = bf(torch.randn(c, c, k, generator=gen) / math.sqrt(c * k))
+            b1 = torch.randn(c, generator=gen) * 0.1
+            w2 = bf(torch.randn(c, c, k, generator=gen) / math.sqrt(c * k))
+            b2 = torch.randn(c, generator=gen) * 0.1
+            ws += [packing.pack_operand_taps(w1).reshape(-1), packing.pack_operand_taps(w2).reshape(-1)]
+            bs += [b1, b2]
+            r = x
+            t = F.conv1d(F.leaky_relu(x, 0.1), w1.double(), b1.double(), dilation=dil, padding=(k - 1) // 2 * dil)
+            x = F.conv1d(F.leaky_relu(t, 0.1), w2.double(), b2.double(), padding=(k - 1) // 2) + r
+        ref_sum = ref_sum + x
+    ref = F.leaky_relu(ref_sum / 3, 0.01).transpose(1, 2)
+    out = torch.full((batch, rows, c), float("nan"), dtype=torch.bfloat16, device=DEV)
+    nat.call("srb_hifigan_mrf_fused", P(u.to(DEV).to(torch.bfloat16).contiguous()), P(torch.cat(ws).to(DEV).contiguous()),
+             P(torch.stack(bs).to(DEV).contiguous()), P(out), batch, rows, c, 0.1, 0.01)
+    torch.cuda.synchronize()
+    return rel_l2(out.float(), ref), 1.2e-2   # two bf16 operand roundings per pair, six pairs deep, fp32 residual stream
+
+
+@check
+def mrf_fused_c16():
+    return _mrf_case(16, 3000)
+
+
+@check
+def mrf_fused_c32():
+    return _mrf_case(32, 1500, seed=1)
+
+
+@check
+def mrf_fused_c16_short():
+    return _mrf_case(16, 41, batch=3, seed=2)
 
 
 @check
