@@ -7,7 +7,8 @@
  * binding a maintainer would add on the reference side.
  *
  * Conventions
- *   - all pointers are DEVICE pointers borrowed from the caller (torch owns the memory); nothing is allocated;
+ *   - all pointers are DEVICE pointers borrowed from the caller (torch owns the memory); nothing is allocated
+ *     (only exception: the tiny `kernel` / `dilation` int32 arrays of srb_hifigan_conv are HOST arrays);
  *   - `stream` is a cudaStream_t passed as void*; launches are asynchronous and CUDA-graph capturable;
  *   - return value 0 = success, negative = error (srb_last_error() gives the text); nothing throws;
  *   - activations are channel-last: (batch, rows, channels) with explicit element strides, bf16 unless noted;
