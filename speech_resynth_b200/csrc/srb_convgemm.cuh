@@ -210,44 +210,64 @@ __device__ __forceinline__ void pair_barrier(int quarter) {
   }
 }
 
+// Global operands of an epilogue that do not depend on the accumulator (the fp32 residual stream, the rotary
+// tables) are fetched in two batches: the first BEFORE the thread waits for the tile's MMAs (so its L2 latency
+// overlaps the tensor work), the second right after the wait while the first is being consumed.  Profiling showed
+// these epilogues stalled on exactly these loads (long-scoreboard on the first dependent FADD/FMUL).
+template <int NHALF>
+__device__ __forceinline__ void resnorm_prefetch(const ConvGemmParams& p, const TileCoord& tc, int q, int half, float4 (&pre)[16]) {
+  constexpr int COLS = 256 / NHALF;
+  if (q < p.group_rows[0]) {
+    const float* res = static_cast<const float*>(p.res[0]) + (long long)tc.b * p.res_batch_stride +
+                       (long long)q * p.res_row_stride + half * COLS;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) pre[j] = *reinterpret_cast<const float4*>(res + 4 * j);
+  }
+}
+
 template <int NHALF>
 __device__ __forceinline__ void epi_resnorm(const ConvGemmParams& p, uint32_t tacc, const TileCoord& tc, int q, int half,
-                                            float* red, int row_in_tile, int quarter) {
+                                            float* red, int row_in_tile, int quarter, const float4 (&pre)[16]) {
   constexpr int COLS = 256 / NHALF;
+  constexpr int NCHUNK = COLS / 32;
+  static_assert(NCHUNK == 4, "RESNORM runs with eight epilogue warps");
   const bool valid = q < p.group_rows[0];
   const long long off = (long long)tc.b * p.out_batch_stride + (long long)q * p.out_row_stride;
-  const float* res = static_cast<const float*>(p.res[0]) + (long long)tc.b * p.res_batch_stride + (long long)q * p.res_row_stride;
-  float* xout = static_cast<float*>(p.out1) + off;
-  float sumsq = 0.f;
-#pragma unroll 1
-  for (int c0 = half * COLS; c0 < (half + 1) * COLS; c0 += 32) {
-    float4 r[8];
-    if (valid) {
+  const float* res = static_cast<const float*>(p.res[0]) + (long long)tc.b * p.res_batch_stride +
+                     (long long)q * p.res_row_stride + half * COLS;
+  float* xout = static_cast<float*>(p.out1) + off + half * COLS;
+  const uint32_t tcol = tacc + half * COLS;
+  float4 late[16];   // residual of chunks 2, 3
+  if (valid) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) r[j] = *reinterpret_cast<const float4*>(res + c0 + 4 * j);
-    }
+    for (int j = 0; j < 16; ++j) late[j] = *reinterpret_cast<const float4*>(res + 64 + 4 * j);
+  }
+  float sumsq = 0.f;
+#pragma unroll
+  for (int c = 0; c < NCHUNK; ++c) {
     uint32_t v[32];
-    tmem_ld32(tacc + c0, v);
+    tmem_ld32(tcol + c * 32, v);
     tmem_ld_wait();
     if (valid) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
+        const float4 r = c < 2 ? pre[(c & 1) * 8 + j] : late[(c & 1) * 8 + j];
         float4 y;
-        y.x = __uint_as_float(v[4 * j + 0]) + r[j].x;
-        y.y = __uint_as_float(v[4 * j + 1]) + r[j].y;
-        y.z = __uint_as_float(v[4 * j + 2]) + r[j].z;
-        y.w = __uint_as_float(v[4 * j + 3]) + r[j].w;
+        y.x = __uint_as_float(v[4 * j + 0]) + r.x;
+        y.y = __uint_as_float(v[4 * j + 1]) + r.y;
+        y.z = __uint_as_float(v[4 * j + 2]) + r.z;
+        y.w = __uint_as_float(v[4 * j + 3]) + r.w;
         if (p.bias) {
-          const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + 4 * j));
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + half * COLS + c * 32 + 4 * j));
           y.x += bb.x; y.y += bb.y; y.z += bb.z; y.w += bb.w;
         }
         sumsq += y.x * y.x + y.y * y.y + y.z * y.z + y.w * y.w;
-        *reinterpret_cast<float4*>(xout + c0 + 4 * j) = y;
+        *reinterpret_cast<float4*>(xout + c * 32 + 4 * j) = y;
         v[4 * j + 0] = __float_as_uint(y.x); v[4 * j + 1] = __float_as_uint(y.y);
         v[4 * j + 2] = __float_as_uint(y.z); v[4 * j + 3] = __float_as_uint(y.w);
       }
     }
-    if (p.norm_mode != 0) tmem_st32(tacc + c0, v);  // stash y for the second pass
+    if (p.norm_mode != 0) tmem_st32(tcol + c * 32, v);  // stash y for the second pass
   }
   if (p.norm_mode == 0) return;
   tmem_st_wait();
@@ -260,22 +280,23 @@ __device__ __forceinline__ void epi_resnorm(const ConvGemmParams& p, uint32_t ta
   if (p.norm_mode == 1) inv = 1.f / fmaxf(sqrtf(sumsq), 1e-12f);           // F.normalize (norm.py:41)
   else inv = rsqrtf(sumsq * (1.f / 256.f) + 1.1920928955078125e-07f);      // nn.RMSNorm eps = finfo(fp32).eps
   const bool keep = valid && (p.lengths == nullptr || q < p.lengths[tc.b]);
-  __nv_bfloat16* xn = static_cast<__nv_bfloat16*>(p.out0) + off;
-#pragma unroll 1
-  for (int c0 = half * COLS; c0 < (half + 1) * COLS; c0 += 32) {
+  __nv_bfloat16* xn = static_cast<__nv_bfloat16*>(p.out0) + off + half * COLS;
+  const float* gv = p.vec0 + half * COLS;
+#pragma unroll
+  for (int c = 0; c < NCHUNK; ++c) {
     uint32_t v[32];
-    tmem_ld32(tacc + c0, v);
+    tmem_ld32(tcol + c * 32, v);
     tmem_ld_wait();
     if (valid) {
       uint32_t o[16];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float4 g = __ldg(reinterpret_cast<const float4*>(p.vec0 + c0 + 4 * j));
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gv + c * 32 + 4 * j));
         // select (not multiply) so a non-finite pad row can never leak into the conv taps of valid frames
         o[2 * j] = keep ? pack_bf16(__uint_as_float(v[4 * j]) * inv * g.x, __uint_as_float(v[4 * j + 1]) * inv * g.y) : 0u;
         o[2 * j + 1] = keep ? pack_bf16(__uint_as_float(v[4 * j + 2]) * inv * g.z, __uint_as_float(v[4 * j + 3]) * inv * g.w) : 0u;
       }
-      uint4* o4 = reinterpret_cast<uint4*>(xn + c0);
+      uint4* o4 = reinterpret_cast<uint4*>(xn + c * 32);
 #pragma unroll
       for (int j = 0; j < 4; ++j) o4[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
     }
@@ -288,20 +309,35 @@ __device__ __forceinline__ void epi_resnorm(const ConvGemmParams& p, uint32_t ta
 
 // to_qkv tile n: 0 = q (2 heads x 128), 1 = k, 2 = v.  Rotary (transformer.py:66-73) on q,k:
 // out[i] = t[i] cos - t[i+64] sin ; out[i+64] = t[i+64] cos + t[i] sin, angle = pos * inv_freq[i], i < 64.
+// With eight epilogue warps, column half h of a lane quarter is head h.
+__device__ __forceinline__ void rope_prefetch(const ConvGemmParams& p, const TileCoord& tc, int q, float4 (&pre)[16]) {
+  if (tc.n != 2 && q < p.group_rows[0]) {
+    const float* cs = p.vec0 + (long long)q * 64;
+    const float* sn = p.vec1 + (long long)q * 64;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      pre[j] = __ldg(reinterpret_cast<const float4*>(cs) + j);        // cos, frequencies 0..31
+      pre[8 + j] = __ldg(reinterpret_cast<const float4*>(sn) + j);    // sin, frequencies 0..31
+    }
+  }
+}
+
 template <int NHALF>
-__device__ __forceinline__ void epi_qkv_rope(const ConvGemmParams& p, uint32_t tacc, const TileCoord& tc, int q, int half) {
+__device__ __forceinline__ void epi_qkv_rope(const ConvGemmParams& p, uint32_t tacc, const TileCoord& tc, int q, int half,
+                                             const float4 (&pre)[16]) {
+  static_assert(NHALF == 2, "QKV_ROPE runs with eight epilogue warps (one head per column half)");
   const bool valid = q < p.group_rows[0];
   __nv_bfloat16* out = static_cast<__nv_bfloat16*>(p.out0) + (long long)tc.b * p.out_batch_stride +
-                       (long long)q * p.out_row_stride + tc.n * 256;
-  constexpr int HEADS_PER = 2 / NHALF;
+                       (long long)q * p.out_row_stride + tc.n * 256 + half * 128;
+  const uint32_t tcol = tacc + half * 128;
   if (tc.n == 2) {
-#pragma unroll 1
-    for (int c0 = half * 128 * HEADS_PER; c0 < (half + 1) * 128 * HEADS_PER; c0 += 32) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
       uint32_t v[32];
-      tmem_ld32(tacc + c0, v);
+      tmem_ld32(tcol + c * 32, v);
       tmem_ld_wait();
       if (valid) {
-        uint4* o4 = reinterpret_cast<uint4*>(out + c0);
+        uint4* o4 = reinterpret_cast<uint4*>(out + c * 32);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           o4[j] = make_uint4(pack_bf16(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1])),
@@ -312,38 +348,43 @@ __device__ __forceinline__ void epi_qkv_rope(const ConvGemmParams& p, uint32_t t
     }
     return;
   }
-  const float* cs = p.vec0 + (long long)(valid ? q : 0) * 64;
-  const float* sn = p.vec1 + (long long)(valid ? q : 0) * 64;
-#pragma unroll 1
-  for (int hh = half * HEADS_PER; hh < (half + 1) * HEADS_PER; ++hh) {
-#pragma unroll 1
-    for (int f0 = 0; f0 < 64; f0 += 32) {
-      uint32_t lo[32], hi[32];
-      tmem_ld32(tacc + hh * 128 + f0, lo);
-      tmem_ld32(tacc + hh * 128 + 64 + f0, hi);
-      tmem_ld_wait();
-      if (valid) {
-        uint32_t olo[16], ohi[16];
+  float4 late[16];   // cos / sin of frequencies 32..63
+  if (valid) {
+    const float* cs = p.vec0 + (long long)q * 64 + 32;
+    const float* sn = p.vec1 + (long long)q * 64 + 32;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 c = __ldg(reinterpret_cast<const float4*>(cs + f0 + 4 * j));
-          const float4 s = __ldg(reinterpret_cast<const float4*>(sn + f0 + 4 * j));
-          const float a0 = __uint_as_float(lo[4 * j]), a1 = __uint_as_float(lo[4 * j + 1]);
-          const float a2 = __uint_as_float(lo[4 * j + 2]), a3 = __uint_as_float(lo[4 * j + 3]);
-          const float b0 = __uint_as_float(hi[4 * j]), b1 = __uint_as_float(hi[4 * j + 1]);
-          const float b2 = __uint_as_float(hi[4 * j + 2]), b3 = __uint_as_float(hi[4 * j + 3]);
-          olo[2 * j] = pack_bf16(a0 * c.x - b0 * s.x, a1 * c.y - b1 * s.y);
-          olo[2 * j + 1] = pack_bf16(a2 * c.z - b2 * s.z, a3 * c.w - b3 * s.w);
-          ohi[2 * j] = pack_bf16(b0 * c.x + a0 * s.x, b1 * c.y + a1 * s.y);
-          ohi[2 * j + 1] = pack_bf16(b2 * c.z + a2 * s.z, b3 * c.w + a3 * s.w);
-        }
-        uint4* l4 = reinterpret_cast<uint4*>(out + hh * 128 + f0);
-        uint4* h4 = reinterpret_cast<uint4*>(out + hh * 128 + 64 + f0);
+    for (int j = 0; j < 8; ++j) {
+      late[j] = __ldg(reinterpret_cast<const float4*>(cs) + j);
+      late[8 + j] = __ldg(reinterpret_cast<const float4*>(sn) + j);
+    }
+  }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          l4[j] = make_uint4(olo[4 * j], olo[4 * j + 1], olo[4 * j + 2], olo[4 * j + 3]);
-          h4[j] = make_uint4(ohi[4 * j], ohi[4 * j + 1], ohi[4 * j + 2], ohi[4 * j + 3]);
-        }
+  for (int f = 0; f < 2; ++f) {
+    uint32_t lo[32], hi[32];
+    tmem_ld32(tcol + f * 32, lo);
+    tmem_ld32(tcol + 64 + f * 32, hi);
+    tmem_ld_wait();
+    if (valid) {
+      uint32_t olo[16], ohi[16];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 c = f == 0 ? pre[j] : late[j];
+        const float4 s = f == 0 ? pre[8 + j] : late[8 + j];
+        const float a0 = __uint_as_float(lo[4 * j]), a1 = __uint_as_float(lo[4 * j + 1]);
+        const float a2 = __uint_as_float(lo[4 * j + 2]), a3 = __uint_as_float(lo[4 * j + 3]);
+        const float b0 = __uint_as_float(hi[4 * j]), b1 = __uint_as_float(hi[4 * j + 1]);
+        const float b2 = __uint_as_float(hi[4 * j + 2]), b3 = __uint_as_float(hi[4 * j + 3]);
+        olo[2 * j] = pack_bf16(a0 * c.x - b0 * s.x, a1 * c.y - b1 * s.y);
+        olo[2 * j + 1] = pack_bf16(a2 * c.z - b2 * s.z, a3 * c.w - b3 * s.w);
+        ohi[2 * j] = pack_bf16(b0 * c.x + a0 * s.x, b1 * c.y + a1 * s.y);
+        ohi[2 * j + 1] = pack_bf16(b2 * c.z + a2 * s.z, b3 * c.w + a3 * s.w);
+      }
+      uint4* l4 = reinterpret_cast<uint4*>(out + f * 32);
+      uint4* h4 = reinterpret_cast<uint4*>(out + 64 + f * 32);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        l4[j] = make_uint4(olo[4 * j], olo[4 * j + 1], olo[4 * j + 2], olo[4 * j + 3]);
+        h4[j] = make_uint4(ohi[4 * j], ohi[4 * j + 1], ohi[4 * j + 2], ohi[4 * j + 3]);
       }
     }
   }
@@ -431,7 +472,7 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   float* red = reinterpret_cast<float*>(smem_gen + (bar_base - smem_base) + 8 * (2 * stages + 4) + 16);  // [2][128]
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform (uniform datapath)
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -457,7 +498,8 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
   if (warp == 0) {
-    if (lane == 0) {
+    // TMA producer: converged warp, one elected lane issues (coordinates stay in uniform registers)
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -471,10 +513,10 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
           const int row = t0 + p.tap_shift[tap0 + t];
           for (int kc = 0; kc < p.kchunks; ++kc) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
-            mbar_expect_tx(full_bar(stage), L::a_bytes + L::w_bytes_raw);
+            mbar_expect_tx_elect(full_bar(stage), L::a_bytes + L::w_bytes_raw);
             const uint32_t a_dst = smem_base + stage * L::stage_bytes;
-            tma_load_3d(a_dst, &p.tmA[src], full_bar(stage), kc * KB, row, tc.b);
-            tma_load_2d(a_dst + L::a_bytes, &p.tmW, full_bar(stage), wk, tc.n * BN);
+            tma_load_3d_elect(a_dst, &p.tmA[src], full_bar(stage), kc * KB, row, tc.b);
+            tma_load_2d_elect(a_dst + L::a_bytes, &p.tmW, full_bar(stage), wk, tc.n * BN);
             wk += KB;
             if (++stage == stages) { stage = 0; phase ^= 1u; }
           }
@@ -483,7 +525,10 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
+    // MMA issuer: the whole warp runs the (warp-uniform) loop converged so descriptors stay in uniform registers;
+    // lane 0 issues.  See umma_bf16_pred.
+    {
+      const uint32_t leader = lane == 0 ? 1u : 0u;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -503,11 +548,11 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
           const uint64_t wdesc = umma_smem_desc<SW>(a_addr + L::a_bytes);
 #pragma unroll
           for (int k = 0; k < KB / 16; ++k)
-            umma_bf16(tacc, adesc + 2 * k, wdesc + 2 * k, IDESC, (ks | k) != 0 ? 1u : 0u);
-          umma_commit(empty_bar(stage));
+            umma_bf16_pred(leader, tacc, adesc + 2 * k, wdesc + 2 * k, IDESC, (ks | k) != 0 ? 1u : 0u);
+          umma_commit_pred(leader, empty_bar(stage));
           if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tfull_bar(buf));
+        umma_commit_pred(leader, tfull_bar(buf));
       }
     }
     __syncwarp();
@@ -520,14 +565,17 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
       const TileCoord tc = decode_tile(p, tile);
       const int buf = it & 1;
       const uint32_t bphase = (it >> 1) & 1;
+      const int q = tc.m * kTileM + lane_base + lane;
+      float4 pre[16];
+      if constexpr (EPI == EPI_RESNORM) resnorm_prefetch<NHALF>(p, tc, q, half, pre);
+      if constexpr (EPI == EPI_QKV_ROPE) rope_prefetch(p, tc, q, pre);
       mbar_wait(tfull_bar(buf), bphase);
       tc_fence_after();
       const uint32_t tacc = tmem_base + (static_cast<uint32_t>(lane_base) << 16) + buf * TBUF;
-      const int q = tc.m * kTileM + lane_base + lane;
       if constexpr (EPI == EPI_GENERIC) epi_generic<BN, NHALF>(p, tacc, tc, q, half);
       else if constexpr (EPI == EPI_GLU) epi_glu<NHALF>(p, tacc, tc, q, half);
-      else if constexpr (EPI == EPI_RESNORM) epi_resnorm<NHALF>(p, tacc, tc, q, half, red, lane_base + lane, quarter);
-      else if constexpr (EPI == EPI_QKV_ROPE) epi_qkv_rope<NHALF>(p, tacc, tc, q, half);
+      else if constexpr (EPI == EPI_RESNORM) epi_resnorm<NHALF>(p, tacc, tc, q, half, red, lane_base + lane, quarter, pre);
+      else if constexpr (EPI == EPI_QKV_ROPE) epi_qkv_rope<NHALF>(p, tacc, tc, q, half, pre);
       else epi_euler(p, tacc, tc, q);
       tc_fence_before();
       __syncwarp();

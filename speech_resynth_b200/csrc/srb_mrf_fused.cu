@@ -124,7 +124,8 @@ __global__ void __launch_bounds__(MrfTeams<C>::threads, 1) mrf_fused_kernel(cons
   const uint32_t u_ready = bar0 + 8u * (NM + 4);
   const uint32_t tmem_slot = sbase + L::off_tmem;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform (keeps role code on the uniform datapath)
 
   // ---- one-time setup: barriers, TMEM, zero guards, identity operand, biases
   if (tid == 0) {
@@ -184,7 +185,9 @@ __global__ void __launch_bounds__(MrfTeams<C>::threads, 1) mrf_fused_kernel(cons
     __syncwarp();
   } else if (warp <= NI) {
     // ================= MMA issuers =================
-    if (lane == 0) {
+    // The whole warp runs the loop converged (uniform descriptor arithmetic); lane 0 is the one that issues.
+    {
+      const uint32_t leader = lane == 0 ? 1u : 0u;
       const int mi = warp - 1;   // this issuer owns tiles m = mi (mod NI)
       uint32_t n_conv = 0;       // convs issued so far (selects weight buffer / phase)
       uint32_t n_tiles_done = 0;
@@ -227,24 +230,24 @@ __global__ void __launch_bounds__(MrfTeams<C>::threads, 1) mrf_fused_kernel(cons
                 // x := u (identity MMA) for this resblock, before the first conv2 accumulates into it
 #pragma unroll
                 for (int s = 0; s < KS; ++s)
-                  umma_bf16(t_dx + m * C, u_desc0 + (uint64_t)(m * 128 + G + s * 2 * RP), i_desc0 + (uint64_t)(s * 2 * C),
-                            IDESC, s != 0 ? 1u : 0u);
+                  umma_bf16_pred(leader, t_dx + m * C, u_desc0 + (uint64_t)(m * 128 + G + s * 2 * RP),
+                                 i_desc0 + (uint64_t)(s * 2 * C), IDESC, s != 0 ? 1u : 0u);
               }
               uint64_t a_desc = a_desc0 + (uint64_t)(m * 128 + G - ((k - 1) / 2) * dil);
               uint64_t w_desc = w_desc0;
               for (int t = 0; t < k; ++t) {
 #pragma unroll
                 for (int s = 0; s < KS; ++s)
-                  umma_bf16(dacc, a_desc + (uint64_t)(s * 2 * RP), w_desc + (uint64_t)(s * 2 * C), IDESC,
-                            (which == 1 || t != 0 || s != 0) ? 1u : 0u);
+                  umma_bf16_pred(leader, dacc, a_desc + (uint64_t)(s * 2 * RP), w_desc + (uint64_t)(s * 2 * C), IDESC,
+                                 (which == 1 || t != 0 || s != 0) ? 1u : 0u);
                 a_desc += (uint64_t)dil;
                 w_desc += (uint64_t)(L::tap_bytes >> 4);
               }
-              umma_commit(acc_ready(m));
+              umma_commit_pred(leader, acc_ready(m));
             }
-            umma_commit(w_free(buf));
+            umma_commit_pred(leader, w_free(buf));
           }
-          ++ev;  // the 7th event of the resblock (epilogue of its last conv) is waited for at the next cc == 0
+          ++ev;  // the 7th event of the resblock (epilogue of its last conv) is not consumed by any conv
         }
       }
     }
