@@ -53,16 +53,16 @@ static CUtensorMapSwizzle swizzle_for(int kb) {
   return kb == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kb == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
 }
 
-// activation view (batch, rows, channels) bf16 -> 3-D map, box = (kb channels, 128 rows, 1)
+// activation view (batch, rows, channels) bf16 -> 3-D map, box = (kb channels, 128 + tap-span rows, 1)
 static int make_act_map(CUtensorMap* m, const void* ptr, int channels, int rows, int batch, long long row_stride,
-                        long long batch_stride, int kb) {
+                        long long batch_stride, int kb, int box_rows) {
   auto enc = get_encode();
   SRB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
   SRB_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "activation pointer not 16-byte aligned");
   SRB_REQUIRE((row_stride * 2) % 16 == 0 && (batch_stride * 2) % 16 == 0, "activation strides must be multiples of 16 bytes");
   cuuint64_t dims[3] = {(cuuint64_t)channels, (cuuint64_t)rows, (cuuint64_t)batch};
   cuuint64_t strides[2] = {(cuuint64_t)row_stride * 2, (cuuint64_t)batch_stride * 2};
-  cuuint32_t box[3] = {(cuuint32_t)kb, (cuuint32_t)kTileM, 1};
+  cuuint32_t box[3] = {(cuuint32_t)kb, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(kb), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -120,12 +120,17 @@ template <int BN, int KB, int EPI>
 static int launch_inst(ConvGemmParams& p, int total_tiles, cudaStream_t stream) {
   using L = StageLayout<BN, KB>;
   auto kernel = convgemm_kernel<BN, KB, EPI>;
-  const int budget = L::stage_bytes >= 40 * 1024 ? 200 * 1024 : (L::stage_bytes >= 16 * 1024 ? 100 * 1024 : 44 * 1024);
-  int stages = budget / L::stage_bytes;
-  stages = stages < 2 ? 2 : (stages > 8 ? 8 : stages);
-  p.stages = stages;
+  // two rings: activation boxes (one per K chunk, reused by all taps) and weight slabs (one per tap and K chunk)
   constexpr int threads = 64 + 32 * EpiWarps<BN, EPI>::value;
-  const int smem = stages * L::stage_bytes + 1024 + 8 * (2 * stages + 4) + 16 + 1024;  // + [2][128] fp32 scratch
+  const int a_bytes = p.a_box_bytes;
+  int a_stages, w_stages;
+  if (L::w_bytes >= 32 * 1024) { a_stages = 3; w_stages = 4; }        // wide tiles: one CTA per SM
+  else if (L::w_bytes >= 8 * 1024) { a_stages = 2; w_stages = 4; }    // two CTAs per SM
+  else { a_stages = 2; w_stages = 6; }
+  while (a_stages * a_bytes + w_stages * L::w_bytes > 208 * 1024 && w_stages > 2) --w_stages;
+  p.a_stages = a_stages;
+  p.w_stages = w_stages;
+  const int smem = a_stages * a_bytes + w_stages * L::w_bytes + 1024 + 8 * (2 * (a_stages + w_stages) + 4) + 16 + 1024;
   static int configured_smem[64] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -133,22 +138,23 @@ static int launch_inst(ConvGemmParams& p, int total_tiles, cudaStream_t stream) 
     SRB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured_smem[dev & 63] = smem;
   }
-  static int blocks_per_sm[64] = {0};
-  if (blocks_per_sm[dev & 63] == 0) {
-    // resident CTAs per SM: shared memory, registers, threads and -- unknown to the occupancy API -- the 512 TMEM
-    // columns every CTA carves its accumulators from
+  // resident CTAs per SM: shared memory, registers, threads and -- unknown to the occupancy API -- the 512 TMEM
+  // columns every CTA carves its accumulators from
+  static int num_regs[64] = {0};
+  if (num_regs[dev & 63] == 0) {
     cudaFuncAttributes fa;
     SRB_CUDA(cudaFuncGetAttributes(&fa, kernel));
-    int occ = 232448 / (smem + 1024);
-    const int by_regs = 65536 / (((fa.numRegs + 7) & ~7) * threads);
-    const int by_threads = 2048 / threads;
-    const int by_tmem = 512 / TmemCols<BN>::total;
-    occ = occ < by_regs ? occ : by_regs;
-    occ = occ < by_threads ? occ : by_threads;
-    occ = occ < by_tmem ? occ : by_tmem;
-    blocks_per_sm[dev & 63] = occ < 1 ? 1 : occ;
+    num_regs[dev & 63] = fa.numRegs;
   }
-  int grid = num_sms() * blocks_per_sm[dev & 63];
+  int occ = 232448 / (smem + 1024);
+  const int by_regs = 65536 / (((num_regs[dev & 63] + 7) & ~7) * threads);
+  const int by_threads = 2048 / threads;
+  const int by_tmem = 512 / TmemCols<BN>::total;
+  occ = occ < by_regs ? occ : by_regs;
+  occ = occ < by_threads ? occ : by_threads;
+  occ = occ < by_tmem ? occ : by_tmem;
+  occ = occ < 1 ? 1 : occ;
+  int grid = num_sms() * occ;
   if (grid > total_tiles) grid = total_tiles;
   if (grid < 1) return 0;
   kernel<<<grid, threads, smem, stream>>>(p, total_tiles);
@@ -190,9 +196,37 @@ static int launch_convgemm(const ConvGemmDesc& d, cudaStream_t stream) {
     p.tap_src[t] = (signed char)(t < n_taps ? d.tap_src[t] : 0);
   }
   const int k_total = n_taps * p.kchunks * kb;
+  // segments: maximal runs of taps with the same source inside a group; one A box (with halo) per segment and chunk
+  int n_seg = 0, span = 0;
+  for (int g = 0; g < d.n_groups; ++g) {
+    p.group_seg_begin[g] = n_seg;
+    int t = d.group_tap_begin[g];
+    const int te = d.group_tap_begin[g + 1];
+    while (t < te) {
+      SRB_REQUIRE(n_seg < kMaxSegs, "too many tap segments");
+      int u = t, lo = d.tap_shift[t], hi = d.tap_shift[t];
+      while (u < te && d.tap_src[u] == d.tap_src[t]) {
+        lo = d.tap_shift[u] < lo ? d.tap_shift[u] : lo;
+        hi = d.tap_shift[u] > hi ? d.tap_shift[u] : hi;
+        ++u;
+      }
+      p.seg_tap_begin[n_seg] = (short)t;
+      p.seg_min_shift[n_seg] = (short)lo;
+      p.seg_src[n_seg] = (signed char)d.tap_src[t];
+      span = (hi - lo) > span ? (hi - lo) : span;
+      ++n_seg;
+      t = u;
+    }
+  }
+  for (int g = d.n_groups; g <= kMaxGroups; ++g) p.group_seg_begin[g] = n_seg;
+  for (int sgi = n_seg; sgi <= kMaxSegs; ++sgi) p.seg_tap_begin[sgi] = (short)n_taps;
+  p.seg_tap_begin[n_seg] = (short)n_taps;
+  SRB_REQUIRE(kTileM + span <= 256, "tap span %d too large for one TMA box", span);
+  p.a_box_rows = kTileM + span;
+  p.a_box_bytes = (p.a_box_rows * kb * 2 + 1023) & ~1023;
   for (int s = 0; s < kMaxSrc; ++s) {
     const ActView& a = d.src[s < d.n_src ? s : 0];
-    int rc = make_act_map(&p.tmA[s], a.ptr, a.channels, a.rows, a.batch, a.row_stride, a.batch_stride, kb);
+    int rc = make_act_map(&p.tmA[s], a.ptr, a.channels, a.rows, a.batch, a.row_stride, a.batch_stride, kb, p.a_box_rows);
     if (rc) return rc;
   }
   int rc = make_weight_map(&p.tmW, d.weight, k_total, d.n_total, kb, bn);

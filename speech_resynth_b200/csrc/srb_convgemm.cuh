@@ -3,12 +3,16 @@
 //   Linear (1 tap), k=3 FFN convs, dilated HiFi-GAN convs (k = 3/7/11), conv_pre (k = 7), the fused MRF tail
 //   (21 taps over 3 source tensors) and the polyphase transposed convs (one tap group per output phase).
 //
-// GEMM view:  D[128 rows (time) x BN (out channels)] += A[128 x KB] * W[BN x KB]^T  per K step, where the A box
-// of a tap is the activation tile shifted by the tap's time offset (3-D tensor map (channels, rows, batch); TMA
-// zero-fills rows outside [0, rows) which is exactly the conv's zero padding and also isolates utterances).
+// GEMM view:  D[128 rows (time) x BN (out channels)] += A[128 x KB] * W[BN x KB]^T  per (tap, K chunk).  The
+// activation tile is loaded ONCE per K chunk with its halo (128 + tap span rows, 3-D tensor map (channels, rows,
+// batch); TMA zero-fills rows outside [0, rows), which is exactly the conv's zero padding and also isolates
+// utterances) and every tap reads it through a descriptor whose start address is moved by (tap shift) rows --
+// the swizzle is a function of the absolute smem address, so row-granular starts are legal (verified on B200,
+// tools/probes/umma_probe_sw128.cu).  Only the weight slab is re-fetched per tap.  This removes the k-fold re-read
+// of activations from L2 that made the k = 7 / 11 convs L2-bandwidth bound.
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue
-// (thread <-> accumulator row / TMEM lane).  smem ring of `stages` {A, W} slots; two TMEM accumulator buffers so
+// (thread <-> accumulator row / TMEM lane).  Two smem rings (activation boxes, weight slabs); two TMEM buffers so
 // the epilogue of tile i overlaps the MMAs of tile i+1; persistent over tiles.
 #pragma once
 #include <cuda.h>
@@ -19,6 +23,7 @@ namespace srb {
 constexpr int kMaxTaps = 32;
 constexpr int kMaxGroups = 5;
 constexpr int kMaxSrc = 3;
+constexpr int kMaxSegs = 8;
 constexpr int kTileM = 128;
 
 enum Epilogue : int { EPI_GENERIC = 0, EPI_GLU = 1, EPI_RESNORM = 2, EPI_QKV_ROPE = 3, EPI_EULER = 4 };
@@ -36,7 +41,14 @@ struct ConvGemmParams {
   int row_mul;
   short tap_shift[kMaxTaps];
   signed char tap_src[kMaxTaps];
-  int stages;
+  // taps of a group are split into segments of equal source tensor: one halo-resident A box per (segment, K chunk)
+  int group_seg_begin[kMaxGroups + 1];
+  short seg_tap_begin[kMaxSegs + 1];
+  short seg_min_shift[kMaxSegs];
+  signed char seg_src[kMaxSegs];
+  int a_box_rows;                                 // 128 + largest tap span of the launch (<= 256)
+  int a_box_bytes;                                // a_box_rows * KB * 2, rounded up to 1024
+  int a_stages, w_stages;
   // epilogue operands
   const float* bias;
   void* out0;                                     // bf16 "activated"/normalised output
@@ -462,23 +474,32 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const int stages = p.stages;
-  const uint32_t bar_base = smem_base + stages * L::stage_bytes;  // 8-byte aligned (stage_bytes % 1024 == 0)
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (stages + s); };
-  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * stages + b); };
-  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * stages + 2 + b); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * stages + 4);
+  const int a_stages = p.a_stages, w_stages = p.w_stages;
+  const uint32_t a_ring = smem_base;
+  const uint32_t w_ring = smem_base + a_stages * p.a_box_bytes;
+  const uint32_t bar_base = w_ring + w_stages * L::w_bytes;       // 1024-aligned
+  auto a_full = [&](int s) { return bar_base + 8u * s; };
+  auto a_empty = [&](int s) { return bar_base + 8u * (a_stages + s); };
+  auto w_full = [&](int s) { return bar_base + 8u * (2 * a_stages + s); };
+  auto w_empty = [&](int s) { return bar_base + 8u * (2 * a_stages + w_stages + s); };
+  const int n_ring_bars = 2 * (a_stages + w_stages);
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (n_ring_bars + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (n_ring_bars + 2 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (n_ring_bars + 4);
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  float* red = reinterpret_cast<float*>(smem_gen + (bar_base - smem_base) + 8 * (2 * stages + 4) + 16);  // [2][128]
+  float* red = reinterpret_cast<float*>(smem_gen + (bar_base - smem_base) + 8 * (n_ring_bars + 4) + 16);  // [2][128]
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform (uniform datapath)
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < stages; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+    for (int s = 0; s < a_stages; ++s) {
+      mbar_init(a_full(s), 1);
+      mbar_init(a_empty(s), 1);
+    }
+    for (int s = 0; s < w_stages; ++s) {
+      mbar_init(w_full(s), 1);
+      mbar_init(w_empty(s), 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);
@@ -500,25 +521,27 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
   if (warp == 0) {
     // TMA producer: converged warp, one elected lane issues (coordinates stay in uniform registers)
     {
-      int stage = 0;
-      uint32_t phase = 0;
+      int ai = 0, wi = 0;
+      uint32_t aph = 0, wph = 0;
+      const uint32_t a_tx = static_cast<uint32_t>(p.a_box_rows) * KB * 2;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(p, tile);
         const int t0 = tc.m * kTileM;
-        const int tap0 = p.group_tap_begin[tc.group];
-        const int ntap = p.group_tap_begin[tc.group + 1] - tap0;
-        int wk = tap0 * p.kchunks * KB;
-        for (int t = 0; t < ntap; ++t) {
-          const int src = p.tap_src[tap0 + t];
-          const int row = t0 + p.tap_shift[tap0 + t];
+        for (int sg = p.group_seg_begin[tc.group]; sg < p.group_seg_begin[tc.group + 1]; ++sg) {
+          const int src = p.seg_src[sg];
+          const int row = t0 + p.seg_min_shift[sg];
+          const int tb = p.seg_tap_begin[sg], te = p.seg_tap_begin[sg + 1];
           for (int kc = 0; kc < p.kchunks; ++kc) {
-            mbar_wait(empty_bar(stage), phase ^ 1u);
-            mbar_expect_tx_elect(full_bar(stage), L::a_bytes + L::w_bytes_raw);
-            const uint32_t a_dst = smem_base + stage * L::stage_bytes;
-            tma_load_3d_elect(a_dst, &p.tmA[src], full_bar(stage), kc * KB, row, tc.b);
-            tma_load_2d_elect(a_dst + L::a_bytes, &p.tmW, full_bar(stage), wk, tc.n * BN);
-            wk += KB;
-            if (++stage == stages) { stage = 0; phase ^= 1u; }
+            mbar_wait(a_empty(ai), aph ^ 1u);
+            mbar_expect_tx_elect(a_full(ai), a_tx);
+            tma_load_3d_elect(a_ring + ai * p.a_box_bytes, &p.tmA[src], a_full(ai), kc * KB, row, tc.b);
+            if (++ai == a_stages) { ai = 0; aph ^= 1u; }
+            for (int t = tb; t < te; ++t) {
+              mbar_wait(w_empty(wi), wph ^ 1u);
+              mbar_expect_tx_elect(w_full(wi), L::w_bytes_raw);
+              tma_load_2d_elect(w_ring + wi * L::w_bytes, &p.tmW, w_full(wi), (t * p.kchunks + kc) * KB, tc.n * BN);
+              if (++wi == w_stages) { wi = 0; wph ^= 1u; }
+            }
           }
         }
       }
@@ -526,33 +549,42 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
     __syncwarp();
   } else if (warp == 1) {
     // MMA issuer: the whole warp runs the (warp-uniform) loop converged so descriptors stay in uniform registers;
-    // lane 0 issues.  See umma_bf16_pred.
+    // one elected lane issues.  See umma_bf16_pred.
     {
-      const uint32_t leader = lane == 0 ? 1u : 0u;
-      int stage = 0;
-      uint32_t phase = 0;
+      int ai = 0, wi = 0;
+      uint32_t aph = 0, wph = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const TileCoord tc = decode_tile(p, tile);
-        const int nk = (p.group_tap_begin[tc.group + 1] - p.group_tap_begin[tc.group]) * p.kchunks;
         const int buf = it & 1;
         const uint32_t bphase = (it >> 1) & 1;
         mbar_wait(tempty_bar(buf), bphase ^ 1u);
         tc_fence_after();
         const uint32_t tacc = tmem_base + buf * TBUF;
-        for (int ks = 0; ks < nk; ++ks) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_base + stage * L::stage_bytes;
-          const uint64_t adesc = umma_smem_desc<SW>(a_addr);
-          const uint64_t wdesc = umma_smem_desc<SW>(a_addr + L::a_bytes);
+        uint32_t first = 1;
+        for (int sg = p.group_seg_begin[tc.group]; sg < p.group_seg_begin[tc.group + 1]; ++sg) {
+          const int min_shift = p.seg_min_shift[sg];
+          const int tb = p.seg_tap_begin[sg], te = p.seg_tap_begin[sg + 1];
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            mbar_wait(a_full(ai), aph);
+            const uint32_t a_addr = a_ring + ai * p.a_box_bytes;
+            for (int t = tb; t < te; ++t) {
+              mbar_wait(w_full(wi), wph);
+              tc_fence_after();
+              const uint64_t adesc = umma_smem_desc<SW>(a_addr + (p.tap_shift[t] - min_shift) * (KB * 2));
+              const uint64_t wdesc = umma_smem_desc<SW>(w_ring + wi * L::w_bytes);
 #pragma unroll
-          for (int k = 0; k < KB / 16; ++k)
-            umma_bf16_pred(leader, tacc, adesc + 2 * k, wdesc + 2 * k, IDESC, (ks | k) != 0 ? 1u : 0u);
-          umma_commit_pred(leader, empty_bar(stage));
-          if (++stage == stages) { stage = 0; phase ^= 1u; }
+              for (int k = 0; k < KB / 16; ++k)
+                umma_bf16_pred(1u, tacc, adesc + 2 * k, wdesc + 2 * k, IDESC, (first && k == 0) ? 0u : 1u);
+              first = 0;
+              umma_commit_pred(1u, w_empty(wi));
+              if (++wi == w_stages) { wi = 0; wph ^= 1u; }
+            }
+            umma_commit_pred(1u, a_empty(ai));
+            if (++ai == a_stages) { ai = 0; aph ^= 1u; }
+          }
         }
-        umma_commit_pred(leader, tfull_bar(buf));
+        umma_commit_pred(1u, tfull_bar(buf));
       }
     }
     __syncwarp();
