@@ -130,7 +130,10 @@ static int launch_inst(ConvGemmParams& p, int total_tiles, cudaStream_t stream) 
   while (a_stages * a_bytes + w_stages * L::w_bytes > 208 * 1024 && w_stages > 2) --w_stages;
   p.a_stages = a_stages;
   p.w_stages = w_stages;
-  const int smem = a_stages * a_bytes + w_stages * L::w_bytes + 1024 + 8 * (2 * (a_stages + w_stages) + 4) + 16 + 1024;
+  constexpr int stage_smem = EpiWarps<BN, EPI>::value * 4096 + 128;   // coalescing buffers of the epilogue warps
+  while (a_stages * a_bytes + w_stages * L::w_bytes + stage_smem > 222 * 1024 && w_stages > 2) --w_stages;
+  p.w_stages = w_stages;
+  const int smem = a_stages * a_bytes + w_stages * L::w_bytes + 1024 + 8 * (2 * (a_stages + w_stages) + 4) + 16 + 1024 + stage_smem;
   static int configured_smem[64] = {0};
   int dev = 0;
   cudaGetDevice(&dev);

@@ -100,50 +100,107 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvGemmParams& p, int ti
 }
 
 // ---------------------------------------------------------------------------------------------- epilogues
-// Thread <-> one accumulator row (TMEM lane).  The epilogue is the throughput limiter of these kernels when it is
-// under-populated (one warp per SM sub-partition cannot hide TMEM / global latency), so wide tiles use EIGHT
-// epilogue warps: warps sharing a TMEM lane quarter split the columns in two halves (`half`, `nhalf`).
-// `tacc` is the TMEM address of (lane base, column 0) of this tile's accumulator buffer.  All 32 lanes of a warp
-// execute every tcgen05.ld/st (sync.aligned); global loads that do not depend on the accumulator are issued
-// before the TMEM wait so their latency overlaps it.
+// Thread <-> one accumulator row (TMEM lane).  Wide tiles use EIGHT epilogue warps (two column halves per TMEM lane
+// quarter): one warp per SM sub-partition cannot hide TMEM / global latency.  `tacc` is the TMEM address of
+// (lane base, column 0) of this tile's accumulator buffer.  All 32 lanes execute every tcgen05.ld/st (sync.aligned).
+//
+// Global traffic is COALESCED through a 4 KB per-warp staging buffer: with thread <-> row every 16-byte access of a
+// warp would touch 32 different cache lines (measured: the LSU, not the tensor core, paced these kernels).  A warp
+// owns a 32-row x (P x 16 B) block; in global memory lane l moves the pieces l, l+32, ... of the row-major block
+// (32/P rows x P*16 contiguous bytes per instruction), in shared memory it reads/writes its own row; 16-byte pieces
+// are XOR-swizzled by row so both sides are bank-conflict free.
+struct EpiWarp {
+  uint8_t* stage;   // 32 rows x 128 B
+  int lane;
+  int row0;         // first tile-local output row q of this warp
+};
+
+__device__ __forceinline__ uint4* stage_slot(uint8_t* stage, int row, int piece) {
+  return reinterpret_cast<uint4*>(stage + row * 128 + ((piece ^ (row & 7)) << 4));
+}
+
+// issue the coalesced loads of a 32 x (P*16 B) block (rows >= valid_rows read as zero)
+template <int P>
+__device__ __forceinline__ void gather_issue(const void* gbase, long long row_stride_bytes, int valid_rows, int lane, uint4* t) {
+  const uint8_t* g = static_cast<const uint8_t*>(gbase);
+#pragma unroll
+  for (int i = 0; i < P; ++i) {
+    const int idx = lane + 32 * i, row = idx / P, piece = idx % P;
+    t[i] = row < valid_rows ? __ldg(reinterpret_cast<const uint4*>(g + row * row_stride_bytes + piece * 16)) : make_uint4(0, 0, 0, 0);
+  }
+}
+// route the loaded pieces through the staging buffer; afterwards v[j] is piece j of this lane's own row
+template <int P>
+__device__ __forceinline__ void gather_finish(const EpiWarp& w, const uint4* t, uint4* v) {
+#pragma unroll
+  for (int i = 0; i < P; ++i) {
+    const int idx = w.lane + 32 * i;
+    *stage_slot(w.stage, idx / P, idx % P) = t[i];
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < P; ++j) v[j] = *stage_slot(w.stage, w.lane, j);
+  __syncwarp();
+}
+// v[j] = piece j of this lane's row  ->  coalesced global stores of the 32 x (P*16 B) block
+template <int P>
+__device__ __forceinline__ void scatter_store(const EpiWarp& w, const uint4* v, void* gbase, long long row_stride_bytes, int valid_rows) {
+#pragma unroll
+  for (int j = 0; j < P; ++j) *stage_slot(w.stage, w.lane, j) = v[j];
+  __syncwarp();
+  uint8_t* g = static_cast<uint8_t*>(gbase);
+#pragma unroll
+  for (int i = 0; i < P; ++i) {
+    const int idx = w.lane + 32 * i, row = idx / P, piece = idx % P;
+    const uint4 x = *stage_slot(w.stage, row, piece);
+    if (row < valid_rows) *reinterpret_cast<uint4*>(g + row * row_stride_bytes + piece * 16) = x;
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ int clamp_rows(int total, int row0) {
+  const int v = total - row0;
+  return v < 0 ? 0 : (v > 32 ? 32 : v);
+}
 
 template <int BN, int NHALF>
-__device__ __forceinline__ void epi_generic(const ConvGemmParams& p, uint32_t tacc, const TileCoord& tc, int q, int half) {
+__device__ __forceinline__ void epi_generic(const ConvGemmParams& p, uint32_t tacc, const TileCoord& tc, int q, int half,
+                                            const EpiWarp& w) {
   constexpr int CW = BN < 32 ? BN : 32;
   constexpr int COLS = BN / NHALF;
-  const bool valid = q < p.group_rows[tc.group];
-  const long long orow = (long long)q * p.row_mul + p.group_row_add[tc.group];
-  const long long obase = (long long)tc.b * p.out_batch_stride + orow * p.out_row_stride + (long long)tc.n * BN;
-  const long long rbase = (long long)tc.b * p.res_batch_stride + orow * p.res_row_stride + (long long)tc.n * BN;
+  constexpr int P = CW / 8;   // 16-byte pieces of bf16 per chunk row
   const float sc = p.scale, sl = p.slope;
+  if (p.row_mul == 1) {
+    // contiguous output rows: coalesced path
+    const int vrows = clamp_rows(p.group_rows[tc.group], w.row0);
+    const long long row0 = (long long)w.row0 + p.group_row_add[tc.group];
+    const long long obase = (long long)tc.b * p.out_batch_stride + row0 * p.out_row_stride + (long long)tc.n * BN;
+    const long long rbase = (long long)tc.b * p.res_batch_stride + row0 * p.res_row_stride + (long long)tc.n * BN;
 #pragma unroll 1
-  for (int c0 = half * COLS; c0 < (half + 1) * COLS; c0 += CW) {
-    uint4 rv[3][CW / 8];
+    for (int c0 = half * COLS; c0 < (half + 1) * COLS; c0 += CW) {
+      uint4 rt[3][P];
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      if (valid && p.res[r]) {
-        const uint4* r4 = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.res[r]) + rbase + c0);
-#pragma unroll
-        for (int j = 0; j < CW / 8; ++j) rv[r][j] = __ldg(r4 + j);
-      }
-    }
-    float y[CW];
-    tmem_ld_f<CW>(tacc + c0, y);
-    if (valid) {
+      for (int r = 0; r < 3; ++r)
+        if (p.res[r])
+          gather_issue<P>(static_cast<const __nv_bfloat16*>(p.res[r]) + rbase + c0, p.res_row_stride * 2, vrows, w.lane, rt[r]);
+      float y[CW];
+      tmem_ld_f<CW>(tacc + c0, y);
       if (p.bias) {
         const float4* b4 = reinterpret_cast<const float4*>(p.bias + tc.n * BN + c0);
 #pragma unroll
         for (int j = 0; j < CW / 4; ++j) {
-          float4 bb = __ldg(b4 + j);
+          const float4 bb = __ldg(b4 + j);
           y[4 * j + 0] += bb.x; y[4 * j + 1] += bb.y; y[4 * j + 2] += bb.z; y[4 * j + 3] += bb.w;
         }
       }
 #pragma unroll
       for (int r = 0; r < 3; ++r) {
         if (p.res[r]) {
+          uint4 rv[P];
+          gather_finish<P>(w, rt[r], rv);
 #pragma unroll
-          for (int j = 0; j < CW / 8; ++j) {
-            const uint4 u = rv[r][j];
+          for (int j = 0; j < P; ++j) {
+            const uint4 u = rv[j];
             y[8 * j + 0] += bf16_lo(u.x); y[8 * j + 1] += bf16_hi(u.x);
             y[8 * j + 2] += bf16_lo(u.y); y[8 * j + 3] += bf16_hi(u.y);
             y[8 * j + 4] += bf16_lo(u.z); y[8 * j + 5] += bf16_hi(u.z);
@@ -154,16 +211,56 @@ __device__ __forceinline__ void epi_generic(const ConvGemmParams& p, uint32_t ta
 #pragma unroll
       for (int j = 0; j < CW; ++j) y[j] *= sc;
       if (p.out1) {
+        uint4 o[P];
+#pragma unroll
+        for (int j = 0; j < P; ++j)
+          o[j] = make_uint4(pack_bf16(y[8 * j], y[8 * j + 1]), pack_bf16(y[8 * j + 2], y[8 * j + 3]),
+                            pack_bf16(y[8 * j + 4], y[8 * j + 5]), pack_bf16(y[8 * j + 6], y[8 * j + 7]));
+        scatter_store<P>(w, o, static_cast<__nv_bfloat16*>(p.out1) + obase + c0, p.out_row_stride * 2, vrows);
+      }
+      if (p.out0) {
+        uint4 o[P];
+#pragma unroll
+        for (int j = 0; j < P; ++j)
+          o[j] = make_uint4(pack_bf16(lrelu(y[8 * j], sl), lrelu(y[8 * j + 1], sl)),
+                            pack_bf16(lrelu(y[8 * j + 2], sl), lrelu(y[8 * j + 3], sl)),
+                            pack_bf16(lrelu(y[8 * j + 4], sl), lrelu(y[8 * j + 5], sl)),
+                            pack_bf16(lrelu(y[8 * j + 6], sl), lrelu(y[8 * j + 7], sl)));
+        scatter_store<P>(w, o, static_cast<__nv_bfloat16*>(p.out0) + obase + c0, p.out_row_stride * 2, vrows);
+      }
+    }
+    return;
+  }
+  // strided output rows (polyphase transposed conv: row = q * stride + phase): per-row stores, no residuals
+  const bool valid = q < p.group_rows[tc.group];
+  const long long orow = (long long)q * p.row_mul + p.group_row_add[tc.group];
+  const long long obase = (long long)tc.b * p.out_batch_stride + orow * p.out_row_stride + (long long)tc.n * BN;
+#pragma unroll 1
+  for (int c0 = half * COLS; c0 < (half + 1) * COLS; c0 += CW) {
+    float y[CW];
+    tmem_ld_f<CW>(tacc + c0, y);
+    if (valid) {
+      if (p.bias) {
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + tc.n * BN + c0);
+#pragma unroll
+        for (int j = 0; j < CW / 4; ++j) {
+          const float4 bb = __ldg(b4 + j);
+          y[4 * j + 0] += bb.x; y[4 * j + 1] += bb.y; y[4 * j + 2] += bb.z; y[4 * j + 3] += bb.w;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < CW; ++j) y[j] *= sc;
+      if (p.out1) {
         uint4* o4 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out1) + obase + c0);
 #pragma unroll
-        for (int j = 0; j < CW / 8; ++j)
+        for (int j = 0; j < P; ++j)
           o4[j] = make_uint4(pack_bf16(y[8 * j], y[8 * j + 1]), pack_bf16(y[8 * j + 2], y[8 * j + 3]),
                              pack_bf16(y[8 * j + 4], y[8 * j + 5]), pack_bf16(y[8 * j + 6], y[8 * j + 7]));
       }
       if (p.out0) {
         uint4* o4 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out0) + obase + c0);
 #pragma unroll
-        for (int j = 0; j < CW / 8; ++j)
+        for (int j = 0; j < P; ++j)
           o4[j] = make_uint4(pack_bf16(lrelu(y[8 * j], sl), lrelu(y[8 * j + 1], sl)),
                              pack_bf16(lrelu(y[8 * j + 2], sl), lrelu(y[8 * j + 3], sl)),
                              pack_bf16(lrelu(y[8 * j + 4], sl), lrelu(y[8 * j + 5], sl)),
@@ -175,12 +272,13 @@ __device__ __forceinline__ void epi_generic(const ConvGemmParams& p, uint32_t ta
 
 // FFN conv1 tile = [128 value columns | 128 gate columns] -> 128 outputs  (fastspeech/modules.py:27-30, 62-69)
 template <int NHALF>
-__device__ __forceinline__ void epi_glu(const ConvGemmParams& p, uint32_t tacc, const TileCoord& tc, int q, int half) {
+__device__ __forceinline__ void epi_glu(const ConvGemmParams& p, uint32_t tacc, const TileCoord& tc, int q, int half,
+                                        const EpiWarp& w) {
   constexpr int COLS = 128 / NHALF;
-  const bool valid = q < p.group_rows[0];
-  const bool keep = valid && q < p.lengths[tc.b];
+  const int vrows = clamp_rows(p.group_rows[0], w.row0);
+  const bool keep = q < p.group_rows[0] && q < p.lengths[tc.b];
   __nv_bfloat16* out = static_cast<__nv_bfloat16*>(p.out0) + (long long)tc.b * p.out_batch_stride +
-                       (long long)q * p.out_row_stride + tc.n * 128;
+                       (long long)w.row0 * p.out_row_stride + tc.n * 128;
   const float* bias = p.bias + tc.n * 256;
 #pragma unroll 1
   for (int c0 = half * COLS; c0 < (half + 1) * COLS; c0 += 32) {
@@ -188,31 +286,27 @@ __device__ __forceinline__ void epi_glu(const ConvGemmParams& p, uint32_t tacc, 
     tmem_ld32(tacc + c0, v);
     tmem_ld32(tacc + 128 + c0, g);
     tmem_ld_wait();
-    if (valid) {
-      uint32_t o[16];
+    uint4 o[4];
+    uint32_t* ow = reinterpret_cast<uint32_t*>(o);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + c0) + j);
-        const float4 bg = __ldg(reinterpret_cast<const float4*>(bias + 128 + c0) + j);
-        const float h0 = silu_fast(__uint_as_float(g[4 * j + 0]) + bg.x) * (__uint_as_float(v[4 * j + 0]) + bv.x);
-        const float h1 = silu_fast(__uint_as_float(g[4 * j + 1]) + bg.y) * (__uint_as_float(v[4 * j + 1]) + bv.y);
-        const float h2 = silu_fast(__uint_as_float(g[4 * j + 2]) + bg.z) * (__uint_as_float(v[4 * j + 2]) + bv.z);
-        const float h3 = silu_fast(__uint_as_float(g[4 * j + 3]) + bg.w) * (__uint_as_float(v[4 * j + 3]) + bv.w);
-        o[2 * j] = keep ? pack_bf16(h0, h1) : 0u;       // pads are zeroed before conv2 (fastspeech/modules.py:69)
-        o[2 * j + 1] = keep ? pack_bf16(h2, h3) : 0u;
-      }
-      uint4* o4 = reinterpret_cast<uint4*>(out + c0);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) o4[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+    for (int j = 0; j < 8; ++j) {
+      const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + c0) + j);
+      const float4 bg = __ldg(reinterpret_cast<const float4*>(bias + 128 + c0) + j);
+      const float h0 = silu_fast(__uint_as_float(g[4 * j + 0]) + bg.x) * (__uint_as_float(v[4 * j + 0]) + bv.x);
+      const float h1 = silu_fast(__uint_as_float(g[4 * j + 1]) + bg.y) * (__uint_as_float(v[4 * j + 1]) + bv.y);
+      const float h2 = silu_fast(__uint_as_float(g[4 * j + 2]) + bg.z) * (__uint_as_float(v[4 * j + 2]) + bv.z);
+      const float h3 = silu_fast(__uint_as_float(g[4 * j + 3]) + bg.w) * (__uint_as_float(v[4 * j + 3]) + bv.w);
+      ow[2 * j] = keep ? pack_bf16(h0, h1) : 0u;       // pads are zeroed before conv2 (fastspeech/modules.py:69)
+      ow[2 * j + 1] = keep ? pack_bf16(h2, h3) : 0u;
     }
+    scatter_store<4>(w, o, out + c0, p.out_row_stride * 2, vrows);
   }
 }
 
 // y = acc + bias + residual (fp32 stream, in place allowed); x_out = y; xn = bf16(norm(y) * g) with pad rows zeroed.
 // A row's 256 columns live in ONE TMEM lane; with two column halves per lane quarter the two warps exchange their
-// partial sums of squares through `red` (smem, [2][128] floats) and a 64-thread named barrier.
-// 64-thread named barrier shared by the two epilogue warps of one TMEM lane quarter (ids 1-4, immediates so that
-// ptxas accounts for them; id 0 is __syncthreads)
+// partial sums of squares through `red` (smem, [2][128] floats) and a 64-thread named barrier (ids 1-4, immediates so
+// that ptxas accounts for them; id 0 is __syncthreads).
 __device__ __forceinline__ void pair_barrier(int quarter) {
   switch (quarter) {
     case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
@@ -222,63 +316,61 @@ __device__ __forceinline__ void pair_barrier(int quarter) {
   }
 }
 
-// Global operands of an epilogue that do not depend on the accumulator (the fp32 residual stream, the rotary
-// tables) are fetched in two batches: the first BEFORE the thread waits for the tile's MMAs (so its L2 latency
-// overlaps the tensor work), the second right after the wait while the first is being consumed.  Profiling showed
-// these epilogues stalled on exactly these loads (long-scoreboard on the first dependent FADD/FMUL).
+// Operands that do not depend on the accumulator (fp32 residual stream, rotary tables) are fetched in two batches:
+// the first BEFORE the warp waits for the tile's MMAs (its L2 latency overlaps the tensor work), the second right
+// after the wait.  pre[] holds two coalesced 32 x 128 B blocks (8 pieces per lane each).
 template <int NHALF>
-__device__ __forceinline__ void resnorm_prefetch(const ConvGemmParams& p, const TileCoord& tc, int q, int half, float4 (&pre)[16]) {
+__device__ __forceinline__ void resnorm_prefetch(const ConvGemmParams& p, const TileCoord& tc, int half, const EpiWarp& w,
+                                                 uint4 (&pre)[16]) {
   constexpr int COLS = 256 / NHALF;
-  if (q < p.group_rows[0]) {
-    const float* res = static_cast<const float*>(p.res[0]) + (long long)tc.b * p.res_batch_stride +
-                       (long long)q * p.res_row_stride + half * COLS;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) pre[j] = *reinterpret_cast<const float4*>(res + 4 * j);
-  }
+  const int vrows = clamp_rows(p.group_rows[0], w.row0);
+  const float* res = static_cast<const float*>(p.res[0]) + (long long)tc.b * p.res_batch_stride +
+                     (long long)w.row0 * p.res_row_stride + half * COLS;
+  gather_issue<8>(res, p.res_row_stride * 4, vrows, w.lane, pre);
+  gather_issue<8>(res + 32, p.res_row_stride * 4, vrows, w.lane, pre + 8);
 }
 
 template <int NHALF>
 __device__ __forceinline__ void epi_resnorm(const ConvGemmParams& p, uint32_t tacc, const TileCoord& tc, int q, int half,
-                                            float* red, int row_in_tile, int quarter, const float4 (&pre)[16]) {
+                                            float* red, int row_in_tile, int quarter, const EpiWarp& w, const uint4 (&pre)[16]) {
   constexpr int COLS = 256 / NHALF;
   constexpr int NCHUNK = COLS / 32;
   static_assert(NCHUNK == 4, "RESNORM runs with eight epilogue warps");
-  const bool valid = q < p.group_rows[0];
-  const long long off = (long long)tc.b * p.out_batch_stride + (long long)q * p.out_row_stride;
+  const int vrows = clamp_rows(p.group_rows[0], w.row0);
+  const long long woff = (long long)tc.b * p.out_batch_stride + (long long)w.row0 * p.out_row_stride + half * COLS;
   const float* res = static_cast<const float*>(p.res[0]) + (long long)tc.b * p.res_batch_stride +
-                     (long long)q * p.res_row_stride + half * COLS;
-  float* xout = static_cast<float*>(p.out1) + off + half * COLS;
+                     (long long)w.row0 * p.res_row_stride + half * COLS;
+  float* xout = static_cast<float*>(p.out1) + woff;
   const uint32_t tcol = tacc + half * COLS;
-  float4 late[16];   // residual of chunks 2, 3
-  if (valid) {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) late[j] = *reinterpret_cast<const float4*>(res + 64 + 4 * j);
-  }
+  uint4 late[16];   // residual blocks of chunks 2, 3
+  gather_issue<8>(res + 64, p.res_row_stride * 4, vrows, w.lane, late);
+  gather_issue<8>(res + 96, p.res_row_stride * 4, vrows, w.lane, late + 8);
   float sumsq = 0.f;
 #pragma unroll
   for (int c = 0; c < NCHUNK; ++c) {
+    uint4 rr[8];
+    gather_finish<8>(w, c < 2 ? pre + (c & 1) * 8 : late + (c & 1) * 8, rr);
     uint32_t v[32];
     tmem_ld32(tcol + c * 32, v);
     tmem_ld_wait();
-    if (valid) {
+    uint4 yo[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 r = c < 2 ? pre[(c & 1) * 8 + j] : late[(c & 1) * 8 + j];
-        float4 y;
-        y.x = __uint_as_float(v[4 * j + 0]) + r.x;
-        y.y = __uint_as_float(v[4 * j + 1]) + r.y;
-        y.z = __uint_as_float(v[4 * j + 2]) + r.z;
-        y.w = __uint_as_float(v[4 * j + 3]) + r.w;
-        if (p.bias) {
-          const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + half * COLS + c * 32 + 4 * j));
-          y.x += bb.x; y.y += bb.y; y.z += bb.z; y.w += bb.w;
-        }
-        sumsq += y.x * y.x + y.y * y.y + y.z * y.z + y.w * y.w;
-        *reinterpret_cast<float4*>(xout + c * 32 + 4 * j) = y;
-        v[4 * j + 0] = __float_as_uint(y.x); v[4 * j + 1] = __float_as_uint(y.y);
-        v[4 * j + 2] = __float_as_uint(y.z); v[4 * j + 3] = __float_as_uint(y.w);
+    for (int j = 0; j < 8; ++j) {
+      float4 y;
+      y.x = __uint_as_float(v[4 * j + 0]) + __uint_as_float(rr[j].x);
+      y.y = __uint_as_float(v[4 * j + 1]) + __uint_as_float(rr[j].y);
+      y.z = __uint_as_float(v[4 * j + 2]) + __uint_as_float(rr[j].z);
+      y.w = __uint_as_float(v[4 * j + 3]) + __uint_as_float(rr[j].w);
+      if (p.bias) {
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + half * COLS + c * 32 + 4 * j));
+        y.x += bb.x; y.y += bb.y; y.z += bb.z; y.w += bb.w;
       }
+      sumsq += y.x * y.x + y.y * y.y + y.z * y.z + y.w * y.w;
+      v[4 * j + 0] = __float_as_uint(y.x); v[4 * j + 1] = __float_as_uint(y.y);
+      v[4 * j + 2] = __float_as_uint(y.z); v[4 * j + 3] = __float_as_uint(y.w);
+      yo[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     }
+    scatter_store<8>(w, yo, xout + c * 32, p.out_row_stride * 4, vrows);
     if (p.norm_mode != 0) tmem_st32(tcol + c * 32, v);  // stash y for the second pass
   }
   if (p.norm_mode == 0) return;
@@ -291,27 +383,24 @@ __device__ __forceinline__ void epi_resnorm(const ConvGemmParams& p, uint32_t ta
   float inv;
   if (p.norm_mode == 1) inv = 1.f / fmaxf(sqrtf(sumsq), 1e-12f);           // F.normalize (norm.py:41)
   else inv = rsqrtf(sumsq * (1.f / 256.f) + 1.1920928955078125e-07f);      // nn.RMSNorm eps = finfo(fp32).eps
-  const bool keep = valid && (p.lengths == nullptr || q < p.lengths[tc.b]);
-  __nv_bfloat16* xn = static_cast<__nv_bfloat16*>(p.out0) + off + half * COLS;
+  const bool keep = q < p.group_rows[0] && (p.lengths == nullptr || q < p.lengths[tc.b]);
+  __nv_bfloat16* xn = static_cast<__nv_bfloat16*>(p.out0) + woff;
   const float* gv = p.vec0 + half * COLS;
 #pragma unroll
   for (int c = 0; c < NCHUNK; ++c) {
     uint32_t v[32];
     tmem_ld32(tcol + c * 32, v);
     tmem_ld_wait();
-    if (valid) {
-      uint32_t o[16];
+    uint4 o[4];
+    uint32_t* ow = reinterpret_cast<uint32_t*>(o);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 g = __ldg(reinterpret_cast<const float4*>(gv + c * 32 + 4 * j));
-        // select (not multiply) so a non-finite pad row can never leak into the conv taps of valid frames
-        o[2 * j] = keep ? pack_bf16(__uint_as_float(v[4 * j]) * inv * g.x, __uint_as_float(v[4 * j + 1]) * inv * g.y) : 0u;
-        o[2 * j + 1] = keep ? pack_bf16(__uint_as_float(v[4 * j + 2]) * inv * g.z, __uint_as_float(v[4 * j + 3]) * inv * g.w) : 0u;
-      }
-      uint4* o4 = reinterpret_cast<uint4*>(xn + c * 32);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) o4[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+    for (int j = 0; j < 8; ++j) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gv + c * 32 + 4 * j));
+      // select (not multiply) so a non-finite pad row can never leak into the conv taps of valid frames
+      ow[2 * j] = keep ? pack_bf16(__uint_as_float(v[4 * j]) * inv * g.x, __uint_as_float(v[4 * j + 1]) * inv * g.y) : 0u;
+      ow[2 * j + 1] = keep ? pack_bf16(__uint_as_float(v[4 * j + 2]) * inv * g.z, __uint_as_float(v[4 * j + 3]) * inv * g.w) : 0u;
     }
+    scatter_store<4>(w, o, xn + c * 32, p.out_row_stride * 2, vrows);
   }
   if constexpr (NHALF == 2) {
     // the pair must not overwrite `red` for the next tile before both have read it
@@ -321,26 +410,24 @@ __device__ __forceinline__ void epi_resnorm(const ConvGemmParams& p, uint32_t ta
 
 // to_qkv tile n: 0 = q (2 heads x 128), 1 = k, 2 = v.  Rotary (transformer.py:66-73) on q,k:
 // out[i] = t[i] cos - t[i+64] sin ; out[i+64] = t[i+64] cos + t[i] sin, angle = pos * inv_freq[i], i < 64.
-// With eight epilogue warps, column half h of a lane quarter is head h.
-__device__ __forceinline__ void rope_prefetch(const ConvGemmParams& p, const TileCoord& tc, int q, float4 (&pre)[16]) {
-  if (tc.n != 2 && q < p.group_rows[0]) {
-    const float* cs = p.vec0 + (long long)q * 64;
-    const float* sn = p.vec1 + (long long)q * 64;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      pre[j] = __ldg(reinterpret_cast<const float4*>(cs) + j);        // cos, frequencies 0..31
-      pre[8 + j] = __ldg(reinterpret_cast<const float4*>(sn) + j);    // sin, frequencies 0..31
-    }
+// With eight epilogue warps, column half h of a lane quarter is head h.  The rotary tables are (rows, 64) fp32 and a
+// warp's 32 consecutive positions are one contiguous 8 KB block: fetched coalesced like a residual.
+__device__ __forceinline__ void rope_prefetch(const ConvGemmParams& p, const TileCoord& tc, const EpiWarp& w, uint4 (&pre)[16]) {
+  if (tc.n != 2) {
+    const int vrows = clamp_rows(p.group_rows[0], w.row0);
+    gather_issue<8>(p.vec0 + (long long)w.row0 * 64, 256, vrows, w.lane, pre);        // cos, frequencies 0..31
+    gather_issue<8>(p.vec1 + (long long)w.row0 * 64, 256, vrows, w.lane, pre + 8);    // sin, frequencies 0..31
   }
 }
 
 template <int NHALF>
-__device__ __forceinline__ void epi_qkv_rope(const ConvGemmParams& p, uint32_t tacc, const TileCoord& tc, int q, int half,
-                                             const float4 (&pre)[16]) {
+__device__ __forceinline__ void epi_qkv_rope(const ConvGemmParams& p, uint32_t tacc, const TileCoord& tc, int half,
+                                             const EpiWarp& w, const uint4 (&pre)[16]) {
   static_assert(NHALF == 2, "QKV_ROPE runs with eight epilogue warps (one head per column half)");
-  const bool valid = q < p.group_rows[0];
+  const int vrows = clamp_rows(p.group_rows[0], w.row0);
   __nv_bfloat16* out = static_cast<__nv_bfloat16*>(p.out0) + (long long)tc.b * p.out_batch_stride +
-                       (long long)q * p.out_row_stride + tc.n * 256 + half * 128;
+                       (long long)w.row0 * p.out_row_stride + tc.n * 256 + half * 128;
+  const long long ostride = p.out_row_stride * 2;
   const uint32_t tcol = tacc + half * 128;
   if (tc.n == 2) {
 #pragma unroll
@@ -348,57 +435,47 @@ __device__ __forceinline__ void epi_qkv_rope(const ConvGemmParams& p, uint32_t t
       uint32_t v[32];
       tmem_ld32(tcol + c * 32, v);
       tmem_ld_wait();
-      if (valid) {
-        uint4* o4 = reinterpret_cast<uint4*>(out + c * 32);
+      uint4 o[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          o4[j] = make_uint4(pack_bf16(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1])),
-                             pack_bf16(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
-                             pack_bf16(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
-                             pack_bf16(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
-      }
+      for (int j = 0; j < 4; ++j)
+        o[j] = make_uint4(pack_bf16(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1])),
+                          pack_bf16(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
+                          pack_bf16(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
+                          pack_bf16(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
+      scatter_store<4>(w, o, out + c * 32, ostride, vrows);
     }
     return;
   }
-  float4 late[16];   // cos / sin of frequencies 32..63
-  if (valid) {
-    const float* cs = p.vec0 + (long long)q * 64 + 32;
-    const float* sn = p.vec1 + (long long)q * 64 + 32;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      late[j] = __ldg(reinterpret_cast<const float4*>(cs) + j);
-      late[8 + j] = __ldg(reinterpret_cast<const float4*>(sn) + j);
-    }
-  }
+  uint4 late[16];   // cos / sin of frequencies 32..63
+  gather_issue<8>(p.vec0 + (long long)w.row0 * 64 + 32, 256, vrows, w.lane, late);
+  gather_issue<8>(p.vec1 + (long long)w.row0 * 64 + 32, 256, vrows, w.lane, late + 8);
 #pragma unroll
   for (int f = 0; f < 2; ++f) {
+    uint4 cs[8], sn[8];
+    gather_finish<8>(w, f == 0 ? pre : late, cs);
+    gather_finish<8>(w, f == 0 ? pre + 8 : late + 8, sn);
     uint32_t lo[32], hi[32];
     tmem_ld32(tcol + f * 32, lo);
     tmem_ld32(tcol + 64 + f * 32, hi);
     tmem_ld_wait();
-    if (valid) {
-      uint32_t olo[16], ohi[16];
+    uint4 olo[4], ohi[4];
+    uint32_t* wl = reinterpret_cast<uint32_t*>(olo);
+    uint32_t* wh = reinterpret_cast<uint32_t*>(ohi);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 c = f == 0 ? pre[j] : late[j];
-        const float4 s = f == 0 ? pre[8 + j] : late[8 + j];
-        const float a0 = __uint_as_float(lo[4 * j]), a1 = __uint_as_float(lo[4 * j + 1]);
-        const float a2 = __uint_as_float(lo[4 * j + 2]), a3 = __uint_as_float(lo[4 * j + 3]);
-        const float b0 = __uint_as_float(hi[4 * j]), b1 = __uint_as_float(hi[4 * j + 1]);
-        const float b2 = __uint_as_float(hi[4 * j + 2]), b3 = __uint_as_float(hi[4 * j + 3]);
-        olo[2 * j] = pack_bf16(a0 * c.x - b0 * s.x, a1 * c.y - b1 * s.y);
-        olo[2 * j + 1] = pack_bf16(a2 * c.z - b2 * s.z, a3 * c.w - b3 * s.w);
-        ohi[2 * j] = pack_bf16(b0 * c.x + a0 * s.x, b1 * c.y + a1 * s.y);
-        ohi[2 * j + 1] = pack_bf16(b2 * c.z + a2 * s.z, b3 * c.w + a3 * s.w);
-      }
-      uint4* l4 = reinterpret_cast<uint4*>(out + f * 32);
-      uint4* h4 = reinterpret_cast<uint4*>(out + 64 + f * 32);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        l4[j] = make_uint4(olo[4 * j], olo[4 * j + 1], olo[4 * j + 2], olo[4 * j + 3]);
-        h4[j] = make_uint4(ohi[4 * j], ohi[4 * j + 1], ohi[4 * j + 2], ohi[4 * j + 3]);
-      }
+    for (int j = 0; j < 8; ++j) {
+      const float cx = __uint_as_float(cs[j].x), cy = __uint_as_float(cs[j].y), cz = __uint_as_float(cs[j].z), cw = __uint_as_float(cs[j].w);
+      const float sx = __uint_as_float(sn[j].x), sy = __uint_as_float(sn[j].y), sz = __uint_as_float(sn[j].z), sw = __uint_as_float(sn[j].w);
+      const float a0 = __uint_as_float(lo[4 * j]), a1 = __uint_as_float(lo[4 * j + 1]);
+      const float a2 = __uint_as_float(lo[4 * j + 2]), a3 = __uint_as_float(lo[4 * j + 3]);
+      const float b0 = __uint_as_float(hi[4 * j]), b1 = __uint_as_float(hi[4 * j + 1]);
+      const float b2 = __uint_as_float(hi[4 * j + 2]), b3 = __uint_as_float(hi[4 * j + 3]);
+      wl[2 * j] = pack_bf16(a0 * cx - b0 * sx, a1 * cy - b1 * sy);
+      wl[2 * j + 1] = pack_bf16(a2 * cz - b2 * sz, a3 * cw - b3 * sw);
+      wh[2 * j] = pack_bf16(b0 * cx + a0 * sx, b1 * cy + a1 * sy);
+      wh[2 * j + 1] = pack_bf16(b2 * cz + a2 * sz, b3 * cw + a3 * sw);
     }
+    scatter_store<4>(w, olo, out + f * 32, ostride, vrows);
+    scatter_store<4>(w, ohi, out + 64 + f * 32, ostride, vrows);
   }
 }
 
@@ -487,7 +564,9 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
   auto tempty_bar = [&](int b) { return bar_base + 8u * (n_ring_bars + 2 + b); };
   const uint32_t tmem_slot = bar_base + 8u * (n_ring_bars + 4);
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  float* red = reinterpret_cast<float*>(smem_gen + (bar_base - smem_base) + 8 * (n_ring_bars + 4) + 16);  // [2][128]
+  const uint32_t red_off = (bar_base - smem_base) + 8 * (n_ring_bars + 4) + 16;
+  float* red = reinterpret_cast<float*>(smem_gen + red_off);  // [2][128]
+  uint8_t* stage_base = smem_gen + ((red_off + 1024 + 127) & ~127u);                 // EW x 4 KB epilogue staging
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform (uniform datapath)
   const int lane = threadIdx.x & 31;
@@ -598,16 +677,20 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
       const int buf = it & 1;
       const uint32_t bphase = (it >> 1) & 1;
       const int q = tc.m * kTileM + lane_base + lane;
-      float4 pre[16];
-      if constexpr (EPI == EPI_RESNORM) resnorm_prefetch<NHALF>(p, tc, q, half, pre);
-      if constexpr (EPI == EPI_QKV_ROPE) rope_prefetch(p, tc, q, pre);
+      EpiWarp ew;
+      ew.stage = stage_base + (warp - 2) * 4096;
+      ew.lane = lane;
+      ew.row0 = tc.m * kTileM + lane_base;
+      uint4 pre[16];
+      if constexpr (EPI == EPI_RESNORM) resnorm_prefetch<NHALF>(p, tc, half, ew, pre);
+      if constexpr (EPI == EPI_QKV_ROPE) rope_prefetch(p, tc, ew, pre);
       mbar_wait(tfull_bar(buf), bphase);
       tc_fence_after();
       const uint32_t tacc = tmem_base + (static_cast<uint32_t>(lane_base) << 16) + buf * TBUF;
-      if constexpr (EPI == EPI_GENERIC) epi_generic<BN, NHALF>(p, tacc, tc, q, half);
-      else if constexpr (EPI == EPI_GLU) epi_glu<NHALF>(p, tacc, tc, q, half);
-      else if constexpr (EPI == EPI_RESNORM) epi_resnorm<NHALF>(p, tacc, tc, q, half, red, lane_base + lane, quarter, pre);
-      else if constexpr (EPI == EPI_QKV_ROPE) epi_qkv_rope<NHALF>(p, tacc, tc, q, half, pre);
+      if constexpr (EPI == EPI_GENERIC) epi_generic<BN, NHALF>(p, tacc, tc, q, half, ew);
+      else if constexpr (EPI == EPI_GLU) epi_glu<NHALF>(p, tacc, tc, q, half, ew);
+      else if constexpr (EPI == EPI_RESNORM) epi_resnorm<NHALF>(p, tacc, tc, q, half, red, lane_base + lane, quarter, ew, pre);
+      else if constexpr (EPI == EPI_QKV_ROPE) epi_qkv_rope<NHALF>(p, tacc, tc, half, ew, pre);
       else epi_euler(p, tacc, tc, q);
       tc_fence_before();
       __syncwarp();
