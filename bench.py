@@ -136,8 +136,9 @@ def op_profile(engine, ids, x0):
     from speech_resynth_b200 import _native as nat
 
     plan = engine._plan(ids.shape[0], ids.shape[1], DT, TRUNC, True)
-    plan.cfm_ws["ids"].copy_(ids)
-    plan.cfm_ws["xt"].copy_(x0)
+    plan.cfm_ws["ids"][:, : ids.shape[1]].copy_(ids)
+    plan.cfm_ws["xt"].zero_()
+    plan.cfm_ws["xt"][:, : ids.shape[1]].copy_(x0)
     torch.cuda.synchronize()
     nat.profile_log = []
     plan.body()

@@ -1,0 +1,339 @@
+// tcgen05 / TMEM attention for the velocity transformer (transformer.py:115-127): 2 heads x d_head 128, scale
+// 1/sqrt(128), keys >= len_b masked, no dropout.  One CTA = one (utterance, head, 128-query tile).
+//
+//   S = Q K^T   : tcgen05.mma M=128 (queries) x N=128 (keys) x K=128 (d), A = Q tile, B = K tile, both K-major
+//                 (d contiguous) straight from the (B, N, ld) q|k buffer through TMA (128-byte swizzle);
+//   O += P V    : M=128 x N=128 (d) x K=128 (keys), A = P (bf16, written to swizzled smem by the softmax warps),
+//                 B = V^T tile.  V is produced already TRANSPOSED ([d][utterance*frames], keys contiguous) by a
+//                 swapped-operand GEMM (srb_cfm_v_transposed), so both operands of P V are K-major as well.
+//
+// Exact two-pass softmax instead of an online one: pass 1 runs Q K^T over all key tiles and keeps only the row
+// maxima, pass 2 recomputes S, forms P = exp2(s*scale - m) with the FINAL maximum and accumulates P V in TMEM.
+// O therefore never needs rescaling (no TMEM read-modify-write on the critical path); the price is a second Q K^T,
+// which is cheap on the tensor core (sequences here are <= a few thousand keys).  S is double-buffered in TMEM so
+// the tensor core computes S(j+1) while the softmax warps work on S(j).
+//
+// Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer (+ TMEM allocator), warps 2-5 softmax/epilogue
+// (thread <-> query row / TMEM lane).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cudaTypedefs.h>
+
+#include "../../include/srb.h"
+#include "srb_common.h"
+#include "srb_convgemm.cuh"   // EpiWarp / scatter_store coalescing helpers, PTX wrappers
+
+namespace srb {
+
+struct AttnParams {
+  CUtensorMap tm_qk;   // 3-D (ld, frames, batch), box (64, 128, 1)
+  CUtensorMap tm_vt;   // 2-D (m_pad, 256), box (64, 128)
+  const int* lengths;
+  __nv_bfloat16* out;  // (B, N, 256)
+  int frames;
+  int k_col;           // first column of k in the q|k buffer (256)
+};
+
+constexpr int kAttnTile = 128;
+constexpr int kHalfBytes = 128 * 128;          // one [128 rows][64 bf16] swizzled half tile = 16 KB
+constexpr int kTileBytes = 2 * kHalfBytes;     // 32 KB
+
+struct AttnSmem {
+  static constexpr int q = 0;
+  static constexpr int k = q + kTileBytes;             // 2 stages
+  static constexpr int v = k + 2 * kTileBytes;         // 2 stages
+  static constexpr int p = v + 2 * kTileBytes;
+  static constexpr int stage = p + kTileBytes;         // 4 x 4 KB coalescing buffers
+  static constexpr int bars = stage + 4 * 4096;
+  static constexpr int n_bars = 16;
+  static constexpr int tmem = bars + 8 * n_bars;
+  static constexpr int total = tmem + 16 + 1024;       // + alignment slack
+};
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(192, 1) attn_tc_kernel(const __grid_constant__ AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (sbase - smem_u32(smem_raw));
+  const uint32_t s_q = sbase + AttnSmem::q, s_k = sbase + AttnSmem::k, s_v = sbase + AttnSmem::v, s_p = sbase + AttnSmem::p;
+  const uint32_t bar0 = sbase + AttnSmem::bars;
+  const uint32_t q_full = bar0;
+  auto k_full = [&](int s) { return bar0 + 8u * (1 + s); };
+  auto k_empty = [&](int s) { return bar0 + 8u * (3 + s); };
+  auto v_full = [&](int s) { return bar0 + 8u * (5 + s); };
+  auto v_empty = [&](int s) { return bar0 + 8u * (7 + s); };
+  auto s_full = [&](int s) { return bar0 + 8u * (9 + s); };
+  auto s_empty = [&](int s) { return bar0 + 8u * (11 + s); };
+  const uint32_t p_full = bar0 + 8u * 13, p_empty = bar0 + 8u * 14, o_full = bar0 + 8u * 15;
+  const uint32_t tmem_slot = sbase + AttnSmem::tmem;
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * kAttnTile;
+  int len = p.lengths[b];
+  len = len < p.frames ? len : p.frames;
+  const int nkv = (len + kAttnTile - 1) / kAttnTile;
+#ifndef SRB_ATTN_DEBUG
+#define SRB_ATTN_DEBUG 3
+#endif
+  const int npass = SRB_ATTN_DEBUG >= 3 ? 2 : (SRB_ATTN_DEBUG == 2 ? 1 : 0);
+
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(k_full(s), 1);
+      mbar_init(k_empty(s), 1);
+      mbar_init(v_full(s), 1);
+      mbar_init(v_empty(s), 1);
+      mbar_init(s_full(s), 1);
+      mbar_init(s_empty(s), 4);
+    }
+    mbar_init(p_full, 4);
+    mbar_init(p_empty, 1);
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&p.tm_qk);
+    tma_prefetch_desc(&p.tm_vt);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + AttnSmem::tmem);
+  const uint32_t t_s0 = tmem_base, t_o = tmem_base + 256;
+  constexpr uint32_t IDESC = umma_idesc_bf16(128, 128);
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    mbar_expect_tx_elect(q_full, kTileBytes);
+    tma_load_3d_elect(s_q, &p.tm_qk, q_full, h * 128, q0, b);
+    tma_load_3d_elect(s_q + kHalfBytes, &p.tm_qk, q_full, h * 128 + 64, q0, b);
+    int kst = 0, vst = 0;
+    uint32_t kph = 0, vph = 0;
+    for (int pass = 0; pass < npass; ++pass) {
+      for (int j = 0; j < nkv; ++j) {
+        mbar_wait(k_empty(kst), kph ^ 1u);
+        mbar_expect_tx_elect(k_full(kst), kTileBytes);
+        tma_load_3d_elect(s_k + kst * kTileBytes, &p.tm_qk, k_full(kst), p.k_col + h * 128, j * kAttnTile, b);
+        tma_load_3d_elect(s_k + kst * kTileBytes + kHalfBytes, &p.tm_qk, k_full(kst), p.k_col + h * 128 + 64, j * kAttnTile, b);
+        if (++kst == 2) { kst = 0; kph ^= 1u; }
+        if (pass == 1) {
+          mbar_wait(v_empty(vst), vph ^ 1u);
+          mbar_expect_tx_elect(v_full(vst), kTileBytes);
+          const int col = b * p.frames + j * kAttnTile;
+#if SRB_ATTN_DEBUG == 4
+          (void)col;
+          tma_load_3d_elect(s_v + vst * kTileBytes, &p.tm_qk, v_full(vst), h * 128, j * kAttnTile, b);
+          tma_load_3d_elect(s_v + vst * kTileBytes + kHalfBytes, &p.tm_qk, v_full(vst), h * 128 + 64, j * kAttnTile, b);
+#else
+          tma_load_2d_elect(s_v + vst * kTileBytes, &p.tm_vt, v_full(vst), col, h * 128);
+          tma_load_2d_elect(s_v + vst * kTileBytes + kHalfBytes, &p.tm_vt, v_full(vst), col + 64, h * 128);
+#endif
+          if (++vst == 2) { vst = 0; vph ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================= MMA issuer (converged warp, elected lane issues) =================
+    mbar_wait(q_full, 0);
+    tc_fence_after();
+    int kst = 0, vst = 0;
+    uint32_t kph = 0, vph = 0;
+    int t = 0;   // S tiles issued so far (buffer = t & 1)
+    auto issue_s = [&]() {
+      const int sb = t & 1;
+      mbar_wait(k_full(kst), kph);
+      mbar_wait(s_empty(sb), ((t >> 1) & 1) ^ 1u);
+      tc_fence_after();
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {
+        const uint32_t off = (kk >> 2) * kHalfBytes + (kk & 3) * 32;
+        umma_bf16_pred(1u, t_s0 + sb * 128, umma_smem_desc<128>(s_q + off), umma_smem_desc<128>(s_k + kst * kTileBytes + off),
+                       IDESC, kk != 0 ? 1u : 0u);
+      }
+      umma_commit_pred(1u, k_empty(kst));
+      umma_commit_pred(1u, s_full(sb));
+      if (++kst == 2) { kst = 0; kph ^= 1u; }
+      ++t;
+    };
+    if (npass >= 1) for (int j = 0; j < nkv; ++j) issue_s();          // pass 1: maxima only
+    if (npass >= 2 && nkv > 0) issue_s();                            // pass 2, tile 0
+    for (int j = 0; j < (npass >= 2 ? nkv : 0); ++j) {
+      if (j + 1 < nkv) issue_s();                      // S(j+1) overlaps the softmax of S(j)
+      mbar_wait(p_full, j & 1);
+      mbar_wait(v_full(vst), vph);
+      tc_fence_after();
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {
+        const uint32_t off = (kk >> 2) * kHalfBytes + (kk & 3) * 32;
+        umma_bf16_pred(1u, t_o, umma_smem_desc<128>(s_p + off), umma_smem_desc<128>(s_v + vst * kTileBytes + off), IDESC,
+                       (j != 0 || kk != 0) ? 1u : 0u);
+      }
+      umma_commit_pred(1u, v_empty(vst));
+      umma_commit_pred(1u, p_empty);
+      if (++vst == 2) { vst = 0; vph ^= 1u; }
+    }
+    umma_commit_pred(1u, o_full);
+    __syncwarp();
+  } else {
+    // ================= softmax / epilogue warps =================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;                  // query row inside the tile = TMEM lane
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    const float sl2 = 0.08838834764831845f * 1.4426950408889634f;   // (1/sqrt(128)) * log2(e)
+    int t = 0;
+    float m = -INFINITY;
+    for (int j = 0; j < (npass >= 1 ? nkv : 0); ++j, ++t) {
+      const int sb = t & 1;
+      mbar_wait(s_full(sb), (t >> 1) & 1);
+      tc_fence_after();
+      const int key0 = j * kAttnTile;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(t_s0 + sb * 128 + lane_addr + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (key0 + c * 32 + i < len) m = fmaxf(m, __uint_as_float(v[i]));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty(sb));
+    }
+    const float m2 = m * sl2;     // finite: every utterance has at least one valid key
+    float l = 0.f;
+    for (int j = 0; j < (npass >= 2 ? nkv : 0); ++j, ++t) {
+      const int sb = t & 1;
+      mbar_wait(s_full(sb), (t >> 1) & 1);
+      tc_fence_after();
+      mbar_wait(p_empty, (j & 1) ^ 1u);   // P V of the previous tile has finished reading the P buffer
+      const int key0 = j * kAttnTile;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(t_s0 + sb * 128 + lane_addr + c * 32, v);
+        tmem_ld_wait();
+        uint32_t o[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int key = key0 + c * 32 + 2 * i;
+          const float p0 = key < len ? ex2_approx(fmaf(__uint_as_float(v[2 * i]), sl2, -m2)) : 0.f;
+          const float p1 = key + 1 < len ? ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), sl2, -m2)) : 0.f;
+          l += p0 + p1;
+          o[i] = pack_bf16(p0, p1);
+        }
+        // P tile: two [128 rows][64 keys] halves, 128-byte rows, 16-byte pieces XOR-swizzled by (row & 7)
+        uint8_t* prow = smem + AttnSmem::p + (c >> 1) * kHalfBytes + row * 128;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int piece = (c & 1) * 4 + i;
+          *reinterpret_cast<uint4*>(prow + ((piece ^ (row & 7)) << 4)) = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(s_empty(sb));
+        mbar_arrive(p_full);
+      }
+    }
+    // ---- epilogue: O / l -> bf16 -> (B, N, 256)
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const float inv = l > 0.f ? 1.f / l : 0.f;
+    EpiWarp w;
+    w.stage = smem + AttnSmem::stage + (warp - 2) * 4096;
+    w.lane = lane;
+    w.row0 = q0 + quarter * 32;
+    const int vrows = clamp_rows(p.frames, w.row0);
+    __nv_bfloat16* out = p.out + ((long long)b * p.frames + w.row0) * 256 + h * 128;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint32_t v[32];
+      tmem_ld32(t_o + lane_addr + c * 32, v);
+      tmem_ld_wait();
+      uint4 o[4];
+      uint32_t* ow = reinterpret_cast<uint32_t*>(o);
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        ow[i] = nkv > 0 ? pack_bf16(__uint_as_float(v[2 * i]) * inv, __uint_as_float(v[2 * i + 1]) * inv) : 0u;
+      scatter_store<4>(w, o, out + c * 32, 512, vrows);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+static PFN_cuTensorMapEncodeTiled_v12000 attn_get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  }
+  return fn;
+}
+
+}  // namespace srb
+
+using namespace srb;
+
+extern "C" int srb_cfm_attention_tc(const void* qk_bf16, int32_t ld, const void* vt_bf16, int64_t m_pad,
+                                    const int32_t* lengths, void* o_bf16, int32_t batch, int32_t frames, void* stream) {
+  if (batch <= 0 || frames <= 0) return 0;
+  auto enc = attn_get_encode();
+  SRB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  SRB_REQUIRE(ld >= 512 && ld % 8 == 0 && m_pad % 8 == 0 && m_pad >= (int64_t)batch * frames, "srb_cfm_attention_tc: bad strides");
+  SRB_REQUIRE(frames % 8 == 0, "srb_cfm_attention_tc: frames must be a multiple of 8 (TMA box origins in v^T must be 16-byte aligned)");
+  AttnParams p;
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)ld, (cuuint64_t)frames, (cuuint64_t)batch};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)frames * ld * 2};
+    cuuint32_t box[3] = {64, 128, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&p.tm_qk, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(qk_bf16), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SRB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(q|k) failed: %d", (int)r);
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)m_pad, 256};
+    cuuint64_t strides[1] = {(cuuint64_t)m_pad * 2};
+    cuuint32_t box[2] = {64, 128};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&p.tm_vt, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(vt_bf16), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SRB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(v^T) failed: %d", (int)r);
+  }
+  p.lengths = lengths;
+  p.out = static_cast<__nv_bfloat16*>(o_bf16);
+  p.frames = frames;
+  p.k_col = 256;
+  static bool configured[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!configured[dev & 63]) {
+    SRB_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::total));
+    configured[dev & 63] = true;
+  }
+  dim3 grid((frames + kAttnTile - 1) / kAttnTile, 2, batch);
+  attn_tc_kernel<<<grid, 192, AttnSmem::total, (cudaStream_t)stream>>>(p);
+  return after_launch("attn_tc_kernel");
+}

@@ -347,6 +347,53 @@ int srb_cfm_qkv_rope(const void* xn_bf16, const void* w_packed, const float* rot
   return launch_convgemm(d, (cudaStream_t)stream);
 }
 
+int srb_cfm_qk_rope(const void* xn_bf16, const void* w_packed, const float* rot_cos, const float* rot_sin,
+                    void* qk_bf16, int32_t batch, int32_t frames, void* stream) {
+  // q and k only (first 512 rows of to_qkv.weight); v is produced transposed by srb_cfm_v_transposed
+  ConvGemmDesc d;
+  d.src[0] = act(xn_bf16, batch, frames, 256);
+  d.weight = w_packed;
+  d.n_total = 512;
+  d.block_n = 256;
+  d.block_k = 64;
+  d.channels = 256;
+  d.group_tap_begin[1] = 1;
+  d.group_rows[0] = frames;
+  d.batch = batch;
+  d.epilogue = EPI_QKV_ROPE;
+  d.epi = empty_epi();
+  d.epi.vec0 = rot_cos;
+  d.epi.vec1 = rot_sin;
+  d.epi.out0 = qk_bf16;
+  d.epi.out_row_stride = 512;
+  d.epi.out_batch_stride = (long long)frames * 512;
+  return launch_convgemm(d, (cudaStream_t)stream);
+}
+
+int srb_cfm_v_transposed(const void* xn_bf16, const void* wv_bf16, void* vt_bf16, int64_t m_pad, void* stream) {
+  // V^T[d][row] = sum_c Wv[d][c] * xn[row][c]: the same GEMM core with the operand roles swapped (the weight
+  // matrix is the "activation" tile, the activations are the K-major B operand), so V comes out keys-contiguous.
+  SRB_REQUIRE(m_pad > 0 && m_pad % 256 == 0, "srb_cfm_v_transposed: m_pad must be a positive multiple of 256");
+  ConvGemmDesc d;
+  d.src[0] = act(wv_bf16, 1, 256, 256);
+  d.weight = xn_bf16;
+  d.n_total = (int)m_pad;
+  d.block_n = 256;
+  d.block_k = 64;
+  d.channels = 256;
+  d.group_tap_begin[1] = 1;
+  d.group_rows[0] = 256;
+  d.batch = 1;
+  d.epilogue = EPI_GENERIC;
+  d.epi = empty_epi();
+  d.epi.out1 = vt_bf16;
+  d.epi.out_row_stride = m_pad;
+  d.epi.out_batch_stride = 0;
+  d.epi.res_row_stride = m_pad;
+  d.epi.res_batch_stride = 0;
+  return launch_convgemm(d, (cudaStream_t)stream);
+}
+
 int srb_cfm_attn_out_norm(const void* o_bf16, const void* w_packed, const float* g, const int32_t* lengths, float* x,
                           void* xn_bf16, int32_t batch, int32_t frames, void* stream) {
   ConvGemmDesc d;

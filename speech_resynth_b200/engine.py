@@ -76,14 +76,21 @@ class CFMSampler:
 
     # -- workspace --------------------------------------------------------------------------------------------
     def workspace(self, batch: int, frames: int) -> Dict[str, torch.Tensor]:
+        """`frames` must be a multiple of 8 (see `padded_frames`): the transposed-V operand of the attention kernel
+        is addressed by TMA per utterance and TMA needs 16-byte aligned box origins."""
+        assert frames % 8 == 0, "CFMSampler.workspace: frames must be padded to a multiple of 8"
         dev, m = self.device, batch * frames
+        m_pad = (m + 255) // 256 * 256
         f32 = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
         b16 = lambda *s: torch.empty(*s, dtype=torch.bfloat16, device=dev)
         return dict(
             ids=torch.zeros(batch, frames, dtype=torch.int64, device=dev),
             lengths=torch.zeros(batch, dtype=torch.int32, device=dev),
-            cond=f32(m, 256), xt=f32(batch, frames, 80), xt_b=b16(batch, frames, 80), x0=f32(m, 256), x=f32(m, 256),
-            xn=b16(m, 256), qkv=b16(m, 768), o=b16(m, 256), h=b16(m, 896),
+            cond=f32(m, 256), xt=torch.zeros(batch, frames, 80, dtype=torch.float32, device=dev),
+            xt_b=b16(batch, frames, 80), x0=f32(m, 256), x=f32(m, 256),
+            # xn is also the B operand of the V^T GEMM, read in 256-row tiles: rows >= m stay zero forever
+            xn=torch.zeros(m_pad, 256, dtype=torch.bfloat16, device=dev),
+            qk=b16(m, 512), vt=b16(256, m_pad), o=b16(m, 256), h=b16(m, 896),
             mel=f32(batch, frames, 80), mel_b=b16(batch, frames, 80),
         )
 
@@ -107,9 +114,13 @@ class CFMSampler:
         nat.call("srb_cfm_posconv_norm", P(ws["x0"]), P(w.dw_w), P(w.dw_b), P(g_step[0]), P(L), P(ws["x"]), P(ws["xn"]), b, n,
                  flops=2.0 * m * 31 * 256, nbytes=m * 256 * (4 + 4 + 2))
         for i in range(self.depth):
-            nat.call("srb_cfm_qkv_rope", P(ws["xn"]), P(w.w_qkv[i]), P(cs), P(sn), P(ws["qkv"]), b, n,
-                     flops=2.0 * m * 256 * 768)
-            nat.call("srb_cfm_attention", P(ws["qkv"]), P(L), P(ws["o"]), b, n, flops=4.0 * m * n * 256)
+            m_pad = ws["vt"].shape[1]
+            nat.call("srb_cfm_qk_rope", P(ws["xn"]), P(w.w_qkv[i]), P(cs), P(sn), P(ws["qk"]), b, n,
+                     flops=2.0 * m * 256 * 512)
+            nat.call("srb_cfm_v_transposed", P(ws["xn"]), P(w.w_qkv[i][512:]), P(ws["vt"]), m_pad,
+                     flops=2.0 * m * 256 * 256)
+            nat.call("srb_cfm_attention_tc", P(ws["qk"]), 512, P(ws["vt"]), m_pad, P(L), P(ws["o"]), b, n,
+                     flops=4.0 * m * n * 256)
             nat.call("srb_cfm_attn_out_norm", P(ws["o"]), P(w.w_out[i]), P(g_step[2 * i + 1]), P(L), P(ws["x"]), P(ws["xn"]), b, n,
                      flops=2.0 * m * 256 * 256)
             nat.call("srb_cfm_ffn_glu", P(ws["xn"]), P(w.w_ff1[i]), P(w.b_ff1[i]), P(L), P(ws["h"]), b, n,
@@ -133,6 +144,12 @@ class CFMSampler:
         nfe = len(times)
         for s in range(nfe):
             self.step(ws, g[s], dt, last=(s == nfe - 1))
+
+
+def padded_frames(frames: int) -> int:
+    """Frames are padded to a multiple of 8 inside the sampler (extra rows are ordinary pad frames: masked
+    everywhere, never visible to valid frames, dropped before the vocoder)."""
+    return (frames + 7) // 8 * 8
 
 
 def waveform_rows(frames: int) -> int:
@@ -267,20 +284,29 @@ class ResynthEngine:
         plan = self._plans.get(key)
         if plan is not None:
             return plan
-        cfm_ws = self.sampler.workspace(batch, frames)
+        n8 = padded_frames(frames)
+        cfm_ws = self.sampler.workspace(batch, n8)
         voc_ws = self.vocoder.workspace(batch, frames) if with_vocoder else {}
         self.sampler.cond_table(ode_times(dt))
-        self.sampler.rotary(frames)
+        self.sampler.rotary(n8)
+        if with_vocoder and n8 != frames:
+            # the vocoder must see exactly the caller's frames (pad frames are vocoded)
+            voc_ws["mel_in"] = torch.empty(batch, frames, 80, dtype=torch.bfloat16, device=self.device)
 
         def body():
             self.sampler.run(cfm_ws, dt, truncation)
             if with_vocoder:
-                self.vocoder.run(cfm_ws["mel_b"], voc_ws)
+                mel_b = cfm_ws["mel_b"]
+                if n8 != frames:
+                    voc_ws["mel_in"].copy_(mel_b[:, :frames])
+                    mel_b = voc_ws["mel_in"]
+                self.vocoder.run(mel_b, voc_ws)
 
         graph, n_launches = None, 0
         if self.use_graphs:
             # warm-up run outside capture (configures kernel attributes, fills caches), then capture
-            cfm_ws["ids"].fill_(1)
+            cfm_ws["ids"].zero_()
+            cfm_ws["ids"][:, :frames].fill_(1)
             cfm_ws["xt"].normal_()
             body()
             torch.cuda.current_stream().synchronize()
@@ -306,11 +332,12 @@ class ResynthEngine:
         b, n = input_ids.shape
         with torch.cuda.device(self.device):
             plan = self._plan(b, n, dt, truncation, with_vocoder)
-            plan.cfm_ws["ids"].copy_(input_ids, non_blocking=True)
+            plan.cfm_ws["ids"][:, :n].copy_(input_ids, non_blocking=True)
             if noise is None:
                 # same call as the reference (models.py:168) so a seeded run draws the same prior on the same device
                 noise = torch.randn(b, n, 80, device=self.device)
-            plan.cfm_ws["xt"].copy_(noise, non_blocking=True)
+            plan.cfm_ws["xt"].zero_()
+            plan.cfm_ws["xt"][:, :n].copy_(noise, non_blocking=True)
             self._launch(plan)
         return plan
 
@@ -318,13 +345,13 @@ class ResynthEngine:
                noise: Optional[torch.Tensor] = None) -> torch.Tensor:
         """ConditionalFlowMatchingModel.sample: (B, N) int64 -> mel (B, N, 80) fp32 (a fresh tensor)."""
         plan = self._run(input_ids, dt, truncation, noise, with_vocoder=False)
-        return plan.cfm_ws["mel"].clone()
+        return plan.cfm_ws["mel"][:, : input_ids.shape[1]].clone()
 
     def resynthesize(self, input_ids: torch.Tensor, dt: float, truncation: Optional[float],
                      noise: Optional[torch.Tensor] = None):
         """Returns (wav (B, 320 N + 80) fp32 [plan-owned buffer], lengths (B,) int32 device tensor, mel)."""
         plan = self._run(input_ids, dt, truncation, noise, with_vocoder=True)
-        return plan.voc_ws["wav"], plan.cfm_ws["lengths"], plan.cfm_ws["mel"]
+        return plan.voc_ws["wav"], plan.cfm_ws["lengths"], plan.cfm_ws["mel"][:, : input_ids.shape[1]]
 
     def vocode(self, mel: torch.Tensor) -> torch.Tensor:
         """decoder.vocoder(mel): (B, T, 80) float -> (B, 320 T + 80) fp32 (a fresh tensor)."""

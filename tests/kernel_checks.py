@@ -387,6 +387,59 @@ def cfm_attention():
 
 
 @check
+def cfm_attention_tc():
+    """tcgen05 attention (q|k buffer + transposed v) against the float64 softmax-attention definition"""
+    worst = 0.0
+    for b, n, lengths in ((3, 200, (200, 131, 64)), (2, 504, (500, 1)), (1, 136, (129,)), (2, 1024, (1024, 700))):
+        L = torch.tensor(lengths, dtype=torch.int32, device=DEV)
+        qkv = bf(torch.randn(b, n, 768, generator=g(6 + n)))
+        m_pad = (b * n + 255) // 256 * 256
+        qk = qkv[..., :512].contiguous().to(DEV).to(torch.bfloat16)
+        vt = torch.zeros(256, m_pad, dtype=torch.bfloat16, device=DEV)
+        vt[:, : b * n] = qkv[..., 512:].reshape(b * n, 256).t().to(DEV).to(torch.bfloat16)
+        o = torch.full((b, n, 256), float("nan"), dtype=torch.bfloat16, device=DEV)
+        nat.call("srb_cfm_attention_tc", P(qk), 512, P(vt), m_pad, P(L), P(o), b, n)
+        torch.cuda.synchronize()
+        q, k, v = (z.reshape(b, n, 2, 128).permute(0, 2, 1, 3).double() for z in qkv.chunk(3, dim=-1))
+        mask = torch.arange(n)[None, :] < torch.tensor(lengths)[:, None]
+        sc = torch.einsum("bhid,bhjd->bhij", q, k) / math.sqrt(128)
+        sc = sc.masked_fill(~mask[:, None, None, :], float("-inf"))
+        ref = torch.einsum("bhij,bhjd->bhid", sc.softmax(-1), v).permute(0, 2, 1, 3).reshape(b, n, 256)
+        worst = max(worst, rel_l2(o.float(), ref))
+    return worst, 1e-2
+
+
+@check
+def cfm_qk_rope_and_v_transposed():
+    s = sd()
+    pk = packing.pack_cfm(s, DEV)
+    b, n = 2, 150
+    m_pad = 512
+    xn_host = bf(torch.randn(b, n, 256, generator=g(5)))
+    xn = torch.zeros(m_pad, 256, dtype=torch.bfloat16, device=DEV)
+    xn[: b * n] = xn_host.reshape(b * n, 256).to(DEV).to(torch.bfloat16)
+    cs = torch.empty(1024, 64, device=DEV)
+    sn = torch.empty(1024, 64, device=DEV)
+    nat.call("srb_rotary_table", P(pk.inv_freq), 1024, P(cs), P(sn))
+    qk = torch.empty(b, n, 512, dtype=torch.bfloat16, device=DEV)
+    vt = torch.full((256, m_pad), float("nan"), dtype=torch.bfloat16, device=DEV)
+    wq = pk.w_qkv[1]
+    nat.call("srb_cfm_qk_rope", P(xn), P(wq), P(cs), P(sn), P(qk), b, n)
+    nat.call("srb_cfm_v_transposed", P(xn), P(wq[512:]), P(vt), m_pad)
+    w = bf(s["model.transformer.layers.1.2.to_qkv.weight"]).double()
+    r = F.linear(xn_host.double(), w)
+    q, k, v = r.chunk(3, dim=-1)
+    rot = oracle.rotary_table(s["model.transformer.rotary_emb.inv_freq"], n).double()
+    hd = lambda z: z.reshape(b, n, 2, 128).permute(0, 2, 1, 3)
+    un = lambda z: z.permute(0, 2, 1, 3).reshape(b, n, 256)
+    q, k = un(oracle.apply_rotary(rot, hd(q))), un(oracle.apply_rotary(rot, hd(k)))
+    e1 = rel_l2(qk.float(), torch.cat([q, k], dim=-1))
+    e2 = rel_l2(vt[:, : b * n].float(), v.reshape(b * n, 256).t())
+    tail_zero = bool((vt[:, b * n:].float() == 0).all())
+    return (max(e1, e2) if tail_zero else 1.0), BF16_TOL
+
+
+@check
 def cfm_attn_out_norm():
     s = sd()
     pk = packing.pack_cfm(s, DEV)
