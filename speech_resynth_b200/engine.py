@@ -36,6 +36,37 @@ def _i32(vals) -> "nat.ctypes.Array":
     return (ctypes.c_int32 * len(vals))(*vals)
 
 
+class _Fork:
+    """Run independent kernel chains on side streams (captured as parallel branches of the CUDA graph): the
+    persistent GEMM kernels leave SMs idle in their last wave, and an independent chain fills those tails."""
+
+    def __init__(self, device, n: int):
+        with torch.cuda.device(device):
+            self.side = [torch.cuda.Stream(device=device) for _ in range(n)]
+        self.enabled = True
+
+    def run(self, branches) -> None:
+        """branches: list of callables; branch 0 runs on the current stream, the others on side streams."""
+        if not self.enabled or len(branches) == 1:
+            for fn in branches:
+                fn()
+            return
+        main = torch.cuda.current_stream()
+        start = torch.cuda.Event()
+        start.record(main)
+        done = []
+        for fn, st in zip(branches[1:], self.side):
+            st.wait_event(start)
+            with torch.cuda.stream(st):
+                fn()
+                ev = torch.cuda.Event()
+                ev.record(st)
+                done.append(ev)
+        branches[0]()
+        for ev in done:
+            main.wait_event(ev)
+
+
 class CFMSampler:
     """ODE sampler over the flow-matching transformer velocity field (kernels: srb_cfm_*)."""
 
@@ -47,6 +78,7 @@ class CFMSampler:
         self.device = packed.w_embed.device
         self._rot: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
         self._cond_cache: Dict[Tuple[float, ...], torch.Tensor] = {}
+        self.fork = _Fork(self.device, 1)
 
     # -- tables -----------------------------------------------------------------------------------------------
     def rotary(self, rows: int) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -115,10 +147,13 @@ class CFMSampler:
                  flops=2.0 * m * 31 * 256, nbytes=m * 256 * (4 + 4 + 2))
         for i in range(self.depth):
             m_pad = ws["vt"].shape[1]
-            nat.call("srb_cfm_qk_rope", P(ws["xn"]), P(w.w_qkv[i]), P(cs), P(sn), P(ws["qk"]), b, n,
-                     flops=2.0 * m * 256 * 512)
-            nat.call("srb_cfm_v_transposed", P(ws["xn"]), P(w.w_qkv[i][512:]), P(ws["vt"]), m_pad,
-                     flops=2.0 * m * 256 * 256)
+            # q|k projection and the transposed-v projection both read xn only: two parallel graph branches
+            self.fork.run([
+                lambda: nat.call("srb_cfm_qk_rope", P(ws["xn"]), P(w.w_qkv[i]), P(cs), P(sn), P(ws["qk"]), b, n,
+                                 flops=2.0 * m * 256 * 512),
+                lambda: nat.call("srb_cfm_v_transposed", P(ws["xn"]), P(w.w_qkv[i][512:]), P(ws["vt"]), m_pad,
+                                 flops=2.0 * m * 256 * 256),
+            ])
             nat.call("srb_cfm_attention_tc", P(ws["qk"]), 512, P(ws["vt"]), m_pad, P(L), P(ws["o"]), b, n,
                      flops=4.0 * m * n * 256)
             nat.call("srb_cfm_attn_out_norm", P(ws["o"]), P(w.w_out[i]), P(g_step[2 * i + 1]), P(L), P(ws["x"]), P(ws["xn"]), b, n,
@@ -167,6 +202,7 @@ class HifiGanGenerator:
         self.w = packed
         self.slope = float(slope)
         self.fuse_mrf = fuse_mrf
+        self.fork = _Fork(packed.w_pre.device, 2)
         self.device = packed.w_pre.device
 
     def workspace(self, batch: int, frames: int) -> Dict[str, object]:
@@ -211,7 +247,9 @@ class HifiGanGenerator:
                          self.slope, slope_next, flops=252.0 * c * c * b * rows)
                 x_act, rows_in, c_in = st["out"], rows, c
                 continue
-            for j, rk in enumerate(RESBLOCK_KERNELS):
+            res: List[Optional[torch.Tensor]] = [None, None, None]
+
+            def chain(j: int, rk: int, st=st, rows=rows, c=c, i=i) -> None:
                 kk = _i32([rk])
                 xr, xa = st["u_raw"], st["u_act"]
                 for q, dil in enumerate(RESBLOCK_DILATIONS):
@@ -225,10 +263,12 @@ class HifiGanGenerator:
                                  P(w.b_c2[i][j][q]), P(xr), None, None, P(st["xr"][j]), P(st["xa"][j]), b, rows, c, c,
                                  1.0, self.slope, flops=2.0 * b * rows * rk * c * c)
                         xr, xa = st["xr"][j], st["xa"][j]
-                if j == 0:
-                    res = [xr]
-                else:
-                    res.append(xr)
+                res[j] = xr
+
+            # the three resblocks of a stage are independent until the MRF mean: three parallel graph branches
+            # (longest chain, k = 11, on the main stream)
+            self.fork.run([lambda: chain(2, RESBLOCK_KERNELS[2]), lambda: chain(1, RESBLOCK_KERNELS[1]),
+                           lambda: chain(0, RESBLOCK_KERNELS[0])])
             # fused MRF tail: the three last conv2's + their residuals + mean (HF:1475-1478) + the next leaky_relu
             # (slope 0.1 before an upsampler, torch default 0.01 before conv_post, HF:1480)
             slope_next = self.slope if i + 1 < n_stage else 0.01
