@@ -62,7 +62,7 @@ int srb_cfm_embed(const void* xt_bf16, const void* w_packed, const float* cond_p
 
 /* ConvPositionEmbed + residual (transformer.py:84-96, models.py:177) fused with the first AdaptiveRMSNorm
  * (norm.py:41-43):  x = gelu(dwconv31(mask(x0)) + b) * mask + x0 ;  xn = bf16(x / max(|x|,1e-12) * g) * mask
- *   dw_w [256][31] fp32, dw_b[256], g[256] (= sqrt(H)(gamma+1) for this step) */
+ *   dw_w [31][256] fp32 (tap-major), dw_b[256], g[256] (= sqrt(H)(gamma+1) for this step) */
 int srb_cfm_posconv_norm(const float* x0, const float* dw_w, const float* dw_b, const float* g, const int32_t* lengths,
                          float* x, void* xn_bf16, int32_t batch, int32_t frames, void* stream);
 

@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(256) posconv_norm_kernel(const float* __restri
   const float* xb = x0 + (long long)b * frames * 256;
   float w[K];
 #pragma unroll
-  for (int j = 0; j < K; ++j) w[j] = __ldg(dw_w + c * K + j);
+  for (int j = 0; j < K; ++j) w[j] = __ldg(dw_w + j * 256 + c);   // tap-major [31][256]: coalesced across channels
   const float bias = __ldg(dw_b + c);
   const float gc = __ldg(g + c);
   float win[ROWS + 2 * HALO];

@@ -74,7 +74,7 @@ class PackedCFM:
     cond_table: torch.Tensor          # (vocab+1, 256) fp32 : E @ W_embed[:, 80:]^T + b_embed (hoisted, loop invariant)
     emb_table: torch.Tensor           # (vocab+1, 768) fp32 : raw embedding (API parity / duration predictor)
     w_embed: torch.Tensor             # bf16 [256][128]  (xt part of to_embed, K padded 80 -> 128)
-    dw_w: torch.Tensor                # fp32 [256][31]
+    dw_w: torch.Tensor                # fp32 [31][256] (tap-major)
     dw_b: torch.Tensor
     four_w: torch.Tensor
     lin_w: torch.Tensor
@@ -138,7 +138,7 @@ def pack_cfm(sd: Dict[str, torch.Tensor], device, depth: int = 4, dim_in: int = 
         cond_table=cond_table,
         emb_table=emb,
         w_embed=w_x.to(torch.bfloat16).contiguous(),
-        dw_w=f("model.conv_embed.dw_conv1d.0.weight").reshape(hidden, -1).contiguous(),
+        dw_w=f("model.conv_embed.dw_conv1d.0.weight").reshape(hidden, -1).t().contiguous(),   # tap-major [31][256]
         dw_b=f("model.conv_embed.dw_conv1d.0.bias").contiguous(),
         four_w=f("model.time_cond_mlp.0.weights").contiguous(),
         lin_w=f("model.time_cond_mlp.1.weight").contiguous(),
