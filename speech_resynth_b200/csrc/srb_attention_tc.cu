@@ -44,8 +44,8 @@ struct AttnSmem {
   static constexpr int k = q + kTileBytes;             // 2 stages
   static constexpr int v = k + 2 * kTileBytes;         // 2 stages
   static constexpr int p = v + 2 * kTileBytes;
-  static constexpr int stage = p + kTileBytes;         // 4 x 4 KB coalescing buffers
-  static constexpr int bars = stage + 4 * 4096;
+  static constexpr int stage = p + kTileBytes;         // 4 x 2 KB coalescing buffers (bf16 blocks, 4 pieces per row)
+  static constexpr int bars = stage + 4 * 2048;
   static constexpr int n_bars = 16;
   static constexpr int tmem = bars + 8 * n_bars;
   static constexpr int total = tmem + 16 + 1024;       // + alignment slack
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(192, 1) attn_tc_kernel(const __grid_constant__
     tc_fence_after();
     const float inv = l > 0.f ? 1.f / l : 0.f;
     EpiWarp w;
-    w.stage = smem + AttnSmem::stage + (warp - 2) * 4096;
+    w.stage = smem + AttnSmem::stage + (warp - 2) * 2048;
     w.lane = lane;
     w.row0 = q0 + quarter * 32;
     const int vrows = clamp_rows(p.frames, w.row0);

@@ -5,6 +5,7 @@
 #include <cudaTypedefs.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/srb.h"
@@ -116,10 +117,19 @@ struct ConvGemmDesc {
   ConvGemmParams epi;                       // only the epilogue-operand fields are read from here
 };
 
-template <int BN, int KB, int EPI>
+static bool multicast_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SRB_MULTICAST");   // opt-in: correct, but no measurable gain yet
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
+template <int BN, int KB, int EPI, int MC = 0>
 static int launch_inst(ConvGemmParams& p, int total_tiles, cudaStream_t stream) {
   using L = StageLayout<BN, KB>;
-  auto kernel = convgemm_kernel<BN, KB, EPI>;
+  auto kernel = convgemm_kernel<BN, KB, EPI, MC>;
   // two rings: activation boxes (one per K chunk, reused by all taps) and weight slabs (one per tap and K chunk)
   constexpr int threads = 64 + 32 * EpiWarps<BN, EPI>::value;
   const int a_bytes = p.a_box_bytes;
@@ -127,10 +137,17 @@ static int launch_inst(ConvGemmParams& p, int total_tiles, cudaStream_t stream) 
   if (L::w_bytes >= 32 * 1024) { a_stages = 3; w_stages = 4; }        // wide tiles: one CTA per SM
   else if (L::w_bytes >= 8 * 1024) { a_stages = 2; w_stages = 4; }    // two CTAs per SM
   else { a_stages = 2; w_stages = 6; }
+  {
+    // experiment knobs (profiling only)
+    const char* ea = getenv("SRB_A_STAGES");
+    const char* ew = getenv("SRB_W_STAGES");
+    if (ea && L::w_bytes >= 32 * 1024) a_stages = atoi(ea);
+    if (ew && L::w_bytes >= 32 * 1024) w_stages = atoi(ew);
+  }
   while (a_stages * a_bytes + w_stages * L::w_bytes > 208 * 1024 && w_stages > 2) --w_stages;
   p.a_stages = a_stages;
   p.w_stages = w_stages;
-  constexpr int stage_smem = EpiWarps<BN, EPI>::value * 4096 + 128;   // coalescing buffers of the epilogue warps
+  constexpr int stage_smem = EpiWarps<BN, EPI>::value * EpiWarps<BN, EPI>::stage_bytes + 128;   // coalescing buffers of the epilogue warps
   while (a_stages * a_bytes + w_stages * L::w_bytes + stage_smem > 222 * 1024 && w_stages > 2) --w_stages;
   p.w_stages = w_stages;
   const int smem = a_stages * a_bytes + w_stages * L::w_bytes + 1024 + 8 * (2 * (a_stages + w_stages) + 4) + 16 + 1024 + stage_smem;
@@ -158,6 +175,27 @@ static int launch_inst(ConvGemmParams& p, int total_tiles, cudaStream_t stream) 
   occ = occ < by_tmem ? occ : by_tmem;
   occ = occ < 1 ? 1 : occ;
   int grid = num_sms() * occ;
+  if constexpr (MC) {
+    // 2-CTA clusters; `total_tiles` counts PAIRS of row tiles here
+    int clusters = grid / 2;
+    if (clusters > total_tiles) clusters = total_tiles;
+    if (clusters < 1) return 0;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SRB_CUDA(cudaLaunchKernelEx(&cfg, kernel, p, total_tiles));
+    return after_launch("convgemm_kernel(multicast)");
+  }
   if (grid > total_tiles) grid = total_tiles;
   if (grid < 1) return 0;
   kernel<<<grid, threads, smem, stream>>>(p, total_tiles);
@@ -235,6 +273,20 @@ static int launch_convgemm(const ConvGemmDesc& d, cudaStream_t stream) {
   int rc = make_weight_map(&p.tmW, d.weight, k_total, d.n_total, kb, bn);
   if (rc) return rc;
   if (tiles == 0) return 0;
+  // weight multicast across 2-CTA clusters for the wide tiles (needs an even number of row tiles)
+  const int row_tiles = d.batch * p.m_tiles[0];
+  const bool mc = multicast_enabled() && bn == 256 && kb == 64 && d.n_groups == 1 && row_tiles % 2 == 0 && row_tiles >= 2;
+  if (mc) {
+    rc = make_weight_map(&p.tmWh, d.weight, k_total, d.n_total, kb, bn / 2);
+    if (rc) return rc;
+    const int pair_tiles = (row_tiles / 2) * p.n_tiles;
+    if (d.epilogue == EPI_GENERIC) return launch_inst<256, 64, EPI_GENERIC, 1>(p, pair_tiles, stream);
+    if (d.epilogue == EPI_GLU) return launch_inst<256, 64, EPI_GLU, 1>(p, pair_tiles, stream);
+    if (d.epilogue == EPI_RESNORM) return launch_inst<256, 64, EPI_RESNORM, 1>(p, pair_tiles, stream);
+    if (d.epilogue == EPI_QKV_ROPE) return launch_inst<256, 64, EPI_QKV_ROPE, 1>(p, pair_tiles, stream);
+  } else {
+    p.tmWh = p.tmW;
+  }
 
 #define SRB_DISPATCH(BN_, KB_, EPI_) \
   if (bn == BN_ && kb == KB_ && d.epilogue == EPI_) return launch_inst<BN_, KB_, EPI_>(p, tiles, stream);

@@ -31,6 +31,7 @@ enum Epilogue : int { EPI_GENERIC = 0, EPI_GLU = 1, EPI_RESNORM = 2, EPI_QKV_ROP
 struct ConvGemmParams {
   CUtensorMap tmA[kMaxSrc];
   CUtensorMap tmW;
+  CUtensorMap tmWh;                               // weight map with a half-height box (2-CTA multicast variant)
   // problem
   int batch, kchunks, n_groups, n_tiles;          // n_tiles = n_total / BN
   int m_tiles[kMaxGroups];                        // row tiles per batch, per group
@@ -110,13 +111,16 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvGemmParams& p, int ti
 // (32/P rows x P*16 contiguous bytes per instruction), in shared memory it reads/writes its own row; 16-byte pieces
 // are XOR-swizzled by row so both sides are bank-conflict free.
 struct EpiWarp {
-  uint8_t* stage;   // 32 rows x 128 B
+  uint8_t* stage;   // 32 rows x (P * 16) bytes, P = pieces per row of the widest block the epilogue moves
   int lane;
   int row0;         // first tile-local output row q of this warp
 };
 
+// row pitch = P * 16 bytes; the XOR keeps every 8-lane phase of a 128-bit access on distinct banks
+template <int P>
 __device__ __forceinline__ uint4* stage_slot(uint8_t* stage, int row, int piece) {
-  return reinterpret_cast<uint4*>(stage + row * 128 + ((piece ^ (row & 7)) << 4));
+  const int swz = P == 8 ? (row & 7) : (P == 4 ? ((row >> 1) & 3) : ((row >> 2) & 1));
+  return reinterpret_cast<uint4*>(stage + row * (P * 16) + ((piece ^ swz) << 4));
 }
 
 // issue the coalesced loads of a 32 x (P*16 B) block (rows >= valid_rows read as zero)
@@ -135,24 +139,24 @@ __device__ __forceinline__ void gather_finish(const EpiWarp& w, const uint4* t, 
 #pragma unroll
   for (int i = 0; i < P; ++i) {
     const int idx = w.lane + 32 * i;
-    *stage_slot(w.stage, idx / P, idx % P) = t[i];
+    *stage_slot<P>(w.stage, idx / P, idx % P) = t[i];
   }
   __syncwarp();
 #pragma unroll
-  for (int j = 0; j < P; ++j) v[j] = *stage_slot(w.stage, w.lane, j);
+  for (int j = 0; j < P; ++j) v[j] = *stage_slot<P>(w.stage, w.lane, j);
   __syncwarp();
 }
 // v[j] = piece j of this lane's row  ->  coalesced global stores of the 32 x (P*16 B) block
 template <int P>
 __device__ __forceinline__ void scatter_store(const EpiWarp& w, const uint4* v, void* gbase, long long row_stride_bytes, int valid_rows) {
 #pragma unroll
-  for (int j = 0; j < P; ++j) *stage_slot(w.stage, w.lane, j) = v[j];
+  for (int j = 0; j < P; ++j) *stage_slot<P>(w.stage, w.lane, j) = v[j];
   __syncwarp();
   uint8_t* g = static_cast<uint8_t*>(gbase);
 #pragma unroll
   for (int i = 0; i < P; ++i) {
     const int idx = w.lane + 32 * i, row = idx / P, piece = idx % P;
-    const uint4 x = *stage_slot(w.stage, row, piece);
+    const uint4 x = *stage_slot<P>(w.stage, row, piece);
     if (row < valid_rows) *reinterpret_cast<uint4*>(g + row * row_stride_bytes + piece * 16) = x;
   }
   __syncwarp();
@@ -292,10 +296,10 @@ __device__ __forceinline__ void epi_glu(const ConvGemmParams& p, uint32_t tacc, 
     for (int j = 0; j < 8; ++j) {
       const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + c0) + j);
       const float4 bg = __ldg(reinterpret_cast<const float4*>(bias + 128 + c0) + j);
-      const float h0 = silu_fast(__uint_as_float(g[4 * j + 0]) + bg.x) * (__uint_as_float(v[4 * j + 0]) + bv.x);
-      const float h1 = silu_fast(__uint_as_float(g[4 * j + 1]) + bg.y) * (__uint_as_float(v[4 * j + 1]) + bv.y);
-      const float h2 = silu_fast(__uint_as_float(g[4 * j + 2]) + bg.z) * (__uint_as_float(v[4 * j + 2]) + bv.z);
-      const float h3 = silu_fast(__uint_as_float(g[4 * j + 3]) + bg.w) * (__uint_as_float(v[4 * j + 3]) + bv.w);
+      const float h0 = silu_tanh(__uint_as_float(g[4 * j + 0]) + bg.x) * (__uint_as_float(v[4 * j + 0]) + bv.x);
+      const float h1 = silu_tanh(__uint_as_float(g[4 * j + 1]) + bg.y) * (__uint_as_float(v[4 * j + 1]) + bv.y);
+      const float h2 = silu_tanh(__uint_as_float(g[4 * j + 2]) + bg.z) * (__uint_as_float(v[4 * j + 2]) + bv.z);
+      const float h3 = silu_tanh(__uint_as_float(g[4 * j + 3]) + bg.w) * (__uint_as_float(v[4 * j + 3]) + bv.w);
       ow[2 * j] = keep ? pack_bf16(h0, h1) : 0u;       // pads are zeroed before conv2 (fastspeech/modules.py:69)
       ow[2 * j + 1] = keep ? pack_bf16(h2, h3) : 0u;
     }
@@ -535,10 +539,27 @@ __device__ __forceinline__ void epi_euler(const ConvGemmParams& p, uint32_t tacc
 template <int BN, int EPI>
 struct EpiWarps {
   // eight epilogue warps (two column halves per TMEM lane quarter) for the wide tiles, four otherwise
-  static constexpr int value = (BN >= 128 && EPI != EPI_EULER) ? 8 : 4;
+  // (sixteen for the FFN GLU tile, whose SiLU epilogue is transcendental-bound and needs the extra latency hiding)
+  static constexpr int value = EPI == EPI_GLU ? 16 : ((BN >= 128 && EPI != EPI_EULER) ? 8 : 4);
+  // staging bytes per epilogue warp: fp32 / rotary-table blocks are 8 pieces wide, bf16 blocks at most 4
+  static constexpr int stage_bytes = (EPI == EPI_RESNORM || EPI == EPI_QKV_ROPE) ? 4096 : 2048;
 };
 
-template <int BN, int KB, int EPI>
+// MC = 1: launched as 2-CTA clusters.  The two CTAs of a cluster work on the same output-channel tile and on adjacent
+// row tiles, so they consume the same weight slabs: each CTA fetches HALF of every slab and TMA-multicasts it into both
+// shared memories, halving the L2 -> SM weight traffic that bounds the wide (BN = 256) GEMMs.  A slab slot is reused
+// only after BOTH CTAs have consumed it (the MMA warps commit onto both CTAs' w_empty barriers).
+__device__ __forceinline__ TileCoord decode_tile_mc(const ConvGemmParams& p, int pair_tile, int rank) {
+  TileCoord c;
+  c.group = 0;
+  c.n = pair_tile % p.n_tiles;
+  const int fm = 2 * (pair_tile / p.n_tiles) + rank;
+  c.b = fm / p.m_tiles[0];
+  c.m = fm % p.m_tiles[0];
+  return c;
+}
+
+template <int BN, int KB, int EPI, int MC = 0>
 __global__ void __launch_bounds__(64 + 32 * EpiWarps<BN, EPI>::value)
 convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
   using L = StageLayout<BN, KB>;
@@ -570,6 +591,11 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform (uniform datapath)
   const int lane = threadIdx.x & 31;
+  // tile walk: CTA (or, with MC, cluster) `walker` of `n_walkers` takes tiles walker, walker + n_walkers, ...
+  const int mc_rank = MC ? static_cast<int>(cluster_ctarank()) : 0;
+  const int walker = MC ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int n_walkers = MC ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  auto decode = [&](int tile) { return MC ? decode_tile_mc(p, tile, mc_rank) : decode_tile(p, tile); };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < a_stages; ++s) {
@@ -578,7 +604,7 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
     }
     for (int s = 0; s < w_stages; ++s) {
       mbar_init(w_full(s), 1);
-      mbar_init(w_empty(s), 1);
+      mbar_init(w_empty(s), MC ? 2 : 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);
@@ -594,6 +620,7 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (MC) cluster_sync_all();   // peer barriers are initialised before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
@@ -603,8 +630,8 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
       int ai = 0, wi = 0;
       uint32_t aph = 0, wph = 0;
       const uint32_t a_tx = static_cast<uint32_t>(p.a_box_rows) * KB * 2;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileCoord tc = decode_tile(p, tile);
+      for (int tile = walker; tile < total_tiles; tile += n_walkers) {
+        const TileCoord tc = decode(tile);
         const int t0 = tc.m * kTileM;
         for (int sg = p.group_seg_begin[tc.group]; sg < p.group_seg_begin[tc.group + 1]; ++sg) {
           const int src = p.seg_src[sg];
@@ -618,7 +645,13 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
             for (int t = tb; t < te; ++t) {
               mbar_wait(w_empty(wi), wph ^ 1u);
               mbar_expect_tx_elect(w_full(wi), L::w_bytes_raw);
-              tma_load_2d_elect(w_ring + wi * L::w_bytes, &p.tmW, w_full(wi), (t * p.kchunks + kc) * KB, tc.n * BN);
+              if constexpr (MC) {
+                // my half of the slab (BN/2 rows), written into both CTAs
+                tma_load_2d_mc_elect(w_ring + wi * L::w_bytes + mc_rank * (L::w_bytes_raw / 2), &p.tmWh, w_full(wi),
+                                     (t * p.kchunks + kc) * KB, tc.n * BN + mc_rank * (BN / 2), (uint16_t)3);
+              } else {
+                tma_load_2d_elect(w_ring + wi * L::w_bytes, &p.tmW, w_full(wi), (t * p.kchunks + kc) * KB, tc.n * BN);
+              }
               if (++wi == w_stages) { wi = 0; wph ^= 1u; }
             }
           }
@@ -633,8 +666,8 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
       int ai = 0, wi = 0;
       uint32_t aph = 0, wph = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const TileCoord tc = decode_tile(p, tile);
+      for (int tile = walker; tile < total_tiles; tile += n_walkers, ++it) {
+        const TileCoord tc = decode(tile);
         const int buf = it & 1;
         const uint32_t bphase = (it >> 1) & 1;
         mbar_wait(tempty_bar(buf), bphase ^ 1u);
@@ -656,7 +689,8 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
               for (int k = 0; k < KB / 16; ++k)
                 umma_bf16_pred(1u, tacc, adesc + 2 * k, wdesc + 2 * k, IDESC, (first && k == 0) ? 0u : 1u);
               first = 0;
-              umma_commit_pred(1u, w_empty(wi));
+              if constexpr (MC) umma_commit_mc_pred(w_empty(wi), (uint16_t)3);
+              else umma_commit_pred(1u, w_empty(wi));
               if (++wi == w_stages) { wi = 0; wph ^= 1u; }
             }
             umma_commit_pred(1u, a_empty(ai));
@@ -672,13 +706,13 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
     const int half = (warp - 2) >> 2;           // column half (0 when EW == 4)
     const int lane_base = quarter * 32;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const TileCoord tc = decode_tile(p, tile);
+    for (int tile = walker; tile < total_tiles; tile += n_walkers, ++it) {
+      const TileCoord tc = decode(tile);
       const int buf = it & 1;
       const uint32_t bphase = (it >> 1) & 1;
       const int q = tc.m * kTileM + lane_base + lane;
       EpiWarp ew;
-      ew.stage = stage_base + (warp - 2) * 4096;
+      ew.stage = stage_base + (warp - 2) * EpiWarps<BN, EPI>::stage_bytes;
       ew.lane = lane;
       ew.row0 = tc.m * kTileM + lane_base;
       uint4 pre[16];
@@ -700,6 +734,7 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (MC) cluster_sync_all();   // no CTA may exit while its peer can still multicast into it
   if (warp == 1) tmem_dealloc(tmem_base, TCOLS);
 }
 

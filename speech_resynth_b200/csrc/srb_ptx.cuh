@@ -97,6 +97,36 @@ __device__ __forceinline__ void tma_load_3d_elect(uint32_t dst, const void* tmap
       : "memory");
 }
 
+// ---- 2-CTA cluster helpers (weight-slab multicast)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose box is written to the same CTA-relative smem offset of every CTA in `mask`, signalling the mbarrier
+// at the same offset in each of them
+__device__ __forceinline__ void tma_load_2d_mc_elect(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;\n\t}"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+// commit that arrives on the mbarrier at the same CTA-relative offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mc_pred(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+      ::"r"(bar), "h"(mask)
+      : "memory");
+}
+
 // ------------------------------------------------------------------ tcgen05
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
@@ -250,5 +280,13 @@ __device__ __forceinline__ float lrelu(float x, float slope) { return x > 0.f ? 
 __device__ __forceinline__ float silu(float x) { return x / (1.f + __expf(-x)); }
 // MUFU.EX2 + MUFU.RCP form (relative error ~2 ulp of fp32; the result is rounded to bf16 right after)
 __device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.f + __expf(-x)); }
+// silu(x) = x * sigmoid(x) = 0.5 x (1 + tanh(0.5 x)): ONE MUFU op (tanh.approx, abs error ~5e-4 on the sigmoid,
+// below the bf16 rounding of the result) instead of EX2 + RCP
+__device__ __forceinline__ float silu_tanh(float x) {
+  float t;
+  const float hx = 0.5f * x;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(hx));
+  return fmaf(hx, t, hx);
+}
 
 }  // namespace srb
