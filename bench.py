@@ -136,6 +136,9 @@ def op_profile(engine, ids, x0):
     from speech_resynth_b200 import _native as nat
 
     plan = engine._plan(ids.shape[0], ids.shape[1], DT, TRUNC, True)
+    # serialise the parallel graph branches for this pass so every kernel is timed alone
+    engine.sampler.fork.enabled = False
+    engine.vocoder.fork.enabled = False
     plan.cfm_ws["ids"][:, : ids.shape[1]].copy_(ids)
     plan.cfm_ws["xt"].zero_()
     plan.cfm_ws["xt"][:, : ids.shape[1]].copy_(x0)
@@ -144,9 +147,11 @@ def op_profile(engine, ids, x0):
     plan.body()
     torch.cuda.synchronize()
     log, nat.profile_log = nat.profile_log, None
+    engine.sampler.fork.enabled = True
+    engine.vocoder.fork.enabled = True
     agg = {}
     for name, tag, e0, e1, flops, nbytes in log:
-        key = (name, tag)
+        key = (name, tag + (int(flops),))   # launches of one op with different kernel sizes are different rows
         a = agg.setdefault(key, {"ms": 0.0, "n": 0, "flops": flops, "bytes": nbytes})
         a["ms"] += e0.elapsed_time(e1)
         a["n"] += 1
@@ -236,9 +241,14 @@ def gpu_run(args):
         achieved = top["flops"] / avg_s / 1e12
         from oracle import cfm_hifigan_oracle as oracle
         flops_step = BATCH * (oracle.transformer_flops(FRAMES, 16, hoisted=True) + oracle.vocoder_flops(FRAMES))
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(top_name)   # dram read+write bytes per launch from an ncu --set full capture
         roofline = {
-            "bound": "tensor", "kernel": f"{top_name}{list(top_tag)}", "achieved": achieved, "peak": pk["bf16_sustained"],
-            "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"], "traffic": None,
+            "bound": "tensor", "kernel": f"{top_name}{list(top_tag[:-1])}", "achieved": achieved, "peak": pk["bf16_sustained"],
+            "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"], "traffic": traffic,
+            "algorithmic_flops_per_launch": top["flops"],
             "peak_source": f"{pk['src']} sustained bf16 (kernel timed inside the step)",
             "launches_per_step": top["n"], "avg_launch_ms": top["ms"] / top["n"], "share_of_step": top["ms"] / total_ms,
             "whole_step": {"algorithmic_tflop": flops_step / 1e12,

@@ -117,13 +117,16 @@ struct ConvGemmDesc {
   ConvGemmParams epi;                       // only the epilogue-operand fields are read from here
 };
 
-static bool multicast_enabled() {
+// cluster mode of the wide (BN = 256) tiles: 0 = single CTA, 1 = weight-slab multicast, 2 = CTA-pair MMA
+// (cta_group::2).  SRB_CLUSTER_MODE overrides the default.
+static int cluster_mode() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("SRB_MULTICAST");   // opt-in: correct, but no measurable gain yet
-    v = (e && e[0] == '1') ? 1 : 0;
+    const char* e = getenv("SRB_CLUSTER_MODE");
+    v = e ? atoi(e) : 0;
+    if (v < 0 || v > 2) v = 0;
   }
-  return v == 1;
+  return v;
 }
 
 template <int BN, int KB, int EPI, int MC = 0>
@@ -144,13 +147,15 @@ static int launch_inst(ConvGemmParams& p, int total_tiles, cudaStream_t stream) 
     if (ea && L::w_bytes >= 32 * 1024) a_stages = atoi(ea);
     if (ew && L::w_bytes >= 32 * 1024) w_stages = atoi(ew);
   }
-  while (a_stages * a_bytes + w_stages * L::w_bytes > 208 * 1024 && w_stages > 2) --w_stages;
+  constexpr int w_stage_bytes = MC == 2 ? L::w_bytes / 2 : L::w_bytes;
+  if (MC == 2) w_stages = 6;
+  while (a_stages * a_bytes + w_stages * w_stage_bytes > 208 * 1024 && w_stages > 2) --w_stages;
   p.a_stages = a_stages;
   p.w_stages = w_stages;
   constexpr int stage_smem = EpiWarps<BN, EPI>::value * EpiWarps<BN, EPI>::stage_bytes + 128;   // coalescing buffers of the epilogue warps
-  while (a_stages * a_bytes + w_stages * L::w_bytes + stage_smem > 222 * 1024 && w_stages > 2) --w_stages;
+  while (a_stages * a_bytes + w_stages * w_stage_bytes + stage_smem > 222 * 1024 && w_stages > 2) --w_stages;
   p.w_stages = w_stages;
-  const int smem = a_stages * a_bytes + w_stages * L::w_bytes + 1024 + 8 * (2 * (a_stages + w_stages) + 4) + 16 + 1024 + stage_smem;
+  const int smem = a_stages * a_bytes + w_stages * w_stage_bytes + 1024 + 8 * (2 * (a_stages + w_stages) + 4) + 16 + 1024 + stage_smem;
   static int configured_smem[64] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -275,15 +280,22 @@ static int launch_convgemm(const ConvGemmDesc& d, cudaStream_t stream) {
   if (tiles == 0) return 0;
   // weight multicast across 2-CTA clusters for the wide tiles (needs an even number of row tiles)
   const int row_tiles = d.batch * p.m_tiles[0];
-  const bool mc = multicast_enabled() && bn == 256 && kb == 64 && d.n_groups == 1 && row_tiles % 2 == 0 && row_tiles >= 2;
-  if (mc) {
+  const int mode = (bn == 256 && kb == 64 && d.n_groups == 1 && row_tiles % 2 == 0 && row_tiles >= 2) ? cluster_mode() : 0;
+  if (mode != 0) {
     rc = make_weight_map(&p.tmWh, d.weight, k_total, d.n_total, kb, bn / 2);
     if (rc) return rc;
     const int pair_tiles = (row_tiles / 2) * p.n_tiles;
-    if (d.epilogue == EPI_GENERIC) return launch_inst<256, 64, EPI_GENERIC, 1>(p, pair_tiles, stream);
-    if (d.epilogue == EPI_GLU) return launch_inst<256, 64, EPI_GLU, 1>(p, pair_tiles, stream);
-    if (d.epilogue == EPI_RESNORM) return launch_inst<256, 64, EPI_RESNORM, 1>(p, pair_tiles, stream);
-    if (d.epilogue == EPI_QKV_ROPE) return launch_inst<256, 64, EPI_QKV_ROPE, 1>(p, pair_tiles, stream);
+    if (mode == 1) {
+      if (d.epilogue == EPI_GENERIC) return launch_inst<256, 64, EPI_GENERIC, 1>(p, pair_tiles, stream);
+      if (d.epilogue == EPI_GLU) return launch_inst<256, 64, EPI_GLU, 1>(p, pair_tiles, stream);
+      if (d.epilogue == EPI_RESNORM) return launch_inst<256, 64, EPI_RESNORM, 1>(p, pair_tiles, stream);
+      if (d.epilogue == EPI_QKV_ROPE) return launch_inst<256, 64, EPI_QKV_ROPE, 1>(p, pair_tiles, stream);
+    } else {
+      if (d.epilogue == EPI_GENERIC) return launch_inst<256, 64, EPI_GENERIC, 2>(p, pair_tiles, stream);
+      if (d.epilogue == EPI_GLU) return launch_inst<256, 64, EPI_GLU, 2>(p, pair_tiles, stream);
+      if (d.epilogue == EPI_RESNORM) return launch_inst<256, 64, EPI_RESNORM, 2>(p, pair_tiles, stream);
+      if (d.epilogue == EPI_QKV_ROPE) return launch_inst<256, 64, EPI_QKV_ROPE, 2>(p, pair_tiles, stream);
+    }
   } else {
     p.tmWh = p.tmW;
   }

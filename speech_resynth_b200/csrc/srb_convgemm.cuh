@@ -545,6 +545,9 @@ struct EpiWarps {
   static constexpr int stage_bytes = (EPI == EPI_RESNORM || EPI == EPI_QKV_ROPE) ? 4096 : 2048;
 };
 
+// MC = 2: CTA-pair MMA (tcgen05 cta_group::2, M = 256 across two SMs): each CTA stages its own 128 activation rows
+// and HALF of the weight slab; the leader CTA issues the MMAs for both; accumulators land in each CTA's own TMEM and
+// each CTA runs its own epilogue.  All loads signal the leader's barriers, the leader's commits release both CTAs.
 // MC = 1: launched as 2-CTA clusters.  The two CTAs of a cluster work on the same output-channel tile and on adjacent
 // row tiles, so they consume the same weight slabs: each CTA fetches HALF of every slab and TMA-multicasts it into both
 // shared memories, halving the L2 -> SM weight traffic that bounds the wide (BN = 256) GEMMs.  A slab slot is reused
@@ -568,14 +571,15 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
   constexpr int TCOLS = TmemCols<BN>::total;
   constexpr int EW = EpiWarps<BN, EPI>::value;
   constexpr int NHALF = EW / 4;
-  constexpr uint32_t IDESC = umma_idesc_bf16(kTileM, BN);
+  constexpr uint32_t IDESC = umma_idesc_bf16(MC == 2 ? 2 * kTileM : kTileM, BN);
+  constexpr int W_STAGE_BYTES = MC == 2 ? L::w_bytes / 2 : L::w_bytes;   // CTA-pair mode keeps half a slab per CTA
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int a_stages = p.a_stages, w_stages = p.w_stages;
   const uint32_t a_ring = smem_base;
   const uint32_t w_ring = smem_base + a_stages * p.a_box_bytes;
-  const uint32_t bar_base = w_ring + w_stages * L::w_bytes;       // 1024-aligned
+  const uint32_t bar_base = w_ring + w_stages * W_STAGE_BYTES;       // 1024-aligned
   auto a_full = [&](int s) { return bar_base + 8u * s; };
   auto a_empty = [&](int s) { return bar_base + 8u * (a_stages + s); };
   auto w_full = [&](int s) { return bar_base + 8u * (2 * a_stages + s); };
@@ -604,19 +608,24 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
     }
     for (int s = 0; s < w_stages; ++s) {
       mbar_init(w_full(s), 1);
-      mbar_init(w_empty(s), MC ? 2 : 1);
+      mbar_init(w_empty(s), MC == 1 ? 2 : 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);
-      mbar_init(tempty_bar(b), EW);
+      mbar_init(tempty_bar(b), MC == 2 ? 2 * EW : EW);
     }
     fence_barrier_init();
     tma_prefetch_desc(&p.tmW);
     tma_prefetch_desc(&p.tmA[0]);
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, TCOLS);
-    tmem_relinquish();
+    if constexpr (MC == 2) {
+      tmem_alloc_2sm(tmem_slot, TCOLS);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(tmem_slot, TCOLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -639,13 +648,26 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
           const int tb = p.seg_tap_begin[sg], te = p.seg_tap_begin[sg + 1];
           for (int kc = 0; kc < p.kchunks; ++kc) {
             mbar_wait(a_empty(ai), aph ^ 1u);
-            mbar_expect_tx_elect(a_full(ai), a_tx);
-            tma_load_3d_elect(a_ring + ai * p.a_box_bytes, &p.tmA[src], a_full(ai), kc * KB, row, tc.b);
+            if constexpr (MC == 2) {
+              // both CTAs' boxes complete on the leader's barrier, which the leader arms for the sum
+              if (mc_rank == 0) mbar_expect_tx_elect(a_full(ai), 2 * a_tx);
+              tma_load_3d_2sm_elect(a_ring + ai * p.a_box_bytes, &p.tmA[src], a_full(ai), kc * KB, row, tc.b);
+            } else {
+              mbar_expect_tx_elect(a_full(ai), a_tx);
+              tma_load_3d_elect(a_ring + ai * p.a_box_bytes, &p.tmA[src], a_full(ai), kc * KB, row, tc.b);
+            }
             if (++ai == a_stages) { ai = 0; aph ^= 1u; }
             for (int t = tb; t < te; ++t) {
               mbar_wait(w_empty(wi), wph ^ 1u);
+              if constexpr (MC == 2) {
+                if (mc_rank == 0) mbar_expect_tx_elect(w_full(wi), L::w_bytes_raw);
+                tma_load_2d_2sm_elect(w_ring + wi * W_STAGE_BYTES, &p.tmWh, w_full(wi), (t * p.kchunks + kc) * KB,
+                                      tc.n * BN + mc_rank * (BN / 2));
+                if (++wi == w_stages) { wi = 0; wph ^= 1u; }
+                continue;
+              }
               mbar_expect_tx_elect(w_full(wi), L::w_bytes_raw);
-              if constexpr (MC) {
+              if constexpr (MC == 1) {
                 // my half of the slab (BN/2 rows), written into both CTAs
                 tma_load_2d_mc_elect(w_ring + wi * L::w_bytes + mc_rank * (L::w_bytes_raw / 2), &p.tmWh, w_full(wi),
                                      (t * p.kchunks + kc) * KB, tc.n * BN + mc_rank * (BN / 2), (uint16_t)3);
@@ -662,7 +684,7 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
   } else if (warp == 1) {
     // MMA issuer: the whole warp runs the (warp-uniform) loop converged so descriptors stay in uniform registers;
     // one elected lane issues.  See umma_bf16_pred.
-    {
+    if (MC != 2 || mc_rank == 0) {
       int ai = 0, wi = 0;
       uint32_t aph = 0, wph = 0;
       int it = 0;
@@ -684,20 +706,25 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
               mbar_wait(w_full(wi), wph);
               tc_fence_after();
               const uint64_t adesc = umma_smem_desc<SW>(a_addr + (p.tap_shift[t] - min_shift) * (KB * 2));
-              const uint64_t wdesc = umma_smem_desc<SW>(w_ring + wi * L::w_bytes);
+              const uint64_t wdesc = umma_smem_desc<SW>(w_ring + wi * W_STAGE_BYTES);
 #pragma unroll
-              for (int k = 0; k < KB / 16; ++k)
-                umma_bf16_pred(1u, tacc, adesc + 2 * k, wdesc + 2 * k, IDESC, (first && k == 0) ? 0u : 1u);
+              for (int k = 0; k < KB / 16; ++k) {
+                if constexpr (MC == 2) umma_bf16_2sm_pred(tacc, adesc + 2 * k, wdesc + 2 * k, IDESC, (first && k == 0) ? 0u : 1u);
+                else umma_bf16_pred(1u, tacc, adesc + 2 * k, wdesc + 2 * k, IDESC, (first && k == 0) ? 0u : 1u);
+              }
               first = 0;
-              if constexpr (MC) umma_commit_mc_pred(w_empty(wi), (uint16_t)3);
+              if constexpr (MC == 2) umma_commit_2sm_pred(w_empty(wi), (uint16_t)3);
+              else if constexpr (MC == 1) umma_commit_mc_pred(w_empty(wi), (uint16_t)3);
               else umma_commit_pred(1u, w_empty(wi));
               if (++wi == w_stages) { wi = 0; wph ^= 1u; }
             }
-            umma_commit_pred(1u, a_empty(ai));
+            if constexpr (MC == 2) umma_commit_2sm_pred(a_empty(ai), (uint16_t)3);
+            else umma_commit_pred(1u, a_empty(ai));
             if (++ai == a_stages) { ai = 0; aph ^= 1u; }
           }
         }
-        umma_commit_pred(1u, tfull_bar(buf));
+        if constexpr (MC == 2) umma_commit_2sm_pred(tfull_bar(buf), (uint16_t)3);
+        else umma_commit_pred(1u, tfull_bar(buf));
       }
     }
     __syncwarp();
@@ -728,14 +755,20 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
       else epi_euler(p, tacc, tc, q);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(buf));
+      if (lane == 0) {
+        if constexpr (MC == 2) mbar_arrive_leader(tempty_bar(buf));   // the leader's MMA warp owns both accumulators
+        else mbar_arrive(tempty_bar(buf));
+      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
   if constexpr (MC) cluster_sync_all();   // no CTA may exit while its peer can still multicast into it
-  if (warp == 1) tmem_dealloc(tmem_base, TCOLS);
+  if (warp == 1) {
+    if constexpr (MC == 2) tmem_dealloc_2sm(tmem_base, TCOLS);
+    else tmem_dealloc(tmem_base, TCOLS);
+  }
 }
 
 }  // namespace srb
