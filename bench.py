@@ -144,6 +144,9 @@ def op_profile(engine, ids, x0):
     plan.cfm_ws["xt"][:, : ids.shape[1]].copy_(x0)
     torch.cuda.synchronize()
     nat.profile_log = []
+    # keep the GPU busy while the host enqueues the whole pass: an eager launch costs the host 20-30 us, more than
+    # many of these kernels run, and an idle GPU would add that wait to the event-to-event time of the next kernel
+    torch.cuda._sleep(int(60e-3 * 1.9e9))
     plan.body()
     torch.cuda.synchronize()
     log, nat.profile_log = nat.profile_log, None

@@ -13,8 +13,11 @@
 // which is cheap on the tensor core (sequences here are <= a few thousand keys).  S is double-buffered in TMEM so
 // the tensor core computes S(j+1) while the softmax warps work on S(j).
 //
-// Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer (+ TMEM allocator), warps 2-5 softmax/epilogue
-// (thread <-> query row / TMEM lane).
+// Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer (+ TMEM allocator), warps 2-9 softmax/epilogue:
+// thread <-> query row (TMEM lane), and the two warps of a lane quarter split the 128 key columns of an S tile (and
+// the 128 output columns of O) in halves.  Four softmax warps (one per SM sub-partition) left the kernel waiting on
+// them -- ncu: 75 % of the samples on the S / P mbarriers -- so each row's work is shared by two threads; the row
+// maximum after pass 1 and the row sum after pass 2 are combined through shared memory, once each.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -44,8 +47,9 @@ struct AttnSmem {
   static constexpr int k = q + kTileBytes;             // 2 stages
   static constexpr int v = k + 2 * kTileBytes;         // 2 stages
   static constexpr int p = v + 2 * kTileBytes;
-  static constexpr int stage = p + kTileBytes;         // 4 x 2 KB coalescing buffers (bf16 blocks, 4 pieces per row)
-  static constexpr int bars = stage + 4 * 2048;
+  static constexpr int stage = p + kTileBytes;         // 8 x 2 KB coalescing buffers (bf16 blocks, 4 pieces per row)
+  static constexpr int red = stage + 8 * 2048;         // [2][128] floats: row max / row sum exchange between halves
+  static constexpr int bars = red + 1024;
   static constexpr int n_bars = 16;
   static constexpr int tmem = bars + 8 * n_bars;
   static constexpr int total = tmem + 16 + 1024;       // + alignment slack
@@ -57,7 +61,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-__global__ void __launch_bounds__(192, 1) attn_tc_kernel(const __grid_constant__ AttnParams p) {
+__global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (sbase - smem_u32(smem_raw));
@@ -92,9 +96,9 @@ __global__ void __launch_bounds__(192, 1) attn_tc_kernel(const __grid_constant__
       mbar_init(v_full(s), 1);
       mbar_init(v_empty(s), 1);
       mbar_init(s_full(s), 1);
-      mbar_init(s_empty(s), 4);
+      mbar_init(s_empty(s), 8);
     }
-    mbar_init(p_full, 4);
+    mbar_init(p_full, 8);
     mbar_init(p_empty, 1);
     mbar_init(o_full, 1);
     fence_barrier_init();
@@ -188,20 +192,22 @@ __global__ void __launch_bounds__(192, 1) attn_tc_kernel(const __grid_constant__
   } else {
     // ================= softmax / epilogue warps =================
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;                     // key-column half of S / output-column half of O
     const int row = quarter * 32 + lane;                  // query row inside the tile = TMEM lane
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     const float sl2 = 0.08838834764831845f * 1.4426950408889634f;   // (1/sqrt(128)) * log2(e)
+    float* red = reinterpret_cast<float*>(smem + AttnSmem::red);
     int t = 0;
     float m = -INFINITY;
     for (int j = 0; j < (npass >= 1 ? nkv : 0); ++j, ++t) {
       const int sb = t & 1;
       mbar_wait(s_full(sb), (t >> 1) & 1);
       tc_fence_after();
-      const int key0 = j * kAttnTile;
+      const int key0 = j * kAttnTile + half * 64;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
-        tmem_ld32(t_s0 + sb * 128 + lane_addr + c * 32, v);
+        tmem_ld32(t_s0 + sb * 128 + lane_addr + half * 64 + c * 32, v);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i)
@@ -211,18 +217,24 @@ __global__ void __launch_bounds__(192, 1) attn_tc_kernel(const __grid_constant__
       __syncwarp();
       if (lane == 0) mbar_arrive(s_empty(sb));
     }
+    // row maximum over both halves
+    red[half * 128 + row] = m;
+    pair_barrier(quarter);
+    m = fmaxf(m, red[(half ^ 1) * 128 + row]);
+    pair_barrier(quarter);                                // both have read before `red` is reused for the sums
     const float m2 = m * sl2;     // finite: every utterance has at least one valid key
     float l = 0.f;
     for (int j = 0; j < (npass >= 2 ? nkv : 0); ++j, ++t) {
       const int sb = t & 1;
       mbar_wait(s_full(sb), (t >> 1) & 1);
       tc_fence_after();
-      mbar_wait(p_empty, (j & 1) ^ 1u);   // P V of the previous tile has finished reading the P buffer
-      const int key0 = j * kAttnTile;
+      const int key0 = j * kAttnTile + half * 64;
+      // this warp's 64 keys are one [128 rows][64 keys] half tile of P: 128-byte rows, 16-byte pieces XOR-swizzled
+      uint8_t* prow = smem + AttnSmem::p + half * kHalfBytes + row * 128;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
-        tmem_ld32(t_s0 + sb * 128 + lane_addr + c * 32, v);
+        tmem_ld32(t_s0 + sb * 128 + lane_addr + half * 64 + c * 32, v);
         tmem_ld_wait();
         uint32_t o[16];
 #pragma unroll
@@ -233,11 +245,10 @@ __global__ void __launch_bounds__(192, 1) attn_tc_kernel(const __grid_constant__
           l += p0 + p1;
           o[i] = pack_bf16(p0, p1);
         }
-        // P tile: two [128 rows][64 keys] halves, 128-byte rows, 16-byte pieces XOR-swizzled by (row & 7)
-        uint8_t* prow = smem + AttnSmem::p + (c >> 1) * kHalfBytes + row * 128;
+        if (c == 0) mbar_wait(p_empty, (j & 1) ^ 1u);   // P V of the previous tile has finished reading the P buffer
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const int piece = (c & 1) * 4 + i;
+          const int piece = c * 4 + i;
           *reinterpret_cast<uint4*>(prow + ((piece ^ (row & 7)) << 4)) = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
         }
       }
@@ -249,7 +260,11 @@ __global__ void __launch_bounds__(192, 1) attn_tc_kernel(const __grid_constant__
         mbar_arrive(p_full);
       }
     }
-    // ---- epilogue: O / l -> bf16 -> (B, N, 256)
+    // row sum over both halves
+    red[half * 128 + row] = l;
+    pair_barrier(quarter);
+    l += red[(half ^ 1) * 128 + row];
+    // ---- epilogue: O / l -> bf16 -> (B, N, 256); this warp takes 64 of the head's 128 output columns
     mbar_wait(o_full, 0);
     tc_fence_after();
     const float inv = l > 0.f ? 1.f / l : 0.f;
@@ -258,11 +273,11 @@ __global__ void __launch_bounds__(192, 1) attn_tc_kernel(const __grid_constant__
     w.lane = lane;
     w.row0 = q0 + quarter * 32;
     const int vrows = clamp_rows(p.frames, w.row0);
-    __nv_bfloat16* out = p.out + ((long long)b * p.frames + w.row0) * 256 + h * 128;
+    __nv_bfloat16* out = p.out + ((long long)b * p.frames + w.row0) * 256 + h * 128 + half * 64;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 2; ++c) {
       uint32_t v[32];
-      tmem_ld32(t_o + lane_addr + c * 32, v);
+      tmem_ld32(t_o + lane_addr + half * 64 + c * 32, v);
       tmem_ld_wait();
       uint4 o[4];
       uint32_t* ow = reinterpret_cast<uint32_t*>(o);
@@ -334,6 +349,6 @@ extern "C" int srb_cfm_attention_tc(const void* qk_bf16, int32_t ld, const void*
     configured[dev & 63] = true;
   }
   dim3 grid((frames + kAttnTile - 1) / kAttnTile, 2, batch);
-  attn_tc_kernel<<<grid, 192, AttnSmem::total, (cudaStream_t)stream>>>(p);
+  attn_tc_kernel<<<grid, 320, AttnSmem::total, (cudaStream_t)stream>>>(p);
   return after_launch("attn_tc_kernel");
 }

@@ -129,10 +129,20 @@ static int cluster_mode() {
   return v;
 }
 
-template <int BN, int KB, int EPI, int MC = 0>
-static int launch_inst(ConvGemmParams& p, int total_tiles, cudaStream_t stream) {
+// SRB_WEIGHT_STATIONARY is a bit mask for A/B measurements: 1 = transformer linears, 2 = vocoder convs (default 3)
+static int weight_stationary_mask() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SRB_WEIGHT_STATIONARY");
+    v = e ? (atoi(e) & 3) : 3;
+  }
+  return v;
+}
+
+template <int BN, int KB, int EPI, int MC = 0, int WS = 0>
+static int launch_inst(ConvGemmParams& p, int total_tiles, cudaStream_t stream, int n_slabs = 0) {
   using L = StageLayout<BN, KB>;
-  auto kernel = convgemm_kernel<BN, KB, EPI, MC>;
+  auto kernel = convgemm_kernel<BN, KB, EPI, MC, WS>;
   // two rings: activation boxes (one per K chunk, reused by all taps) and weight slabs (one per tap and K chunk)
   constexpr int threads = 64 + 32 * EpiWarps<BN, EPI>::value;
   const int a_bytes = p.a_box_bytes;
@@ -148,12 +158,29 @@ static int launch_inst(ConvGemmParams& p, int total_tiles, cudaStream_t stream) 
     if (ew && L::w_bytes >= 32 * 1024) w_stages = atoi(ew);
   }
   constexpr int w_stage_bytes = MC == 2 ? L::w_bytes / 2 : L::w_bytes;
+  // RESNORM: two residual-stream buffers per epilogue warp when the K loop is short (the epilogue, not the MMAs,
+  // paces those launches); one when the long K loop (FFN conv2) needs the shared memory for its weight ring
+  p.res_bufs = (EPI == EPI_RESNORM && n_slabs <= 8) ? 2 : 1;
+  if (EPI == EPI_RESNORM && n_slabs > 8) a_stages = 2;
+  // coalescing / streaming buffers of the epilogue warps + CTA-wide epilogue tables
+  const int stage_smem = EpiWarps<BN, EPI>::value * EpiWarps<BN, EPI>::stage_bytes(p.res_bufs) + EpiWarps<BN, EPI>::extra_bytes + 128;
   if (MC == 2) w_stages = 6;
-  while (a_stages * a_bytes + w_stages * w_stage_bytes > 208 * 1024 && w_stages > 2) --w_stages;
+  if (!WS && n_slabs > 0 && w_stages > n_slabs) w_stages = n_slabs < 2 ? 2 : n_slabs;
+  if (WS) {
+    // every slab resident; the activation ring takes what is left (at most 4 boxes)
+    w_stages = n_slabs;
+    a_stages = L::w_bytes >= 32 * 1024 ? 4 : 3;
+    while (a_stages > 2 && a_stages * a_bytes + w_stages * w_stage_bytes + stage_smem > 220 * 1024) --a_stages;
+    // narrow tiles: prefer two resident CTAs (their epilogues overlap) over a third activation box
+    if (a_stages == 3 && 3 * a_bytes + w_stages * w_stage_bytes + stage_smem > 108 * 1024 &&
+        2 * a_bytes + w_stages * w_stage_bytes + stage_smem <= 108 * 1024)
+      a_stages = 2;
+    SRB_REQUIRE(a_stages * a_bytes + w_stages * w_stage_bytes + stage_smem <= 222 * 1024, "weight-stationary slabs do not fit");
+  }
+  while (a_stages * a_bytes + w_stages * w_stage_bytes > 208 * 1024 && w_stages > 2 && !WS) --w_stages;
   p.a_stages = a_stages;
   p.w_stages = w_stages;
-  constexpr int stage_smem = EpiWarps<BN, EPI>::value * EpiWarps<BN, EPI>::stage_bytes + 128;   // coalescing buffers of the epilogue warps
-  while (a_stages * a_bytes + w_stages * w_stage_bytes + stage_smem > 222 * 1024 && w_stages > 2) --w_stages;
+  while (a_stages * a_bytes + w_stages * w_stage_bytes + stage_smem > 222 * 1024 && w_stages > 2 && !WS) --w_stages;
   p.w_stages = w_stages;
   const int smem = a_stages * a_bytes + w_stages * w_stage_bytes + 1024 + 8 * (2 * (a_stages + w_stages) + 4) + 16 + 1024 + stage_smem;
   static int configured_smem[64] = {0};
@@ -200,6 +227,15 @@ static int launch_inst(ConvGemmParams& p, int total_tiles, cudaStream_t stream) 
     cfg.numAttrs = 1;
     SRB_CUDA(cudaLaunchKernelEx(&cfg, kernel, p, total_tiles));
     return after_launch("convgemm_kernel(multicast)");
+  }
+  if constexpr (WS) {
+    // CTA c keeps channel tile c % n_tiles: the grid is a multiple of n_tiles, no more row walkers than row tiles
+    int walkers = grid / p.n_tiles;
+    if (walkers > total_tiles) walkers = total_tiles;
+    if (walkers < 1) walkers = 1;
+    grid = walkers * p.n_tiles;
+    kernel<<<grid, threads, smem, stream>>>(p, total_tiles);
+    return after_launch("convgemm_kernel(weight-stationary)");
   }
   if (grid > total_tiles) grid = total_tiles;
   if (grid < 1) return 0;
@@ -286,22 +322,37 @@ static int launch_convgemm(const ConvGemmDesc& d, cudaStream_t stream) {
     if (rc) return rc;
     const int pair_tiles = (row_tiles / 2) * p.n_tiles;
     if (mode == 1) {
-      if (d.epilogue == EPI_GENERIC) return launch_inst<256, 64, EPI_GENERIC, 1>(p, pair_tiles, stream);
-      if (d.epilogue == EPI_GLU) return launch_inst<256, 64, EPI_GLU, 1>(p, pair_tiles, stream);
-      if (d.epilogue == EPI_RESNORM) return launch_inst<256, 64, EPI_RESNORM, 1>(p, pair_tiles, stream);
-      if (d.epilogue == EPI_QKV_ROPE) return launch_inst<256, 64, EPI_QKV_ROPE, 1>(p, pair_tiles, stream);
+      if (d.epilogue == EPI_GENERIC) return launch_inst<256, 64, EPI_GENERIC, 1>(p, pair_tiles, stream, n_taps * p.kchunks);
+      if (d.epilogue == EPI_GLU) return launch_inst<256, 64, EPI_GLU, 1>(p, pair_tiles, stream, n_taps * p.kchunks);
+      if (d.epilogue == EPI_RESNORM) return launch_inst<256, 64, EPI_RESNORM, 1>(p, pair_tiles, stream, n_taps * p.kchunks);
+      if (d.epilogue == EPI_QKV_ROPE) return launch_inst<256, 64, EPI_QKV_ROPE, 1>(p, pair_tiles, stream, n_taps * p.kchunks);
     } else {
-      if (d.epilogue == EPI_GENERIC) return launch_inst<256, 64, EPI_GENERIC, 2>(p, pair_tiles, stream);
-      if (d.epilogue == EPI_GLU) return launch_inst<256, 64, EPI_GLU, 2>(p, pair_tiles, stream);
-      if (d.epilogue == EPI_RESNORM) return launch_inst<256, 64, EPI_RESNORM, 2>(p, pair_tiles, stream);
-      if (d.epilogue == EPI_QKV_ROPE) return launch_inst<256, 64, EPI_QKV_ROPE, 2>(p, pair_tiles, stream);
+      if (d.epilogue == EPI_GENERIC) return launch_inst<256, 64, EPI_GENERIC, 2>(p, pair_tiles, stream, n_taps * p.kchunks);
+      if (d.epilogue == EPI_GLU) return launch_inst<256, 64, EPI_GLU, 2>(p, pair_tiles, stream, n_taps * p.kchunks);
+      if (d.epilogue == EPI_RESNORM) return launch_inst<256, 64, EPI_RESNORM, 2>(p, pair_tiles, stream, n_taps * p.kchunks);
+      if (d.epilogue == EPI_QKV_ROPE) return launch_inst<256, 64, EPI_QKV_ROPE, 2>(p, pair_tiles, stream, n_taps * p.kchunks);
     }
   } else {
     p.tmWh = p.tmW;
   }
 
+  // weight-stationary form when all slabs of a channel tile fit beside the activation ring (see convgemm_kernel)
+  {
+    const int n_slabs = n_taps * p.kchunks;
+    const long long w_res = (long long)n_slabs * ((bn * kb * 2 + 1023) & ~1023);
+    const int ws_bit = d.epilogue == EPI_GENERIC ? 2 : 1;
+    const bool fits = d.n_groups == 1 && w_res + 2 * p.a_box_bytes <= 184 * 1024 && (weight_stationary_mask() & ws_bit);
+    if (fits) {
+#define SRB_DISPATCH_WS(BN_, KB_, EPI_) \
+  if (bn == BN_ && kb == KB_ && d.epilogue == EPI_) return launch_inst<BN_, KB_, EPI_, 0, 1>(p, row_tiles, stream, n_slabs);
+      SRB_DISPATCH_WS(256, 64, EPI_QKV_ROPE)
+      SRB_DISPATCH_WS(64, 64, EPI_GENERIC)
+#undef SRB_DISPATCH_WS
+    }
+  }
+
 #define SRB_DISPATCH(BN_, KB_, EPI_) \
-  if (bn == BN_ && kb == KB_ && d.epilogue == EPI_) return launch_inst<BN_, KB_, EPI_>(p, tiles, stream);
+  if (bn == BN_ && kb == KB_ && d.epilogue == EPI_) return launch_inst<BN_, KB_, EPI_>(p, tiles, stream, n_taps * p.kchunks);
   SRB_DISPATCH(256, 64, EPI_GENERIC)
   SRB_DISPATCH(128, 64, EPI_GENERIC)
   SRB_DISPATCH(64, 64, EPI_GENERIC)

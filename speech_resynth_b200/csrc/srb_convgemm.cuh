@@ -50,6 +50,7 @@ struct ConvGemmParams {
   int a_box_rows;                                 // 128 + largest tap span of the launch (<= 256)
   int a_box_bytes;                                // a_box_rows * KB * 2, rounded up to 1024
   int a_stages, w_stages;
+  int res_bufs;                                   // RESNORM: residual-stream buffers per epilogue warp (1 or 2)
   // epilogue operands
   const float* bias;
   void* out0;                                     // bf16 "activated"/normalised output
@@ -160,6 +161,22 @@ __device__ __forceinline__ void scatter_store(const EpiWarp& w, const uint4* v, 
     if (row < valid_rows) *reinterpret_cast<uint4*>(g + row * row_stride_bytes + piece * 16) = x;
   }
   __syncwarp();
+}
+
+// asynchronous form of gather_issue: the block goes global -> (swizzled) warp-private shared buffer with cp.async, no
+// registers involved, so several blocks can be in flight per warp while it works.  Rows >= valid_rows are zero-filled
+// (src-size 0; `safe` is any valid address of the tensor, used so that no out-of-range address is ever formed).
+template <int P>
+__device__ __forceinline__ void async_gather(uint8_t* buf, const void* gbase, long long row_stride_bytes, int valid_rows,
+                                             int lane, const void* safe) {
+  const uint8_t* g = static_cast<const uint8_t*>(gbase);
+#pragma unroll
+  for (int i = 0; i < P; ++i) {
+    const int idx = lane + 32 * i, row = idx / P, piece = idx % P;
+    const bool ok = row < valid_rows;
+    cp_async_16(smem_u32(stage_slot<P>(buf, row, piece)), ok ? static_cast<const void*>(g + row * row_stride_bytes + piece * 16) : safe,
+                ok ? 16u : 0u);
+  }
 }
 
 __device__ __forceinline__ int clamp_rows(int total, int row0) {
@@ -320,40 +337,36 @@ __device__ __forceinline__ void pair_barrier(int quarter) {
   }
 }
 
-// Operands that do not depend on the accumulator (fp32 residual stream, rotary tables) are fetched in two batches:
-// the first BEFORE the warp waits for the tile's MMAs (its L2 latency overlaps the tensor work), the second right
-// after the wait.  pre[] holds two coalesced 32 x 128 B blocks (8 pieces per lane each).
-template <int NHALF>
-__device__ __forceinline__ void resnorm_prefetch(const ConvGemmParams& p, const TileCoord& tc, int half, const EpiWarp& w,
-                                                 uint4 (&pre)[16]) {
-  constexpr int COLS = 256 / NHALF;
-  const int vrows = clamp_rows(p.group_rows[0], w.row0);
-  const float* res = static_cast<const float*>(p.res[0]) + (long long)tc.b * p.res_batch_stride +
-                     (long long)w.row0 * p.res_row_stride + half * COLS;
-  gather_issue<8>(res, p.res_row_stride * 4, vrows, w.lane, pre);
-  gather_issue<8>(res + 32, p.res_row_stride * 4, vrows, w.lane, pre + 8);
-}
-
-template <int NHALF>
+// The fp32 residual blocks (32 rows x 32 columns = 4 KB) of a warp's column half form a STREAM -- chunk after chunk,
+// tile after tile -- that is copied asynchronously (cp.async) into `nb` rotating warp-private buffers ahead of use:
+// the copy of chunk s + nb is issued as soon as chunk s has left its buffer, also across tile boundaries, so the L2
+// latency of the residual never sits on the epilogue's critical path and no registers hold data in flight (the
+// register-staged form spilled its prefetch arrays and stalled on the spill stores).  The buffer of a chunk doubles as
+// the coalescing stage of that chunk's fp32 output.  `issue_next(buf)` issues the next chunk of the stream into `buf`
+// and commits one cp.async group (an empty one past the end of the stream).
+template <int NHALF, typename IssueNext>
 __device__ __forceinline__ void epi_resnorm(const ConvGemmParams& p, uint32_t tacc, const TileCoord& tc, int q, int half,
-                                            float* red, int row_in_tile, int quarter, const EpiWarp& w, const uint4 (&pre)[16]) {
+                                            float* red, int row_in_tile, int quarter, const EpiWarp& w, int nb, int& chunk_seq,
+                                            IssueNext&& issue_next) {
   constexpr int COLS = 256 / NHALF;
   constexpr int NCHUNK = COLS / 32;
   static_assert(NCHUNK == 4, "RESNORM runs with eight epilogue warps");
   const int vrows = clamp_rows(p.group_rows[0], w.row0);
   const long long woff = (long long)tc.b * p.out_batch_stride + (long long)w.row0 * p.out_row_stride + half * COLS;
-  const float* res = static_cast<const float*>(p.res[0]) + (long long)tc.b * p.res_batch_stride +
-                     (long long)w.row0 * p.res_row_stride + half * COLS;
   float* xout = static_cast<float*>(p.out1) + woff;
   const uint32_t tcol = tacc + half * COLS;
-  uint4 late[16];   // residual blocks of chunks 2, 3
-  gather_issue<8>(res + 64, p.res_row_stride * 4, vrows, w.lane, late);
-  gather_issue<8>(res + 96, p.res_row_stride * 4, vrows, w.lane, late + 8);
   float sumsq = 0.f;
 #pragma unroll
   for (int c = 0; c < NCHUNK; ++c) {
+    EpiWarp wb = w;
+    wb.stage = w.stage + (nb == 2 ? (chunk_seq & 1) * 4096 : 0);
+    if (nb == 2) cp_async_wait<1>();
+    else cp_async_wait<0>();
+    __syncwarp();
     uint4 rr[8];
-    gather_finish<8>(w, c < 2 ? pre + (c & 1) * 8 : late + (c & 1) * 8, rr);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) rr[j] = *stage_slot<8>(wb.stage, w.lane, j);
+    __syncwarp();   // every lane has its row before the buffer becomes the store stage
     uint32_t v[32];
     tmem_ld32(tcol + c * 32, v);
     tmem_ld_wait();
@@ -374,7 +387,9 @@ __device__ __forceinline__ void epi_resnorm(const ConvGemmParams& p, uint32_t ta
       v[4 * j + 2] = __float_as_uint(y.z); v[4 * j + 3] = __float_as_uint(y.w);
       yo[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     }
-    scatter_store<8>(w, yo, xout + c * 32, p.out_row_stride * 4, vrows);
+    scatter_store<8>(wb, yo, xout + c * 32, p.out_row_stride * 4, vrows);
+    issue_next(wb.stage);
+    ++chunk_seq;
     if (p.norm_mode != 0) tmem_st32(tcol + c * 32, v);  // stash y for the second pass
   }
   if (p.norm_mode == 0) return;
@@ -390,6 +405,8 @@ __device__ __forceinline__ void epi_resnorm(const ConvGemmParams& p, uint32_t ta
   const bool keep = q < p.group_rows[0] && (p.lengths == nullptr || q < p.lengths[tc.b]);
   __nv_bfloat16* xn = static_cast<__nv_bfloat16*>(p.out0) + woff;
   const float* gv = p.vec0 + half * COLS;
+  EpiWarp wn = w;
+  wn.stage = w.stage + nb * 4096;   // bf16 stage, separate from the residual buffers (which hold copies in flight)
 #pragma unroll
   for (int c = 0; c < NCHUNK; ++c) {
     uint32_t v[32];
@@ -404,7 +421,7 @@ __device__ __forceinline__ void epi_resnorm(const ConvGemmParams& p, uint32_t ta
       ow[2 * j] = keep ? pack_bf16(__uint_as_float(v[4 * j]) * inv * g.x, __uint_as_float(v[4 * j + 1]) * inv * g.y) : 0u;
       ow[2 * j + 1] = keep ? pack_bf16(__uint_as_float(v[4 * j + 2]) * inv * g.z, __uint_as_float(v[4 * j + 3]) * inv * g.w) : 0u;
     }
-    scatter_store<4>(w, o, xn + c * 32, p.out_row_stride * 2, vrows);
+    scatter_store<4>(wn, o, xn + c * 32, p.out_row_stride * 2, vrows);
   }
   if constexpr (NHALF == 2) {
     // the pair must not overwrite `red` for the next tile before both have read it
@@ -414,19 +431,25 @@ __device__ __forceinline__ void epi_resnorm(const ConvGemmParams& p, uint32_t ta
 
 // to_qkv tile n: 0 = q (2 heads x 128), 1 = k, 2 = v.  Rotary (transformer.py:66-73) on q,k:
 // out[i] = t[i] cos - t[i+64] sin ; out[i+64] = t[i+64] cos + t[i] sin, angle = pos * inv_freq[i], i < 64.
-// With eight epilogue warps, column half h of a lane quarter is head h.  The rotary tables are (rows, 64) fp32 and a
-// warp's 32 consecutive positions are one contiguous 8 KB block: fetched coalesced like a residual.
-__device__ __forceinline__ void rope_prefetch(const ConvGemmParams& p, const TileCoord& tc, const EpiWarp& w, uint4 (&pre)[16]) {
-  if (tc.n != 2) {
-    const int vrows = clamp_rows(p.group_rows[0], w.row0);
-    gather_issue<8>(p.vec0 + (long long)w.row0 * 64, 256, vrows, w.lane, pre);        // cos, frequencies 0..31
-    gather_issue<8>(p.vec1 + (long long)w.row0 * 64, 256, vrows, w.lane, pre + 8);    // sin, frequencies 0..31
+// With eight epilogue warps, column half h of a lane quarter is head h.
+// The (rows, 64) fp32 cos/sin tables are NOT streamed per row (that was 128 KB of L2 reads per tile, register-staged
+// and spilled): a warp's 32 positions are pos = r0 + lane with r0 a multiple of 32, so
+//   cos(pos f) = cos(r0 f) cos(lane f) - sin(r0 f) sin(lane f),  sin(pos f) = sin(r0 f) cos(lane f) + cos(r0 f) sin(lane f)
+// with row r0 of the tables read warp-uniformly (broadcast, L1 resident) and rows 0..31 kept in shared memory for the
+// whole kernel (`tab_b`: [cos | sin][32 rows][256 B], 16-byte pieces XOR-swizzled by row).  The sum formula differs from
+// the tabulated fp32 value only by the rounding of the fp32 angle the reference itself carries (<= ulp(pos f) ~ 3e-5).
+__device__ __forceinline__ void rope_table_to_smem(const ConvGemmParams& p, uint8_t* tab_b) {
+  // 2 tables x 32 rows x 16 pieces of 16 bytes
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
+    const int t = i >> 9, row = (i >> 4) & 31, piece = i & 15;
+    const float4 v = __ldg(reinterpret_cast<const float4*>((t ? p.vec1 : p.vec0) + row * 64) + piece);
+    *reinterpret_cast<float4*>(tab_b + t * 8192 + row * 256 + ((piece ^ (row & 7)) << 4)) = v;
   }
 }
 
 template <int NHALF>
 __device__ __forceinline__ void epi_qkv_rope(const ConvGemmParams& p, uint32_t tacc, const TileCoord& tc, int half,
-                                             const EpiWarp& w, const uint4 (&pre)[16]) {
+                                             const EpiWarp& w, const uint8_t* tab_b) {
   static_assert(NHALF == 2, "QKV_ROPE runs with eight epilogue warps (one head per column half)");
   const int vrows = clamp_rows(p.group_rows[0], w.row0);
   __nv_bfloat16* out = static_cast<__nv_bfloat16*>(p.out0) + (long long)tc.b * p.out_batch_stride +
@@ -450,14 +473,15 @@ __device__ __forceinline__ void epi_qkv_rope(const ConvGemmParams& p, uint32_t t
     }
     return;
   }
-  uint4 late[16];   // cos / sin of frequencies 32..63
-  gather_issue<8>(p.vec0 + (long long)w.row0 * 64 + 32, 256, vrows, w.lane, late);
-  gather_issue<8>(p.vec1 + (long long)w.row0 * 64 + 32, 256, vrows, w.lane, late + 8);
+  // table row r0 exists whenever the warp has a valid row; otherwise nothing is stored and row 0 stands in
+  const long long r0 = vrows > 0 ? w.row0 : 0;
+  const float4* ca4 = reinterpret_cast<const float4*>(p.vec0 + r0 * 64);
+  const float4* sa4 = reinterpret_cast<const float4*>(p.vec1 + r0 * 64);
+  const uint8_t* cb_row = tab_b + w.lane * 256;
+  const uint8_t* sb_row = tab_b + 8192 + w.lane * 256;
+  const int swz = w.lane & 7;
 #pragma unroll
   for (int f = 0; f < 2; ++f) {
-    uint4 cs[8], sn[8];
-    gather_finish<8>(w, f == 0 ? pre : late, cs);
-    gather_finish<8>(w, f == 0 ? pre + 8 : late + 8, sn);
     uint32_t lo[32], hi[32];
     tmem_ld32(tcol + f * 32, lo);
     tmem_ld32(tcol + 64 + f * 32, hi);
@@ -467,8 +491,14 @@ __device__ __forceinline__ void epi_qkv_rope(const ConvGemmParams& p, uint32_t t
     uint32_t* wh = reinterpret_cast<uint32_t*>(ohi);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float cx = __uint_as_float(cs[j].x), cy = __uint_as_float(cs[j].y), cz = __uint_as_float(cs[j].z), cw = __uint_as_float(cs[j].w);
-      const float sx = __uint_as_float(sn[j].x), sy = __uint_as_float(sn[j].y), sz = __uint_as_float(sn[j].z), sw = __uint_as_float(sn[j].w);
+      const int piece = f * 8 + j;
+      const float4 ca = __ldg(ca4 + piece), sa = __ldg(sa4 + piece);
+      const float4 cb = *reinterpret_cast<const float4*>(cb_row + ((piece ^ swz) << 4));
+      const float4 sb = *reinterpret_cast<const float4*>(sb_row + ((piece ^ swz) << 4));
+      const float cx = ca.x * cb.x - sa.x * sb.x, sx = sa.x * cb.x + ca.x * sb.x;
+      const float cy = ca.y * cb.y - sa.y * sb.y, sy = sa.y * cb.y + ca.y * sb.y;
+      const float cz = ca.z * cb.z - sa.z * sb.z, sz = sa.z * cb.z + ca.z * sb.z;
+      const float cw = ca.w * cb.w - sa.w * sb.w, sw = sa.w * cb.w + ca.w * sb.w;
       const float a0 = __uint_as_float(lo[4 * j]), a1 = __uint_as_float(lo[4 * j + 1]);
       const float a2 = __uint_as_float(lo[4 * j + 2]), a3 = __uint_as_float(lo[4 * j + 3]);
       const float b0 = __uint_as_float(hi[4 * j]), b1 = __uint_as_float(hi[4 * j + 1]);
@@ -541,8 +571,11 @@ struct EpiWarps {
   // eight epilogue warps (two column halves per TMEM lane quarter) for the wide tiles, four otherwise
   // (sixteen for the FFN GLU tile, whose SiLU epilogue is transcendental-bound and needs the extra latency hiding)
   static constexpr int value = EPI == EPI_GLU ? 16 : ((BN >= 128 && EPI != EPI_EULER) ? 8 : 4);
-  // staging bytes per epilogue warp: fp32 / rotary-table blocks are 8 pieces wide, bf16 blocks at most 4
-  static constexpr int stage_bytes = (EPI == EPI_RESNORM || EPI == EPI_QKV_ROPE) ? 4096 : 2048;
+  // staging bytes per epilogue warp: bf16 output blocks are 2 KB (4 pieces per row); RESNORM adds `res_bufs` 4 KB
+  // buffers for the asynchronous fp32 residual stream (they double as the fp32 output stage)
+  __host__ __device__ static constexpr int stage_bytes(int res_bufs) { return EPI == EPI_RESNORM ? res_bufs * 4096 + 2048 : 2048; }
+  // CTA-wide extra: the rotary offset table (cos | sin of positions 0..31)
+  static constexpr int extra_bytes = EPI == EPI_QKV_ROPE ? 16384 : 0;
 };
 
 // MC = 2: CTA-pair MMA (tcgen05 cta_group::2, M = 256 across two SMs): each CTA stages its own 128 activation rows
@@ -562,9 +595,16 @@ __device__ __forceinline__ TileCoord decode_tile_mc(const ConvGemmParams& p, int
   return c;
 }
 
-template <int BN, int KB, int EPI, int MC = 0>
+// WS = 1: weight-stationary.  When every (tap, K chunk) slab of a CTA's output-channel tile fits in shared memory
+// (the K = 80 / 256 linears of the transformer, the C = 64 vocoder convs), a CTA keeps ONE channel tile for its whole
+// life, loads its slabs once and then streams only activation boxes.  The L2 -> SM fabric (~43 B/clk per SM with all
+// SMs pulling), not the tensor core, bounds the streamed form: a 128 x 256 x 16 MMA step needs 8 KB of weights per
+// 128 clk.  `total_tiles` counts ROW tiles here; CTA c owns channel tile c % n_tiles and walks row tiles
+// c / n_tiles, + gridDim / n_tiles, ...  (the host makes the grid a multiple of n_tiles).
+template <int BN, int KB, int EPI, int MC = 0, int WS = 0>
 __global__ void __launch_bounds__(64 + 32 * EpiWarps<BN, EPI>::value)
 convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
+  static_assert(!(WS && MC), "weight-stationary mode runs without clusters");
   using L = StageLayout<BN, KB>;
   constexpr int SW = KB * 2;
   constexpr int TBUF = TmemCols<BN>::buf;
@@ -591,15 +631,31 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t red_off = (bar_base - smem_base) + 8 * (n_ring_bars + 4) + 16;
   float* red = reinterpret_cast<float*>(smem_gen + red_off);  // [2][128]
-  uint8_t* stage_base = smem_gen + ((red_off + 1024 + 127) & ~127u);                 // EW x 4 KB epilogue staging
+  uint8_t* extra_base = smem_gen + ((red_off + 1024 + 127) & ~127u);                 // CTA-wide epilogue tables
+  uint8_t* stage_base = extra_base + EpiWarps<BN, EPI>::extra_bytes;                 // EW warp-private staging areas
+  const int stage_bytes = EpiWarps<BN, EPI>::stage_bytes(p.res_bufs);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform (uniform datapath)
   const int lane = threadIdx.x & 31;
   // tile walk: CTA (or, with MC, cluster) `walker` of `n_walkers` takes tiles walker, walker + n_walkers, ...
   const int mc_rank = MC ? static_cast<int>(cluster_ctarank()) : 0;
-  const int walker = MC ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
-  const int n_walkers = MC ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
-  auto decode = [&](int tile) { return MC ? decode_tile_mc(p, tile, mc_rank) : decode_tile(p, tile); };
+  const int ws_n = WS ? static_cast<int>(blockIdx.x) % p.n_tiles : 0;
+  const int walker = MC ? static_cast<int>(blockIdx.x >> 1)
+                        : (WS ? static_cast<int>(blockIdx.x) / p.n_tiles : static_cast<int>(blockIdx.x));
+  const int n_walkers = MC ? static_cast<int>(gridDim.x >> 1)
+                           : (WS ? static_cast<int>(gridDim.x) / p.n_tiles : static_cast<int>(gridDim.x));
+  auto decode = [&](int tile) {
+    if constexpr (WS) {
+      TileCoord c;
+      c.group = 0;
+      c.n = ws_n;
+      c.b = tile / p.m_tiles[0];
+      c.m = tile - c.b * p.m_tiles[0];
+      return c;
+    } else {
+      return MC ? decode_tile_mc(p, tile, mc_rank) : decode_tile(p, tile);
+    }
+  };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < a_stages; ++s) {
@@ -618,6 +674,7 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
     tma_prefetch_desc(&p.tmW);
     tma_prefetch_desc(&p.tmA[0]);
   }
+  if constexpr (EPI == EPI_QKV_ROPE) rope_table_to_smem(p, extra_base);
   if (warp == 1) {
     if constexpr (MC == 2) {
       tmem_alloc_2sm(tmem_slot, TCOLS);
@@ -639,6 +696,15 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
       int ai = 0, wi = 0;
       uint32_t aph = 0, wph = 0;
       const uint32_t a_tx = static_cast<uint32_t>(p.a_box_rows) * KB * 2;
+      if constexpr (WS) {
+        // slab s = tap * kchunks + chunk lives in slot s for the whole kernel
+        if (walker < total_tiles) {
+          for (int s = 0; s < w_stages; ++s) {
+            mbar_expect_tx_elect(w_full(s), L::w_bytes_raw);
+            tma_load_2d_elect(w_ring + s * L::w_bytes, &p.tmW, w_full(s), s * KB, ws_n * BN);
+          }
+        }
+      }
       for (int tile = walker; tile < total_tiles; tile += n_walkers) {
         const TileCoord tc = decode(tile);
         const int t0 = tc.m * kTileM;
@@ -657,6 +723,7 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
               tma_load_3d_elect(a_ring + ai * p.a_box_bytes, &p.tmA[src], a_full(ai), kc * KB, row, tc.b);
             }
             if (++ai == a_stages) { ai = 0; aph ^= 1u; }
+            if constexpr (WS) continue;
             for (int t = tb; t < te; ++t) {
               mbar_wait(w_empty(wi), wph ^ 1u);
               if constexpr (MC == 2) {
@@ -703,7 +770,12 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
             mbar_wait(a_full(ai), aph);
             const uint32_t a_addr = a_ring + ai * p.a_box_bytes;
             for (int t = tb; t < te; ++t) {
-              mbar_wait(w_full(wi), wph);
+              if constexpr (WS) {
+                wi = t * p.kchunks + kc;
+                if (it == 0) mbar_wait(w_full(wi), 0u);
+              } else {
+                mbar_wait(w_full(wi), wph);
+              }
               tc_fence_after();
               const uint64_t adesc = umma_smem_desc<SW>(a_addr + (p.tap_shift[t] - min_shift) * (KB * 2));
               const uint64_t wdesc = umma_smem_desc<SW>(w_ring + wi * W_STAGE_BYTES);
@@ -713,6 +785,7 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
                 else umma_bf16_pred(1u, tacc, adesc + 2 * k, wdesc + 2 * k, IDESC, (first && k == 0) ? 0u : 1u);
               }
               first = 0;
+              if constexpr (WS) continue;
               if constexpr (MC == 2) umma_commit_2sm_pred(w_empty(wi), (uint16_t)3);
               else if constexpr (MC == 1) umma_commit_mc_pred(w_empty(wi), (uint16_t)3);
               else umma_commit_pred(1u, w_empty(wi));
@@ -732,6 +805,28 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
     const int quarter = warp & 3;               // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;           // column half (0 when EW == 4)
     const int lane_base = quarter * 32;
+    uint8_t* my_stage = stage_base + (warp - 2) * stage_bytes;
+    // RESNORM: asynchronous residual stream of this warp (see epi_resnorm); chunk s of the stream is chunk s & 3 of the
+    // warp's (s >> 2)-th tile
+    const int nb = p.res_bufs;
+    int chunk_seq = 0, issue_seq = 0;
+    auto issue_next = [&](uint8_t* buf) {
+      if constexpr (EPI == EPI_RESNORM) {
+        const int s = issue_seq++;
+        const int tile = walker + (s >> 2) * n_walkers;
+        if (tile < total_tiles) {
+          const TileCoord t2 = decode(tile);
+          const int row0 = t2.m * kTileM + lane_base;
+          const float* src = static_cast<const float*>(p.res[0]) + (long long)t2.b * p.res_batch_stride +
+                             (long long)row0 * p.res_row_stride + half * (256 / NHALF) + (s & 3) * 32;
+          async_gather<8>(buf, src, p.res_row_stride * 4, clamp_rows(p.group_rows[0], row0), lane, p.res[0]);
+        }
+        cp_async_commit();
+      }
+    };
+    if constexpr (EPI == EPI_RESNORM) {
+      for (int i = 0; i < nb; ++i) issue_next(my_stage + i * 4096);
+    }
     int it = 0;
     for (int tile = walker; tile < total_tiles; tile += n_walkers, ++it) {
       const TileCoord tc = decode(tile);
@@ -739,19 +834,16 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
       const uint32_t bphase = (it >> 1) & 1;
       const int q = tc.m * kTileM + lane_base + lane;
       EpiWarp ew;
-      ew.stage = stage_base + (warp - 2) * EpiWarps<BN, EPI>::stage_bytes;
+      ew.stage = my_stage;
       ew.lane = lane;
       ew.row0 = tc.m * kTileM + lane_base;
-      uint4 pre[16];
-      if constexpr (EPI == EPI_RESNORM) resnorm_prefetch<NHALF>(p, tc, half, ew, pre);
-      if constexpr (EPI == EPI_QKV_ROPE) rope_prefetch(p, tc, ew, pre);
       mbar_wait(tfull_bar(buf), bphase);
       tc_fence_after();
       const uint32_t tacc = tmem_base + (static_cast<uint32_t>(lane_base) << 16) + buf * TBUF;
       if constexpr (EPI == EPI_GENERIC) epi_generic<BN, NHALF>(p, tacc, tc, q, half, ew);
       else if constexpr (EPI == EPI_GLU) epi_glu<NHALF>(p, tacc, tc, q, half, ew);
-      else if constexpr (EPI == EPI_RESNORM) epi_resnorm<NHALF>(p, tacc, tc, q, half, red, lane_base + lane, quarter, ew, pre);
-      else if constexpr (EPI == EPI_QKV_ROPE) epi_qkv_rope<NHALF>(p, tacc, tc, half, ew, pre);
+      else if constexpr (EPI == EPI_RESNORM) epi_resnorm<NHALF>(p, tacc, tc, q, half, red, lane_base + lane, quarter, ew, nb, chunk_seq, issue_next);
+      else if constexpr (EPI == EPI_QKV_ROPE) epi_qkv_rope<NHALF>(p, tacc, tc, half, ew, extra_base);
       else epi_euler(p, tacc, tc, q);
       tc_fence_before();
       __syncwarp();
@@ -760,6 +852,7 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
         else mbar_arrive(tempty_bar(buf));
       }
     }
+    if constexpr (EPI == EPI_RESNORM) cp_async_wait<0>();
   }
 
   tc_fence_before();

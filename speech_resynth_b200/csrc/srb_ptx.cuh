@@ -97,6 +97,18 @@ __device__ __forceinline__ void tma_load_3d_elect(uint32_t dst, const void* tmap
       : "memory");
 }
 
+// ---- Ampere-style asynchronous 16-byte copies (LDGSTS): epilogue operands go global -> shared without passing
+// through registers, so a warp can keep whole blocks in flight while it works on the previous one.
+// src_bytes = 0 zero-fills the destination without reading.
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // ---- 2-CTA cluster helpers (weight-slab multicast)
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

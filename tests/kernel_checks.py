@@ -198,6 +198,10 @@ _make_conv_check("conv_c16_k3_d3", 16, 16, 3, 3)
 _make_conv_check("conv_c16_k11_d5", 16, 16, 11, 5, rows=1000, batch=3)
 _make_conv_check("conv_pre_80_512_k7", 80, 512, 7, 1, with_res=False, rows=130)
 _make_conv_check("conv_rows_lt_tile", 64, 64, 3, 1, rows=17, batch=1)
+# weight-stationary form of the C = 64 convs: more row tiles than resident CTAs (several tiles per CTA), halo boxes
+_make_conv_check("conv_c64_k3_d1_many_tiles", 64, 64, 3, 1, rows=5000, batch=9)
+_make_conv_check("conv_c64_k7_d5_many_tiles", 64, 64, 7, 5, rows=4099, batch=10, seed=3)
+_make_conv_check("conv_c64_k11_d3_many_tiles", 64, 64, 11, 3, rows=3001, batch=7, seed=4)
 
 
 @check
@@ -409,18 +413,15 @@ def cfm_attention_tc():
     return worst, 1e-2
 
 
-@check
-def cfm_qk_rope_and_v_transposed():
+def _qk_rope_vt_case(b, n, m_pad):
     s = sd()
     pk = packing.pack_cfm(s, DEV)
-    b, n = 2, 150
-    m_pad = 512
     xn_host = bf(torch.randn(b, n, 256, generator=g(5)))
     xn = torch.zeros(m_pad, 256, dtype=torch.bfloat16, device=DEV)
     xn[: b * n] = xn_host.reshape(b * n, 256).to(DEV).to(torch.bfloat16)
-    cs = torch.empty(1024, 64, device=DEV)
-    sn = torch.empty(1024, 64, device=DEV)
-    nat.call("srb_rotary_table", P(pk.inv_freq), 1024, P(cs), P(sn))
+    cs = torch.empty(max(1024, n), 64, device=DEV)
+    sn = torch.empty(max(1024, n), 64, device=DEV)
+    nat.call("srb_rotary_table", P(pk.inv_freq), max(1024, n), P(cs), P(sn))
     qk = torch.empty(b, n, 512, dtype=torch.bfloat16, device=DEV)
     vt = torch.full((256, m_pad), float("nan"), dtype=torch.bfloat16, device=DEV)
     wq = pk.w_qkv[1]
@@ -437,6 +438,17 @@ def cfm_qk_rope_and_v_transposed():
     e2 = rel_l2(vt[:, : b * n].float(), v.reshape(b * n, 256).t())
     tail_zero = bool((vt[:, b * n:].float() == 0).all())
     return (max(e1, e2) if tail_zero else 1.0), BF16_TOL
+
+
+@check
+def cfm_qk_rope_and_v_transposed():
+    return _qk_rope_vt_case(2, 150, 512)
+
+
+@check
+def cfm_qk_rope_long_positions():
+    """60 s utterance (config 5): rotary angles up to 3000 rad through the angle-addition tables"""
+    return _qk_rope_vt_case(1, 3000, 3072)
 
 
 @check
