@@ -75,17 +75,28 @@ int srb_cfm_attention(const void* qkv_bf16, const int32_t* lengths, void* o_bf16
                       void* stream);
 
 /* tcgen05 attention path (same math as srb_cfm_attention, transformer.py:109-127):
- *   srb_cfm_qk_rope      : qk (B, N, 512) bf16 = rope(xn @ Wqk^T), Wqk = first 512 rows of to_qkv.weight
+ *   srb_cfm_qk_rope      : qk (B, N, 512) bf16 = rope(xn @ Wqk^T), Wqk = first 512 rows of to_qkv.weight.  rot_cos /
+ *                          rot_sin: (rows, 64) fp32 tables of srb_rotary_table with rows >= max(frames, 32).
+ *                          qk_norm2_max (nullable): (B, 2 [q|k], 2 [head], 2 [frequency half]) fp32, zeroed by the
+ *                          caller; the kernel raises each entry to the largest partial squared row norm (over the
+ *                          head's columns i, i + 64 with i in that half of [0, 64)) it produced (atomic max); the
+ *                          sum of the two halves bounds the largest squared row norm.
+ *                          qk_norm2_clear (nullable, != qk_norm2_max): a second such buffer this launch zeroes, so that
+ *                          two buffers used alternately by successive projections need no separate clearing
  *   srb_cfm_v_transposed : vt [256][m_pad] bf16, vt[h*128 + d][b*N + n] = v[b, n, h, d]  (swapped-operand GEMM; xn must
  *                          be readable for m_pad rows, rows >= B*N zero; m_pad multiple of 256)
- *   srb_cfm_attention_tc : o (B, N, 256) bf16 = softmax(q k^T / sqrt(128) + key mask) v, two-pass exact softmax,
- *                          S and O accumulators in TMEM.  ld = row pitch of qk (>= 512); frames % 8 == 0 (TMA box
- *                          origins inside v^T must be 16-byte aligned; the host pads with masked frames). */
+ *   srb_cfm_attention_tc : o (B, N, 256) bf16 = softmax(q k^T / sqrt(128) + key mask) v, exact softmax, S and O
+ *                          accumulators in TMEM.  With qk_norm2_max (the bounds srb_cfm_qk_rope recorded) and
+ *                          |q|max |k|max log2(e) / sqrt(128) <= 100 the softmax is a single pass with shift 0;
+ *                          otherwise (or with NULL) two passes (row maxima first).  ld = row pitch of qk (>= 512);
+ *                          frames % 8 == 0 (TMA box origins inside v^T must be 16-byte aligned; the host pads with
+ *                          masked frames). */
 int srb_cfm_qk_rope(const void* xn_bf16, const void* w_packed, const float* rot_cos, const float* rot_sin,
-                    void* qk_bf16, int32_t batch, int32_t frames, void* stream);
+                    void* qk_bf16, float* qk_norm2_max, float* qk_norm2_clear, int32_t batch, int32_t frames,
+                    void* stream);
 int srb_cfm_v_transposed(const void* xn_bf16, const void* wv_bf16, void* vt_bf16, int64_t m_pad, void* stream);
 int srb_cfm_attention_tc(const void* qk_bf16, int32_t ld, const void* vt_bf16, int64_t m_pad, const int32_t* lengths,
-                         void* o_bf16, int32_t batch, int32_t frames, void* stream);
+                         const float* qk_norm2_max, void* o_bf16, int32_t batch, int32_t frames, void* stream);
 
 /* to_out + residual (transformer.py:129-130,203) fused with the following AdaptiveRMSNorm:
  *   x += o @ Wout^T ; xn = bf16(adanorm(x, g)) * mask */

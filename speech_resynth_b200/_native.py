@@ -14,6 +14,8 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsrb.so")
+if os.environ.get("SRB_DEBUG_LIB"):   # tools/trace_kernels.py: instrumented build of the same sources
+    LIB_PATH = os.environ["SRB_DEBUG_LIB"]
 
 _P = c_void_p
 _I = c_int32
@@ -33,9 +35,9 @@ _PROTOTYPES = {
     "srb_cfm_posconv_norm": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P],
     "srb_cfm_qkv_rope": [_P, _P, _P, _P, _P, _I, _I, _P],
     "srb_cfm_attention": [_P, _P, _P, _I, _I, _P],
-    "srb_cfm_qk_rope": [_P, _P, _P, _P, _P, _I, _I, _P],
+    "srb_cfm_qk_rope": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P],
     "srb_cfm_v_transposed": [_P, _P, _P, _L, _P],
-    "srb_cfm_attention_tc": [_P, _I, _P, _L, _P, _P, _I, _I, _P],
+    "srb_cfm_attention_tc": [_P, _I, _P, _L, _P, _P, _P, _I, _I, _P],
     "srb_cfm_attn_out_norm": [_P, _P, _P, _P, _P, _P, _I, _I, _P],
     "srb_cfm_ffn_glu": [_P, _P, _P, _P, _P, _I, _I, _P],
     "srb_cfm_ffn_out_norm": [_P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _P],

@@ -5,12 +5,21 @@ cd "$(dirname "$0")"
 OUT=../libsrb.so
 NVCC=${NVCC:-nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -O2"
+if [ "$1" = "trace" ]; then
+  # instrumented build for tools/trace_kernels.py (kept out of the package directory)
+  EXTRA="$EXTRA -DSRB_TRACE=1"
+  OUT=../../build/libsrb_trace.so
+  mkdir -p ../../build/trace
+  OBJ=../../build/trace
+else
+  OBJ=../../build
+fi
 mkdir -p ../../build
 pids=()
 for f in srb_convgemm srb_elementwise srb_attention srb_attention_tc srb_mrf_fused; do
-  $NVCC $FLAGS $EXTRA -c $f.cu -o ../../build/$f.o &
+  $NVCC $FLAGS $EXTRA -c $f.cu -o $OBJ/$f.o &
   pids+=($!)
 done
 for p in "${pids[@]}"; do wait $p; done
-$NVCC -shared -o $OUT ../../build/srb_convgemm.o ../../build/srb_elementwise.o ../../build/srb_attention.o ../../build/srb_attention_tc.o ../../build/srb_mrf_fused.o -lcudart
+$NVCC -shared -o $OUT $OBJ/srb_convgemm.o $OBJ/srb_elementwise.o $OBJ/srb_attention.o $OBJ/srb_attention_tc.o $OBJ/srb_mrf_fused.o -lcudart
 echo "built $(realpath $OUT)"

@@ -7,11 +7,15 @@
 //                 B = V^T tile.  V is produced already TRANSPOSED ([d][utterance*frames], keys contiguous) by a
 //                 swapped-operand GEMM (srb_cfm_v_transposed), so both operands of P V are K-major as well.
 //
-// Exact two-pass softmax instead of an online one: pass 1 runs Q K^T over all key tiles and keeps only the row
-// maxima, pass 2 recomputes S, forms P = exp2(s*scale - m) with the FINAL maximum and accumulates P V in TMEM.
-// O therefore never needs rescaling (no TMEM read-modify-write on the critical path); the price is a second Q K^T,
-// which is cheap on the tensor core (sequences here are <= a few thousand keys).  S is double-buffered in TMEM so
-// the tensor core computes S(j+1) while the softmax warps work on S(j).
+// Softmax is exact and never rescales O (no TMEM read-modify-write on the critical path).  Two forms:
+//   * single pass (the common case).  softmax is shift invariant, and in floating point (fp32 sums, bf16 P: both carry
+//     the fp32 exponent range) ANY shift works as long as nothing overflows or the row's largest term underflows.
+//     The caller supplies max |q|^2 and max |k|^2 per (utterance, head) (srb_cfm_qk_rope records them in its
+//     epilogue); by Cauchy-Schwarz every scaled logit lies in [-B, B], B = |q|max |k|max log2(e)/sqrt(128).  When
+//     B <= 100 the kernel uses shift 0: P = exp2(s*scale) in [2^-100, 2^100], one sweep over K and V;
+//   * two passes otherwise (or when no bounds are given): pass 1 runs Q K^T over all key tiles and keeps only the row
+//     maxima, pass 2 recomputes S and forms P = exp2(s*scale - m) with the FINAL maximum.
+// S is double-buffered in TMEM so the tensor core computes S(j+1) while the softmax warps work on S(j).
 //
 // Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer (+ TMEM allocator), warps 2-9 softmax/epilogue:
 // thread <-> query row (TMEM lane), and the two warps of a lane quarter split the 128 key columns of an S tile (and
@@ -33,6 +37,7 @@ struct AttnParams {
   CUtensorMap tm_qk;   // 3-D (ld, frames, batch), box (64, 128, 1)
   CUtensorMap tm_vt;   // 2-D (m_pad, 256), box (64, 128)
   const int* lengths;
+  const float* qk_norm2_max;   // (B, 2 [q|k], 2 [head], 2 [frequency half]) partial bounds of the squared row norms, or null
   __nv_bfloat16* out;  // (B, N, 256)
   int frames;
   int k_col;           // first column of k in the q|k buffer (256)
@@ -80,14 +85,6 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * kAttnTile;
-  int len = p.lengths[b];
-  len = len < p.frames ? len : p.frames;
-  const int nkv = (len + kAttnTile - 1) / kAttnTile;
-#ifndef SRB_ATTN_DEBUG
-#define SRB_ATTN_DEBUG 3
-#endif
-  const int npass = SRB_ATTN_DEBUG >= 3 ? 2 : (SRB_ATTN_DEBUG == 2 ? 1 : 0);
-
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
     for (int s = 0; s < 2; ++s) {
@@ -109,9 +106,25 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();   // q|k, v^T, lengths and the norm bounds are produced by the preceding kernels
+  int len = p.lengths[b];
+  len = len < p.frames ? len : p.frames;
+  const int nkv = (len + kAttnTile - 1) / kAttnTile;
+  const float sl2 = 0.08838834764831845f * 1.4426950408889634f;   // (1/sqrt(128)) * log2(e)
+  bool two_pass = true;
+  if (p.qk_norm2_max != nullptr) {
+    // two partial maxima per head (one per rotary frequency half, see epi_qkv_rope); their sum bounds the row norm
+    const float* nq = p.qk_norm2_max + ((b * 2 + 0) * 2 + h) * 2;
+    const float* nk = p.qk_norm2_max + ((b * 2 + 1) * 2 + h) * 2;
+    const float q2 = nq[0] + nq[1], k2 = nk[0] + nk[1];
+    // 2 % slack covers the bf16 rounding of q and k after the norms were taken; NaN compares false -> two passes
+    two_pass = !(sqrtf(q2 * k2) * sl2 * 1.02f <= 100.f);
+  }
+
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + AttnSmem::tmem);
   const uint32_t t_s0 = tmem_base, t_o = tmem_base + 256;
   constexpr uint32_t IDESC = umma_idesc_bf16(128, 128);
@@ -123,28 +136,30 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
     tma_load_3d_elect(s_q + kHalfBytes, &p.tm_qk, q_full, h * 128 + 64, q0, b);
     int kst = 0, vst = 0;
     uint32_t kph = 0, vph = 0;
-    for (int pass = 0; pass < npass; ++pass) {
-      for (int j = 0; j < nkv; ++j) {
-        mbar_wait(k_empty(kst), kph ^ 1u);
-        mbar_expect_tx_elect(k_full(kst), kTileBytes);
-        tma_load_3d_elect(s_k + kst * kTileBytes, &p.tm_qk, k_full(kst), p.k_col + h * 128, j * kAttnTile, b);
-        tma_load_3d_elect(s_k + kst * kTileBytes + kHalfBytes, &p.tm_qk, k_full(kst), p.k_col + h * 128 + 64, j * kAttnTile, b);
-        if (++kst == 2) { kst = 0; kph ^= 1u; }
-        if (pass == 1) {
-          mbar_wait(v_empty(vst), vph ^ 1u);
-          mbar_expect_tx_elect(v_full(vst), kTileBytes);
-          const int col = b * p.frames + j * kAttnTile;
-#if SRB_ATTN_DEBUG == 4
-          (void)col;
-          tma_load_3d_elect(s_v + vst * kTileBytes, &p.tm_qk, v_full(vst), h * 128, j * kAttnTile, b);
-          tma_load_3d_elect(s_v + vst * kTileBytes + kHalfBytes, &p.tm_qk, v_full(vst), h * 128 + 64, j * kAttnTile, b);
-#else
-          tma_load_2d_elect(s_v + vst * kTileBytes, &p.tm_vt, v_full(vst), col, h * 128);
-          tma_load_2d_elect(s_v + vst * kTileBytes + kHalfBytes, &p.tm_vt, v_full(vst), col + 64, h * 128);
-#endif
-          if (++vst == 2) { vst = 0; vph ^= 1u; }
-        }
-      }
+    auto load_k = [&](int j) {
+      mbar_wait(k_empty(kst), kph ^ 1u);
+      mbar_expect_tx_elect(k_full(kst), kTileBytes);
+      tma_load_3d_elect(s_k + kst * kTileBytes, &p.tm_qk, k_full(kst), p.k_col + h * 128, j * kAttnTile, b);
+      tma_load_3d_elect(s_k + kst * kTileBytes + kHalfBytes, &p.tm_qk, k_full(kst), p.k_col + h * 128 + 64, j * kAttnTile, b);
+      if (++kst == 2) { kst = 0; kph ^= 1u; }
+    };
+    auto load_v = [&](int j) {
+      mbar_wait(v_empty(vst), vph ^ 1u);
+      mbar_expect_tx_elect(v_full(vst), kTileBytes);
+      const int col = b * p.frames + j * kAttnTile;
+      tma_load_2d_elect(s_v + vst * kTileBytes, &p.tm_vt, v_full(vst), col, h * 128);
+      tma_load_2d_elect(s_v + vst * kTileBytes + kHalfBytes, &p.tm_vt, v_full(vst), col + 64, h * 128);
+      if (++vst == 2) { vst = 0; vph ^= 1u; }
+    };
+    int v_ahead = 0;
+    if (two_pass) {
+      // the V ring is idle during the maxima pass: fill it first
+      for (; v_ahead < 2 && v_ahead < nkv; ++v_ahead) load_v(v_ahead);
+      for (int j = 0; j < nkv; ++j) load_k(j);
+    }
+    for (int j = 0; j < nkv; ++j) {
+      load_k(j);
+      if (j >= v_ahead) load_v(j);
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -170,9 +185,9 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
       if (++kst == 2) { kst = 0; kph ^= 1u; }
       ++t;
     };
-    if (npass >= 1) for (int j = 0; j < nkv; ++j) issue_s();          // pass 1: maxima only
-    if (npass >= 2 && nkv > 0) issue_s();                            // pass 2, tile 0
-    for (int j = 0; j < (npass >= 2 ? nkv : 0); ++j) {
+    if (two_pass) for (int j = 0; j < nkv; ++j) issue_s();           // maxima pass
+    if (nkv > 0) issue_s();                                          // main pass, tile 0
+    for (int j = 0; j < nkv; ++j) {
       if (j + 1 < nkv) issue_s();                      // S(j+1) overlaps the softmax of S(j)
       mbar_wait(p_full, j & 1);
       mbar_wait(v_full(vst), vph);
@@ -195,11 +210,10 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
     const int half = (warp - 2) >> 2;                     // key-column half of S / output-column half of O
     const int row = quarter * 32 + lane;                  // query row inside the tile = TMEM lane
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
-    const float sl2 = 0.08838834764831845f * 1.4426950408889634f;   // (1/sqrt(128)) * log2(e)
     float* red = reinterpret_cast<float*>(smem + AttnSmem::red);
     int t = 0;
     float m = -INFINITY;
-    for (int j = 0; j < (npass >= 1 ? nkv : 0); ++j, ++t) {
+    for (int j = 0; j < (two_pass ? nkv : 0); ++j, ++t) {
       const int sb = t & 1;
       mbar_wait(s_full(sb), (t >> 1) & 1);
       tc_fence_after();
@@ -217,14 +231,17 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
       __syncwarp();
       if (lane == 0) mbar_arrive(s_empty(sb));
     }
-    // row maximum over both halves
-    red[half * 128 + row] = m;
-    pair_barrier(quarter);
-    m = fmaxf(m, red[(half ^ 1) * 128 + row]);
-    pair_barrier(quarter);                                // both have read before `red` is reused for the sums
-    const float m2 = m * sl2;     // finite: every utterance has at least one valid key
+    float m2 = 0.f;               // single pass: shift 0 (see the header comment)
+    if (two_pass) {
+      // row maximum over both halves
+      red[half * 128 + row] = m;
+      pair_barrier(quarter);
+      m = fmaxf(m, red[(half ^ 1) * 128 + row]);
+      pair_barrier(quarter);                              // both have read before `red` is reused for the sums
+      m2 = m * sl2;               // finite: every utterance has at least one valid key
+    }
     float l = 0.f;
-    for (int j = 0; j < (npass >= 2 ? nkv : 0); ++j, ++t) {
+    for (int j = 0; j < nkv; ++j, ++t) {
       const int sb = t & 1;
       mbar_wait(s_full(sb), (t >> 1) & 1);
       tc_fence_after();
@@ -310,7 +327,8 @@ static PFN_cuTensorMapEncodeTiled_v12000 attn_get_encode() {
 using namespace srb;
 
 extern "C" int srb_cfm_attention_tc(const void* qk_bf16, int32_t ld, const void* vt_bf16, int64_t m_pad,
-                                    const int32_t* lengths, void* o_bf16, int32_t batch, int32_t frames, void* stream) {
+                                    const int32_t* lengths, const float* qk_norm2_max, void* o_bf16, int32_t batch,
+                                    int32_t frames, void* stream) {
   if (batch <= 0 || frames <= 0) return 0;
   auto enc = attn_get_encode();
   SRB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
@@ -338,6 +356,7 @@ extern "C" int srb_cfm_attention_tc(const void* qk_bf16, int32_t ld, const void*
     SRB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(v^T) failed: %d", (int)r);
   }
   p.lengths = lengths;
+  p.qk_norm2_max = qk_norm2_max;
   p.out = static_cast<__nv_bfloat16*>(o_bf16);
   p.frames = frames;
   p.k_col = 256;
@@ -349,6 +368,6 @@ extern "C" int srb_cfm_attention_tc(const void* qk_bf16, int32_t ld, const void*
     configured[dev & 63] = true;
   }
   dim3 grid((frames + kAttnTile - 1) / kAttnTile, 2, batch);
-  attn_tc_kernel<<<grid, 320, AttnSmem::total, (cudaStream_t)stream>>>(p);
+  SRB_CUDA(launch_pdl(attn_tc_kernel, grid, dim3(320), AttnSmem::total, (cudaStream_t)stream, p));
   return after_launch("attn_tc_kernel");
 }

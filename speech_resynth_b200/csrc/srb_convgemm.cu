@@ -28,6 +28,31 @@ int check_cuda(cudaError_t e, const char* what) {
   set_error("%s: %s", what, cudaGetErrorString(e));
   return -1;
 }
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SRB_PDL");
+    v = e ? (atoi(e) != 0) : 1;
+  }
+  return v != 0;
+}
+bool l2_persist_reserve() {
+  // 0 = not tried, 1 = reserved, -1 = unavailable (per device)
+  static int state[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& st = state[dev & 63];
+  if (st == 0) {
+    int max_persist = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+    // the fp32 residual stream of the largest single-GPU bucket (64 x 504 x 256 x 4 B = 33 MB) with headroom
+    size_t want = 48u << 20;
+    if ((size_t)max_persist < want) want = (size_t)max_persist;
+    st = (want > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) ? 1 : -1;
+    cudaGetLastError();
+  }
+  return st > 0;
+}
 int num_sms() {
   static int sms[64] = {0};
   int dev = 0;
@@ -88,6 +113,30 @@ static int make_weight_map(CUtensorMap* m, const void* ptr, int k_total, int n_t
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SRB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weight) failed: %d (K=%d N=%d kb=%d bn=%d)", (int)r, k_total,
               n_total, kb, bn);
+  return 0;
+}
+
+// epilogue I/O view (batch, rows, columns) of 2- or 4-byte elements -> 3-D map, box = (32 columns, 32 rows, 1): the block
+// one epilogue warp stages.  The swizzle equals the row width (64 B for bf16, 128 B for fp32), which is exactly the
+// XOR pattern of stage_slot<4> / stage_slot<8>.
+static int make_io_map(CUtensorMap* m, const void* ptr, int elt_bytes, int columns, int rows, int batch, long long row_stride,
+                       long long batch_stride) {
+  auto enc = get_encode();
+  SRB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+  SRB_REQUIRE(elt_bytes == 2 || elt_bytes == 4, "epilogue I/O maps are bf16 or fp32");
+  SRB_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "epilogue tensor not 16-byte aligned");
+  SRB_REQUIRE((row_stride * elt_bytes) % 16 == 0 && (batch_stride * elt_bytes) % 16 == 0 && columns % 32 == 0,
+              "epilogue tensor strides must be multiples of 16 bytes and its width a multiple of 32 columns");
+  cuuint64_t dims[3] = {(cuuint64_t)columns, (cuuint64_t)rows, (cuuint64_t)batch};
+  cuuint64_t strides[2] = {(cuuint64_t)row_stride * elt_bytes, (cuuint64_t)(batch > 1 ? batch_stride : (long long)rows * row_stride) * elt_bytes};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, elt_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr),
+                   dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   elt_bytes == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SRB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(epilogue I/O) failed: %d (cols=%d rows=%d B=%d rs=%lld bs=%lld)", (int)r,
+              columns, rows, batch, row_stride, batch_stride);
   return 0;
 }
 
@@ -161,9 +210,8 @@ static int launch_inst(ConvGemmParams& p, int total_tiles, cudaStream_t stream, 
   // RESNORM: two residual-stream buffers per epilogue warp when the K loop is short (the epilogue, not the MMAs,
   // paces those launches); one when the long K loop (FFN conv2) needs the shared memory for its weight ring
   p.res_bufs = (EPI == EPI_RESNORM && n_slabs <= 8) ? 2 : 1;
-  if (EPI == EPI_RESNORM && n_slabs > 8) a_stages = 2;
   // coalescing / streaming buffers of the epilogue warps + CTA-wide epilogue tables
-  const int stage_smem = EpiWarps<BN, EPI>::value * EpiWarps<BN, EPI>::stage_bytes(p.res_bufs) + EpiWarps<BN, EPI>::extra_bytes + 128;
+  const int stage_smem = EpiWarps<BN, EPI>::value * EpiWarps<BN, EPI>::stage_bytes(p.res_bufs) + EpiWarps<BN, EPI>::extra_bytes;
   if (MC == 2) w_stages = 6;
   if (!WS && n_slabs > 0 && w_stages > n_slabs) w_stages = n_slabs < 2 ? 2 : n_slabs;
   if (WS) {
@@ -182,7 +230,9 @@ static int launch_inst(ConvGemmParams& p, int total_tiles, cudaStream_t stream, 
   p.w_stages = w_stages;
   while (a_stages * a_bytes + w_stages * w_stage_bytes + stage_smem > 222 * 1024 && w_stages > 2 && !WS) --w_stages;
   p.w_stages = w_stages;
-  const int smem = a_stages * a_bytes + w_stages * w_stage_bytes + 1024 + 8 * (2 * (a_stages + w_stages) + 4) + 16 + 1024 + stage_smem;
+  // alignment slack + rings + 2 KB bookkeeping block (barriers, TMEM slot, norm exchange) + epilogue staging / tables
+  SRB_REQUIRE(8 * (2 * (a_stages + w_stages) + 4) + 16 + 1024 + 128 <= 2048, "too many pipeline stages for the bookkeeping block");
+  const int smem = 1024 + a_stages * a_bytes + w_stages * w_stage_bytes + 2048 + stage_smem;
   static int configured_smem[64] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -218,13 +268,15 @@ static int launch_inst(ConvGemmParams& p, int total_tiles, cudaStream_t stream, 
     cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     SRB_CUDA(cudaLaunchKernelEx(&cfg, kernel, p, total_tiles));
     return after_launch("convgemm_kernel(multicast)");
   }
@@ -234,17 +286,31 @@ static int launch_inst(ConvGemmParams& p, int total_tiles, cudaStream_t stream, 
     if (walkers > total_tiles) walkers = total_tiles;
     if (walkers < 1) walkers = 1;
     grid = walkers * p.n_tiles;
-    kernel<<<grid, threads, smem, stream>>>(p, total_tiles);
+    SRB_CUDA(launch_pdl(kernel, dim3(grid), dim3(threads), smem, stream, p, total_tiles));
     return after_launch("convgemm_kernel(weight-stationary)");
   }
   if (grid > total_tiles) grid = total_tiles;
   if (grid < 1) return 0;
-  kernel<<<grid, threads, smem, stream>>>(p, total_tiles);
+  L2Window win;
+  if (EPI == EPI_RESNORM && p.l2_keep == 2) {
+    // the residual stream is updated in place: keep it in the persisting part of L2 between its two uses per layer
+    win.base = p.out1;
+    win.bytes = (size_t)p.batch * (size_t)p.out_batch_stride * 4;
+  }
+  SRB_CUDA(launch_pdl_window(kernel, dim3(grid), dim3(threads), smem, stream, win, p, total_tiles));
   return after_launch("convgemm_kernel");
 }
 
+#ifdef SRB_TRACE
+static unsigned long long* g_trace = nullptr;
+extern "C" void srb_debug_set_trace(unsigned long long* buf) { g_trace = buf; }
+#endif
+
 static int launch_convgemm(const ConvGemmDesc& d, cudaStream_t stream) {
   ConvGemmParams p = d.epi;
+#ifdef SRB_TRACE
+  p.trace = g_trace;
+#endif
   const int bn = d.block_n, kb = d.block_k;
   SRB_REQUIRE(d.n_total % bn == 0, "n_total %d not a multiple of block_n %d", d.n_total, bn);
   SRB_REQUIRE(d.n_groups >= 1 && d.n_groups <= kMaxGroups, "bad group count %d", d.n_groups);
@@ -314,6 +380,21 @@ static int launch_convgemm(const ConvGemmDesc& d, cudaStream_t stream) {
   int rc = make_weight_map(&p.tmW, d.weight, k_total, d.n_total, kb, bn);
   if (rc) return rc;
   if (tiles == 0) return 0;
+  if (d.epilogue == EPI_RESNORM || d.epilogue == EPI_QKV_ROPE) {
+    // epilogue I/O through TMA (see epi_resnorm): all of these tensors are (batch, rows, row_stride columns)
+    const int rows = d.group_rows[0];
+    if (d.epilogue == EPI_RESNORM) {
+      SRB_REQUIRE(p.res[0] != nullptr && p.out1 != nullptr, "RESNORM needs a residual and an fp32 output");
+      rc = make_io_map(&p.tmR, p.res[0], 4, (int)p.res_row_stride, rows, d.batch, p.res_row_stride, p.res_batch_stride);
+      if (rc) return rc;
+      rc = make_io_map(&p.tmO1, p.out1, 4, (int)p.out_row_stride, rows, d.batch, p.out_row_stride, p.out_batch_stride);
+      if (rc) return rc;
+    }
+    if (p.out0 != nullptr) {
+      rc = make_io_map(&p.tmO0, p.out0, 2, (int)p.out_row_stride, rows, d.batch, p.out_row_stride, p.out_batch_stride);
+      if (rc) return rc;
+    }
+  }
   // weight multicast across 2-CTA clusters for the wide tiles (needs an even number of row tiles)
   const int row_tiles = d.batch * p.m_tiles[0];
   const int mode = (bn == 256 && kb == 64 && d.n_groups == 1 && row_tiles % 2 == 0 && row_tiles >= 2) ? cluster_mode() : 0;
@@ -367,6 +448,17 @@ static int launch_convgemm(const ConvGemmDesc& d, cudaStream_t stream) {
 #undef SRB_DISPATCH
   set_error("no convgemm instantiation for block_n=%d block_k=%d epilogue=%d", bn, kb, d.epilogue);
   return -4;
+}
+
+// residual stream residency (A/B knob SRB_L2_KEEP): 0 = none, 1 = evict_last policy on its TMA transfers (default),
+// 2 = persisting L2 window as a launch attribute (costs the vocoder its share of L2)
+static int l2_keep_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SRB_L2_KEEP");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
 }
 
 static ConvGemmParams empty_epi() {
@@ -463,7 +555,8 @@ int srb_cfm_qkv_rope(const void* xn_bf16, const void* w_packed, const float* rot
 }
 
 int srb_cfm_qk_rope(const void* xn_bf16, const void* w_packed, const float* rot_cos, const float* rot_sin,
-                    void* qk_bf16, int32_t batch, int32_t frames, void* stream) {
+                    void* qk_bf16, float* qk_norm2_max, float* qk_norm2_clear, int32_t batch, int32_t frames, void* stream) {
+  SRB_REQUIRE(qk_norm2_clear == nullptr || qk_norm2_clear != qk_norm2_max, "srb_cfm_qk_rope: the buffer to clear must differ from the one to fill");
   // q and k only (first 512 rows of to_qkv.weight); v is produced transposed by srb_cfm_v_transposed
   ConvGemmDesc d;
   d.src[0] = act(xn_bf16, batch, frames, 256);
@@ -480,6 +573,8 @@ int srb_cfm_qk_rope(const void* xn_bf16, const void* w_packed, const float* rot_
   d.epi.vec0 = rot_cos;
   d.epi.vec1 = rot_sin;
   d.epi.out0 = qk_bf16;
+  d.epi.aux0 = qk_norm2_max;
+  d.epi.aux1 = qk_norm2_clear;
   d.epi.out_row_stride = 512;
   d.epi.out_batch_stride = (long long)frames * 512;
   return launch_convgemm(d, (cudaStream_t)stream);
@@ -524,6 +619,7 @@ int srb_cfm_attn_out_norm(const void* o_bf16, const void* w_packed, const float*
   d.epilogue = EPI_RESNORM;
   d.epi = empty_epi();
   d.epi.norm_mode = 1;
+  d.epi.l2_keep = l2_keep_enabled();
   d.epi.vec0 = g;
   d.epi.lengths = lengths;
   d.epi.res[0] = x;
@@ -579,6 +675,7 @@ int srb_cfm_ffn_out_norm(const void* h_bf16, const void* w_packed, const float* 
   d.epilogue = EPI_RESNORM;
   d.epi = empty_epi();
   d.epi.norm_mode = norm_mode;
+  d.epi.l2_keep = l2_keep_enabled();
   d.epi.bias = bias;
   d.epi.vec0 = g;
   d.epi.lengths = lengths;

@@ -32,6 +32,9 @@ struct ConvGemmParams {
   CUtensorMap tmA[kMaxSrc];
   CUtensorMap tmW;
   CUtensorMap tmWh;                               // weight map with a half-height box (2-CTA multicast variant)
+  // epilogue I/O through TMA (RESNORM, QKV_ROPE): 3-D maps (columns, rows, batch) with a 32-column x 32-row box --
+  // one epilogue warp's block.  tmR: fp32 residual, tmO1: fp32 output stream, tmO0: bf16 output.
+  CUtensorMap tmR, tmO1, tmO0;
   // problem
   int batch, kchunks, n_groups, n_tiles;          // n_tiles = n_total / BN
   int m_tiles[kMaxGroups];                        // row tiles per batch, per group
@@ -51,6 +54,7 @@ struct ConvGemmParams {
   int a_box_bytes;                                // a_box_rows * KB * 2, rounded up to 1024
   int a_stages, w_stages;
   int res_bufs;                                   // RESNORM: residual-stream buffers per epilogue warp (1 or 2)
+  int l2_keep;                                    // RESNORM: 1 = evict_last policy on the residual stream's TMA transfers
   // epilogue operands
   const float* bias;
   void* out0;                                     // bf16 "activated"/normalised output
@@ -66,7 +70,25 @@ struct ConvGemmParams {
   float f0, f1, f2, f3;                           // EULER: dt, std, mean, pad
   void* aux0;                                     // EULER: mel fp32 (or null)
   void* aux1;                                     // EULER: mel bf16
+#ifdef SRB_TRACE
+  unsigned long long* trace;                      // debug build only: %globaltimer stamps, see SRB_TRACE_AT
+#endif
 };
+
+// Debug-only timeline (built with -DSRB_TRACE into libsrb_trace.so by tools/trace_kernels.py; never in libsrb.so):
+// stamp slot (CTA, role, tile, k) with the global nanosecond timer.
+#ifdef SRB_TRACE
+__device__ __forceinline__ void srb_trace_at(const ConvGemmParams& p, int role, int tile_it, int k) {
+  if (p.trace != nullptr && blockIdx.x < 8 && tile_it < 8) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.trace[((blockIdx.x * 3 + role) * 8 + tile_it) * 4 + k] = t;
+  }
+}
+#define SRB_TRACE_AT(role, it, k) do { if (lane == 0) srb_trace_at(p, role, it, k); } while (0)
+#else
+#define SRB_TRACE_AT(role, it, k) do { } while (0)
+#endif
 
 template <int BN>
 struct TmemCols {
@@ -174,8 +196,8 @@ __device__ __forceinline__ void async_gather(uint8_t* buf, const void* gbase, lo
   for (int i = 0; i < P; ++i) {
     const int idx = lane + 32 * i, row = idx / P, piece = idx % P;
     const bool ok = row < valid_rows;
-    cp_async_16(smem_u32(stage_slot<P>(buf, row, piece)), ok ? static_cast<const void*>(g + row * row_stride_bytes + piece * 16) : safe,
-                ok ? 16u : 0u);
+    const void* src = ok ? static_cast<const void*>(g + row * row_stride_bytes + piece * 16) : safe;
+    cp_async_16(smem_u32(stage_slot<P>(buf, row, piece)), src, ok ? 16u : 0u);
   }
 }
 
@@ -337,36 +359,49 @@ __device__ __forceinline__ void pair_barrier(int quarter) {
   }
 }
 
+// Epilogue I/O goes through TMA.  In-kernel timelines showed the register / LSU path (ld.global or cp.async into a
+// staging buffer, st.shared + ld.shared + st.global out of it) pacing every small-K launch: 7-10 us of epilogue per
+// 128 x 256 tile against 1 us of MMAs, bound by LSU / shared-memory-pipe throughput (neither more warps nor L2
+// residency moved it).  With TMA a block costs the warp one instruction on one lane; the staging buffers use the
+// tensor maps' own swizzle (128-byte rows: stage_slot<8>, 64-byte rows: stage_slot<4>), so a thread reads / writes its
+// own row bank-conflict free and rows outside the tensor are zero-filled on load and clipped on store.
+//
 // The fp32 residual blocks (32 rows x 32 columns = 4 KB) of a warp's column half form a STREAM -- chunk after chunk,
-// tile after tile -- that is copied asynchronously (cp.async) into `nb` rotating warp-private buffers ahead of use:
-// the copy of chunk s + nb is issued as soon as chunk s has left its buffer, also across tile boundaries, so the L2
-// latency of the residual never sits on the epilogue's critical path and no registers hold data in flight (the
-// register-staged form spilled its prefetch arrays and stalled on the spill stores).  The buffer of a chunk doubles as
-// the coalescing stage of that chunk's fp32 output.  `issue_next(buf)` issues the next chunk of the stream into `buf`
-// and commits one cp.async group (an empty one past the end of the stream).
-template <int NHALF, typename IssueNext>
+// tile after tile.  Chunk s lands in load buffer s % nb and signals that buffer's mbarrier (phase (s / nb) & 1);
+// `issue_load(s, buf, bar)` asks for chunk s (nothing past the end of the stream).
+//   nb == 2: separate 4 KB store stage; a load buffer is refilled as soon as the warp has read it, also across tiles.
+//   nb == 1 (long K loops, shared memory goes to the weight ring): the output is staged in place and the buffer is
+//            refilled once the store has read it (the latency hides under the MMAs of the next tile).
+struct ResStream {
+  uint32_t buf;        // shared address of the nb load buffers (1024-byte aligned), then the store stage when nb == 2
+  uint32_t bar;        // nb mbarriers
+  uint8_t* gen;        // generic pointer to `buf`
+  int nb;
+  int seq;             // chunks consumed so far
+};
+
+template <int NHALF, typename IssueLoad>
 __device__ __forceinline__ void epi_resnorm(const ConvGemmParams& p, uint32_t tacc, const TileCoord& tc, int q, int half,
-                                            float* red, int row_in_tile, int quarter, const EpiWarp& w, int nb, int& chunk_seq,
-                                            IssueNext&& issue_next) {
+                                            float* red, int row_in_tile, int quarter, const EpiWarp& w, ResStream& rs,
+                                            IssueLoad&& issue_load) {
   constexpr int COLS = 256 / NHALF;
   constexpr int NCHUNK = COLS / 32;
   static_assert(NCHUNK == 4, "RESNORM runs with eight epilogue warps");
-  const int vrows = clamp_rows(p.group_rows[0], w.row0);
-  const long long woff = (long long)tc.b * p.out_batch_stride + (long long)w.row0 * p.out_row_stride + half * COLS;
-  float* xout = static_cast<float*>(p.out1) + woff;
   const uint32_t tcol = tacc + half * COLS;
+  const int nb = rs.nb;
+  const uint32_t st_stage = rs.buf + (nb == 2 ? 2 * 4096 : 0);
+  uint8_t* st_gen = rs.gen + (nb == 2 ? 2 * 4096 : 0);
   float sumsq = 0.f;
 #pragma unroll
   for (int c = 0; c < NCHUNK; ++c) {
-    EpiWarp wb = w;
-    wb.stage = w.stage + (nb == 2 ? (chunk_seq & 1) * 4096 : 0);
-    if (nb == 2) cp_async_wait<1>();
-    else cp_async_wait<0>();
-    __syncwarp();
+    const int s = rs.seq;
+    const int bi = nb == 2 ? (s & 1) : 0;
+    mbar_wait(rs.bar + 8u * bi, nb == 2 ? ((s >> 1) & 1) : (s & 1));
     uint4 rr[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) rr[j] = *stage_slot<8>(wb.stage, w.lane, j);
-    __syncwarp();   // every lane has its row before the buffer becomes the store stage
+    for (int j = 0; j < 8; ++j) rr[j] = *stage_slot<8>(rs.gen + bi * 4096, w.lane, j);
+    __syncwarp();   // every lane has its row
+    if (nb == 2) issue_load(s + 2, bi);
     uint32_t v[32];
     tmem_ld32(tcol + c * 32, v);
     tmem_ld_wait();
@@ -387,9 +422,26 @@ __device__ __forceinline__ void epi_resnorm(const ConvGemmParams& p, uint32_t ta
       v[4 * j + 2] = __float_as_uint(y.z); v[4 * j + 3] = __float_as_uint(y.w);
       yo[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     }
-    scatter_store<8>(wb, yo, xout + c * 32, p.out_row_stride * 4, vrows);
-    issue_next(wb.stage);
-    ++chunk_seq;
+    if (nb == 2) {
+      if (w.lane == 0) bulk_wait_read<0>();   // the previous block has left the store stage
+      __syncwarp();
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) *stage_slot<8>(st_gen, w.lane, j) = yo[j];
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (w.lane == 0) {
+      if (p.l2_keep) tma_store_3d_hint(&p.tmO1, st_stage, half * COLS + c * 32, w.row0, tc.b, kL2EvictLast);
+      else tma_store_3d(&p.tmO1, st_stage, half * COLS + c * 32, w.row0, tc.b);
+      bulk_commit();
+      // in place: the buffer takes the next chunk once the store has read it; the last chunk of a tile waits until
+      // the bf16 pass below has used the buffer as its stage
+      if (nb != 2 && (c < NCHUNK - 1 || p.norm_mode == 0)) {
+        bulk_wait_read<0>();
+        issue_load(s + 1, 0);
+      }
+    }
+    ++rs.seq;
     if (p.norm_mode != 0) tmem_st32(tcol + c * 32, v);  // stash y for the second pass
   }
   if (p.norm_mode == 0) return;
@@ -403,10 +455,8 @@ __device__ __forceinline__ void epi_resnorm(const ConvGemmParams& p, uint32_t ta
   if (p.norm_mode == 1) inv = 1.f / fmaxf(sqrtf(sumsq), 1e-12f);           // F.normalize (norm.py:41)
   else inv = rsqrtf(sumsq * (1.f / 256.f) + 1.1920928955078125e-07f);      // nn.RMSNorm eps = finfo(fp32).eps
   const bool keep = q < p.group_rows[0] && (p.lengths == nullptr || q < p.lengths[tc.b]);
-  __nv_bfloat16* xn = static_cast<__nv_bfloat16*>(p.out0) + woff;
   const float* gv = p.vec0 + half * COLS;
-  EpiWarp wn = w;
-  wn.stage = w.stage + nb * 4096;   // bf16 stage, separate from the residual buffers (which hold copies in flight)
+  // bf16 blocks (32 rows x 64 B = 2 KB) alternate between the two halves of the 4 KB store stage
 #pragma unroll
   for (int c = 0; c < NCHUNK; ++c) {
     uint32_t v[32];
@@ -421,7 +471,24 @@ __device__ __forceinline__ void epi_resnorm(const ConvGemmParams& p, uint32_t ta
       ow[2 * j] = keep ? pack_bf16(__uint_as_float(v[4 * j]) * inv * g.x, __uint_as_float(v[4 * j + 1]) * inv * g.y) : 0u;
       ow[2 * j + 1] = keep ? pack_bf16(__uint_as_float(v[4 * j + 2]) * inv * g.z, __uint_as_float(v[4 * j + 3]) * inv * g.w) : 0u;
     }
-    scatter_store<4>(wn, o, xn + c * 32, p.out_row_stride * 2, vrows);
+    if (w.lane == 0) {
+      if (c < 2) bulk_wait_read<0>();   // fp32 blocks (and, in place, the whole buffer) have been read
+      else bulk_wait_read<1>();         // the other half may still be draining
+    }
+    __syncwarp();
+    uint8_t* hb = st_gen + (c & 1) * 2048;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) *stage_slot<4>(hb, w.lane, j) = o[j];
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (w.lane == 0) {
+      tma_store_3d(&p.tmO0, st_stage + (c & 1) * 2048, half * COLS + c * 32, w.row0, tc.b);
+      bulk_commit();
+    }
+  }
+  if (nb != 2 && w.lane == 0) {
+    bulk_wait_read<0>();
+    issue_load(rs.seq, 0);
   }
   if constexpr (NHALF == 2) {
     // the pair must not overwrite `red` for the next tile before both have read it
@@ -447,15 +514,37 @@ __device__ __forceinline__ void rope_table_to_smem(const ConvGemmParams& p, uint
   }
 }
 
+// row r0 of the cos | sin tables, one 16-byte piece per lane (issued before the warp waits for the tile's MMAs)
+__device__ __forceinline__ float4 rope_row_fetch(const ConvGemmParams& p, const TileCoord& tc, const EpiWarp& w) {
+  if (tc.n == 2) return make_float4(0.f, 0.f, 0.f, 0.f);
+  // the row exists whenever the warp has a valid row; otherwise nothing is stored and row 0 stands in
+  const long long r0 = clamp_rows(p.group_rows[0], w.row0) > 0 ? w.row0 : 0;
+  return __ldg(reinterpret_cast<const float4*>((w.lane < 16 ? p.vec0 : p.vec1) + r0 * 64) + (w.lane & 15));
+}
+
 template <int NHALF>
 __device__ __forceinline__ void epi_qkv_rope(const ConvGemmParams& p, uint32_t tacc, const TileCoord& tc, int half,
-                                             const EpiWarp& w, const uint8_t* tab_b) {
+                                             const EpiWarp& w, const uint8_t* tab_b, const float4& row_piece) {
   static_assert(NHALF == 2, "QKV_ROPE runs with eight epilogue warps (one head per column half)");
-  const int vrows = clamp_rows(p.group_rows[0], w.row0);
-  __nv_bfloat16* out = static_cast<__nv_bfloat16*>(p.out0) + (long long)tc.b * p.out_batch_stride +
-                       (long long)w.row0 * p.out_row_stride + tc.n * 256 + half * 128;
-  const long long ostride = p.out_row_stride * 2;
+  const int col0 = tc.n * 256 + half * 128;   // first output column of this warp
   const uint32_t tcol = tacc + half * 128;
+  const uint32_t stage_s = smem_u32(w.stage);
+  // output blocks (32 rows x 64 B = 2 KB, 64-byte swizzle) alternate between the two halves of the 4 KB stage
+  int blk = 0;
+  auto put_block = [&](const uint4 (&o)[4], int col) {
+    if (w.lane == 0) bulk_wait_read<1>();   // the block stored from this half two blocks ago has been read
+    __syncwarp();
+    uint8_t* hb = w.stage + (blk & 1) * 2048;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) *stage_slot<4>(hb, w.lane, j) = o[j];
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (w.lane == 0) {
+      tma_store_3d(&p.tmO0, stage_s + (blk & 1) * 2048, col, w.row0, tc.b);
+      bulk_commit();
+    }
+    ++blk;
+  };
   if (tc.n == 2) {
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -469,19 +558,20 @@ __device__ __forceinline__ void epi_qkv_rope(const ConvGemmParams& p, uint32_t t
                           pack_bf16(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
                           pack_bf16(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
                           pack_bf16(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
-      scatter_store<4>(w, o, out + c * 32, ostride, vrows);
+      put_block(o, col0 + c * 32);
     }
     return;
   }
-  // table row r0 exists whenever the warp has a valid row; otherwise nothing is stored and row 0 stands in
-  const long long r0 = vrows > 0 ? w.row0 : 0;
-  const float4* ca4 = reinterpret_cast<const float4*>(p.vec0 + r0 * 64);
-  const float4* sa4 = reinterpret_cast<const float4*>(p.vec1 + r0 * 64);
+  // table row r0 (cos pieces 0..15 | sin pieces 0..15) goes through a warp-private 512-byte area: broadcast reads
+  float4* tab_a = reinterpret_cast<float4*>(w.stage + 4096);
+  tab_a[w.lane] = row_piece;
+  __syncwarp();
   const uint8_t* cb_row = tab_b + w.lane * 256;
   const uint8_t* sb_row = tab_b + 8192 + w.lane * 256;
   const int swz = w.lane & 7;
 #pragma unroll
   for (int f = 0; f < 2; ++f) {
+    float norm2 = 0.f;   // squared norm of columns i, i + 64 (i in this frequency half) of the row: rotation invariant
     uint32_t lo[32], hi[32];
     tmem_ld32(tcol + f * 32, lo);
     tmem_ld32(tcol + 64 + f * 32, hi);
@@ -492,7 +582,7 @@ __device__ __forceinline__ void epi_qkv_rope(const ConvGemmParams& p, uint32_t t
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int piece = f * 8 + j;
-      const float4 ca = __ldg(ca4 + piece), sa = __ldg(sa4 + piece);
+      const float4 ca = tab_a[piece], sa = tab_a[16 + piece];
       const float4 cb = *reinterpret_cast<const float4*>(cb_row + ((piece ^ swz) << 4));
       const float4 sb = *reinterpret_cast<const float4*>(sb_row + ((piece ^ swz) << 4));
       const float cx = ca.x * cb.x - sa.x * sb.x, sx = sa.x * cb.x + ca.x * sb.x;
@@ -503,13 +593,21 @@ __device__ __forceinline__ void epi_qkv_rope(const ConvGemmParams& p, uint32_t t
       const float a2 = __uint_as_float(lo[4 * j + 2]), a3 = __uint_as_float(lo[4 * j + 3]);
       const float b0 = __uint_as_float(hi[4 * j]), b1 = __uint_as_float(hi[4 * j + 1]);
       const float b2 = __uint_as_float(hi[4 * j + 2]), b3 = __uint_as_float(hi[4 * j + 3]);
+      norm2 += (a0 * a0 + b0 * b0) + (a1 * a1 + b1 * b1) + (a2 * a2 + b2 * b2) + (a3 * a3 + b3 * b3);
       wl[2 * j] = pack_bf16(a0 * cx - b0 * sx, a1 * cy - b1 * sy);
       wl[2 * j + 1] = pack_bf16(a2 * cz - b2 * sz, a3 * cw - b3 * sw);
       wh[2 * j] = pack_bf16(b0 * cx + a0 * sx, b1 * cy + a1 * sy);
       wh[2 * j + 1] = pack_bf16(b2 * cz + a2 * sz, b3 * cw + a3 * sw);
     }
-    scatter_store<4>(w, olo, out + f * 32, ostride, vrows);
-    scatter_store<4>(w, ohi, out + 64 + f * 32, ostride, vrows);
+    put_block(olo, col0 + f * 32);
+    put_block(ohi, col0 + 64 + f * 32);
+    if (p.aux0 != nullptr) {
+      // per-(utterance, q|k, head, f) maximum of the partial squared row norms for the attention kernel's single-pass
+      // test (max_f0 + max_f1 bounds the maximum of the sum); non-negative floats order like their bit patterns, rows
+      // outside the tensor have zero accumulators
+      const unsigned mx = __reduce_max_sync(0xffffffffu, __float_as_uint(norm2));
+      if (w.lane == 0) atomicMax(static_cast<unsigned*>(p.aux0) + ((tc.b * 2 + tc.n) * 2 + half) * 2 + f, mx);
+    }
   }
 }
 
@@ -573,7 +671,10 @@ struct EpiWarps {
   static constexpr int value = EPI == EPI_GLU ? 16 : ((BN >= 128 && EPI != EPI_EULER) ? 8 : 4);
   // staging bytes per epilogue warp: bf16 output blocks are 2 KB (4 pieces per row); RESNORM adds `res_bufs` 4 KB
   // buffers for the asynchronous fp32 residual stream (they double as the fp32 output stage)
-  __host__ __device__ static constexpr int stage_bytes(int res_bufs) { return EPI == EPI_RESNORM ? res_bufs * 4096 + 2048 : 2048; }
+  // (multiples of 1024: the TMA-staged blocks need their swizzle alignment)
+  __host__ __device__ static constexpr int stage_bytes(int res_bufs) {
+    return EPI == EPI_RESNORM ? (res_bufs == 2 ? 3 * 4096 : 4096) : (EPI == EPI_QKV_ROPE ? 5120 : 2048);
+  }
   // CTA-wide extra: the rotary offset table (cos | sin of positions 0..31)
   static constexpr int extra_bytes = EPI == EPI_QKV_ROPE ? 16384 : 0;
 };
@@ -631,9 +732,13 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t red_off = (bar_base - smem_base) + 8 * (n_ring_bars + 4) + 16;
   float* red = reinterpret_cast<float*>(smem_gen + red_off);  // [2][128]
-  uint8_t* extra_base = smem_gen + ((red_off + 1024 + 127) & ~127u);                 // CTA-wide epilogue tables
-  uint8_t* stage_base = extra_base + EpiWarps<BN, EPI>::extra_bytes;                 // EW warp-private staging areas
+  const uint32_t epi_bar = smem_base + ((red_off + 1024 + 15) & ~15u);               // EW x 2 residual-stream mbarriers
+  // the bookkeeping block (ring barriers, TMEM slot, `red`, epilogue barriers) is 2 KB; bar_base is 1024-aligned
+  // (written as an explicitly aligned offset: with the plain sum the compiler lost the 1024-byte alignment of the
+  // staging areas and spent ~50 % more integer instructions on every swizzled slot address)
+  uint8_t* stage_base = smem_gen + ((red_off + 1024 + 128 + 1023) & ~1023u);         // EW warp-private staging areas
   const int stage_bytes = EpiWarps<BN, EPI>::stage_bytes(p.res_bufs);
+  uint8_t* extra_base = stage_base + EW * stage_bytes;                               // CTA-wide epilogue tables
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform (uniform datapath)
   const int lane = threadIdx.x & 31;
@@ -657,6 +762,7 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
     }
   };
 
+  if (warp == 0) SRB_TRACE_AT(0, 0, 0);   // kernel entry
   if (threadIdx.x == 0) {
     for (int s = 0; s < a_stages; ++s) {
       mbar_init(a_full(s), 1);
@@ -670,6 +776,12 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
       mbar_init(tfull_bar(b), 1);
       mbar_init(tempty_bar(b), MC == 2 ? 2 * EW : EW);
     }
+    if constexpr (EPI == EPI_RESNORM) {
+      for (int i = 0; i < 2 * EW; ++i) mbar_init(epi_bar + 8u * i, 1);
+      tma_prefetch_desc(&p.tmR);
+      tma_prefetch_desc(&p.tmO1);
+    }
+    if constexpr (EPI == EPI_RESNORM || EPI == EPI_QKV_ROPE) tma_prefetch_desc(&p.tmO0);
     fence_barrier_init();
     tma_prefetch_desc(&p.tmW);
     tma_prefetch_desc(&p.tmA[0]);
@@ -684,11 +796,21 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
       tmem_relinquish();
     }
   }
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   if constexpr (MC) cluster_sync_all();   // peer barriers are initialised before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+  // everything above touched only shared / tensor memory and constant tables; activations come after this point
+  if (warp == 0) SRB_TRACE_AT(0, 0, 1);   // prologue done
+  pdl_wait();
+  if (warp == 0) SRB_TRACE_AT(0, 0, 2);   // dependencies satisfied
+  if constexpr (EPI == EPI_QKV_ROPE) {
+    // clear the norm-bound buffer of the NEXT q|k projection (nobody reads or fills it while this launch runs)
+    if (blockIdx.x == 0 && p.aux1 != nullptr)
+      for (int i = threadIdx.x; i < p.batch * 8; i += blockDim.x) static_cast<float*>(p.aux1)[i] = 0.f;
+  }
 
   if (warp == 0) {
     // TMA producer: converged warp, one elected lane issues (coordinates stay in uniform registers)
@@ -761,6 +883,7 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
         const uint32_t bphase = (it >> 1) & 1;
         mbar_wait(tempty_bar(buf), bphase ^ 1u);
         tc_fence_after();
+        SRB_TRACE_AT(1, it, 0);   // accumulator buffer free
         const uint32_t tacc = tmem_base + buf * TBUF;
         uint32_t first = 1;
         for (int sg = p.group_seg_begin[tc.group]; sg < p.group_seg_begin[tc.group + 1]; ++sg) {
@@ -768,6 +891,7 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
           const int tb = p.seg_tap_begin[sg], te = p.seg_tap_begin[sg + 1];
           for (int kc = 0; kc < p.kchunks; ++kc) {
             mbar_wait(a_full(ai), aph);
+            if (kc == 0 && sg == p.group_seg_begin[tc.group]) SRB_TRACE_AT(1, it, 1);   // first activation box landed
             const uint32_t a_addr = a_ring + ai * p.a_box_bytes;
             for (int t = tb; t < te; ++t) {
               if constexpr (WS) {
@@ -798,6 +922,7 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
         }
         if constexpr (MC == 2) umma_commit_2sm_pred(tfull_bar(buf), (uint16_t)3);
         else umma_commit_pred(1u, tfull_bar(buf));
+        SRB_TRACE_AT(1, it, 2);   // all MMAs of the tile issued
       }
     }
     __syncwarp();
@@ -806,26 +931,31 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
     const int half = (warp - 2) >> 2;           // column half (0 when EW == 4)
     const int lane_base = quarter * 32;
     uint8_t* my_stage = stage_base + (warp - 2) * stage_bytes;
-    // RESNORM: asynchronous residual stream of this warp (see epi_resnorm); chunk s of the stream is chunk s & 3 of the
-    // warp's (s >> 2)-th tile
-    const int nb = p.res_bufs;
-    int chunk_seq = 0, issue_seq = 0;
-    auto issue_next = [&](uint8_t* buf) {
+    // RESNORM: residual stream of this warp (see epi_resnorm); chunk s of the stream is chunk s & 3 of the warp's
+    // (s >> 2)-th tile
+    ResStream rs;
+    rs.buf = smem_u32(my_stage);
+    rs.gen = my_stage;
+    rs.bar = epi_bar + 16u * (warp - 2);
+    rs.nb = p.res_bufs;
+    rs.seq = 0;
+    auto issue_load = [&](int s, int bi) {
       if constexpr (EPI == EPI_RESNORM) {
-        const int s = issue_seq++;
         const int tile = walker + (s >> 2) * n_walkers;
-        if (tile < total_tiles) {
+        if (lane == 0 && tile < total_tiles) {
           const TileCoord t2 = decode(tile);
-          const int row0 = t2.m * kTileM + lane_base;
-          const float* src = static_cast<const float*>(p.res[0]) + (long long)t2.b * p.res_batch_stride +
-                             (long long)row0 * p.res_row_stride + half * (256 / NHALF) + (s & 3) * 32;
-          async_gather<8>(buf, src, p.res_row_stride * 4, clamp_rows(p.group_rows[0], row0), lane, p.res[0]);
+          mbar_expect_tx(rs.bar + 8u * bi, 4096);
+          if (p.l2_keep)
+            tma_load_3d_hint(rs.buf + bi * 4096, &p.tmR, rs.bar + 8u * bi, half * (256 / NHALF) + (s & 3) * 32,
+                             t2.m * kTileM + lane_base, t2.b, kL2EvictLast);
+          else
+            tma_load_3d(rs.buf + bi * 4096, &p.tmR, rs.bar + 8u * bi, half * (256 / NHALF) + (s & 3) * 32,
+                        t2.m * kTileM + lane_base, t2.b);
         }
-        cp_async_commit();
       }
     };
     if constexpr (EPI == EPI_RESNORM) {
-      for (int i = 0; i < nb; ++i) issue_next(my_stage + i * 4096);
+      for (int i = 0; i < rs.nb; ++i) issue_load(i, i);
     }
     int it = 0;
     for (int tile = walker; tile < total_tiles; tile += n_walkers, ++it) {
@@ -837,24 +967,33 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
       ew.stage = my_stage;
       ew.lane = lane;
       ew.row0 = tc.m * kTileM + lane_base;
+      float4 rope_row = make_float4(0.f, 0.f, 0.f, 0.f);
+      if constexpr (EPI == EPI_QKV_ROPE) rope_row = rope_row_fetch(p, tc, ew);
+      if (warp == 2) SRB_TRACE_AT(2, it, 0);   // epilogue warp ready for the tile
       mbar_wait(tfull_bar(buf), bphase);
       tc_fence_after();
+      if (warp == 2) SRB_TRACE_AT(2, it, 1);   // accumulator complete
       const uint32_t tacc = tmem_base + (static_cast<uint32_t>(lane_base) << 16) + buf * TBUF;
       if constexpr (EPI == EPI_GENERIC) epi_generic<BN, NHALF>(p, tacc, tc, q, half, ew);
       else if constexpr (EPI == EPI_GLU) epi_glu<NHALF>(p, tacc, tc, q, half, ew);
-      else if constexpr (EPI == EPI_RESNORM) epi_resnorm<NHALF>(p, tacc, tc, q, half, red, lane_base + lane, quarter, ew, nb, chunk_seq, issue_next);
-      else if constexpr (EPI == EPI_QKV_ROPE) epi_qkv_rope<NHALF>(p, tacc, tc, half, ew, extra_base);
+      else if constexpr (EPI == EPI_RESNORM) epi_resnorm<NHALF>(p, tacc, tc, q, half, red, lane_base + lane, quarter, ew, rs, issue_load);
+      else if constexpr (EPI == EPI_QKV_ROPE) epi_qkv_rope<NHALF>(p, tacc, tc, half, ew, extra_base, rope_row);
       else epi_euler(p, tacc, tc, q);
       tc_fence_before();
       __syncwarp();
+      if (warp == 2) SRB_TRACE_AT(2, it, 2);   // epilogue of the tile done
       if (lane == 0) {
         if constexpr (MC == 2) mbar_arrive_leader(tempty_bar(buf));   // the leader's MMA warp owns both accumulators
         else mbar_arrive(tempty_bar(buf));
       }
     }
-    if constexpr (EPI == EPI_RESNORM) cp_async_wait<0>();
+    // stores still reading the staging buffers must finish before the CTA releases its shared memory
+    if constexpr (EPI == EPI_RESNORM || EPI == EPI_QKV_ROPE) {
+      if (lane == 0) bulk_wait_all();
+    }
   }
 
+  if (warp == 0) SRB_TRACE_AT(0, 0, 3);   // producer finished
   tc_fence_before();
   __syncthreads();
   if constexpr (MC) cluster_sync_all();   // no CTA may exit while its peer can still multicast into it

@@ -16,6 +16,8 @@ namespace srb {
 __global__ void __launch_bounds__(256) embed_gather_kernel(const float4* __restrict__ table, const int64_t* __restrict__ ids,
                                                            float4* __restrict__ out, long long m, int vocab_rows,
                                                            int dim4) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long warps = (long long)gridDim.x * (blockDim.x >> 5);
   for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < m; row += warps) {
@@ -31,6 +33,8 @@ __global__ void __launch_bounds__(256) embed_gather_kernel(const float4* __restr
 }
 
 __global__ void unit_lengths_kernel(const int64_t* __restrict__ ids, int* __restrict__ lengths, int frames) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x;
   int cnt = 0;
   for (int t = threadIdx.x; t < frames; t += blockDim.x) cnt += ids[(long long)b * frames + t] != 0;
@@ -89,6 +93,8 @@ __global__ void rotary_table_kernel(const float* __restrict__ inv_freq, int rows
 }
 
 __global__ void prior_prepare_kernel(float4* __restrict__ xt, uint2* __restrict__ xtb, long long n4, float tv) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 v = xt[i];
     if (tv > 0.f) {
@@ -110,6 +116,8 @@ __global__ void __launch_bounds__(256) posconv_norm_kernel(const float* __restri
                                                            const float* __restrict__ dw_b, const float* __restrict__ g,
                                                            const int* __restrict__ lengths, float* __restrict__ x,
                                                            __nv_bfloat16* __restrict__ xn, int frames) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int K = 31, HALO = 15;
   const int b = blockIdx.y, t0 = blockIdx.x * ROWS, c = threadIdx.x;
   const int len = lengths[b];
@@ -162,6 +170,8 @@ __global__ void __launch_bounds__(256) posconv_norm_kernel(const float* __restri
 // wav[b, t] = tanh(bias + sum_{j<7, c<16} w[j][c] * x[b, t + j - 3, c]);  x already leaky_relu(0.01)'ed.  HF:1480-1482
 __global__ void __launch_bounds__(256) post_tanh_kernel(const uint4* __restrict__ x, const float* __restrict__ w, float bias,
                                                         float* __restrict__ wav, int rows) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ uint4 tile[(256 + 6) * 2];
   __shared__ float ws[7 * 16];
   const int b = blockIdx.y, t0 = blockIdx.x * 256;
@@ -192,6 +202,8 @@ __global__ void __launch_bounds__(256) post_tanh_kernel(const uint4* __restrict_
 
 __global__ void crop_concat_kernel(const float* __restrict__ wav, const int* __restrict__ lengths,
                                    const int64_t* __restrict__ offsets, float* __restrict__ dst, int rows) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.y;
   const int n = 320 * lengths[b] + 80;  // models.py:211-221
   const float* src = wav + (long long)b * rows;
@@ -213,14 +225,13 @@ int srb_embed_gather(const float* table, const int64_t* ids, float* out, int64_t
   long long blocks = (m + 7) / 8;
   const long long cap = (long long)num_sms() * 8;
   if (blocks > cap) blocks = cap;
-  embed_gather_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const float4*>(table), ids, reinterpret_cast<float4*>(out), m, vocab_rows, dim / 4);
+  SRB_CUDA(launch_pdl(embed_gather_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, reinterpret_cast<const float4*>(table), ids, reinterpret_cast<float4*>(out), (long long)m, (int)vocab_rows, (int)(dim / 4)));
   return after_launch("embed_gather_kernel");
 }
 
 int srb_unit_lengths(const int64_t* ids, int32_t* lengths, int32_t batch, int32_t frames, void* stream) {
   if (batch <= 0) return 0;
-  unit_lengths_kernel<<<batch, 256, 0, (cudaStream_t)stream>>>(ids, lengths, frames);
+  SRB_CUDA(launch_pdl(unit_lengths_kernel, dim3(batch), dim3(256), 0, (cudaStream_t)stream, ids, lengths, frames));
   return after_launch("unit_lengths_kernel");
 }
 
@@ -244,9 +255,8 @@ int srb_prior_prepare(float* xt, void* xt_bf16, int64_t n, float truncation, voi
   long long blocks = (n / 4 + 255) / 256;
   const long long cap = (long long)num_sms() * 8;
   if (blocks > cap) blocks = cap;
-  prior_prepare_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float4*>(xt),
-                                                                            reinterpret_cast<uint2*>(xt_bf16), n / 4,
-                                                                            truncation);
+  SRB_CUDA(launch_pdl(prior_prepare_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream,
+                      reinterpret_cast<float4*>(xt), reinterpret_cast<uint2*>(xt_bf16), (long long)(n / 4), truncation));
   return after_launch("prior_prepare_kernel");
 }
 
@@ -255,8 +265,8 @@ int srb_cfm_posconv_norm(const float* x0, const float* dw_w, const float* dw_b, 
   if (batch <= 0 || frames <= 0) return 0;
   constexpr int ROWS = 16;
   dim3 grid((frames + ROWS - 1) / ROWS, batch);
-  posconv_norm_kernel<ROWS><<<grid, 256, 0, (cudaStream_t)stream>>>(x0, dw_w, dw_b, g, lengths, x,
-                                                                     static_cast<__nv_bfloat16*>(xn_bf16), frames);
+  SRB_CUDA(launch_pdl(posconv_norm_kernel<ROWS>, grid, dim3(256), 0, (cudaStream_t)stream, x0, dw_w, dw_b, g, lengths, x,
+                      static_cast<__nv_bfloat16*>(xn_bf16), frames));
   return after_launch("posconv_norm_kernel");
 }
 
@@ -264,7 +274,7 @@ int srb_hifigan_post(const void* x_act, const float* w, float bias, float* wav, 
                      void* stream) {
   if (batch <= 0 || rows <= 0) return 0;
   dim3 grid((rows + 255) / 256, batch);
-  post_tanh_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(static_cast<const uint4*>(x_act), w, bias, wav, rows);
+  SRB_CUDA(launch_pdl(post_tanh_kernel, grid, dim3(256), 0, (cudaStream_t)stream, static_cast<const uint4*>(x_act), w, bias, wav, rows));
   return after_launch("post_tanh_kernel");
 }
 
@@ -272,7 +282,7 @@ int srb_crop_concat(const float* wav, const int32_t* lengths, const int64_t* off
                     int32_t rows, void* stream) {
   if (batch <= 0) return 0;
   dim3 grid((rows + 1023) / 1024, batch);
-  crop_concat_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(wav, lengths, offsets, dst, rows);
+  SRB_CUDA(launch_pdl(crop_concat_kernel, grid, dim3(256), 0, (cudaStream_t)stream, wav, lengths, offsets, dst, rows));
   return after_launch("crop_concat_kernel");
 }
 

@@ -156,10 +156,12 @@ __global__ void __launch_bounds__(MrfTeams<C>::threads, 1) mrf_fused_kernel(cons
     }
     for (int i = tid; i < 18 * C; i += blockDim.x) bias_s[i] = p.bias[i];
   }
+  pdl_launch_dependents();
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();   // setup above read only weights / biases; the up-sampler output is read from here on
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + L::off_tmem);
   const uint32_t t_dt = tmem_base, t_dx = tmem_base + NM * C, t_f = tmem_base + 2 * NM * C;
 
@@ -417,7 +419,7 @@ static int launch_mrf(const MrfParams& p0, cudaStream_t stream) {
   int grid = num_sms();
   if (grid > p.total_tiles) grid = p.total_tiles;
   if (grid < 1) return 0;
-  kernel<<<grid, MrfTeams<C>::threads, L::total, stream>>>(p);
+  SRB_CUDA(launch_pdl(kernel, dim3(grid), dim3(MrfTeams<C>::threads), L::total, stream, p));
   return after_launch("mrf_fused_kernel");
 }
 

@@ -21,6 +21,13 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// launch_dependents: the next kernel of the stream may start launching its CTAs (they run their prologue and then
+// block in pdl_wait); wait: every kernel this one depends on has completed and its memory is visible.  Both are
+// no-ops when the kernel was launched without the programmatic-serialization attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -73,6 +80,33 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint
       : "memory");
 }
 
+// ---- TMA stores (shared -> global, tile mode).  Completion is tracked per issuing THREAD in bulk async-groups:
+// the same lane must issue, commit and wait.  wait_group.read N: all but the N most recent groups have finished
+// READING shared memory (the staging buffer may be overwritten); wait_group 0: fully complete.
+__device__ __forceinline__ void tma_store_3d(const void* tmap, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+// variants carrying an L2 cache policy (kL2EvictLast: keep the lines on chip; the form CUTLASS uses for TMA)
+__device__ __forceinline__ void tma_store_3d_hint(const void* tmap, uint32_t src, int c0, int c1, int c2, uint64_t policy) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4}], [%1], %5;"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(src), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_hint(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // converged-warp variants (one elected lane issues; operands stay warp-uniform)
 __device__ __forceinline__ void mbar_expect_tx_elect(uint32_t bar, uint32_t bytes) {
   asm volatile(
@@ -108,6 +142,15 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
+
+// ---- L2 residency hints.  The fp32 residual stream of the transformer (33 MB at 64 x 500 frames) is read and rewritten
+// twice per layer with ~150 MB of other activations flowing through the 126 MB L2 in between; marking its lines
+// evict_last keeps it on chip, which removes a third of the HBM traffic of a layer.
+// (the value createpolicy.fractional.L2::evict_last.b64 p, 1.0 returns -- read back on a B200 with
+// tools/probes/l2_hint_probe.cu; it is the constant CUTLASS ships as CacheHintSm90::EVICT_LAST)
+constexpr uint64_t kL2EvictLast = 0x14F0000000000000ull;
+// (ld/st/cp.async with .L2::cache_hint raised "illegal instruction" inside the GEMM kernel on B200 with this toolkit;
+// the hints are attached to the TMA transfers instead)
 
 // ---- 2-CTA cluster helpers (weight-slab multicast)
 __device__ __forceinline__ uint32_t cluster_ctarank() {

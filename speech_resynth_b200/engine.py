@@ -124,6 +124,9 @@ class CFMSampler:
             xn=torch.zeros(m_pad, 256, dtype=torch.bfloat16, device=dev),
             qk=b16(m, 512), vt=b16(256, m_pad), o=b16(m, 256), h=b16(m, 896),
             mel=f32(batch, frames, 80), mel_b=b16(batch, frames, 80),
+            # max |q|^2, |k|^2 per (utterance, head), recorded by qk_rope, read by the attention kernel; two buffers used
+            # alternately by successive layers (each projection clears the other one for its successor)
+            qkmax=torch.zeros(2, batch, 2, 2, 2, dtype=torch.float32, device=dev),
         )
 
     # -- the loop ---------------------------------------------------------------------------------------------
@@ -135,6 +138,8 @@ class CFMSampler:
                  self.w.cond_table.shape[0], 256, nbytes=b * n * (2 * 256 * 4 + 8))
         tv = float(truncation) if truncation is not None else 0.0
         nat.call("srb_prior_prepare", P(ws["xt"]), P(ws["xt_b"]), b * n * 80, tv)
+        ws["qkmax"].zero_()
+        self._qk_calls = 0
 
     def step(self, ws: Dict[str, torch.Tensor], g_step: torch.Tensor, dt: float, last: bool) -> None:
         """One velocity evaluation + Euler update (models.py:173-184); `last` adds :186-187."""
@@ -147,14 +152,16 @@ class CFMSampler:
                  flops=2.0 * m * 31 * 256, nbytes=m * 256 * (4 + 4 + 2))
         for i in range(self.depth):
             m_pad = ws["vt"].shape[1]
+            qk_cur, qk_next = ws["qkmax"][self._qk_calls % 2], ws["qkmax"][(self._qk_calls + 1) % 2]
+            self._qk_calls += 1
             # q|k projection and the transposed-v projection both read xn only: two parallel graph branches
             self.fork.run([
-                lambda: nat.call("srb_cfm_qk_rope", P(ws["xn"]), P(w.w_qkv[i]), P(cs), P(sn), P(ws["qk"]), b, n,
-                                 flops=2.0 * m * 256 * 512),
+                lambda: nat.call("srb_cfm_qk_rope", P(ws["xn"]), P(w.w_qkv[i]), P(cs), P(sn), P(ws["qk"]),
+                                 P(qk_cur), P(qk_next), b, n, flops=2.0 * m * 256 * 512),
                 lambda: nat.call("srb_cfm_v_transposed", P(ws["xn"]), P(w.w_qkv[i][512:]), P(ws["vt"]), m_pad,
                                  flops=2.0 * m * 256 * 256),
             ])
-            nat.call("srb_cfm_attention_tc", P(ws["qk"]), 512, P(ws["vt"]), m_pad, P(L), P(ws["o"]), b, n,
+            nat.call("srb_cfm_attention_tc", P(ws["qk"]), 512, P(ws["vt"]), m_pad, P(L), P(qk_cur), P(ws["o"]), b, n,
                      flops=4.0 * m * n * 256)
             nat.call("srb_cfm_attn_out_norm", P(ws["o"]), P(w.w_out[i]), P(g_step[2 * i + 1]), P(L), P(ws["x"]), P(ws["xn"]), b, n,
                      flops=2.0 * m * 256 * 256)

@@ -390,19 +390,33 @@ def cfm_attention():
     return rel_l2(o.float(), ref), 1e-2   # P is rounded to bf16 before P.V (as in any flash kernel) + bf16 store
 
 
-@check
-def cfm_attention_tc():
-    """tcgen05 attention (q|k buffer + transposed v) against the float64 softmax-attention definition"""
+def _norm_bounds(qk: torch.Tensor) -> torch.Tensor:
+    """(B, N, 512) -> (B, 2 [q|k], 2 [head], 2 [f]): max over rows of the squared norm over columns i, i + 64 of the
+    head with i in [32 f, 32 f + 32)"""
+    b, n, _ = qk.shape
+    z = qk.reshape(b, n, 2, 2, 2, 2, 32).double().pow(2)      # (b, n, q|k, head, lo|hi, f, 32)
+    return z.sum(dim=(4, 6)).amax(dim=1).float().contiguous()
+
+
+def _attention_tc_case(bounds: str, scale: float = 1.0):
+    """tcgen05 attention (q|k buffer + transposed v) against the float64 softmax-attention definition.
+    bounds: "none" -> two-pass path; "given" -> exact norm bounds (single pass when they allow it)"""
     worst = 0.0
     for b, n, lengths in ((3, 200, (200, 131, 64)), (2, 504, (500, 1)), (1, 136, (129,)), (2, 1024, (1024, 700))):
         L = torch.tensor(lengths, dtype=torch.int32, device=DEV)
-        qkv = bf(torch.randn(b, n, 768, generator=g(6 + n)))
+        qkv = torch.randn(b, n, 768, generator=g(6 + n))
+        qkv[..., :512] *= scale
+        qkv = bf(qkv)
         m_pad = (b * n + 255) // 256 * 256
         qk = qkv[..., :512].contiguous().to(DEV).to(torch.bfloat16)
         vt = torch.zeros(256, m_pad, dtype=torch.bfloat16, device=DEV)
         vt[:, : b * n] = qkv[..., 512:].reshape(b * n, 256).t().to(DEV).to(torch.bfloat16)
         o = torch.full((b, n, 256), float("nan"), dtype=torch.bfloat16, device=DEV)
-        nat.call("srb_cfm_attention_tc", P(qk), 512, P(vt), m_pad, P(L), P(o), b, n)
+        nb = None
+        if bounds == "given":
+            # (B, 2 [q|k], 2 [head], 2 [frequency half]) maxima of the partial squared row norms
+            nb = _norm_bounds(qkv[..., :512]).to(DEV)
+        nat.call("srb_cfm_attention_tc", P(qk), 512, P(vt), m_pad, P(L), P(nb), P(o), b, n)
         torch.cuda.synchronize()
         q, k, v = (z.reshape(b, n, 2, 128).permute(0, 2, 1, 3).double() for z in qkv.chunk(3, dim=-1))
         mask = torch.arange(n)[None, :] < torch.tensor(lengths)[:, None]
@@ -411,6 +425,24 @@ def cfm_attention_tc():
         ref = torch.einsum("bhij,bhjd->bhid", sc.softmax(-1), v).permute(0, 2, 1, 3).reshape(b, n, 256)
         worst = max(worst, rel_l2(o.float(), ref))
     return worst, 1e-2
+
+
+@check
+def cfm_attention_tc():
+    """no bounds supplied: two-pass path"""
+    return _attention_tc_case("none")
+
+
+@check
+def cfm_attention_tc_single_pass():
+    """unit-variance q, k: |q||k| log2(e)/sqrt(128) ~ 20 -> single pass, shift 0"""
+    return _attention_tc_case("given")
+
+
+@check
+def cfm_attention_tc_bound_fallback():
+    """q, k scaled x3: bound ~ 190 > 100 -> the kernel must choose the two-pass path by itself (peaky softmax)"""
+    return _attention_tc_case("given", scale=3.0)
 
 
 def _qk_rope_vt_case(b, n, m_pad):
@@ -425,7 +457,9 @@ def _qk_rope_vt_case(b, n, m_pad):
     qk = torch.empty(b, n, 512, dtype=torch.bfloat16, device=DEV)
     vt = torch.full((256, m_pad), float("nan"), dtype=torch.bfloat16, device=DEV)
     wq = pk.w_qkv[1]
-    nat.call("srb_cfm_qk_rope", P(xn), P(wq), P(cs), P(sn), P(qk), b, n)
+    nb = torch.zeros(b, 2, 2, 2, device=DEV)
+    nb_other = torch.full((b, 2, 2, 2), 7.0, device=DEV)
+    nat.call("srb_cfm_qk_rope", P(xn), P(wq), P(cs), P(sn), P(qk), P(nb), P(nb_other), b, n)
     nat.call("srb_cfm_v_transposed", P(xn), P(wq[512:]), P(vt), m_pad)
     w = bf(s["model.transformer.layers.1.2.to_qkv.weight"]).double()
     r = F.linear(xn_host.double(), w)
@@ -437,7 +471,11 @@ def _qk_rope_vt_case(b, n, m_pad):
     e1 = rel_l2(qk.float(), torch.cat([q, k], dim=-1))
     e2 = rel_l2(vt[:, : b * n].float(), v.reshape(b * n, 256).t())
     tail_zero = bool((vt[:, b * n:].float() == 0).all())
-    return (max(e1, e2) if tail_zero else 1.0), BF16_TOL
+    # recorded bounds: max squared row norm per (utterance, q|k, head), of the fp32 values before the bf16 rounding
+    nb_ref = _norm_bounds(torch.cat([q, k], dim=-1))
+    e3 = rel_l2(nb, nb_ref)
+    cleared = bool((nb_other == 0).all())
+    return (max(e1, e2, e3 * 100) if tail_zero and cleared else 1.0), BF16_TOL
 
 
 @check
