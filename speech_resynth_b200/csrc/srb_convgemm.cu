@@ -120,20 +120,22 @@ static int make_weight_map(CUtensorMap* m, const void* ptr, int k_total, int n_t
 // one epilogue warp stages.  The swizzle equals the row width (64 B for bf16, 128 B for fp32), which is exactly the
 // XOR pattern of stage_slot<4> / stage_slot<8>.
 static int make_io_map(CUtensorMap* m, const void* ptr, int elt_bytes, int columns, int rows, int batch, long long row_stride,
-                       long long batch_stride) {
+                       long long batch_stride, int box_cols = 32) {
   auto enc = get_encode();
   SRB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
   SRB_REQUIRE(elt_bytes == 2 || elt_bytes == 4, "epilogue I/O maps are bf16 or fp32");
   SRB_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "epilogue tensor not 16-byte aligned");
-  SRB_REQUIRE((row_stride * elt_bytes) % 16 == 0 && (batch_stride * elt_bytes) % 16 == 0 && columns % 32 == 0,
-              "epilogue tensor strides must be multiples of 16 bytes and its width a multiple of 32 columns");
+  SRB_REQUIRE((row_stride * elt_bytes) % 16 == 0 && (batch_stride * elt_bytes) % 16 == 0 && columns % box_cols == 0,
+              "epilogue tensor strides must be multiples of 16 bytes and its width a multiple of the block width");
+  const int row_bytes = box_cols * elt_bytes;
+  SRB_REQUIRE(row_bytes == 32 || row_bytes == 64 || row_bytes == 128, "epilogue block rows are 32, 64 or 128 bytes");
   cuuint64_t dims[3] = {(cuuint64_t)columns, (cuuint64_t)rows, (cuuint64_t)batch};
   cuuint64_t strides[2] = {(cuuint64_t)row_stride * elt_bytes, (cuuint64_t)(batch > 1 ? batch_stride : (long long)rows * row_stride) * elt_bytes};
-  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t box[3] = {(cuuint32_t)box_cols, 32, 1};
   cuuint32_t estr[3] = {1, 1, 1};
+  const CUtensorMapSwizzle swz = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   CUresult r = enc(m, elt_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr),
-                   dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   elt_bytes == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SRB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(epilogue I/O) failed: %d (cols=%d rows=%d B=%d rs=%lld bs=%lld)", (int)r,
               columns, rows, batch, row_stride, batch_stride);
@@ -209,7 +211,7 @@ static int launch_inst(ConvGemmParams& p, int total_tiles, cudaStream_t stream, 
   constexpr int w_stage_bytes = MC == 2 ? L::w_bytes / 2 : L::w_bytes;
   // RESNORM: two residual-stream buffers per epilogue warp when the K loop is short (the epilogue, not the MMAs,
   // paces those launches); one when the long K loop (FFN conv2) needs the shared memory for its weight ring
-  p.res_bufs = (EPI == EPI_RESNORM && n_slabs <= 8) ? 2 : 1;
+  if (EPI != EPI_GENERIC) p.res_bufs = (EPI == EPI_RESNORM && n_slabs <= 8) ? 2 : 1;   // (GENERIC: residual count, set by the caller)
   // coalescing / streaming buffers of the epilogue warps + CTA-wide epilogue tables
   const int stage_smem = EpiWarps<BN, EPI>::value * EpiWarps<BN, EPI>::stage_bytes(p.res_bufs) + EpiWarps<BN, EPI>::extra_bytes;
   if (MC == 2) w_stages = 6;
@@ -393,6 +395,40 @@ static int launch_convgemm(const ConvGemmDesc& d, cudaStream_t stream) {
     if (p.out0 != nullptr) {
       rc = make_io_map(&p.tmO0, p.out0, 2, (int)p.out_row_stride, rows, d.batch, p.out_row_stride, p.out_batch_stride);
       if (rc) return rc;
+    }
+  }
+  if (d.epilogue == EPI_GENERIC) {
+    // residuals first (packed), then per tap group the raw / activated output views (row = q * row_mul + row_add)
+    const int cw = bn < 32 ? bn : 32;
+    int n_res = 0;
+    for (int r = 0; r < 3; ++r) {
+      if (p.res[r] == nullptr) continue;
+      SRB_REQUIRE(d.row_mul == 1, "residuals are not supported with strided output rows");
+      rc = make_io_map(&p.tmRes[n_res], p.res[r], 2, d.n_total, d.group_rows[0], d.batch, p.res_row_stride, p.res_batch_stride, cw);
+      if (rc) return rc;
+      ++n_res;
+    }
+    p.n_res = n_res;
+    // Epilogue form.  Launches whose MMA phase dominates (wide tiles with many taps, the fused tails) keep the register /
+    // LSU epilogue: it hides under the MMAs and its 2 KB of staging leaves the shared memory to the weight ring.  The
+    // memory-bound ones (k = 3 convs, the C = 64 stage, the transposed convs, v^T) go through TMA, double buffered
+    // where the tile is wide enough to afford it.  SRB_GENERIC_EPILOGUE = lsu | tma forces one form (A/B knob).
+    const char* force = getenv("SRB_GENERIC_EPILOGUE");
+    const int work = (d.group_tap_begin[1] - d.group_tap_begin[0]) * p.kchunks;   // K steps of a tile (first group)
+    p.gen_lsu = (n_res >= 2 || (bn >= 128 && work > 16 && d.row_mul == 1)) ? 1 : 0;
+    if (force && n_res < 2) p.gen_lsu = strcmp(force, "lsu") == 0;
+    p.gen_nbuf = bn >= 128 ? 2 : 1;
+    p.res_bufs = p.gen_lsu ? -1 : p.gen_nbuf * (n_res + 1);
+    void* outs[2] = {p.out1, p.out0};
+    for (int k = 0; k < 2; ++k) {
+      if (outs[k] == nullptr) continue;
+      for (int g = 0; g < d.n_groups; ++g) {
+        if (d.group_rows[g] <= 0) continue;
+        const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>(outs[k]) + (long long)d.group_row_add[g] * p.out_row_stride;
+        rc = make_io_map(&p.tmOut[k][g], base, 2, d.n_total, d.group_rows[g], d.batch, p.out_row_stride * d.row_mul,
+                         p.out_batch_stride, cw);
+        if (rc) return rc;
+      }
     }
   }
   // weight multicast across 2-CTA clusters for the wide tiles (needs an even number of row tiles)

@@ -35,6 +35,10 @@ struct ConvGemmParams {
   // epilogue I/O through TMA (RESNORM, QKV_ROPE): 3-D maps (columns, rows, batch) with a 32-column x 32-row box --
   // one epilogue warp's block.  tmR: fp32 residual, tmO1: fp32 output stream, tmO0: bf16 output.
   CUtensorMap tmR, tmO1, tmO0;
+  // GENERIC: bf16 residuals (same geometry as the output) and, per tap group, the raw / activated outputs: a group of
+  // a polyphase transposed conv writes rows q * row_mul + phase, which is a plain 3-D view with a row_mul-fold pitch
+  CUtensorMap tmRes[3];
+  CUtensorMap tmOut[2][kMaxGroups];
   // problem
   int batch, kchunks, n_groups, n_tiles;          // n_tiles = n_total / BN
   int m_tiles[kMaxGroups];                        // row tiles per batch, per group
@@ -53,7 +57,11 @@ struct ConvGemmParams {
   int a_box_rows;                                 // 128 + largest tap span of the launch (<= 256)
   int a_box_bytes;                                // a_box_rows * KB * 2, rounded up to 1024
   int a_stages, w_stages;
-  int res_bufs;                                   // RESNORM: residual-stream buffers per epilogue warp (1 or 2)
+  int res_bufs;                                   // RESNORM: residual-stream buffers per epilogue warp (1 or 2);
+                                                  // GENERIC: staging blocks per epilogue warp (-1: LSU epilogue)
+  int n_res;                                      // GENERIC: number of residual tensors (0..3)
+  int gen_lsu;                                    // GENERIC: 1 = register / LSU epilogue (MMA-bound launches, fused tails)
+  int gen_nbuf;                                   // GENERIC TMA epilogue: staging depth (1 or 2) of residual and output blocks
   int l2_keep;                                    // RESNORM: 1 = evict_last policy on the residual stream's TMA transfers
   // epilogue operands
   const float* bias;
@@ -206,8 +214,10 @@ __device__ __forceinline__ int clamp_rows(int total, int row0) {
   return v < 0 ? 0 : (v > 32 ? 32 : v);
 }
 
+// Register / LSU form of the GENERIC epilogue (kept for launches with two or three residual tensors -- the fused MRF
+// tails, whose long MMA phase hides it: their TMA staging would take the shared memory of two weight-ring stages).
 template <int BN, int NHALF>
-__device__ __forceinline__ void epi_generic(const ConvGemmParams& p, uint32_t tacc, const TileCoord& tc, int q, int half,
+__device__ __forceinline__ void epi_generic_lsu(const ConvGemmParams& p, uint32_t tacc, const TileCoord& tc, int q, int half,
                                             const EpiWarp& w) {
   constexpr int CW = BN < 32 ? BN : 32;
   constexpr int COLS = BN / NHALF;
@@ -309,6 +319,105 @@ __device__ __forceinline__ void epi_generic(const ConvGemmParams& p, uint32_t ta
                              pack_bf16(lrelu(y[8 * j + 4], sl), lrelu(y[8 * j + 5], sl)),
                              pack_bf16(lrelu(y[8 * j + 6], sl), lrelu(y[8 * j + 7], sl)));
       }
+    }
+  }
+}
+
+// GENERIC epilogue (vocoder convs, v^T): y = (acc + bias + residuals) * scale -> raw bf16 and / or leaky_relu bf16.
+// All global traffic is TMA (see the note above epi_resnorm): the bf16 residual blocks (32 rows x CW columns) of the
+// warp form a stream over chunks and tiles, double buffered, one mbarrier per buffer armed for all n_res blocks of a
+// chunk; outputs are staged in two alternating blocks and stored with cp.async.bulk.tensor.  Per-warp staging:
+// [2 buffers][n_res blocks] then [2 output blocks], every block CW * 64 bytes.  (n_res <= 1 here; see epi_generic_lsu.)
+struct GenStream {
+  uint32_t buf, bar;
+  uint8_t* gen;
+  int n_res;
+  int nbuf;   // staging depth: 2 = double buffered, 1 = single
+  int seq;    // chunks consumed so far
+  int nout;   // output blocks stored so far
+};
+
+template <int BN, int NHALF, typename IssueLoad>
+__device__ __forceinline__ void epi_generic(const ConvGemmParams& p, uint32_t tacc, const TileCoord& tc, int half,
+                                            const EpiWarp& w, GenStream& gs, IssueLoad&& issue_load) {
+  constexpr int CW = BN < 32 ? BN : 32;
+  constexpr int COLS = BN / NHALF;
+  constexpr int P = CW / 8;             // 16-byte pieces of bf16 per block row
+  constexpr int BLK = CW * 64;          // bytes of a 32-row block
+  const float sc = p.scale, sl = p.slope;
+  const int n_res = gs.n_res, nbuf = gs.nbuf;
+  const uint32_t out_stage = gs.buf + nbuf * n_res * BLK;
+  uint8_t* out_gen = gs.gen + nbuf * n_res * BLK;
+  const int g = tc.group;
+  auto put_block = [&](const uint4 (&o)[P], const CUtensorMap* tm, int col) {
+    // the block last stored from this staging slot has been read
+    if (w.lane == 0) {
+      if (nbuf == 2) bulk_wait_read<1>();
+      else bulk_wait_read<0>();
+    }
+    __syncwarp();
+    const int slot = nbuf == 2 ? (gs.nout & 1) : 0;
+    uint8_t* hb = out_gen + slot * BLK;
+#pragma unroll
+    for (int j = 0; j < P; ++j) *stage_slot<P>(hb, w.lane, j) = o[j];
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (w.lane == 0) {
+      tma_store_3d(tm, out_stage + slot * BLK, col, w.row0, tc.b);
+      bulk_commit();
+    }
+    ++gs.nout;
+  };
+#pragma unroll 1
+  for (int c0 = half * COLS; c0 < (half + 1) * COLS; c0 += CW) {
+    float y[CW];
+    tmem_ld_f<CW>(tacc + c0, y);
+    if (p.bias) {
+      const float4* b4 = reinterpret_cast<const float4*>(p.bias + tc.n * BN + c0);
+#pragma unroll
+      for (int j = 0; j < CW / 4; ++j) {
+        const float4 bb = __ldg(b4 + j);
+        y[4 * j + 0] += bb.x; y[4 * j + 1] += bb.y; y[4 * j + 2] += bb.z; y[4 * j + 3] += bb.w;
+      }
+    }
+    if (n_res == 1) {
+      const int s = gs.seq, bi = nbuf == 2 ? (s & 1) : 0;
+      mbar_wait(gs.bar + 8u * bi, nbuf == 2 ? ((s >> 1) & 1) : (s & 1));
+#pragma unroll 1
+      for (int r = 0; r < n_res; ++r) {
+        const uint8_t* rb = gs.gen + (bi * n_res + r) * BLK;
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+          const uint4 u = *stage_slot<P>(const_cast<uint8_t*>(rb), w.lane, j);
+          y[8 * j + 0] += bf16_lo(u.x); y[8 * j + 1] += bf16_hi(u.x);
+          y[8 * j + 2] += bf16_lo(u.y); y[8 * j + 3] += bf16_hi(u.y);
+          y[8 * j + 4] += bf16_lo(u.z); y[8 * j + 5] += bf16_hi(u.z);
+          y[8 * j + 6] += bf16_lo(u.w); y[8 * j + 7] += bf16_hi(u.w);
+        }
+      }
+      __syncwarp();   // every lane has its rows: the buffer takes the chunk after next (the next one when single)
+      issue_load(s + nbuf, bi);
+      ++gs.seq;
+    }
+#pragma unroll
+    for (int j = 0; j < CW; ++j) y[j] *= sc;
+    if (p.out1) {
+      uint4 o[P];
+#pragma unroll
+      for (int j = 0; j < P; ++j)
+        o[j] = make_uint4(pack_bf16(y[8 * j], y[8 * j + 1]), pack_bf16(y[8 * j + 2], y[8 * j + 3]),
+                          pack_bf16(y[8 * j + 4], y[8 * j + 5]), pack_bf16(y[8 * j + 6], y[8 * j + 7]));
+      put_block(o, &p.tmOut[0][g], tc.n * BN + c0);
+    }
+    if (p.out0) {
+      uint4 o[P];
+#pragma unroll
+      for (int j = 0; j < P; ++j)
+        o[j] = make_uint4(pack_bf16(lrelu(y[8 * j], sl), lrelu(y[8 * j + 1], sl)),
+                          pack_bf16(lrelu(y[8 * j + 2], sl), lrelu(y[8 * j + 3], sl)),
+                          pack_bf16(lrelu(y[8 * j + 4], sl), lrelu(y[8 * j + 5], sl)),
+                          pack_bf16(lrelu(y[8 * j + 6], sl), lrelu(y[8 * j + 7], sl)));
+      put_block(o, &p.tmOut[1][g], tc.n * BN + c0);
     }
   }
 }
@@ -672,8 +781,13 @@ struct EpiWarps {
   // staging bytes per epilogue warp: bf16 output blocks are 2 KB (4 pieces per row); RESNORM adds `res_bufs` 4 KB
   // buffers for the asynchronous fp32 residual stream (they double as the fp32 output stage)
   // (multiples of 1024: the TMA-staged blocks need their swizzle alignment)
+  // GENERIC: res_bufs = number of staging blocks (32 rows x min(BN, 32) bf16 columns) of the TMA epilogue, or -1 for
+  // the LSU epilogue's 2 KB
   __host__ __device__ static constexpr int stage_bytes(int res_bufs) {
-    return EPI == EPI_RESNORM ? (res_bufs == 2 ? 3 * 4096 : 4096) : (EPI == EPI_QKV_ROPE ? 5120 : 2048);
+    return EPI == EPI_RESNORM ? (res_bufs == 2 ? 3 * 4096 : 4096)
+           : EPI == EPI_QKV_ROPE ? 5120
+           : EPI == EPI_GENERIC ? (res_bufs < 0 ? 2048 : ((res_bufs * (BN < 32 ? BN : 32) * 64 + 1023) & ~1023))
+                                : 2048;
   }
   // CTA-wide extra: the rotary offset table (cos | sin of positions 0..31)
   static constexpr int extra_bytes = EPI == EPI_QKV_ROPE ? 16384 : 0;
@@ -776,8 +890,10 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
       mbar_init(tfull_bar(b), 1);
       mbar_init(tempty_bar(b), MC == 2 ? 2 * EW : EW);
     }
-    if constexpr (EPI == EPI_RESNORM) {
+    if constexpr (EPI == EPI_RESNORM || EPI == EPI_GENERIC) {
       for (int i = 0; i < 2 * EW; ++i) mbar_init(epi_bar + 8u * i, 1);
+    }
+    if constexpr (EPI == EPI_RESNORM) {
       tma_prefetch_desc(&p.tmR);
       tma_prefetch_desc(&p.tmO1);
     }
@@ -957,6 +1073,36 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
     if constexpr (EPI == EPI_RESNORM) {
       for (int i = 0; i < rs.nb; ++i) issue_load(i, i);
     }
+    // GENERIC: residual stream; chunk s of the stream is chunk s % NC of the warp's (s / NC)-th tile
+    constexpr int G_CW = BN < 32 ? BN : 32;
+    constexpr int G_NC = (BN / NHALF) / G_CW;
+    GenStream gs;
+    gs.buf = smem_u32(my_stage);
+    gs.gen = my_stage;
+    gs.bar = epi_bar + 16u * (warp - 2);
+    gs.n_res = p.n_res;
+    gs.nbuf = p.gen_nbuf;
+    gs.seq = 0;
+    gs.nout = 0;
+    auto issue_gen = [&](int s, int bi) {
+      if constexpr (EPI == EPI_GENERIC) {
+        const int tile = walker + (s / G_NC) * n_walkers;
+        if (lane == 0 && tile < total_tiles) {
+          const TileCoord t2 = decode(tile);
+          const int col = t2.n * BN + half * (BN / NHALF) + (s % G_NC) * G_CW;
+          mbar_expect_tx(gs.bar + 8u * bi, gs.n_res * G_CW * 64);
+          for (int r = 0; r < gs.n_res; ++r)
+            tma_load_3d(gs.buf + (bi * gs.n_res + r) * (G_CW * 64), &p.tmRes[r], gs.bar + 8u * bi, col,
+                        t2.m * kTileM + lane_base, t2.b);
+        }
+      }
+    };
+    if constexpr (EPI == EPI_GENERIC) {
+      if (gs.n_res == 1 && !p.gen_lsu) {
+        issue_gen(0, 0);
+        if (gs.nbuf == 2) issue_gen(1, 1);
+      }
+    }
     int it = 0;
     for (int tile = walker; tile < total_tiles; tile += n_walkers, ++it) {
       const TileCoord tc = decode(tile);
@@ -974,7 +1120,10 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
       tc_fence_after();
       if (warp == 2) SRB_TRACE_AT(2, it, 1);   // accumulator complete
       const uint32_t tacc = tmem_base + (static_cast<uint32_t>(lane_base) << 16) + buf * TBUF;
-      if constexpr (EPI == EPI_GENERIC) epi_generic<BN, NHALF>(p, tacc, tc, q, half, ew);
+      if constexpr (EPI == EPI_GENERIC) {
+        if (p.gen_lsu) epi_generic_lsu<BN, NHALF>(p, tacc, tc, q, half, ew);
+        else epi_generic<BN, NHALF>(p, tacc, tc, half, ew, gs, issue_gen);
+      }
       else if constexpr (EPI == EPI_GLU) epi_glu<NHALF>(p, tacc, tc, q, half, ew);
       else if constexpr (EPI == EPI_RESNORM) epi_resnorm<NHALF>(p, tacc, tc, q, half, red, lane_base + lane, quarter, ew, rs, issue_load);
       else if constexpr (EPI == EPI_QKV_ROPE) epi_qkv_rope<NHALF>(p, tacc, tc, half, ew, extra_base, rope_row);
@@ -988,7 +1137,7 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
       }
     }
     // stores still reading the staging buffers must finish before the CTA releases its shared memory
-    if constexpr (EPI == EPI_RESNORM || EPI == EPI_QKV_ROPE) {
+    if constexpr (EPI == EPI_RESNORM || EPI == EPI_QKV_ROPE || EPI == EPI_GENERIC) {
       if (lane == 0) bulk_wait_all();
     }
   }

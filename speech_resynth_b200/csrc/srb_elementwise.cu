@@ -109,60 +109,103 @@ __global__ void prior_prepare_kernel(float4* __restrict__ xt, uint2* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------ positional conv
-// x = gelu(dwconv31(mask(x0)) + b) * mask + x0, then the first AdaptiveRMSNorm.  Block = 256 threads (one per
-// channel) x ROWS consecutive frames of one utterance; each thread keeps its channel's 31-tap window in registers.
+// x = gelu(dwconv31(mask(x0)) + b) * mask + x0, then the first AdaptiveRMSNorm (transformer.py:84-96, models.py:177,
+// norm.py:41-43).  CUDA-core work, instruction-issue bound in its first form (one thread per channel, 159 instructions
+// per output, ncu: 0.62 IPC, 66 us): this form spends ~40.
+//   * a thread owns TWO adjacent channels and ROWS output rows: the 31-tap window (ROWS + 30 rows) sits in registers
+//     as float2 and every multiply-add is a packed fma.rn.f32x2 (two FMAs per issue slot on sm_100);
+//   * taps are the outer loop (one float2 weight load per tap and thread, ROWS independent accumulator chains);
+//   * exact-GELU's erf is Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, one EX2 + one RCP + 5 FMAs) instead of erff;
+//   * row sums of squares go through shared memory once per block (a warp reduces four rows) instead of five
+//     shuffles per thread and row.
+// Bytes per row and channel: 4 (x0) + 4 (x) + 2 (xn) = 10 -> 82 MB at 64 x 504 frames.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)),
+        "l"(reinterpret_cast<unsigned long long&>(c)));
+  return d;
+}
+// erf(x), |abs error| <= 1.5e-7 (Abramowitz & Stegun 7.1.26 carried to fp32 with fast exp / reciprocal)
+__device__ __forceinline__ float erf_as(float x) {
+  const float ax = fabsf(x);
+  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float r = 1.f - poly * t * __expf(-ax * ax);
+  return copysignf(r, x);
+}
+__device__ __forceinline__ float gelu_exact(float a) { return 0.5f * a * (1.f + erf_as(a * 0.70710678118654752440f)); }
+
 template <int ROWS>
-__global__ void __launch_bounds__(256) posconv_norm_kernel(const float* __restrict__ x0, const float* __restrict__ dw_w,
+__global__ void __launch_bounds__(128) posconv_norm_kernel(const float* __restrict__ x0, const float* __restrict__ dw_w,
                                                            const float* __restrict__ dw_b, const float* __restrict__ g,
                                                            const int* __restrict__ lengths, float* __restrict__ x,
                                                            __nv_bfloat16* __restrict__ xn, int frames) {
-  pdl_launch_dependents();
-  pdl_wait();
   constexpr int K = 31, HALO = 15;
-  const int b = blockIdx.y, t0 = blockIdx.x * ROWS, c = threadIdx.x;
-  const int len = lengths[b];
-  const float* xb = x0 + (long long)b * frames * 256;
-  float w[K];
-#pragma unroll
-  for (int j = 0; j < K; ++j) w[j] = __ldg(dw_w + j * 256 + c);   // tap-major [31][256]: coalesced across channels
-  const float bias = __ldg(dw_b + c);
-  const float gc = __ldg(g + c);
-  float win[ROWS + 2 * HALO];
+  static_assert(ROWS % 4 == 0, "four warps share the row reduction");
+  __shared__ float sq_s[ROWS][128];
+  __shared__ float inv_s[ROWS];
+  pdl_launch_dependents();
+  const int b = blockIdx.y, t0 = blockIdx.x * ROWS, cp = threadIdx.x;   // cp: channel pair (channels 2cp, 2cp + 1)
+  const float2 bias = __ldg(reinterpret_cast<const float2*>(dw_b) + cp);
+  const float2 gc = __ldg(reinterpret_cast<const float2*>(g) + cp);
+  pdl_wait();   // x0 and lengths come from the preceding kernels
+  const int len = min(lengths[b], frames);
+  const float2* xb = reinterpret_cast<const float2*>(x0 + (long long)b * frames * 256) + cp;
+  float2 win[ROWS + 2 * HALO];
 #pragma unroll
   for (int i = 0; i < ROWS + 2 * HALO; ++i) {
     const int t = t0 - HALO + i;
-    win[i] = (t >= 0 && t < len && t < frames) ? __ldg(xb + (long long)t * 256 + c) : 0.f;
+    win[i] = (t >= 0 && t < len) ? __ldg(xb + (long long)t * 128) : make_float2(0.f, 0.f);   // masked input
   }
-  __shared__ float red[ROWS][8];
-  float xv[ROWS];
+  float2 acc[ROWS];
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) acc[r] = bias;
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    const float2 wj = __ldg(reinterpret_cast<const float2*>(dw_w + j * 256) + cp);   // tap-major [31][256]
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) acc[r] = ffma2(wj, win[r + j], acc[r]);
+  }
 #pragma unroll
   for (int r = 0; r < ROWS; ++r) {
     const int t = t0 + r;
-    float acc = bias;
+    float2 v;
+    if (t < len) {
+      v.x = gelu_exact(acc[r].x) + win[r + HALO].x;
+      v.y = gelu_exact(acc[r].y) + win[r + HALO].y;
+    } else {
+      // pad row: the conv output is masked, the residual is the unmasked x0
+      v = t < frames ? __ldg(xb + (long long)t * 128) : make_float2(0.f, 0.f);
+    }
+    acc[r] = v;
+    sq_s[r][cp] = v.x * v.x + v.y * v.y;
+  }
+  __syncthreads();
+  {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
-    for (int j = 0; j < K; ++j) acc = fmaf(w[j], win[r + j], acc);
-    float y = 0.5f * acc * (1.f + erff(acc * 0.70710678118654752440f));  // exact GELU (transformer.py:81)
-    const bool in = t < frames;
-    if (t >= len) y = 0.f;
-    const float orig = in ? __ldg(xb + (long long)t * 256 + c) : 0.f;  // residual uses the unmasked x0
-    const float v = y + orig;
-    xv[r] = v;
-    float sq = v * v;
-    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-    if ((c & 31) == 0) red[r][c >> 5] = sq;
+    for (int rr = 0; rr < ROWS / 4; ++rr) {
+      const int r = warp * (ROWS / 4) + rr;
+      float s = (sq_s[r][lane] + sq_s[r][lane + 32]) + (sq_s[r][lane + 64] + sq_s[r][lane + 96]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) inv_s[r] = 1.f / fmaxf(sqrtf(s), 1e-12f);   // F.normalize (norm.py:41)
+    }
   }
   __syncthreads();
 #pragma unroll
   for (int r = 0; r < ROWS; ++r) {
     const int t = t0 + r;
     if (t >= frames) break;
-    float tot = 0.f;
-#pragma unroll
-    for (int wv = 0; wv < 8; ++wv) tot += red[r][wv];
-    const float inv = 1.f / fmaxf(sqrtf(tot), 1e-12f);
-    const long long o = ((long long)b * frames + t) * 256 + c;
-    x[o] = xv[r];
-    xn[o] = (t < len) ? __float2bfloat16_rn(xv[r] * inv * gc) : __float2bfloat16_rn(0.f);
+    const long long o = ((long long)b * frames + t) * 128 + cp;
+    reinterpret_cast<float2*>(x)[o] = acc[r];
+    const float inv = inv_s[r];
+    reinterpret_cast<uint32_t*>(xn)[o] = t < len ? pack_bf16(acc[r].x * inv * gc.x, acc[r].y * inv * gc.y) : 0u;
   }
 }
 
@@ -265,7 +308,7 @@ int srb_cfm_posconv_norm(const float* x0, const float* dw_w, const float* dw_b, 
   if (batch <= 0 || frames <= 0) return 0;
   constexpr int ROWS = 16;
   dim3 grid((frames + ROWS - 1) / ROWS, batch);
-  SRB_CUDA(launch_pdl(posconv_norm_kernel<ROWS>, grid, dim3(256), 0, (cudaStream_t)stream, x0, dw_w, dw_b, g, lengths, x,
+  SRB_CUDA(launch_pdl(posconv_norm_kernel<ROWS>, grid, dim3(128), 0, (cudaStream_t)stream, x0, dw_w, dw_b, g, lengths, x,
                       static_cast<__nv_bfloat16*>(xn_bf16), frames));
   return after_launch("posconv_norm_kernel");
 }
