@@ -41,6 +41,8 @@ struct AttnParams {
   __nv_bfloat16* out;  // (B, N, 256)
   int frames;
   int k_col;           // first column of k in the q|k buffer (256)
+  int q_tiles;         // 128-query tiles per utterance
+  int n_items;         // batch * 2 heads * q_tiles
 };
 
 constexpr int kAttnTile = 128;
@@ -54,16 +56,51 @@ struct AttnSmem {
   static constexpr int p = v + 2 * kTileBytes;
   static constexpr int stage = p + kTileBytes;         // 8 x 2 KB coalescing buffers (bf16 blocks, 4 pieces per row)
   static constexpr int red = stage + 8 * 2048;         // [2][128] floats: row max / row sum exchange between halves
-  static constexpr int bars = red + 1024;
-  static constexpr int n_bars = 16;
+  static constexpr int items = red + 1024;             // kItemCache work descriptors of this CTA
+  static constexpr int bars = items + 512;
+  static constexpr int n_bars = 20;
   static constexpr int tmem = bars + 8 * n_bars;
   static constexpr int total = tmem + 16 + 1024;       // + alignment slack
 };
+
+constexpr float kAttnScaleLog2 = 0.08838834764831845f * 1.4426950408889634f;   // (1/sqrt(128)) * log2(e)
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+// Persistent: CTA c works on items c, c + gridDim.x, ... where an item is one (utterance, head, 128-query tile); the
+// K / V / S / P rings and the double-buffered O accumulator run across item boundaries, so while the softmax warps
+// finish item i the producer is already fetching Q, K, V of item i + 1 and the tensor core computes its first S tiles.
+// (One CTA per item paid ~3.5 us of launch, TMEM allocation and first-load latency per item -- a third of its time.)
+struct AttnItem {
+  int b, h, q0, len, nkv;
+  int two_pass;
+};
+constexpr int kItemCache = 16;   // 16 x 24 bytes <= 512
+
+__device__ __forceinline__ AttnItem attn_item(const AttnParams& p, int item) {
+  AttnItem it;
+  const int qt = item % p.q_tiles;
+  const int bh = item / p.q_tiles;
+  it.h = bh & 1;
+  it.b = bh >> 1;
+  it.q0 = qt * kAttnTile;
+  int len = p.lengths[it.b];
+  it.len = len < p.frames ? len : p.frames;
+  it.nkv = (it.len + kAttnTile - 1) / kAttnTile;
+  it.two_pass = 1;
+  if (p.qk_norm2_max != nullptr) {
+    // two partial maxima per head (one per rotary frequency half, see epi_qkv_rope); their sum bounds the row norm
+    const float* nq = p.qk_norm2_max + ((it.b * 2 + 0) * 2 + it.h) * 2;
+    const float* nk = p.qk_norm2_max + ((it.b * 2 + 1) * 2 + it.h) * 2;
+    const float q2 = nq[0] + nq[1], k2 = nk[0] + nk[1];
+    // 2 % slack covers the bf16 rounding of q and k after the norms were taken; NaN compares false -> two passes
+    it.two_pass = (sqrtf(q2 * k2) * kAttnScaleLog2 * 1.02f <= 100.f) ? 0 : 1;
+  }
+  return it;
 }
 
 __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__ AttnParams p) {
@@ -72,21 +109,23 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
   uint8_t* smem = smem_raw + (sbase - smem_u32(smem_raw));
   const uint32_t s_q = sbase + AttnSmem::q, s_k = sbase + AttnSmem::k, s_v = sbase + AttnSmem::v, s_p = sbase + AttnSmem::p;
   const uint32_t bar0 = sbase + AttnSmem::bars;
-  const uint32_t q_full = bar0;
-  auto k_full = [&](int s) { return bar0 + 8u * (1 + s); };
-  auto k_empty = [&](int s) { return bar0 + 8u * (3 + s); };
-  auto v_full = [&](int s) { return bar0 + 8u * (5 + s); };
-  auto v_empty = [&](int s) { return bar0 + 8u * (7 + s); };
-  auto s_full = [&](int s) { return bar0 + 8u * (9 + s); };
-  auto s_empty = [&](int s) { return bar0 + 8u * (11 + s); };
-  const uint32_t p_full = bar0 + 8u * 13, p_empty = bar0 + 8u * 14, o_full = bar0 + 8u * 15;
+  const uint32_t q_full = bar0, q_empty = bar0 + 8u;
+  auto k_full = [&](int s) { return bar0 + 8u * (2 + s); };
+  auto k_empty = [&](int s) { return bar0 + 8u * (4 + s); };
+  auto v_full = [&](int s) { return bar0 + 8u * (6 + s); };
+  auto v_empty = [&](int s) { return bar0 + 8u * (8 + s); };
+  auto s_full = [&](int s) { return bar0 + 8u * (10 + s); };
+  auto s_empty = [&](int s) { return bar0 + 8u * (12 + s); };
+  const uint32_t p_full = bar0 + 8u * 14, p_empty = bar0 + 8u * 15;
+  auto o_full = [&](int s) { return bar0 + 8u * (16 + s); };
+  auto o_empty = [&](int s) { return bar0 + 8u * (18 + s); };
   const uint32_t tmem_slot = sbase + AttnSmem::tmem;
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
-  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * kAttnTile;
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(k_full(s), 1);
       mbar_init(k_empty(s), 1);
@@ -94,10 +133,11 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
       mbar_init(v_empty(s), 1);
       mbar_init(s_full(s), 1);
       mbar_init(s_empty(s), 8);
+      mbar_init(o_full(s), 1);
+      mbar_init(o_empty(s), 8);
     }
     mbar_init(p_full, 8);
     mbar_init(p_empty, 1);
-    mbar_init(o_full, 1);
     fence_barrier_init();
     tma_prefetch_desc(&p.tm_qk);
     tma_prefetch_desc(&p.tm_vt);
@@ -111,98 +151,113 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
   __syncthreads();
   tc_fence_after();
   pdl_wait();   // q|k, v^T, lengths and the norm bounds are produced by the preceding kernels
-  int len = p.lengths[b];
-  len = len < p.frames ? len : p.frames;
-  const int nkv = (len + kAttnTile - 1) / kAttnTile;
-  const float sl2 = 0.08838834764831845f * 1.4426950408889634f;   // (1/sqrt(128)) * log2(e)
-  bool two_pass = true;
-  if (p.qk_norm2_max != nullptr) {
-    // two partial maxima per head (one per rotary frequency half, see epi_qkv_rope); their sum bounds the row norm
-    const float* nq = p.qk_norm2_max + ((b * 2 + 0) * 2 + h) * 2;
-    const float* nk = p.qk_norm2_max + ((b * 2 + 1) * 2 + h) * 2;
-    const float q2 = nq[0] + nq[1], k2 = nk[0] + nk[1];
-    // 2 % slack covers the bf16 rounding of q and k after the norms were taken; NaN compares false -> two passes
-    two_pass = !(sqrtf(q2 * k2) * sl2 * 1.02f <= 100.f);
-  }
 
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + AttnSmem::tmem);
-  const uint32_t t_s0 = tmem_base, t_o = tmem_base + 256;
+  const uint32_t t_s0 = tmem_base, t_o0 = tmem_base + 256;   // S buffers at +0, +128; O buffers at +256, +384
   constexpr uint32_t IDESC = umma_idesc_bf16(128, 128);
+  const int first = blockIdx.x, step = gridDim.x;
+  // the descriptors of this CTA's first items (lengths, pass count) are resolved once, by one thread each: reading
+  // them from global memory at every item start cost each role an L2 round trip per item
+  AttnItem* item_cache = reinterpret_cast<AttnItem*>(smem + AttnSmem::items);
+  if (threadIdx.x < kItemCache && first + (int)threadIdx.x * step < p.n_items)
+    item_cache[threadIdx.x] = attn_item(p, first + threadIdx.x * step);
+  __syncthreads();
+  auto get_item = [&](int n, int item) { return n < kItemCache ? item_cache[n] : attn_item(p, item); };
 
   if (warp == 0) {
     // ================= TMA producer =================
-    mbar_expect_tx_elect(q_full, kTileBytes);
-    tma_load_3d_elect(s_q, &p.tm_qk, q_full, h * 128, q0, b);
-    tma_load_3d_elect(s_q + kHalfBytes, &p.tm_qk, q_full, h * 128 + 64, q0, b);
     int kst = 0, vst = 0;
     uint32_t kph = 0, vph = 0;
-    auto load_k = [&](int j) {
-      mbar_wait(k_empty(kst), kph ^ 1u);
-      mbar_expect_tx_elect(k_full(kst), kTileBytes);
-      tma_load_3d_elect(s_k + kst * kTileBytes, &p.tm_qk, k_full(kst), p.k_col + h * 128, j * kAttnTile, b);
-      tma_load_3d_elect(s_k + kst * kTileBytes + kHalfBytes, &p.tm_qk, k_full(kst), p.k_col + h * 128 + 64, j * kAttnTile, b);
-      if (++kst == 2) { kst = 0; kph ^= 1u; }
-    };
-    auto load_v = [&](int j) {
-      mbar_wait(v_empty(vst), vph ^ 1u);
-      mbar_expect_tx_elect(v_full(vst), kTileBytes);
-      const int col = b * p.frames + j * kAttnTile;
-      tma_load_2d_elect(s_v + vst * kTileBytes, &p.tm_vt, v_full(vst), col, h * 128);
-      tma_load_2d_elect(s_v + vst * kTileBytes + kHalfBytes, &p.tm_vt, v_full(vst), col + 64, h * 128);
-      if (++vst == 2) { vst = 0; vph ^= 1u; }
-    };
-    int v_ahead = 0;
-    if (two_pass) {
-      // the V ring is idle during the maxima pass: fill it first
-      for (; v_ahead < 2 && v_ahead < nkv; ++v_ahead) load_v(v_ahead);
-      for (int j = 0; j < nkv; ++j) load_k(j);
-    }
-    for (int j = 0; j < nkv; ++j) {
-      load_k(j);
-      if (j >= v_ahead) load_v(j);
+    int n = 0;
+    for (int item = first; item < p.n_items; item += step, ++n) {
+      const AttnItem it = get_item(n, item);
+      auto load_k = [&](int j) {
+        mbar_wait(k_empty(kst), kph ^ 1u);
+        mbar_expect_tx_elect(k_full(kst), kTileBytes);
+        tma_load_3d_elect(s_k + kst * kTileBytes, &p.tm_qk, k_full(kst), p.k_col + it.h * 128, j * kAttnTile, it.b);
+        tma_load_3d_elect(s_k + kst * kTileBytes + kHalfBytes, &p.tm_qk, k_full(kst), p.k_col + it.h * 128 + 64, j * kAttnTile, it.b);
+        if (++kst == 2) { kst = 0; kph ^= 1u; }
+      };
+      auto load_v = [&](int j) {
+        mbar_wait(v_empty(vst), vph ^ 1u);
+        mbar_expect_tx_elect(v_full(vst), kTileBytes);
+        const int col = it.b * p.frames + j * kAttnTile;
+        tma_load_2d_elect(s_v + vst * kTileBytes, &p.tm_vt, v_full(vst), col, it.h * 128);
+        tma_load_2d_elect(s_v + vst * kTileBytes + kHalfBytes, &p.tm_vt, v_full(vst), col + 64, it.h * 128);
+        if (++vst == 2) { vst = 0; vph ^= 1u; }
+      };
+      mbar_wait(q_empty, (n & 1) ^ 1u);   // every S tile of the previous item has consumed its Q
+      mbar_expect_tx_elect(q_full, kTileBytes);
+      tma_load_3d_elect(s_q, &p.tm_qk, q_full, it.h * 128, it.q0, it.b);
+      tma_load_3d_elect(s_q + kHalfBytes, &p.tm_qk, q_full, it.h * 128 + 64, it.q0, it.b);
+      int v_ahead = 0;
+      if (it.two_pass) {
+        // the V ring is idle during the maxima pass: fill it first
+        for (; v_ahead < 2 && v_ahead < it.nkv; ++v_ahead) load_v(v_ahead);
+        for (int j = 0; j < it.nkv; ++j) load_k(j);
+      }
+      for (int j = 0; j < it.nkv; ++j) {
+        load_k(j);
+        if (j >= v_ahead) load_v(j);
+      }
     }
     __syncwarp();
   } else if (warp == 1) {
     // ================= MMA issuer (converged warp, elected lane issues) =================
-    mbar_wait(q_full, 0);
-    tc_fence_after();
     int kst = 0, vst = 0;
     uint32_t kph = 0, vph = 0;
-    int t = 0;   // S tiles issued so far (buffer = t & 1)
-    auto issue_s = [&]() {
-      const int sb = t & 1;
-      mbar_wait(k_full(kst), kph);
-      mbar_wait(s_empty(sb), ((t >> 1) & 1) ^ 1u);
+    int t = 0;    // S tiles issued so far (buffer = t & 1)
+    int pv = 0;   // P V products issued so far
+    int n = 0;
+    for (int item = first; item < p.n_items; item += step, ++n) {
+      const AttnItem it = get_item(n, item);
+      const int ob = n & 1;
+      const uint32_t t_o = t_o0 + ob * 128;
+      mbar_wait(q_full, n & 1);
       tc_fence_after();
+      const int s_total = it.two_pass ? 2 * it.nkv : it.nkv;
+      int s_issued = 0;
+      auto issue_s = [&]() {
+        const int sb = t & 1;
+        mbar_wait(k_full(kst), kph);
+        mbar_wait(s_empty(sb), ((t >> 1) & 1) ^ 1u);
+        tc_fence_after();
 #pragma unroll
-      for (int kk = 0; kk < 8; ++kk) {
-        const uint32_t off = (kk >> 2) * kHalfBytes + (kk & 3) * 32;
-        umma_bf16_pred(1u, t_s0 + sb * 128, umma_smem_desc<128>(s_q + off), umma_smem_desc<128>(s_k + kst * kTileBytes + off),
-                       IDESC, kk != 0 ? 1u : 0u);
-      }
-      umma_commit_pred(1u, k_empty(kst));
-      umma_commit_pred(1u, s_full(sb));
-      if (++kst == 2) { kst = 0; kph ^= 1u; }
-      ++t;
-    };
-    if (two_pass) for (int j = 0; j < nkv; ++j) issue_s();           // maxima pass
-    if (nkv > 0) issue_s();                                          // main pass, tile 0
-    for (int j = 0; j < nkv; ++j) {
-      if (j + 1 < nkv) issue_s();                      // S(j+1) overlaps the softmax of S(j)
-      mbar_wait(p_full, j & 1);
-      mbar_wait(v_full(vst), vph);
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint32_t off = (kk >> 2) * kHalfBytes + (kk & 3) * 32;
+          umma_bf16_pred(1u, t_s0 + sb * 128, umma_smem_desc<128>(s_q + off), umma_smem_desc<128>(s_k + kst * kTileBytes + off),
+                         IDESC, kk != 0 ? 1u : 0u);
+        }
+        umma_commit_pred(1u, k_empty(kst));
+        umma_commit_pred(1u, s_full(sb));
+        if (++s_issued == s_total) umma_commit_pred(1u, q_empty);   // Q may be replaced by the next item's
+        if (++kst == 2) { kst = 0; kph ^= 1u; }
+        ++t;
+      };
+      if (it.nkv == 0) umma_commit_pred(1u, q_empty);
+      if (it.two_pass) for (int j = 0; j < it.nkv; ++j) issue_s();     // maxima pass
+      if (it.nkv > 0) issue_s();                                       // main pass, tile 0
+      // the epilogue of the item that used this O buffer two items ago has read it
+      mbar_wait(o_empty(ob), ((n >> 1) & 1) ^ 1u);
       tc_fence_after();
+      for (int j = 0; j < it.nkv; ++j) {
+        if (j + 1 < it.nkv) issue_s();                    // S(j+1) overlaps the softmax of S(j)
+        mbar_wait(p_full, pv & 1);
+        mbar_wait(v_full(vst), vph);
+        tc_fence_after();
 #pragma unroll
-      for (int kk = 0; kk < 8; ++kk) {
-        const uint32_t off = (kk >> 2) * kHalfBytes + (kk & 3) * 32;
-        umma_bf16_pred(1u, t_o, umma_smem_desc<128>(s_p + off), umma_smem_desc<128>(s_v + vst * kTileBytes + off), IDESC,
-                       (j != 0 || kk != 0) ? 1u : 0u);
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint32_t off = (kk >> 2) * kHalfBytes + (kk & 3) * 32;
+          umma_bf16_pred(1u, t_o, umma_smem_desc<128>(s_p + off), umma_smem_desc<128>(s_v + vst * kTileBytes + off), IDESC,
+                         (j != 0 || kk != 0) ? 1u : 0u);
+        }
+        umma_commit_pred(1u, v_empty(vst));
+        umma_commit_pred(1u, p_empty);
+        if (++vst == 2) { vst = 0; vph ^= 1u; }
+        ++pv;
       }
-      umma_commit_pred(1u, v_empty(vst));
-      umma_commit_pred(1u, p_empty);
-      if (++vst == 2) { vst = 0; vph ^= 1u; }
+      umma_commit_pred(1u, o_full(ob));
     }
-    umma_commit_pred(1u, o_full);
     __syncwarp();
   } else {
     // ================= softmax / epilogue warps =================
@@ -210,98 +265,114 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
     const int half = (warp - 2) >> 2;                     // key-column half of S / output-column half of O
     const int row = quarter * 32 + lane;                  // query row inside the tile = TMEM lane
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    const float sl2 = kAttnScaleLog2;
     float* red = reinterpret_cast<float*>(smem + AttnSmem::red);
-    int t = 0;
-    float m = -INFINITY;
-    for (int j = 0; j < (two_pass ? nkv : 0); ++j, ++t) {
-      const int sb = t & 1;
-      mbar_wait(s_full(sb), (t >> 1) & 1);
-      tc_fence_after();
-      const int key0 = j * kAttnTile + half * 64;
+    int t = 0;    // S tiles consumed
+    int pv = 0;   // P tiles produced
+    int n = 0;
+    for (int item = first; item < p.n_items; item += step, ++n) {
+      const AttnItem it = get_item(n, item);
+      const int len = it.len, nkv = it.nkv;
+      const int ob = n & 1;
+      const uint32_t t_o = t_o0 + ob * 128;
+      float m = -INFINITY;
+      for (int j = 0; j < (it.two_pass ? nkv : 0); ++j, ++t) {
+        const int sb = t & 1;
+        mbar_wait(s_full(sb), (t >> 1) & 1);
+        tc_fence_after();
+        const int key0 = j * kAttnTile + half * 64;
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        tmem_ld32(t_s0 + sb * 128 + lane_addr + half * 64 + c * 32, v);
-        tmem_ld_wait();
+        for (int c = 0; c < 2; ++c) {
+          uint32_t v[32];
+          tmem_ld32(t_s0 + sb * 128 + lane_addr + half * 64 + c * 32, v);
+          tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (key0 + c * 32 + i < len) m = fmaxf(m, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; ++i)
+            if (key0 + c * 32 + i < len) m = fmaxf(m, __uint_as_float(v[i]));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_empty(sb));
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(s_empty(sb));
-    }
-    float m2 = 0.f;               // single pass: shift 0 (see the header comment)
-    if (two_pass) {
-      // row maximum over both halves
-      red[half * 128 + row] = m;
+      float m2 = 0.f;               // single pass: shift 0 (see the header comment)
+      if (it.two_pass) {
+        // row maximum over both halves
+        red[half * 128 + row] = m;
+        pair_barrier(quarter);
+        m = fmaxf(m, red[(half ^ 1) * 128 + row]);
+        pair_barrier(quarter);                              // both have read before `red` is reused for the sums
+        m2 = m * sl2;               // finite: every utterance has at least one valid key
+      }
+      float l = 0.f;
+      for (int j = 0; j < nkv; ++j, ++t, ++pv) {
+        const int sb = t & 1;
+        mbar_wait(s_full(sb), (t >> 1) & 1);
+        tc_fence_after();
+        const int key0 = j * kAttnTile + half * 64;
+        // this warp's 64 keys are one [128 rows][64 keys] half tile of P: 128-byte rows, 16-byte pieces XOR-swizzled
+        uint8_t* prow = smem + AttnSmem::p + half * kHalfBytes + row * 128;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t v[32];
+          tmem_ld32(t_s0 + sb * 128 + lane_addr + half * 64 + c * 32, v);
+          tmem_ld_wait();
+          uint32_t o[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int key = key0 + c * 32 + 2 * i;
+            const float p0 = key < len ? ex2_approx(fmaf(__uint_as_float(v[2 * i]), sl2, -m2)) : 0.f;
+            const float p1 = key + 1 < len ? ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), sl2, -m2)) : 0.f;
+            l += p0 + p1;
+            o[i] = pack_bf16(p0, p1);
+          }
+          if (c == 0) mbar_wait(p_empty, (pv & 1) ^ 1u);   // P V of the previous tile has finished reading the P buffer
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int piece = c * 4 + i;
+            *reinterpret_cast<uint4*>(prow + ((piece ^ (row & 7)) << 4)) = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(s_empty(sb));
+          mbar_arrive(p_full);
+        }
+      }
+      // row sum over both halves
+      red[half * 128 + row] = l;
       pair_barrier(quarter);
-      m = fmaxf(m, red[(half ^ 1) * 128 + row]);
-      pair_barrier(quarter);                              // both have read before `red` is reused for the sums
-      m2 = m * sl2;               // finite: every utterance has at least one valid key
-    }
-    float l = 0.f;
-    for (int j = 0; j < nkv; ++j, ++t) {
-      const int sb = t & 1;
-      mbar_wait(s_full(sb), (t >> 1) & 1);
+      l += red[(half ^ 1) * 128 + row];
+      pair_barrier(quarter);        // `red` is free for the next item
+      // ---- epilogue: O / l -> bf16 -> (B, N, 256); this warp takes 64 of the head's 128 output columns
+      mbar_wait(o_full(ob), (n >> 1) & 1);
       tc_fence_after();
-      const int key0 = j * kAttnTile + half * 64;
-      // this warp's 64 keys are one [128 rows][64 keys] half tile of P: 128-byte rows, 16-byte pieces XOR-swizzled
-      uint8_t* prow = smem + AttnSmem::p + half * kHalfBytes + row * 128;
+      const float inv = l > 0.f ? 1.f / l : 0.f;
+      EpiWarp w;
+      w.stage = smem + AttnSmem::stage + (warp - 2) * 2048;
+      w.lane = lane;
+      w.row0 = it.q0 + quarter * 32;
+      const int vrows = clamp_rows(p.frames, w.row0);
+      __nv_bfloat16* out = p.out + ((long long)it.b * p.frames + w.row0) * 256 + it.h * 128 + half * 64;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
-        tmem_ld32(t_s0 + sb * 128 + lane_addr + half * 64 + c * 32, v);
+        tmem_ld32(t_o + lane_addr + half * 64 + c * 32, v);
         tmem_ld_wait();
-        uint32_t o[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int key = key0 + c * 32 + 2 * i;
-          const float p0 = key < len ? ex2_approx(fmaf(__uint_as_float(v[2 * i]), sl2, -m2)) : 0.f;
-          const float p1 = key + 1 < len ? ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), sl2, -m2)) : 0.f;
-          l += p0 + p1;
-          o[i] = pack_bf16(p0, p1);
+        if (c == 1) {
+          // O has been read into registers: the MMA warp may reuse this accumulator (two items from now)
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(o_empty(ob));
         }
-        if (c == 0) mbar_wait(p_empty, (j & 1) ^ 1u);   // P V of the previous tile has finished reading the P buffer
+        uint4 o[4];
+        uint32_t* ow = reinterpret_cast<uint32_t*>(o);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int piece = c * 4 + i;
-          *reinterpret_cast<uint4*>(prow + ((piece ^ (row & 7)) << 4)) = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
-        }
+        for (int i = 0; i < 16; ++i)
+          ow[i] = nkv > 0 ? pack_bf16(__uint_as_float(v[2 * i]) * inv, __uint_as_float(v[2 * i + 1]) * inv) : 0u;
+        scatter_store<4>(w, o, out + c * 32, 512, vrows);
       }
-      fence_proxy_async_smem();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(s_empty(sb));
-        mbar_arrive(p_full);
-      }
-    }
-    // row sum over both halves
-    red[half * 128 + row] = l;
-    pair_barrier(quarter);
-    l += red[(half ^ 1) * 128 + row];
-    // ---- epilogue: O / l -> bf16 -> (B, N, 256); this warp takes 64 of the head's 128 output columns
-    mbar_wait(o_full, 0);
-    tc_fence_after();
-    const float inv = l > 0.f ? 1.f / l : 0.f;
-    EpiWarp w;
-    w.stage = smem + AttnSmem::stage + (warp - 2) * 2048;
-    w.lane = lane;
-    w.row0 = q0 + quarter * 32;
-    const int vrows = clamp_rows(p.frames, w.row0);
-    __nv_bfloat16* out = p.out + ((long long)b * p.frames + w.row0) * 256 + h * 128 + half * 64;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t v[32];
-      tmem_ld32(t_o + lane_addr + half * 64 + c * 32, v);
-      tmem_ld_wait();
-      uint4 o[4];
-      uint32_t* ow = reinterpret_cast<uint32_t*>(o);
-#pragma unroll
-      for (int i = 0; i < 16; ++i)
-        ow[i] = nkv > 0 ? pack_bf16(__uint_as_float(v[2 * i]) * inv, __uint_as_float(v[2 * i + 1]) * inv) : 0u;
-      scatter_store<4>(w, o, out + c * 32, 512, vrows);
     }
   }
 
@@ -367,7 +438,10 @@ extern "C" int srb_cfm_attention_tc(const void* qk_bf16, int32_t ld, const void*
     SRB_CUDA(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::total));
     configured[dev & 63] = true;
   }
-  dim3 grid((frames + kAttnTile - 1) / kAttnTile, 2, batch);
-  SRB_CUDA(launch_pdl(attn_tc_kernel, grid, dim3(320), AttnSmem::total, (cudaStream_t)stream, p));
+  p.q_tiles = (frames + kAttnTile - 1) / kAttnTile;
+  p.n_items = batch * 2 * p.q_tiles;
+  int grid = num_sms();
+  if (grid > p.n_items) grid = p.n_items;
+  SRB_CUDA(launch_pdl(attn_tc_kernel, dim3(grid), dim3(320), AttnSmem::total, (cudaStream_t)stream, p));
   return after_launch("attn_tc_kernel");
 }

@@ -354,7 +354,9 @@ class ResynthEngine:
             # warm-up run outside capture (configures kernel attributes, fills caches), then capture
             cfm_ws["ids"].zero_()
             cfm_ws["ids"][:, :frames].fill_(1)
-            cfm_ws["xt"].normal_()
+            # (private generator: the warm-up must not advance the global CUDA RNG, or the first call of a new shape
+            # would draw a different prior than the reference's torch.randn with the same seed)
+            cfm_ws["xt"].normal_(generator=torch.Generator(device=self.device).manual_seed(0))
             body()
             torch.cuda.current_stream().synchronize()
             graph = torch.cuda.CUDAGraph()

@@ -144,3 +144,69 @@ def test_full_size_properties(decoder):
         m = valid[i]
         assert rel_l2(mel2[j][m], mel[i][m]) <= 1e-3
     assert rel_l2(wav2[0], wav[0]) <= 1e-2
+
+
+def test_config3_bucketed_sharded_call_matches_per_bucket_calls(decoder):
+    """BASELINE configs[2], scaled to one GPU: 96 utterances of 2-20 s through sharding.resynthesize_sharded (length
+    buckets, caller order restored).  Parity is per bucket: every utterance must equal what
+    its own padded bucket gives when synthesised directly with the same prior."""
+    from speech_resynth_b200 import sharding
+
+    gen = torch.Generator().manual_seed(11)
+    lengths = torch.randint(100, 1001, (96,), generator=gen).tolist()
+    units = [torch.randint(1, 2001, (n,), generator=gen) for n in lengths]
+    def bucket_seed(ids):
+        # one reproducible prior per bucket (derived from its content), so the direct call below can repeat it
+        return 1000 + int(ids.sum()) % 100003
+
+    def synth(ids):
+        torch.manual_seed(bucket_seed(ids))
+        return [w.clone() for w in decoder(ids, 0.25, 1.0)]
+
+    outs = sharding.resynthesize_sharded(units, synth, rank=0, world=1, nfe=4, device=torch.device("cuda"))
+    assert [o.shape[-1] for o in outs] == [320 * n + 80 for n in lengths]
+    assert all(bool(torch.isfinite(o).all()) and float(o.abs().max()) <= 1.0 for o in outs)
+    buckets = sharding.bucket_by_length(lengths)
+    assert sorted(i for b in buckets for i in b.indices) == list(range(96))
+    for b in buckets[:3] + buckets[-2:]:
+        ids = sharding.pad_bucket(units, b).cuda()
+        torch.manual_seed(bucket_seed(ids))
+        direct = decoder(ids, 0.25, 1.0)
+        for i, w in zip(b.indices, direct):
+            assert torch.equal(w, outs[i])
+
+
+def test_config4_vocoder_alone_properties(decoder, state_dict):
+    """BASELINE configs[3] (HiFi-GAN alone, mel -> waveform), 48 x 500 frames here: every row of a big batch equals the
+    same mel vocoded on its own (rows are independent; both go through the same kernels, so the match is tight), the
+    first row matches the CPU oracle, and the output obeys |wav| <= 1."""
+    gen = torch.Generator().manual_seed(13)
+    mel = torch.randn(48, 500, 80, generator=gen) * 2.26 - 5.88
+    wav = decoder.vocoder(mel.cuda())
+    assert wav.shape == (48, 320 * 500 + 80)
+    assert bool(torch.isfinite(wav).all()) and float(wav.abs().max()) <= 1.0
+    for i in (0, 17, 47):
+        alone = decoder.vocoder(mel[i: i + 1].cuda())
+        assert rel_l2(alone[0], wav[i]) <= 1e-3
+    ref = oracle.hifigan(state_dict, mel[:1].to(torch.bfloat16).float())
+    assert rel_l2(wav[0], ref[0]) <= WAV_TOL
+
+
+@pytest.mark.parametrize("nfe", [1, 4, 32])
+def test_config5_long_form_step_sweep(decoder, state_dict, nfe):
+    """BASELINE configs[4]: 60 s utterances (3000 frames: 24 key tiles per attention row, rotary angles up to 3000 rad)
+    at several ODE step counts.  NFE 1 is checked against the CPU oracle; all of them for the size-independent
+    properties (finite, exact pad constant, waveform length rule, |wav| <= 1)."""
+    lengths = [3000, 2417]
+    ids = synthetic.make_units(2, 3000, seed=41, lengths=lengths)
+    x0 = torch.randn(2, 3000, 80, generator=torch.Generator().manual_seed(6))
+    dt = 1.0 / nfe
+    wav, lens, mel = decoder.engine().resynthesize(ids.cuda(), dt, 1.0, noise=x0.cuda())
+    wav, mel = wav.clone().cpu(), mel.clone().cpu()
+    assert lens.cpu().tolist() == lengths and wav.shape == (2, 320 * 3000 + 80)
+    assert bool(torch.isfinite(wav).all()) and float(wav.abs().max()) <= 1.0
+    valid = ids.ne(0)
+    assert bool((mel[~valid] == oracle.pad_value()).all()) and bool(torch.isfinite(mel).all())
+    if nfe == 1:
+        ref = oracle.sample(state_dict, ids, x0, dt, 1.0)
+        assert rel_l2((mel[valid] - MEAN) / STD, (ref[valid] - MEAN) / STD) <= MEL_TOL_NORM
