@@ -54,6 +54,17 @@ int srb_rotary_table(const float* inv_freq, int32_t rows, float* cos_out, float*
  * xt_bf16 = bf16(xt).  n = batch*frames*80 */
 int srb_prior_prepare(float* xt, void* xt_bf16, int64_t n, float truncation, void* stream);
 
+/* Duration-prediction variant (models.py:157-164; fastspeech/modules.py:76-107; transformers length_regulator HF:88-134):
+ *   srb_duration_predict : durations[b, n] = clamp(round(exp(conv_k3(E[ids])[b, n]) - 1), 0), 0 at pads; totals[b] = sum.
+ *                          dur_table (3, vocab_rows) fp32 = per-unit dot products of the Conv1d(768 -> 1, k 3) taps with the
+ *                          embedding rows (row 0 = pad = 0), bias = conv bias.
+ *   srb_length_regulate  : out_ids (B, frames_out) = every id repeated durations[b, n] times, right-padded with 0;
+ *                          all_one != 0: treat every duration as 1 (the regulator's all-zero rule, HF:113-114). */
+int srb_duration_predict(const int64_t* ids, const float* dur_table, float bias, int32_t* durations, int32_t* totals,
+                         int32_t batch, int32_t frames, int32_t vocab_rows, void* stream);
+int srb_length_regulate(const int64_t* ids, const int32_t* durations, int64_t* out_ids, int32_t batch, int32_t frames,
+                        int32_t frames_out, int32_t all_one, void* stream);
+
 /* ---- ODE loop body ------------------------------------------------------------------------------------------
  * to_embed: x0 = xt @ W[:, :80]^T + cond_proj       (models.py:175-176; cond_proj = hoisted cond part + bias, fp32)
  *   xt_bf16 (B, N, 80) bf16; w_packed [256][128]; cond_proj, x0: (B, N, 256) fp32 */

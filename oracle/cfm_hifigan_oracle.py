@@ -28,7 +28,7 @@ from __future__ import annotations
 
 import math
 import warnings
-from typing import Dict, List, Optional, Sequence
+from typing import Dict, List, Optional, Tuple, Sequence
 
 import torch
 import torch.nn.functional as F
@@ -195,6 +195,31 @@ def sample(sd: Dict[str, Tensor], ids: Tensor, x0: Tensor, dt: float = 0.1,
 # --------------------------------------------------------------------------------------
 # HiFi-GAN generator (third-party transformers code restated; HF:1308-1367, 1451-1491)
 # --------------------------------------------------------------------------------------
+def duration_predict(sd: Dict[str, Tensor], ids: Tensor) -> Tensor:
+    """ConditionalFlowMatchingDurationPredictor.forward in eval mode + the pad masking of sample()
+    -- fastspeech/modules.py:87-107, models.py:158-159.  (B, N) ids -> (B, N) int64 frames per unit."""
+    hs = embed_gather(sd["model.to_cond_emb.weight"], ids)
+    x = F.conv1d(hs.transpose(1, 2), sd["model.duration_predictor.conv.weight"], sd["model.duration_predictor.conv.bias"],
+                 padding=1).squeeze(1)
+    d = torch.clamp(torch.round(x.exp() - 1.0), min=0).long()
+    return d.masked_fill(~ids.ne(0), 0)
+
+
+def length_regulate_ids(ids: Tensor, durations: Tensor) -> Tuple[Tensor, Tensor]:
+    """transformers length_regulator (HF:88-134) applied to the unit ids instead of their embeddings (the embedding of
+    the pad id is the zero row, so gathering the expanded ids gives exactly the regulator's zero-padded output), and
+    the mask update of models.py:162-164.  Returns (expanded ids (B, max_len), lengths (B,))."""
+    durations = durations.clone()
+    if int(durations.sum()) == 0:
+        durations[durations.sum(dim=1).eq(0)] = 1      # HF:113-114 (in place in the reference: lengths see it too)
+    lengths = durations.sum(dim=1)
+    out = torch.zeros(ids.shape[0], int(lengths.max()), dtype=ids.dtype)
+    for b in range(ids.shape[0]):
+        rep = torch.repeat_interleave(ids[b], durations[b])
+        out[b, : rep.numel()] = rep
+    return out, lengths
+
+
 def conv_transpose1d_polyphase(x: Tensor, w: Tensor, bias: Tensor, stride: int, padding: int) -> Tensor:
     """ConvTranspose1d written in the polyphase (gather) form the CUDA kernels use.
 

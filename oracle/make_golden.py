@@ -150,6 +150,43 @@ def _main():
                         t=np.float32(0.4375), v=v_ref.numpy(), time_emb=temb[0].numpy())
     print("velocity_b2_n40", json.dumps(info))
 
+    # duration-prediction variant (configs/resynth/mhubert-expresso-2000-duration-prediction.yaml): de-duplicated units,
+    # the model predicts frames per unit and expands (models.py:157-164)
+    sd_d = dict(sd, **synthetic.duration_predictor_state(0))
+    ref_d = ref_loader.build_reference_model(sd_d, predict_duration=True)
+    ids = synthetic.make_units(3, 48, seed=31, lengths=[48, 30, 5])
+    with torch.inference_mode():
+        dur_ref = ref_d.model.duration_predictor(ref_d.model.to_cond_emb(ids)).masked_fill(~ids.ne(0), 0)
+    dur_or = oracle.duration_predict(sd_d, ids)
+    exp_ids, exp_len = oracle.length_regulate_ids(ids, dur_or)
+    torch.manual_seed(104)
+    with torch.inference_mode():
+        ref_mel = ref_d.model.sample(ids, 0.25, 1.0)
+    torch.manual_seed(104)
+    with torch.inference_mode():
+        ref_wavs = ref_d(ids, 0.25, 1.0)
+    torch.manual_seed(104)
+    x0 = torch.randn(3, int(exp_len.max()), 80)
+    o_mel = oracle.sample(sd_d, exp_ids, x0, 0.25, 1.0)
+    valid = exp_ids.ne(0)
+    # distance of every logit from the nearest rounding boundary of round(exp(x) - 1): how robust the integer parity is
+    with torch.inference_mode():
+        hs = ref_d.model.to_cond_emb(ids)
+        logit = ref_d.model.duration_predictor.conv(hs.transpose(1, 2)).squeeze(1)
+    frac = (logit.exp() - 1.0)[ids.ne(0)]
+    margin = float(((frac - torch.floor(frac)) - 0.5).abs().min())
+    info = {"durations_equal_oracle_vs_ref": bool(torch.equal(dur_or, dur_ref)), "expanded_lengths": exp_len.tolist(),
+            "mel_shape": list(ref_mel.shape), "mel_rel_l2_oracle32_vs_ref": rel_l2(o_mel[valid], ref_mel[valid]),
+            "wav_lengths": [int(w.shape[-1]) for w in ref_wavs], "rounding_margin": margin,
+            "duration_histogram": torch.bincount(dur_ref[ids.ne(0)]).tolist()}
+    assert list(ref_mel.shape) == [3, int(exp_len.max()), 80] and info["durations_equal_oracle_vs_ref"]
+    manifest["cases"]["duration_b3_n48"] = dict(dt=0.25, truncation=1.0, ids_seed=31, noise_seed=104, **info)
+    np.savez_compressed(os.path.join(GOLDEN, "duration_b3_n48.npz"), ids=ids.numpy(), durations=dur_ref.numpy(),
+                        expanded_ids=exp_ids.numpy(), x0=x0.numpy(), mel=ref_mel.numpy(),
+                        wav_flat=torch.cat([w.reshape(-1) for w in ref_wavs]).numpy(),
+                        wav_lengths=np.array(info["wav_lengths"], dtype=np.int64))
+    print("duration_b3_n48", json.dumps(info))
+
     with open(os.path.join(GOLDEN, "MANIFEST.json"), "w") as f:
         json.dump(manifest, f, indent=1)
 

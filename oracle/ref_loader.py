@@ -54,11 +54,11 @@ def load_reference():
     return ConditionalFlowMatchingWithHifiGan, ConditionalFlowMatchingWithHifiGanConfig, ConditionalFlowMatchingConfig
 
 
-def build_reference_model(state_dict):
+def build_reference_model(state_dict, predict_duration: bool = False):
     """Reference model in eval mode carrying ``state_dict`` (strict)."""
     cls, cfg_cls, cfm_cfg_cls = load_reference()
     cfg = cfg_cls(
-        model_config=cfm_cfg_cls().to_dict(),
+        model_config=cfm_cfg_cls(predict_duration=predict_duration).to_dict(),
         vocoder_config=dict(upsample_rates=[5, 4, 4, 2, 2], upsample_kernel_sizes=[10, 9, 8, 4, 4], normalize_before=False),
     )
     model = cls(cfg).eval()

@@ -108,6 +108,80 @@ __global__ void prior_prepare_kernel(float4* __restrict__ xt, uint2* __restrict_
   }
 }
 
+// ------------------------------------------------------------------------------------------ duration prediction
+// Duration-prediction variant (models.py:157-164): d[b, n] = clamp(round(exp(conv_k3(E[ids])[b, n]) - 1), 0), pads 0
+// (fastspeech/modules.py:87-107).  The Conv1d(768 -> 1, k 3) over embedding rows is linear in the rows, so it is
+// three lookups in a (3, vocab + 1) table of per-unit dot products (dur_table[tap][u] = <W[0, :, tap], E[u]>, built in
+// float64 at pack time) + bias.  One block per utterance; it also sums the durations (the expanded length).
+__global__ void __launch_bounds__(256) duration_predict_kernel(const int64_t* __restrict__ ids, const float* __restrict__ dur_table,
+                                                               float bias, int* __restrict__ durations, int* __restrict__ totals,
+                                                               int frames, int vocab_rows) {
+  __shared__ int part[8];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.x;
+  const int64_t* row = ids + (long long)b * frames;
+  int sum = 0;
+  for (int n = threadIdx.x; n < frames; n += blockDim.x) {
+    const int64_t u = row[n];
+    int d = 0;
+    if (u != 0) {
+      const int64_t um = n > 0 ? row[n - 1] : 0, up = n + 1 < frames ? row[n + 1] : 0;   // zero padding of the conv
+      const float x = (dur_table[um] + dur_table[vocab_rows + u]) + (dur_table[2 * vocab_rows + up] + bias);
+      const float r = rintf(expf(x) - 1.f);   // torch.round: half to even
+      d = r > 0.f ? (r < 1048576.f ? (int)r : 1048576) : 0;
+    }
+    durations[(long long)b * frames + n] = d;
+    sum += d;
+  }
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < 8; ++w) t += part[w];
+    totals[b] = t;
+  }
+}
+
+// length_regulator (HF:88-134) on unit ids: out[b, pos] = ids[b, n] for pos in [cum[n], cum[n] + d[n]), 0 beyond the
+// utterance's expanded length.  One block per utterance: chunked inclusive scan of the durations, then every thread
+// writes its unit's run.  all_one != 0 applies HF:113-114 (every duration of the batch was 0 -> all become 1).
+__global__ void __launch_bounds__(256) length_regulate_kernel(const int64_t* __restrict__ ids, const int* __restrict__ durations,
+                                                              int64_t* __restrict__ out, int frames, int frames_out, int all_one) {
+  __shared__ int warp_tot[8];
+  __shared__ int carry_s;
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t* row = ids + (long long)b * frames;
+  int64_t* orow = out + (long long)b * frames_out;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < frames; base += blockDim.x) {
+    const int n = base + threadIdx.x;
+    const int d = n < frames ? (all_one ? 1 : durations[(long long)b * frames + n]) : 0;
+    int incl = d;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    int off = carry_s;
+    for (int w = 0; w < warp; ++w) off += warp_tot[w];
+    const int start = off + incl - d;
+    if (n < frames) {
+      const int64_t u = row[n];
+      for (int k = 0; k < d && start + k < frames_out; ++k) orow[start + k] = u;
+    }
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry_s = off + incl;
+    __syncthreads();
+  }
+  for (int pos = carry_s + threadIdx.x; pos < frames_out; pos += blockDim.x) orow[pos] = 0;
+}
+
 // ------------------------------------------------------------------------------------------ positional conv
 // x = gelu(dwconv31(mask(x0)) + b) * mask + x0, then the first AdaptiveRMSNorm (transformer.py:84-96, models.py:177,
 // norm.py:41-43).  CUDA-core work, instruction-issue bound in its first form (one thread per channel, 159 instructions
@@ -301,6 +375,22 @@ int srb_prior_prepare(float* xt, void* xt_bf16, int64_t n, float truncation, voi
   SRB_CUDA(launch_pdl(prior_prepare_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream,
                       reinterpret_cast<float4*>(xt), reinterpret_cast<uint2*>(xt_bf16), (long long)(n / 4), truncation));
   return after_launch("prior_prepare_kernel");
+}
+
+int srb_duration_predict(const int64_t* ids, const float* dur_table, float bias, int32_t* durations, int32_t* totals,
+                         int32_t batch, int32_t frames, int32_t vocab_rows, void* stream) {
+  if (batch <= 0 || frames <= 0) return 0;
+  SRB_CUDA(launch_pdl(duration_predict_kernel, dim3(batch), dim3(256), 0, (cudaStream_t)stream, ids, dur_table, bias, durations,
+                      totals, frames, vocab_rows));
+  return after_launch("duration_predict_kernel");
+}
+
+int srb_length_regulate(const int64_t* ids, const int32_t* durations, int64_t* out_ids, int32_t batch, int32_t frames,
+                        int32_t frames_out, int32_t all_one, void* stream) {
+  if (batch <= 0 || frames <= 0 || frames_out <= 0) return 0;
+  SRB_CUDA(launch_pdl(length_regulate_kernel, dim3(batch), dim3(256), 0, (cudaStream_t)stream, ids, durations, out_ids, frames,
+                      frames_out, all_one));
+  return after_launch("length_regulate_kernel");
 }
 
 int srb_cfm_posconv_norm(const float* x0, const float* dw_w, const float* dw_b, const float* g, const int32_t* lengths,

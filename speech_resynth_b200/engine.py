@@ -106,6 +106,26 @@ class CFMSampler:
             self._last_time_emb = temb
         return g
 
+    # -- duration-prediction variant ---------------------------------------------------------------------------
+    def regulate(self, input_ids: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """models.py:157-164: predict frames per unit and expand the ids (length_regulator on ids: the pad id's embedding
+        is the zero row).  Returns (expanded ids (B, max_len) int64, durations (B, N) int32).  One host sync: the
+        expanded length decides the shapes of everything downstream, exactly like `lengths.max()` in the reference."""
+        if self.w.dur_table is None:
+            raise RuntimeError("this checkpoint has no duration predictor (config.predict_duration is False)")
+        ids = input_ids.contiguous()
+        b, n = ids.shape
+        dur = torch.empty(b, n, dtype=torch.int32, device=self.device)
+        tot = torch.empty(b, dtype=torch.int32, device=self.device)
+        nat.call("srb_duration_predict", P(ids), P(self.w.dur_table), self.w.dur_bias, P(dur), P(tot), b, n,
+                 self.w.dur_table.shape[1])
+        totals = tot.cpu()
+        all_one = int(totals.sum()) == 0          # the regulator's all-zero rule (HF:113-114)
+        n_out = n if all_one else int(totals.max())
+        out = torch.empty(b, n_out, dtype=torch.int64, device=self.device)
+        nat.call("srb_length_regulate", P(ids), P(dur), P(out), b, n, n_out, 1 if all_one else 0)
+        return out, dur
+
     # -- workspace --------------------------------------------------------------------------------------------
     def workspace(self, batch: int, frames: int) -> Dict[str, torch.Tensor]:
         """`frames` must be a multiple of 8 (see `padded_frames`): the transposed-V operand of the attention kernel

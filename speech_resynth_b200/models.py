@@ -71,6 +71,12 @@ class FeedForward(_ParamsOnly):  # fastspeech/modules.py:39-47
         self.conv2 = nn.Conv1d(intermediate_size, hidden_size, kernel_size, padding=pad)
 
 
+class ConditionalFlowMatchingDurationPredictor(_ParamsOnly):  # fastspeech/modules.py:76-86
+    def __init__(self, dim_cond_emb: int):
+        super().__init__()
+        self.conv = nn.Conv1d(dim_cond_emb, 1, kernel_size=3, padding=1)
+
+
 class Transformer(_ParamsOnly):  # transformer.py:133-170
     def __init__(self, hidden_size: int, depth: int, heads: int, intermediate_size: int):
         super().__init__()
@@ -112,9 +118,8 @@ class ConditionalFlowMatchingModel(PreTrainedModel):
     def __init__(self, config: ConditionalFlowMatchingConfig, embedding: Optional[nn.Embedding] = None):
         super().__init__(config)
         self.config = config
-        if config.use_unet_skip_connection or config.predict_duration:
-            raise NotImplementedError(
-                "use_unet_skip_connection / predict_duration variants are not built yet (SURVEY.md section 8(f) N1)")
+        if config.use_unet_skip_connection:
+            raise NotImplementedError("the U-Net skip variant is not built (no shipped config uses it)")
         if (config.hidden_size, config.heads, config.dim_in, config.intermediate_size, config.conv_pos_embed_kernel_size) != (
                 256, 2, 80, 896, 31) or config.conv_pos_embed_groups != config.hidden_size:
             raise NotImplementedError("kernels are specialised to the mhubert-expresso-2000 architecture")
@@ -127,7 +132,8 @@ class ConditionalFlowMatchingModel(PreTrainedModel):
         self.conv_embed = ConvPositionEmbed(h, config.conv_pos_embed_kernel_size, config.conv_pos_embed_groups)
         self.transformer = Transformer(h, config.depth, config.heads, config.intermediate_size)
         self.to_pred = nn.Linear(h, config.dim_in, bias=False)
-        self.duration_predictor = None
+        # second shipped config (mhubert-expresso-2000-duration-prediction.yaml): de-duplicated units + predicted durations
+        self.duration_predictor = ConditionalFlowMatchingDurationPredictor(config.dim_cond_emb) if config.predict_duration else None
         self._sampler = None
         self._engine = None
         self.post_init()
@@ -165,8 +171,19 @@ class ConditionalFlowMatchingModel(PreTrainedModel):
 
     @torch.inference_mode()
     def sample(self, input_ids: torch.LongTensor, dt: float = 0.1, truncation_value: Optional[float] = None) -> torch.FloatTensor:
-        """Same contract as the reference (models.py:132-189): (B, N) unit ids (0 = pad) -> (B, N, 80) log-mel."""
-        return self._own_engine().sample(input_ids.to(self.device), dt, truncation_value)
+        """Same contract as the reference (models.py:132-189): (B, N) unit ids (0 = pad) -> (B, N, 80) log-mel; with
+        config.predict_duration the units are first expanded by their predicted durations (models.py:157-164) and N
+        becomes the longest expanded length."""
+        ids = input_ids.to(self.device)
+        if self.config.predict_duration:
+            ids, _ = self.sampler().regulate(ids)
+        return self._own_engine().sample(ids, dt, truncation_value)
+
+    @torch.inference_mode()
+    def predict_durations(self, input_ids: torch.LongTensor) -> torch.LongTensor:
+        """duration_predictor(to_cond_emb(ids)).masked_fill(~mask, 0) (models.py:158-159): (B, N) frames per unit."""
+        _, dur = self.sampler().regulate(input_ids.to(self.device))
+        return dur.long()
 
     @torch.inference_mode()
     def embed_units(self, input_ids: torch.LongTensor) -> torch.FloatTensor:
@@ -315,7 +332,10 @@ class ConditionalFlowMatchingWithHifiGan(PreTrainedModel):
         exact pad value, models.py:245-247 -- identical result, see tests) and are read back once instead of once
         per utterance.
         """
-        wav, lengths, _ = self.engine().resynthesize(input_ids.to(self.device), dt, truncation_value)
+        ids = input_ids.to(self.device)
+        if self.config.model_config.predict_duration:
+            ids, _ = self.model.sampler().regulate(ids)     # models.py:157-164
+        wav, lengths, _ = self.engine().resynthesize(ids, dt, truncation_value)
         wav_lengths = self._get_waveform_lengths(lengths.to("cpu", torch.int64)).tolist()
         wav = wav.clone()  # the engine's buffer is reused by the next call
         return [wav[i, :n].unsqueeze(0) for i, n in enumerate(wav_lengths)]

@@ -89,6 +89,9 @@ class PackedCFM:
     b_ff2: List[torch.Tensor] = field(default_factory=list)
     final_norm_w: torch.Tensor = None
     w_pred: torch.Tensor = None       # bf16 [80][256]
+    # duration-prediction variant only: per-unit dot products of the Conv1d(768 -> 1, k 3) taps, (3, vocab+1) fp32
+    dur_table: torch.Tensor = None
+    dur_bias: float = 0.0
 
 
 @dataclass
@@ -148,6 +151,11 @@ def pack_cfm(sd: Dict[str, torch.Tensor], device, depth: int = 4, dim_in: int = 
         final_norm_w=f("model.transformer.final_norm.weight").contiguous(),
         w_pred=f("model.to_pred.weight").to(torch.bfloat16).contiguous(),
     )
+    if "model.duration_predictor.conv.weight" in sd:
+        # conv over embedding rows = three table lookups (fastspeech/modules.py:86,103); fp64 product, rounded once
+        wd = f("model.duration_predictor.conv.weight")[0].double()            # (768, 3)
+        p.dur_table = (wd.t() @ emb.double().t()).float().contiguous()        # (3, vocab+1); column 0 = pad row = 0
+        p.dur_bias = float(sd["model.duration_predictor.conv.bias"].reshape(-1)[0])
     perm = glu_row_permutation(inter, device)
     for i in range(depth):
         pre = f"model.transformer.layers.{i}."

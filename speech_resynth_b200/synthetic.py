@@ -96,6 +96,14 @@ def make_state_dict(seed: int = 0, dtype: torch.dtype = torch.float32) -> Dict[s
     return sd
 
 
+def duration_predictor_state(seed: int = 0, dim_cond: int = 768) -> Dict[str, torch.Tensor]:
+    """Extra tensors of the duration-prediction variant (models.py:71, fastspeech/modules.py:76-86): Conv1d(768 -> 1, k 3).
+    Scaled so that round(exp(x) - 1) spreads over 0..4 frames per unit on the synthetic embedding table."""
+    g = torch.Generator(device="cpu").manual_seed(1000 + seed)
+    w = torch.randn(1, dim_cond, 3, generator=g) * (0.45 / math.sqrt(dim_cond * 3))
+    return {"model.duration_predictor.conv.weight": w, "model.duration_predictor.conv.bias": torch.tensor([0.85])}
+
+
 def make_units(batch: int, frames: int, seed: int = 7, lengths=None, vocab: int = 2000) -> torch.Tensor:
     """Random unit ids in [1, vocab] (ids = unit + 1, 0 = pad; synthesize.py:39-42), right-padded to ``frames``."""
     g = torch.Generator(device="cpu").manual_seed(seed)

@@ -210,3 +210,35 @@ def test_config5_long_form_step_sweep(decoder, state_dict, nfe):
     if nfe == 1:
         ref = oracle.sample(state_dict, ids, x0, dt, 1.0)
         assert rel_l2((mel[valid] - MEAN) / STD, (ref[valid] - MEAN) / STD) <= MEL_TOL_NORM
+
+
+def test_duration_prediction_variant_matches_reference_golden(state_dict, golden_dir):
+    """SURVEY.md section 8(f) N1 -- the second shipped config (predict_duration): integer durations and the expanded
+    sequence bit exact against the live reference, mel / waveforms within the bf16 tolerances."""
+    import speech_resynth_b200 as srb
+    from speech_resynth_b200.configs import REFERENCE_VOCODER_KWARGS
+
+    z, info = _load(golden_dir, "duration_b3_n48")
+    cfg = srb.ConditionalFlowMatchingWithHifiGanConfig(
+        model_config=srb.ConditionalFlowMatchingConfig(predict_duration=True).to_dict(), vocoder_config=dict(REFERENCE_VOCODER_KWARGS))
+    m = srb.ConditionalFlowMatchingWithHifiGan(cfg).eval()
+    m.load_state_dict(dict(state_dict, **synthetic.duration_predictor_state(0)), strict=True)
+    m = m.cuda()
+    ids = torch.from_numpy(z["ids"]).cuda()
+    assert torch.equal(m.model.predict_durations(ids).cpu(), torch.from_numpy(z["durations"]))
+    exp_ids, _ = m.model.sampler().regulate(ids)
+    assert torch.equal(exp_ids.cpu(), torch.from_numpy(z["expanded_ids"]))
+    x0 = torch.from_numpy(z["x0"]).cuda()
+    wav, lengths, mel = m.engine().resynthesize(exp_ids, 0.25, 1.0, noise=x0)
+    valid = exp_ids.ne(0).cpu()
+    ref_mel = torch.from_numpy(z["mel"])
+    assert tuple(mel.shape) == tuple(ref_mel.shape)
+    assert rel_l2((mel.cpu()[valid] - MEAN) / STD, (ref_mel[valid] - MEAN) / STD) <= MEL_TOL_NORM
+    outs = m(ids, 0.25, 1.0)                                   # public call: expansion inside, list of waveforms out
+    assert [o.shape[-1] for o in outs] == info["wav_lengths"]
+    ref_wavs = np.split(z["wav_flat"], np.cumsum(z["wav_lengths"])[:-1])
+    for b, ref_w in enumerate(ref_wavs):
+        assert rel_l2(wav[b, : len(ref_w)], torch.from_numpy(ref_w)) <= WAV_TOL
+    # all-zero rule of the length regulator (HF:113-114)
+    out, dur = m.model.sampler().regulate(torch.zeros(2, 5, dtype=torch.int64, device="cuda"))
+    assert out.shape == (2, 5) and int(dur.sum()) == 0 and int(out.sum()) == 0

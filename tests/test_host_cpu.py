@@ -66,9 +66,23 @@ def test_no_cpu_fallback(model):
 
 
 def test_unsupported_variants_are_rejected():
-    cfg = srb.ConditionalFlowMatchingConfig(predict_duration=True)
+    cfg = srb.ConditionalFlowMatchingConfig(use_unet_skip_connection=True)
     with pytest.raises(NotImplementedError):
         srb.ConditionalFlowMatchingModel(cfg)
+
+
+def test_duration_variant_has_the_reference_parameter_names(state_dict):
+    """predict_duration adds exactly `duration_predictor.conv.{weight (1, 768, 3), bias (1,)}` (models.py:71,
+    fastspeech/modules.py:86) and the extended state-dict loads strictly."""
+    from speech_resynth_b200 import synthetic
+
+    m = srb.ConditionalFlowMatchingModel(srb.ConditionalFlowMatchingConfig(predict_duration=True))
+    extra = synthetic.duration_predictor_state(0)
+    keys = set(m.state_dict())
+    assert {k[len("model."):] for k in extra} <= keys
+    assert tuple(m.state_dict()["duration_predictor.conv.weight"].shape) == (1, 768, 3)
+    sd = {k[len("model."):]: v for k, v in dict(state_dict, **extra).items() if k.startswith("model.")}
+    m.load_state_dict(sd, strict=True)
 
 
 # ------------------------------------------------------------------------------------------------ packing

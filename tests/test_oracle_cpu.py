@@ -125,3 +125,29 @@ def test_oracle_against_live_reference(state_dict):
         wavs = oracle.resynthesize(state_dict, ids, x0, 0.25, 1.0)
     for a, r in zip(wavs, ref_wavs):
         assert a.shape == r.shape and rel_l2(a, r) <= 1e-5
+
+
+def test_oracle_duration_variant_matches_reference_golden(state_dict, golden_dir):
+    """Duration-prediction variant (models.py:157-164): integer durations and the expanded ids are bit exact against the
+    live reference, the mel sampled on the expanded sequence within fp32 noise."""
+    from speech_resynth_b200 import synthetic
+
+    z = np.load(os.path.join(golden_dir, "duration_b3_n48.npz"))
+    sd = dict(state_dict, **synthetic.duration_predictor_state(0))
+    ids = torch.from_numpy(z["ids"])
+    dur = oracle.duration_predict(sd, ids)
+    assert torch.equal(dur, torch.from_numpy(z["durations"]))
+    exp_ids, lengths = oracle.length_regulate_ids(ids, dur)
+    assert torch.equal(exp_ids, torch.from_numpy(z["expanded_ids"]))
+    assert [320 * int(n) + 80 for n in lengths] == z["wav_lengths"].tolist()
+    mel = oracle.sample(sd, exp_ids, torch.from_numpy(z["x0"]), 0.25, 1.0)
+    valid = exp_ids.ne(0)
+    ref = torch.from_numpy(z["mel"])
+    assert float((mel[valid] - ref[valid]).norm() / ref[valid].norm()) <= 1e-5
+
+
+def test_length_regulator_all_zero_rule():
+    """HF:113-114: when every predicted duration of the batch is 0, all of them become 1 (pads included)."""
+    ids = torch.tensor([[5, 9, 0], [7, 0, 0]])
+    out, lengths = oracle.length_regulate_ids(ids, torch.zeros(2, 3, dtype=torch.long))
+    assert torch.equal(out, ids) and lengths.tolist() == [3, 3]
