@@ -41,6 +41,9 @@ struct AttnParams {
   __nv_bfloat16* out;  // (B, N, 256)
   int frames;
   int k_col;           // first column of k in the q|k buffer (256)
+#ifdef SRB_TRACE
+  unsigned long long* trace;   // debug build: per CTA (< 4) and role (producer, MMA, softmax warp 2) 256 time stamps in order
+#endif
   int q_tiles;         // 128-query tiles per utterance
   int n_items;         // batch * 2 heads * q_tiles
 };
@@ -53,17 +56,30 @@ struct AttnSmem {
   static constexpr int q = 0;
   static constexpr int k = q + kTileBytes;             // 2 stages
   static constexpr int v = k + 2 * kTileBytes;         // 2 stages
-  static constexpr int p = v + 2 * kTileBytes;
-  static constexpr int stage = p + kTileBytes;         // 8 x 2 KB coalescing buffers (bf16 blocks, 4 pieces per row)
-  static constexpr int red = stage + 8 * 2048;         // [2][128] floats: row max / row sum exchange between halves
+  static constexpr int p = v + 2 * kTileBytes;         // 2 buffers: the softmax of tile j+1 must not wait for P V of tile j
+  static constexpr int red = p + 2 * kTileBytes;       // [2][128] floats: row max / row sum exchange between halves
   static constexpr int items = red + 1024;             // kItemCache work descriptors of this CTA
   static constexpr int bars = items + 512;
-  static constexpr int n_bars = 20;
+  static constexpr int n_bars = 22;
   static constexpr int tmem = bars + 8 * n_bars;
   static constexpr int total = tmem + 16 + 1024;       // + alignment slack
+  static_assert(total <= 232448, "attention kernel shared memory");
 };
 
 constexpr float kAttnScaleLog2 = 0.08838834764831845f * 1.4426950408889634f;   // (1/sqrt(128)) * log2(e)
+
+#ifdef SRB_TRACE
+#define ATTN_STAMP(role)                                                                      \
+  do {                                                                                        \
+    if (p.trace != nullptr && blockIdx.x < 4 && lane == 0 && trace_n < 256) {                 \
+      unsigned long long t_;                                                                  \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                  \
+      p.trace[(blockIdx.x * 3 + (role)) * 256 + trace_n++] = t_;                              \
+    }                                                                                         \
+  } while (0)
+#else
+#define ATTN_STAMP(role) do { } while (0)
+#endif
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -116,13 +132,17 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
   auto v_empty = [&](int s) { return bar0 + 8u * (8 + s); };
   auto s_full = [&](int s) { return bar0 + 8u * (10 + s); };
   auto s_empty = [&](int s) { return bar0 + 8u * (12 + s); };
-  const uint32_t p_full = bar0 + 8u * 14, p_empty = bar0 + 8u * 15;
-  auto o_full = [&](int s) { return bar0 + 8u * (16 + s); };
-  auto o_empty = [&](int s) { return bar0 + 8u * (18 + s); };
+  auto p_full = [&](int s) { return bar0 + 8u * (14 + s); };
+  auto p_empty = [&](int s) { return bar0 + 8u * (16 + s); };
+  auto o_full = [&](int s) { return bar0 + 8u * (18 + s); };
+  auto o_empty = [&](int s) { return bar0 + 8u * (20 + s); };
   const uint32_t tmem_slot = sbase + AttnSmem::tmem;
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
+  int trace_n = 0;
+  (void)trace_n;
+  if (warp <= 2) ATTN_STAMP(warp);   // kernel entry
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
     mbar_init(q_empty, 1);
@@ -135,9 +155,9 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
       mbar_init(s_empty(s), 8);
       mbar_init(o_full(s), 1);
       mbar_init(o_empty(s), 8);
+      mbar_init(p_full(s), 8);
+      mbar_init(p_empty(s), 1);
     }
-    mbar_init(p_full, 8);
-    mbar_init(p_empty, 1);
     fence_barrier_init();
     tma_prefetch_desc(&p.tm_qk);
     tma_prefetch_desc(&p.tm_vt);
@@ -187,6 +207,7 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
         if (++vst == 2) { vst = 0; vph ^= 1u; }
       };
       mbar_wait(q_empty, (n & 1) ^ 1u);   // every S tile of the previous item has consumed its Q
+      ATTN_STAMP(0);   // item: Q slot free
       mbar_expect_tx_elect(q_full, kTileBytes);
       tma_load_3d_elect(s_q, &p.tm_qk, q_full, it.h * 128, it.q0, it.b);
       tma_load_3d_elect(s_q + kHalfBytes, &p.tm_qk, q_full, it.h * 128 + 64, it.q0, it.b);
@@ -215,13 +236,16 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
       const uint32_t t_o = t_o0 + ob * 128;
       mbar_wait(q_full, n & 1);
       tc_fence_after();
+      ATTN_STAMP(1);   // item: Q landed
       const int s_total = it.two_pass ? 2 * it.nkv : it.nkv;
       int s_issued = 0;
       auto issue_s = [&]() {
         const int sb = t & 1;
         mbar_wait(k_full(kst), kph);
+        ATTN_STAMP(1);   // S: K landed
         mbar_wait(s_empty(sb), ((t >> 1) & 1) ^ 1u);
         tc_fence_after();
+        ATTN_STAMP(1);   // S: buffer free, issuing
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
           const uint32_t off = (kk >> 2) * kHalfBytes + (kk & 3) * 32;
@@ -242,17 +266,20 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
       tc_fence_after();
       for (int j = 0; j < it.nkv; ++j) {
         if (j + 1 < it.nkv) issue_s();                    // S(j+1) overlaps the softmax of S(j)
-        mbar_wait(p_full, pv & 1);
+        const int pb = pv & 1;
+        mbar_wait(p_full(pb), (pv >> 1) & 1);
+        ATTN_STAMP(1);   // PV: P ready
         mbar_wait(v_full(vst), vph);
         tc_fence_after();
+        ATTN_STAMP(1);   // PV: V landed, issuing
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
           const uint32_t off = (kk >> 2) * kHalfBytes + (kk & 3) * 32;
-          umma_bf16_pred(1u, t_o, umma_smem_desc<128>(s_p + off), umma_smem_desc<128>(s_v + vst * kTileBytes + off), IDESC,
-                         (j != 0 || kk != 0) ? 1u : 0u);
+          umma_bf16_pred(1u, t_o, umma_smem_desc<128>(s_p + pb * kTileBytes + off), umma_smem_desc<128>(s_v + vst * kTileBytes + off),
+                         IDESC, (j != 0 || kk != 0) ? 1u : 0u);
         }
         umma_commit_pred(1u, v_empty(vst));
-        umma_commit_pred(1u, p_empty);
+        umma_commit_pred(1u, p_empty(pb));
         if (++vst == 2) { vst = 0; vph ^= 1u; }
         ++pv;
       }
@@ -306,11 +333,14 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
       float l = 0.f;
       for (int j = 0; j < nkv; ++j, ++t, ++pv) {
         const int sb = t & 1;
+        if (warp == 2) ATTN_STAMP(2);   // tile: waiting for S
         mbar_wait(s_full(sb), (t >> 1) & 1);
         tc_fence_after();
+        if (warp == 2) ATTN_STAMP(2);   // tile: S ready
         const int key0 = j * kAttnTile + half * 64;
         // this warp's 64 keys are one [128 rows][64 keys] half tile of P: 128-byte rows, 16-byte pieces XOR-swizzled
-        uint8_t* prow = smem + AttnSmem::p + half * kHalfBytes + row * 128;
+        const int pb = pv & 1;
+        uint8_t* prow = smem + AttnSmem::p + pb * kTileBytes + half * kHalfBytes + row * 128;
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           uint32_t v[32];
@@ -325,7 +355,11 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
             l += p0 + p1;
             o[i] = pack_bf16(p0, p1);
           }
-          if (c == 0) mbar_wait(p_empty, (pv & 1) ^ 1u);   // P V of the previous tile has finished reading the P buffer
+          if (c == 0) {
+            if (warp == 2) ATTN_STAMP(2);   // tile: first 32 columns done
+            mbar_wait(p_empty(pb), ((pv >> 1) & 1) ^ 1u);   // the P V that last read this P buffer (two tiles ago) is done
+            if (warp == 2) ATTN_STAMP(2);   // tile: P buffer free
+          }
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int piece = c * 4 + i;
@@ -337,8 +371,9 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
         __syncwarp();
         if (lane == 0) {
           mbar_arrive(s_empty(sb));
-          mbar_arrive(p_full);
+          mbar_arrive(p_full(pb));
         }
+        if (warp == 2) ATTN_STAMP(2);   // tile: P published
       }
       // row sum over both halves
       red[half * 128 + row] = l;
@@ -346,11 +381,14 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
       l += red[(half ^ 1) * 128 + row];
       pair_barrier(quarter);        // `red` is free for the next item
       // ---- epilogue: O / l -> bf16 -> (B, N, 256); this warp takes 64 of the head's 128 output columns
+      if (warp == 2) ATTN_STAMP(2);   // item: sums exchanged, waiting for O
       mbar_wait(o_full(ob), (n >> 1) & 1);
       tc_fence_after();
+      if (warp == 2) ATTN_STAMP(2);   // item: O complete
       const float inv = l > 0.f ? 1.f / l : 0.f;
       EpiWarp w;
-      w.stage = smem + AttnSmem::stage + (warp - 2) * 2048;
+      // every P V of the item has completed: the warp's own 32 rows of P buffer 0 (4 KB) serve as its coalescing stage
+      w.stage = smem + AttnSmem::p + half * kHalfBytes + quarter * 32 * 128;
       w.lane = lane;
       w.row0 = it.q0 + quarter * 32;
       const int vrows = clamp_rows(p.frames, w.row0);
@@ -427,6 +465,9 @@ extern "C" int srb_cfm_attention_tc(const void* qk_bf16, int32_t ld, const void*
     SRB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(v^T) failed: %d", (int)r);
   }
   p.lengths = lengths;
+#ifdef SRB_TRACE
+  p.trace = debug_trace_buffer();
+#endif
   p.qk_norm2_max = qk_norm2_max;
   p.out = static_cast<__nv_bfloat16*>(o_bf16);
   p.frames = frames;

@@ -33,6 +33,9 @@ inline int after_launch(const char* name) {
 }
 
 int num_sms();
+#ifdef SRB_TRACE
+unsigned long long* debug_trace_buffer();   // debug build only (tools/trace_kernels.py)
+#endif
 
 // Programmatic dependent launch: every kernel of the path is launched with programmatic stream serialization, so the
 // CTAs of kernel N+1 start (barrier init, TMEM allocation, tensor-map prefetch, constant tables) on SMs that kernel N

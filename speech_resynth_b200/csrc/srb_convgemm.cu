@@ -306,6 +306,7 @@ static int launch_inst(ConvGemmParams& p, int total_tiles, cudaStream_t stream, 
 #ifdef SRB_TRACE
 static unsigned long long* g_trace = nullptr;
 extern "C" void srb_debug_set_trace(unsigned long long* buf) { g_trace = buf; }
+unsigned long long* debug_trace_buffer() { return g_trace; }
 #endif
 
 static int launch_convgemm(const ConvGemmDesc& d, cudaStream_t stream) {

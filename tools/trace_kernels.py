@@ -72,6 +72,17 @@ if __name__ == "__main__":
         "embed": lambda: nat.call("srb_cfm_embed", P(ws["xt_b"]), P(w.w_embed), P(ws["cond"]), P(ws["x0"]), b, n8),
         "pred_euler": lambda: nat.call("srb_cfm_pred_euler", P(ws["xn"]), P(w.w_pred), 0.0625, P(ws["xt"]), P(ws["xt_b"]), None, None, 2.26, -5.88, -11.5, P(L), b, n8),
     }
+    # attention: raw ordered stamps per role (see ATTN_STAMP in csrc/srb_attention_tc.cu)
+    att = torch.zeros(4 * 3 * 256, dtype=torch.int64, device="cuda")
+    lib.srb_debug_set_trace(att.data_ptr())
+    nat.call("srb_cfm_attention_tc", P(ws["qk"]), 512, P(ws["vt"]), ws["vt"].shape[1], P(L), P(ws["qkmax"][0]), P(ws["o"]), b, n8)
+    torch.cuda.synchronize()
+    lib.srb_debug_set_trace(None)
+    a = att.cpu().view(4, 3, 256)
+    t0 = int(a[0, 0, 0])
+    for role, nm in enumerate(("producer", "mma", "softmax warp 2")):
+        vals = [int(v) for v in a[0, role] if int(v) != 0]
+        print(f"== attention cta 0 {nm}: " + " ".join(f"{(v - t0) / 1e3:.2f}" for v in vals))
     for name, fn in calls.items():
         trace.zero_()
         torch.cuda.synchronize()
