@@ -3,6 +3,7 @@
 // coalesced; none of them is GEMM shaped.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <math.h>
 
 #include "../../include/srb.h"
@@ -396,6 +397,17 @@ int srb_length_regulate(const int64_t* ids, const int32_t* durations, int64_t* o
 int srb_cfm_posconv_norm(const float* x0, const float* dw_w, const float* dw_b, const float* g, const int32_t* lengths,
                          float* x, void* xn_bf16, int32_t batch, int32_t frames, void* stream) {
   if (batch <= 0 || frames <= 0) return 0;
+  static int rows_sel = -1;
+  if (rows_sel < 0) {
+    const char* e = getenv("SRB_POSCONV_ROWS");   // A/B knob: 8 (more resident blocks, default: 41.8 vs 45.4 us) or 16 (fewer window loads)
+    rows_sel = (e && atoi(e) == 16) ? 16 : 8;
+  }
+  if (rows_sel == 8) {
+    dim3 grid((frames + 7) / 8, batch);
+    SRB_CUDA(launch_pdl(posconv_norm_kernel<8>, grid, dim3(128), 0, (cudaStream_t)stream, x0, dw_w, dw_b, g, lengths, x,
+                        static_cast<__nv_bfloat16*>(xn_bf16), frames));
+    return after_launch("posconv_norm_kernel");
+  }
   constexpr int ROWS = 16;
   dim3 grid((frames + ROWS - 1) / ROWS, batch);
   SRB_CUDA(launch_pdl(posconv_norm_kernel<ROWS>, grid, dim3(128), 0, (cudaStream_t)stream, x0, dw_w, dw_b, g, lengths, x,

@@ -213,3 +213,22 @@ def test_library_exports_every_symbol_declared_in_the_header():
     for name in declared:
         assert hasattr(lib, name), name
     assert lib.srb_version() == 100
+
+
+# ------------------------------------------------------------------------------------------------ synthesize driver
+@pytest.mark.parametrize("bits", [32, 16])
+def test_wav_writer_round_trip(tmp_path, bits):
+    """The driver's RIFF writer (float32 like torchaudio.save of a float tensor, or 16-bit PCM) read back by scipy."""
+    from scipy.io import wavfile
+
+    from speech_resynth_b200.synthesize import write_wav
+
+    x = (torch.rand(16123, generator=torch.Generator().manual_seed(3)) * 2 - 1).numpy()
+    path = str(tmp_path / "sub" / f"a{bits}.wav")
+    write_wav(path, x, 16000, bits)
+    rate, y = wavfile.read(path)
+    assert rate == 16000 and y.shape == x.shape
+    if bits == 32:
+        assert y.dtype.kind == "f" and (y == x).all()
+    else:
+        assert y.dtype == "int16" and abs(y.astype("float64") / 32768.0 - x).max() <= 0.5 / 32768 + 1e-9
