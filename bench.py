@@ -83,6 +83,40 @@ def cpu_reference_run(steps: int, warmup: int, n_gpus: int, as_arm: bool):
     }
 
 
+# ------------------------------------------------------------------------------------------------ eager-PyTorch bar
+def eager_gpu_run(steps: int, warmup: int):
+    """The "existing Blackwell library kernels" bar of SURVEY.md section 8(d): the same algorithm as plain eager PyTorch
+    ops on the B200 (cuBLAS / cuDNN / SDPA kernels through the oracle port -- the live reference cannot travel to the GPU
+    box), config 2, in fp32 and under bf16 autocast (the reference's own low-precision mode, train.py:174).  Reported
+    beside the product numbers in profiles/; not part of the default bench line."""
+    from oracle import cfm_hifigan_oracle as oracle
+    from speech_resynth_b200 import synthetic
+
+    dev = torch.device("cuda", 0)
+    sd = {k: v.to(dev) for k, v in synthetic.make_state_dict(0).items()}
+    ids = synthetic.make_units(BATCH, FRAMES, seed=7).to(dev)
+    x0 = torch.randn(BATCH, FRAMES, 80, device=dev)
+    secs = audio_seconds([FRAMES] * BATCH)
+    out = {"impl": "eager-pytorch-on-gpu", "metric": METRIC, "unit": UNIT, "config": workload_config(1), "modes": {}}
+    for mode in ("fp32", "fp32_tf32", "bf16_autocast"):
+        torch.backends.cuda.matmul.allow_tf32 = mode == "fp32_tf32"
+        torch.backends.cudnn.allow_tf32 = mode == "fp32_tf32"
+        ctx = torch.autocast("cuda", dtype=torch.bfloat16) if mode == "bf16_autocast" else torch.autocast("cuda", enabled=False)
+        with torch.inference_mode(), ctx:
+            for _ in range(warmup):
+                oracle.resynthesize(sd, ids, x0, DT, TRUNC)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                oracle.resynthesize(sd, ids, x0, DT, TRUNC)
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out["modes"][mode] = {"ms_per_step": ms, "value": secs / (ms / 1e3)}
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -298,7 +332,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "eager-gpu"])
     ap.add_argument("--ops", default=None, help="write the per-op device-time table (csv) here")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -307,6 +341,9 @@ def main():
         if int(os.environ.get("RANK", "0")) != 0:
             return
         print(json.dumps(cpu_reference_run(args.steps, args.warmup, args.gpus, as_arm=True)), flush=True)
+        return
+    if args.impl == "eager-gpu":
+        print(json.dumps(eager_gpu_run(args.steps, args.warmup)), flush=True)
         return
     out = gpu_run(args)
     if out is not None:

@@ -70,7 +70,7 @@ def time_embedding(sd: Dict[str, Tensor], t: Tensor) -> Tensor:
     so one row (256,) is returned.  freqs = ((t*w)*2)*pi in that association order.
     """
     w = sd["model.time_cond_mlp.0.weights"]
-    t = t.reshape(1).to(w.dtype)
+    t = t.reshape(1).to(device=w.device, dtype=w.dtype)
     freqs = (t[:, None] * w[None, :]) * 2 * math.pi
     four = torch.cat([t[:, None], freqs.sin(), freqs.cos()], dim=-1)  # pack((x, sin, cos), "b *")
     h = F.linear(four, sd["model.time_cond_mlp.1.weight"], sd["model.time_cond_mlp.1.bias"])
@@ -86,7 +86,7 @@ def adaptive_rmsnorm(x: Tensor, cond: Tensor, to_weight: Tensor) -> Tensor:
 
 def rotary_table(inv_freq: Tensor, n: int) -> Tensor:
     """RotaryEmbedding.forward -- transformer.py:55-63: pos*inv_freq, cat(freqs, freqs)."""
-    t = torch.arange(n).to(inv_freq.dtype)
+    t = torch.arange(n, device=inv_freq.device).to(inv_freq.dtype)
     freqs = t[:, None] * inv_freq[None, :]
     return torch.cat([freqs, freqs], dim=-1)
 
@@ -311,7 +311,7 @@ def resynthesize(sd: Dict[str, Tensor], ids: Tensor, x0: Tensor, dt: float = 0.1
                  truncation_value: Optional[float] = None) -> List[Tensor]:
     """ConditionalFlowMatchingWithHifiGan.forward -- models.py:223-256 (x0 injected)."""
     mel = sample(sd, ids, x0, dt, truncation_value)
-    pv = torch.tensor(pad_value(), dtype=mel.dtype)
+    pv = torch.tensor(pad_value(), dtype=mel.dtype, device=mel.device)
     lengths = mel.ne(pv).all(dim=2).sum(dim=1)
     wav_len = waveform_lengths(lengths)
     wav = hifigan(sd, mel)
