@@ -327,6 +327,16 @@ def gpu_run(args):
     return out
 
 
+def _claim_stdout():
+    """Keep the process's stdout for the ONE JSON line: libraries (NCCL prints its version banner at communicator
+    creation) write to file descriptor 1 directly, so fd 1 is pointed at stderr and the line goes to a duplicate of
+    the original descriptor."""
+    sys.stdout.flush()
+    keep = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(keep, "w")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -345,9 +355,10 @@ def main():
     if args.impl == "eager-gpu":
         print(json.dumps(eager_gpu_run(args.steps, args.warmup)), flush=True)
         return
+    real_stdout = _claim_stdout()
     out = gpu_run(args)
     if out is not None:
-        print(json.dumps(out), flush=True)
+        print(json.dumps(out), file=real_stdout, flush=True)
 
 
 if __name__ == "__main__":
