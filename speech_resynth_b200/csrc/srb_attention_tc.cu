@@ -17,7 +17,9 @@
 //     maxima, pass 2 recomputes S and forms P = exp2(s*scale - m) with the FINAL maximum.
 // S is double-buffered in TMEM so the tensor core computes S(j+1) while the softmax warps work on S(j).
 //
-// Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer (+ TMEM allocator), warps 2-9 softmax/epilogue:
+// Warp roles (448 threads): warp 0 TMA producer, warp 1 MMA issuer (+ TMEM allocator), warps 10-13 output (O / l -> bf16
+// -> global, one warp per TMEM lane quarter: the softmax warps hand over the row sums and start the next item at once;
+// waiting for the last P V and writing the output was 1.7 of the 6.35 us an item took them), warps 2-9 softmax:
 // thread <-> query row (TMEM lane), and the two warps of a lane quarter split the 128 key columns of an S tile (and
 // the 128 output columns of O) in halves.  Four softmax warps (one per SM sub-partition) left the kernel waiting on
 // them -- ncu: 75 % of the samples on the S / P mbarriers -- so each row's work is shared by two threads; the row
@@ -54,15 +56,18 @@ constexpr int kTileBytes = 2 * kHalfBytes;     // 32 KB
 
 struct AttnSmem {
   static constexpr int q = 0;
-  static constexpr int k = q + kTileBytes;             // 2 stages
+  static constexpr int k = q + 2 * kTileBytes;         // (Q: 2 buffers, the next item's Q lands while this item runs) 2 stages
   static constexpr int v = k + 2 * kTileBytes;         // 2 stages
-  static constexpr int p = v + 2 * kTileBytes;         // 2 buffers: the softmax of tile j+1 must not wait for P V of tile j
-  static constexpr int red = p + 2 * kTileBytes;       // [2][128] floats: row max / row sum exchange between halves
-  static constexpr int items = red + 1024;             // kItemCache work descriptors of this CTA
+  static constexpr int p = v + 2 * kTileBytes;         // 1 buffer (the wait for P V of the previous tile measured 0.1 us)
+  static constexpr int red = p + kTileBytes;           // [2][128] floats: row max / row sum exchange between halves
+  static constexpr int lsum = red + 1024;              // [2 O buffers][128] floats: row sums handed to the output warps
+  static constexpr int items = lsum + 1024;            // kItemCache work descriptors of this CTA
   static constexpr int bars = items + 512;
-  static constexpr int n_bars = 22;
+  static constexpr int n_bars = 26;
   static constexpr int tmem = bars + 8 * n_bars;
-  static constexpr int total = tmem + 16 + 1024;       // + alignment slack
+  // no alignment slack: the dynamic shared-memory window of a kernel without static shared memory starts 1 KB aligned
+  // (checked at kernel entry: the kernel traps otherwise)
+  static constexpr int total = tmem + 16;
   static_assert(total <= 232448, "attention kernel shared memory");
 };
 
@@ -119,13 +124,15 @@ __device__ __forceinline__ AttnItem attn_item(const AttnParams& p, int item) {
   return it;
 }
 
-__global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__ AttnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem = smem_raw + (sbase - smem_u32(smem_raw));
+__global__ void __launch_bounds__(448, 1) attn_tc_kernel(const __grid_constant__ AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t sbase = smem_u32(smem_raw);
+  if ((sbase & 1023u) != 0u) __trap();   // the swizzled tiles below need 1 KB alignment
+  uint8_t* smem = smem_raw;
   const uint32_t s_q = sbase + AttnSmem::q, s_k = sbase + AttnSmem::k, s_v = sbase + AttnSmem::v, s_p = sbase + AttnSmem::p;
   const uint32_t bar0 = sbase + AttnSmem::bars;
-  const uint32_t q_full = bar0, q_empty = bar0 + 8u;
+  auto q_full = [&](int s) { return bar0 + 8u * (24 + s); };
+  auto q_empty = [&](int s) { return bar0 + 8u * s; };
   auto k_full = [&](int s) { return bar0 + 8u * (2 + s); };
   auto k_empty = [&](int s) { return bar0 + 8u * (4 + s); };
   auto v_full = [&](int s) { return bar0 + 8u * (6 + s); };
@@ -136,6 +143,7 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
   auto p_empty = [&](int s) { return bar0 + 8u * (16 + s); };
   auto o_full = [&](int s) { return bar0 + 8u * (18 + s); };
   auto o_empty = [&](int s) { return bar0 + 8u * (20 + s); };
+  auto l_ready = [&](int s) { return bar0 + 8u * (22 + s); };
   const uint32_t tmem_slot = sbase + AttnSmem::tmem;
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
@@ -144,9 +152,9 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
   (void)trace_n;
   if (warp <= 2) ATTN_STAMP(warp);   // kernel entry
   if (threadIdx.x == 0) {
-    mbar_init(q_full, 1);
-    mbar_init(q_empty, 1);
     for (int s = 0; s < 2; ++s) {
+      mbar_init(q_full(s), 1);
+      mbar_init(q_empty(s), 1);
       mbar_init(k_full(s), 1);
       mbar_init(k_empty(s), 1);
       mbar_init(v_full(s), 1);
@@ -154,7 +162,8 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
       mbar_init(s_full(s), 1);
       mbar_init(s_empty(s), 8);
       mbar_init(o_full(s), 1);
-      mbar_init(o_empty(s), 8);
+      mbar_init(o_empty(s), 4);
+      mbar_init(l_ready(s), 8);
       mbar_init(p_full(s), 8);
       mbar_init(p_empty(s), 1);
     }
@@ -206,11 +215,20 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
         tma_load_2d_elect(s_v + vst * kTileBytes + kHalfBytes, &p.tm_vt, v_full(vst), col + 64, it.h * 128);
         if (++vst == 2) { vst = 0; vph ^= 1u; }
       };
-      mbar_wait(q_empty, (n & 1) ^ 1u);   // every S tile of the previous item has consumed its Q
-      ATTN_STAMP(0);   // item: Q slot free
-      mbar_expect_tx_elect(q_full, kTileBytes);
-      tma_load_3d_elect(s_q, &p.tm_qk, q_full, it.h * 128, it.q0, it.b);
-      tma_load_3d_elect(s_q + kHalfBytes, &p.tm_qk, q_full, it.h * 128 + 64, it.q0, it.b);
+      // Q of item n lives in buffer n & 1; the NEXT item's Q is requested before this item's K / V tiles, so it lands
+      // long before the tensor core gets there (with one buffer the softmax warps idled ~2 us at every item boundary)
+      auto load_q = [&](int nn, const AttnItem& iq) {
+        const int qb = nn & 1;
+        mbar_wait(q_empty(qb), ((nn >> 1) & 1) ^ 1u);   // every S tile of item nn - 2 has consumed its Q
+        mbar_expect_tx_elect(q_full(qb), kTileBytes);
+        tma_load_3d_elect(s_q + qb * kTileBytes, &p.tm_qk, q_full(qb), iq.h * 128, iq.q0, iq.b);
+        tma_load_3d_elect(s_q + qb * kTileBytes + kHalfBytes, &p.tm_qk, q_full(qb), iq.h * 128 + 64, iq.q0, iq.b);
+      };
+      if (n == 0) {
+        ATTN_STAMP(0);
+        load_q(0, it);
+      }
+      if (item + step < p.n_items) load_q(n + 1, get_item(n + 1, item + step));
       int v_ahead = 0;
       if (it.two_pass) {
         // the V ring is idle during the maxima pass: fill it first
@@ -225,49 +243,74 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
     __syncwarp();
   } else if (warp == 1) {
     // ================= MMA issuer (converged warp, elected lane issues) =================
+    // S tiles form ONE stream across items (per item: the maxima sweep if it needs two passes, then the main sweep);
+    // the stream runs one tile ahead of the P V products, also across item boundaries, so the first S of item n + 1 is
+    // being computed while the softmax warps finish item n.
     int kst = 0, vst = 0;
     uint32_t kph = 0, vph = 0;
-    int t = 0;    // S tiles issued so far (buffer = t & 1)
+    int t = 0;    // S tiles issued so far (ring buffer = t & 1)
     int pv = 0;   // P V products issued so far
+    // S stream cursor
+    int s_n = 0, s_item = first, s_j = 0, s_left = 0;   // item ordinal / id, next tile inside the item, tiles left in it
+    AttnItem s_it;
+    bool s_open = false;
+    auto next_s = [&]() {
+      // advance to an item with tiles left
+      while (!s_open || s_left == 0) {
+        if (s_open) {
+          // (the previous item's last S tile has been issued: its Q buffer may be refilled)
+          s_item += step;
+          ++s_n;
+          s_open = false;
+        }
+        if (s_item >= p.n_items) return;
+        s_it = get_item(s_n, s_item);
+        s_left = s_it.two_pass ? 2 * s_it.nkv : s_it.nkv;
+        s_j = 0;
+        mbar_wait(q_full(s_n & 1), (s_n >> 1) & 1);
+        tc_fence_after();
+        ATTN_STAMP(1);   // item: Q landed
+        s_open = true;
+        if (s_left == 0) umma_commit_pred(1u, q_empty(s_n & 1));
+      }
+      const int sb = t & 1;
+      mbar_wait(k_full(kst), kph);
+      ATTN_STAMP(1);   // S: K landed
+      mbar_wait(s_empty(sb), ((t >> 1) & 1) ^ 1u);
+      tc_fence_after();
+      ATTN_STAMP(1);   // S: buffer free, issuing
+      const uint32_t qa = s_q + (s_n & 1) * kTileBytes;
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {
+        const uint32_t off = (kk >> 2) * kHalfBytes + (kk & 3) * 32;
+        umma_bf16_pred(1u, t_s0 + sb * 128, umma_smem_desc<128>(qa + off), umma_smem_desc<128>(s_k + kst * kTileBytes + off),
+                       IDESC, kk != 0 ? 1u : 0u);
+      }
+      umma_commit_pred(1u, k_empty(kst));
+      umma_commit_pred(1u, s_full(sb));
+      if (--s_left == 0) umma_commit_pred(1u, q_empty(s_n & 1));   // Q may be replaced by the item after next
+      if (++kst == 2) { kst = 0; kph ^= 1u; }
+      ++s_j;
+      ++t;
+    };
     int n = 0;
     for (int item = first; item < p.n_items; item += step, ++n) {
       const AttnItem it = get_item(n, item);
       const int ob = n & 1;
       const uint32_t t_o = t_o0 + ob * 128;
-      mbar_wait(q_full, n & 1);
-      tc_fence_after();
-      ATTN_STAMP(1);   // item: Q landed
-      const int s_total = it.two_pass ? 2 * it.nkv : it.nkv;
-      int s_issued = 0;
-      auto issue_s = [&]() {
-        const int sb = t & 1;
-        mbar_wait(k_full(kst), kph);
-        ATTN_STAMP(1);   // S: K landed
-        mbar_wait(s_empty(sb), ((t >> 1) & 1) ^ 1u);
-        tc_fence_after();
-        ATTN_STAMP(1);   // S: buffer free, issuing
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          const uint32_t off = (kk >> 2) * kHalfBytes + (kk & 3) * 32;
-          umma_bf16_pred(1u, t_s0 + sb * 128, umma_smem_desc<128>(s_q + off), umma_smem_desc<128>(s_k + kst * kTileBytes + off),
-                         IDESC, kk != 0 ? 1u : 0u);
-        }
-        umma_commit_pred(1u, k_empty(kst));
-        umma_commit_pred(1u, s_full(sb));
-        if (++s_issued == s_total) umma_commit_pred(1u, q_empty);   // Q may be replaced by the next item's
-        if (++kst == 2) { kst = 0; kph ^= 1u; }
-        ++t;
-      };
-      if (it.nkv == 0) umma_commit_pred(1u, q_empty);
-      if (it.two_pass) for (int j = 0; j < it.nkv; ++j) issue_s();     // maxima pass
-      if (it.nkv > 0) issue_s();                                       // main pass, tile 0
-      // the epilogue of the item that used this O buffer two items ago has read it
+      // S tiles of this item that must exist before its first P V: the maxima sweep and main tile 0
+      const int need = (it.two_pass ? it.nkv : 0) + (it.nkv > 0 ? 1 : 0);
+      while (s_n < n || (s_n == n && (!s_open || s_j < need))) {
+        if (s_n == n && s_open && s_left == 0) break;
+        next_s();
+        if (s_item >= p.n_items && !s_open) break;
+      }
+      // the output warps have read the O buffer this item accumulates into (two items ago)
       mbar_wait(o_empty(ob), ((n >> 1) & 1) ^ 1u);
       tc_fence_after();
       for (int j = 0; j < it.nkv; ++j) {
-        if (j + 1 < it.nkv) issue_s();                    // S(j+1) overlaps the softmax of S(j)
-        const int pb = pv & 1;
-        mbar_wait(p_full(pb), (pv >> 1) & 1);
+        next_s();                                         // one S tile ahead (possibly the next item's first)
+        mbar_wait(p_full(0), pv & 1);
         ATTN_STAMP(1);   // PV: P ready
         mbar_wait(v_full(vst), vph);
         tc_fence_after();
@@ -275,19 +318,58 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
           const uint32_t off = (kk >> 2) * kHalfBytes + (kk & 3) * 32;
-          umma_bf16_pred(1u, t_o, umma_smem_desc<128>(s_p + pb * kTileBytes + off), umma_smem_desc<128>(s_v + vst * kTileBytes + off),
-                         IDESC, (j != 0 || kk != 0) ? 1u : 0u);
+          umma_bf16_pred(1u, t_o, umma_smem_desc<128>(s_p + off), umma_smem_desc<128>(s_v + vst * kTileBytes + off), IDESC,
+                         (j != 0 || kk != 0) ? 1u : 0u);
         }
         umma_commit_pred(1u, v_empty(vst));
-        umma_commit_pred(1u, p_empty(pb));
+        umma_commit_pred(1u, p_empty(0));
         if (++vst == 2) { vst = 0; vph ^= 1u; }
         ++pv;
       }
       umma_commit_pred(1u, o_full(ob));
     }
     __syncwarp();
+  } else if (warp >= 10) {
+    // ================= output warps =================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    const float* lsum = reinterpret_cast<const float*>(smem + AttnSmem::lsum);
+    int n = 0;
+    for (int item = first; item < p.n_items; item += step, ++n) {
+      const AttnItem it = get_item(n, item);
+      const int ob = n & 1;
+      mbar_wait(l_ready(ob), (n >> 1) & 1);
+      mbar_wait(o_full(ob), (n >> 1) & 1);
+      tc_fence_after();
+      const float l = lsum[ob * 128 + row];
+      const float inv = (l > 0.f && it.nkv > 0) ? 1.f / l : 0.f;
+      const int q = it.q0 + row;
+      // thread <-> query row: the row's 128 output columns of this head are 256 contiguous bytes
+      uint4* out = reinterpret_cast<uint4*>(p.out + ((long long)it.b * p.frames + q) * 256 + it.h * 128);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(t_o0 + ob * 128 + lane_addr + c * 32, v);
+        tmem_ld_wait();
+        if (c == 3) {
+          // O and the row sum are in registers: the accumulator and lsum[ob] are free for the item after next
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(o_empty(ob));
+        }
+        if (q < p.frames) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            out[c * 4 + i] = make_uint4(pack_bf16(__uint_as_float(v[8 * i]) * inv, __uint_as_float(v[8 * i + 1]) * inv),
+                                        pack_bf16(__uint_as_float(v[8 * i + 2]) * inv, __uint_as_float(v[8 * i + 3]) * inv),
+                                        pack_bf16(__uint_as_float(v[8 * i + 4]) * inv, __uint_as_float(v[8 * i + 5]) * inv),
+                                        pack_bf16(__uint_as_float(v[8 * i + 6]) * inv, __uint_as_float(v[8 * i + 7]) * inv));
+        }
+      }
+    }
   } else {
-    // ================= softmax / epilogue warps =================
+    // ================= softmax warps =================
     const int quarter = warp & 3;
     const int half = (warp - 2) >> 2;                     // key-column half of S / output-column half of O
     const int row = quarter * 32 + lane;                  // query row inside the tile = TMEM lane
@@ -339,8 +421,7 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
         if (warp == 2) ATTN_STAMP(2);   // tile: S ready
         const int key0 = j * kAttnTile + half * 64;
         // this warp's 64 keys are one [128 rows][64 keys] half tile of P: 128-byte rows, 16-byte pieces XOR-swizzled
-        const int pb = pv & 1;
-        uint8_t* prow = smem + AttnSmem::p + pb * kTileBytes + half * kHalfBytes + row * 128;
+        uint8_t* prow = smem + AttnSmem::p + half * kHalfBytes + row * 128;
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           uint32_t v[32];
@@ -357,7 +438,7 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
           }
           if (c == 0) {
             if (warp == 2) ATTN_STAMP(2);   // tile: first 32 columns done
-            mbar_wait(p_empty(pb), ((pv >> 1) & 1) ^ 1u);   // the P V that last read this P buffer (two tiles ago) is done
+            mbar_wait(p_empty(0), (pv & 1) ^ 1u);   // P V of the previous tile has finished reading the P tile
             if (warp == 2) ATTN_STAMP(2);   // tile: P buffer free
           }
 #pragma unroll
@@ -371,46 +452,20 @@ __global__ void __launch_bounds__(320, 1) attn_tc_kernel(const __grid_constant__
         __syncwarp();
         if (lane == 0) {
           mbar_arrive(s_empty(sb));
-          mbar_arrive(p_full(pb));
+          mbar_arrive(p_full(0));
         }
         if (warp == 2) ATTN_STAMP(2);   // tile: P published
       }
-      // row sum over both halves
+      // row sum over both halves, handed to the output warps
       red[half * 128 + row] = l;
       pair_barrier(quarter);
       l += red[(half ^ 1) * 128 + row];
+      // lsum[ob] was last read by the output warps two items ago (they release it together with the O buffer)
+      mbar_wait(o_empty(ob), ((n >> 1) & 1) ^ 1u);
+      if (half == 0) reinterpret_cast<float*>(smem + AttnSmem::lsum)[ob * 128 + row] = l;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(l_ready(ob));
       pair_barrier(quarter);        // `red` is free for the next item
-      // ---- epilogue: O / l -> bf16 -> (B, N, 256); this warp takes 64 of the head's 128 output columns
-      if (warp == 2) ATTN_STAMP(2);   // item: sums exchanged, waiting for O
-      mbar_wait(o_full(ob), (n >> 1) & 1);
-      tc_fence_after();
-      if (warp == 2) ATTN_STAMP(2);   // item: O complete
-      const float inv = l > 0.f ? 1.f / l : 0.f;
-      EpiWarp w;
-      // every P V of the item has completed: the warp's own 32 rows of P buffer 0 (4 KB) serve as its coalescing stage
-      w.stage = smem + AttnSmem::p + half * kHalfBytes + quarter * 32 * 128;
-      w.lane = lane;
-      w.row0 = it.q0 + quarter * 32;
-      const int vrows = clamp_rows(p.frames, w.row0);
-      __nv_bfloat16* out = p.out + ((long long)it.b * p.frames + w.row0) * 256 + it.h * 128 + half * 64;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        tmem_ld32(t_o + lane_addr + half * 64 + c * 32, v);
-        tmem_ld_wait();
-        if (c == 1) {
-          // O has been read into registers: the MMA warp may reuse this accumulator (two items from now)
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(o_empty(ob));
-        }
-        uint4 o[4];
-        uint32_t* ow = reinterpret_cast<uint32_t*>(o);
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          ow[i] = nkv > 0 ? pack_bf16(__uint_as_float(v[2 * i]) * inv, __uint_as_float(v[2 * i + 1]) * inv) : 0u;
-        scatter_store<4>(w, o, out + c * 32, 512, vrows);
-      }
     }
   }
 
@@ -483,6 +538,6 @@ extern "C" int srb_cfm_attention_tc(const void* qk_bf16, int32_t ld, const void*
   p.n_items = batch * 2 * p.q_tiles;
   int grid = num_sms();
   if (grid > p.n_items) grid = p.n_items;
-  SRB_CUDA(launch_pdl(attn_tc_kernel, dim3(grid), dim3(320), AttnSmem::total, (cudaStream_t)stream, p));
+  SRB_CUDA(launch_pdl(attn_tc_kernel, dim3(grid), dim3(448), AttnSmem::total, (cudaStream_t)stream, p));
   return after_launch("attn_tc_kernel");
 }
