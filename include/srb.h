@@ -54,6 +54,13 @@ int srb_rotary_table(const float* inv_freq, int32_t rows, float* cos_out, float*
  * xt_bf16 = bf16(xt).  n = batch*frames*80 */
 int srb_prior_prepare(float* xt, void* xt_bf16, int64_t n, float truncation, void* stream);
 
+/* Log-mel front end = mel_spectrogram of src/hifigan/data.py:17-53 (n_fft 400, hop 320, hann window, center=False,
+ * 80 slaney mel bands 0-8 kHz, log(max(., 1e-5))):  wav (B, samples) fp32 with row pitch wav_stride ->
+ * out (B, 80, frames) fp32, frames <= 1 + (samples - 400) / 320.  window[400] = hann; tw_cos / tw_sin[400] =
+ * cos / sin(2 pi i / 400); mel_basis (80, 201) = librosa.filters.mel(sr=16000, n_fft=400, n_mels=80, fmin=0, fmax=8000). */
+int srb_log_mel(const float* wav, int64_t wav_stride, int32_t batch, int32_t samples, const float* window, const float* tw_cos,
+                const float* tw_sin, const float* mel_basis, float* out, int32_t frames, void* stream);
+
 /* Duration-prediction variant (models.py:157-164; fastspeech/modules.py:76-107; transformers length_regulator HF:88-134):
  *   srb_duration_predict : durations[b, n] = clamp(round(exp(conv_k3(E[ids])[b, n]) - 1), 0), 0 at pads; totals[b] = sum.
  *                          dur_table (3, vocab_rows) fp32 = per-unit dot products of the Conv1d(768 -> 1, k 3) taps with the

@@ -318,6 +318,42 @@ def resynthesize(sd: Dict[str, Tensor], ids: Tensor, x0: Tensor, dt: float = 0.1
     return [w[:n].unsqueeze(0) for w, n in zip(wav, wav_len)]
 
 
+# --------------------------------------------------------------------------------------
+# Log-mel front end (src/hifigan/data.py:17-53); the mel filter bank is third-party (librosa, not installed here):
+# restated from librosa.filters.mel's published definition (Slaney scale, area normalisation) -- PARITY UNPINNED for the
+# filter bank itself; the rest of the function is pinned by running the live reference with this bank injected.
+# --------------------------------------------------------------------------------------
+def librosa_mel_filter_bank(sr: int = 16000, n_fft: int = 400, n_mels: int = 80, fmin: float = 0.0,
+                            fmax: float = 8000.0) -> Tensor:
+    f_sp, min_log_hz, logstep = 200.0 / 3, 1000.0, math.log(6.4) / 27.0
+
+    def hz_to_mel(f: float) -> float:
+        return f / f_sp if f < min_log_hz else min_log_hz / f_sp + math.log(f / min_log_hz) / logstep
+
+    def mel_to_hz(m: float) -> float:
+        return f_sp * m if m < min_log_hz / f_sp else min_log_hz * math.exp(logstep * (m - min_log_hz / f_sp))
+
+    lo, hi = hz_to_mel(fmin), hz_to_mel(fmax)
+    mel_f = [mel_to_hz(lo + (hi - lo) * i / (n_mels + 1)) for i in range(n_mels + 2)]
+    nb = 1 + n_fft // 2
+    freqs = [sr / 2.0 * k / (nb - 1) for k in range(nb)]
+    w = torch.zeros(n_mels, nb, dtype=torch.float64)
+    for i in range(n_mels):
+        for k, f in enumerate(freqs):
+            lower = (f - mel_f[i]) / (mel_f[i + 1] - mel_f[i])
+            upper = (mel_f[i + 2] - f) / (mel_f[i + 2] - mel_f[i + 1])
+            w[i, k] = max(0.0, min(lower, upper)) * 2.0 / (mel_f[i + 2] - mel_f[i])
+    return w.float()
+
+
+def mel_spectrogram(y: Tensor, mel_basis: Optional[Tensor] = None) -> Tensor:
+    """mel_spectrogram -- hifigan/data.py:17-53 with its defaults: (B, T) -> (B, 80, 1 + (T - 400) // 320)."""
+    basis = librosa_mel_filter_bank() if mel_basis is None else mel_basis
+    spec = torch.stft(y, 400, hop_length=320, window=torch.hann_window(400).to(y), center=False, onesided=True,
+                      return_complex=True).abs()
+    return torch.log(torch.clamp(torch.matmul(basis.to(spec), spec), min=1e-5))
+
+
 def to_dtype(sd: Dict[str, Tensor], dtype: torch.dtype) -> Dict[str, Tensor]:
     return {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in sd.items()}
 

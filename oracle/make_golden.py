@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import hashlib
 import json
+import math
 import os
 import sys
 
@@ -186,6 +187,28 @@ def _main():
                         wav_flat=torch.cat([w.reshape(-1) for w in ref_wavs]).numpy(),
                         wav_lengths=np.array(info["wav_lengths"], dtype=np.int64))
     print("duration_b3_n48", json.dumps(info))
+
+    # log-mel front end (hifigan/data.py:17-53): the LIVE reference function with the restated librosa filter bank injected
+    # (librosa itself is not installed: the bank is the one unpinned piece, see the oracle header)
+    import sys as _sys
+
+    _sys.modules["librosa.filters"].mel = lambda **kw: oracle.librosa_mel_filter_bank(
+        kw["sr"], kw["n_fft"], kw["n_mels"], kw["fmin"], kw["fmax"]).numpy()
+    import src.hifigan.data as ref_data
+
+    ref_data.librosa_mel_fn = _sys.modules["librosa.filters"].mel
+    gy = torch.Generator().manual_seed(17)
+    y = (torch.rand(2, 6480 + 133, generator=gy) * 2 - 1) * torch.tensor([[0.9], [0.05]])
+    y[1, 3000:] = 0.0          # silence: exercises the 1e-5 clamp
+    with torch.inference_mode():
+        ref_mel = ref_data.mel_spectrogram(y)
+    o_mel = oracle.mel_spectrogram(y)
+    info = {"mel_shape": list(ref_mel.shape), "max_abs_oracle_vs_ref": float((o_mel - ref_mel).abs().max()),
+            "filter_bank": "restated from librosa.filters.mel (librosa not installed): parity unpinned for the bank",
+            "clamped_fraction": float((ref_mel == math.log(1e-5)).float().mean())}
+    manifest["cases"]["logmel_b2"] = info
+    np.savez_compressed(os.path.join(GOLDEN, "logmel_b2.npz"), y=y.numpy(), mel=ref_mel.numpy())
+    print("logmel_b2", json.dumps(info))
 
     with open(os.path.join(GOLDEN, "MANIFEST.json"), "w") as f:
         json.dump(manifest, f, indent=1)

@@ -31,6 +31,7 @@ _PROTOTYPES = {
     "srb_time_cond_table": [_P, _I, _P, _P, _P, _P, _I, _P, _P, _P],
     "srb_rotary_table": [_P, _I, _P, _P, _P],
     "srb_prior_prepare": [_P, _P, _L, _F, _P],
+    "srb_log_mel": [_P, _L, _I, _I, _P, _P, _P, _P, _P, _I, _P],
     "srb_duration_predict": [_P, _P, _F, _P, _P, _I, _I, _I, _P],
     "srb_length_regulate": [_P, _P, _P, _I, _I, _I, _I, _P],
     "srb_cfm_embed": [_P, _P, _P, _P, _I, _I, _P],

@@ -183,6 +183,71 @@ __global__ void __launch_bounds__(256) length_regulate_kernel(const int64_t* __r
   for (int pos = carry_s + threadIdx.x; pos < frames_out; pos += blockDim.x) orow[pos] = 0;
 }
 
+// ------------------------------------------------------------------------------------------ log-mel front end
+// mel_spectrogram of src/hifigan/data.py:17-53 (the reference's feature extractor / validation metric):
+// hann(400) windowed frames, hop 320, center=False -> 201-bin |DFT| -> 80 slaney mel bands -> log(max(., 1e-5)).
+// One block = 16 frames of one waveform.  The DFT is direct (n_fft = 400 is not a power of two and a frame is tiny):
+// thread <-> frequency bin keeps 16 frames x (re, im) in registers and walks the 400 samples; the twiddle for (bin b,
+// sample k) is entry (b k mod 400) of ONE 400-entry cos / sin table in shared memory, advanced incrementally; the 16
+// frames' samples are stored [sample][frame] so a step reads them as four broadcast 16-byte loads.
+// FLOPs: 201 x 400 x 2 FMA per frame (+ 80 x 201 for the mel matrix); bytes: 400 x 4 in, 80 x 4 out per frame.
+constexpr int kMelFft = 400, kMelHop = 320, kMelBins = 201, kMelBands = 80, kMelFrames = 16;
+
+__global__ void __launch_bounds__(224) log_mel_kernel(const float* __restrict__ wav, long long wav_stride, int samples,
+                                                      const float* __restrict__ window, const float* __restrict__ tw_cos,
+                                                      const float* __restrict__ tw_sin, const float* __restrict__ mel_basis,
+                                                      float* __restrict__ out, int frames) {
+  __shared__ __align__(16) float xw[kMelFft][kMelFrames];     // windowed samples, [sample][frame]
+  __shared__ float cs[kMelFft], sn[kMelFft];
+  __shared__ float spec[kMelFrames][kMelBins];                 // 201 is odd: frame-strided reads are conflict free
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.y, f0 = blockIdx.x * kMelFrames, tid = threadIdx.x;
+  const float* y = wav + (long long)b * wav_stride;
+  for (int i = tid; i < kMelFft; i += blockDim.x) {
+    cs[i] = tw_cos[i];
+    sn[i] = tw_sin[i];
+  }
+  for (int i = tid; i < kMelFft * kMelFrames; i += blockDim.x) {
+    const int f = i / kMelFft, k = i - f * kMelFft;             // consecutive threads: consecutive samples of a frame
+    const long long pos = (long long)(f0 + f) * kMelHop + k;
+    xw[k][f] = (f0 + f < frames && pos < samples) ? y[pos] * window[k] : 0.f;
+  }
+  __syncthreads();
+  if (tid < kMelBins) {
+    float re[kMelFrames], im[kMelFrames];
+#pragma unroll
+    for (int f = 0; f < kMelFrames; ++f) re[f] = im[f] = 0.f;
+    int idx = 0;
+#pragma unroll 2
+    for (int k = 0; k < kMelFft; ++k) {
+      const float c = cs[idx], s = sn[idx];
+      const float4* xr = reinterpret_cast<const float4*>(&xw[k][0]);
+#pragma unroll
+      for (int q = 0; q < kMelFrames / 4; ++q) {
+        const float4 x = xr[q];
+        re[4 * q + 0] = fmaf(x.x, c, re[4 * q + 0]); im[4 * q + 0] = fmaf(-x.x, s, im[4 * q + 0]);
+        re[4 * q + 1] = fmaf(x.y, c, re[4 * q + 1]); im[4 * q + 1] = fmaf(-x.y, s, im[4 * q + 1]);
+        re[4 * q + 2] = fmaf(x.z, c, re[4 * q + 2]); im[4 * q + 2] = fmaf(-x.z, s, im[4 * q + 2]);
+        re[4 * q + 3] = fmaf(x.w, c, re[4 * q + 3]); im[4 * q + 3] = fmaf(-x.w, s, im[4 * q + 3]);
+      }
+      idx += tid;
+      if (idx >= kMelFft) idx -= kMelFft;
+    }
+#pragma unroll
+    for (int f = 0; f < kMelFrames; ++f) spec[f][tid] = sqrtf(re[f] * re[f] + im[f] * im[f]);   // spec.abs()
+  }
+  __syncthreads();
+  for (int o = tid; o < kMelBands * kMelFrames; o += blockDim.x) {
+    const int m = o / kMelFrames, f = o - m * kMelFrames;
+    if (f0 + f >= frames) continue;
+    const float* wrow = mel_basis + m * kMelBins;
+    float acc = 0.f;
+    for (int k = 0; k < kMelBins; ++k) acc = fmaf(__ldg(wrow + k), spec[f][k], acc);
+    out[((long long)b * kMelBands + m) * frames + f0 + f] = logf(fmaxf(acc, 1e-5f));   // dynamic_range_compression_torch
+  }
+}
+
 // ------------------------------------------------------------------------------------------ positional conv
 // x = gelu(dwconv31(mask(x0)) + b) * mask + x0, then the first AdaptiveRMSNorm (transformer.py:84-96, models.py:177,
 // norm.py:41-43).  CUDA-core work, instruction-issue bound in its first form (one thread per channel, 159 instructions
@@ -392,6 +457,16 @@ int srb_length_regulate(const int64_t* ids, const int32_t* durations, int64_t* o
   SRB_CUDA(launch_pdl(length_regulate_kernel, dim3(batch), dim3(256), 0, (cudaStream_t)stream, ids, durations, out_ids, frames,
                       frames_out, all_one));
   return after_launch("length_regulate_kernel");
+}
+
+int srb_log_mel(const float* wav, int64_t wav_stride, int32_t batch, int32_t samples, const float* window, const float* tw_cos,
+                const float* tw_sin, const float* mel_basis, float* out, int32_t frames, void* stream) {
+  if (batch <= 0 || frames <= 0) return 0;
+  SRB_REQUIRE(samples >= 400 && frames <= 1 + (samples - 400) / 320, "srb_log_mel: frames exceed 1 + (samples - 400) / 320");
+  dim3 grid((frames + kMelFrames - 1) / kMelFrames, batch);
+  SRB_CUDA(launch_pdl(log_mel_kernel, grid, dim3(224), 0, (cudaStream_t)stream, wav, (long long)wav_stride, (int)samples, window,
+                      tw_cos, tw_sin, mel_basis, out, (int)frames));
+  return after_launch("log_mel_kernel");
 }
 
 int srb_cfm_posconv_norm(const float* x0, const float* dw_w, const float* dw_b, const float* g, const int32_t* lengths,

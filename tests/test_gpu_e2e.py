@@ -266,3 +266,26 @@ def test_synthesize_driver_writes_what_the_decoder_returns(decoder, tmp_path):
         for i, w in zip(b.indices, outs):
             rate, y = wavfile.read(paths[i])
             assert rate == 16000 and (torch.from_numpy(y) == w[0].cpu()).all()
+
+
+def test_log_mel_front_end_matches_reference_golden(golden_dir, decoder):
+    """mel_spectrogram on the GPU against the golden minted from the live reference function,
+    against the oracle on a longer random waveform, and as the reference uses it -- a mel-L1 self-check of a
+    resynthesised waveform (src/hifigan/train.py:233-235): finite and of the right shape."""
+    from speech_resynth_b200.features import mel_spectrogram
+
+    z, _ = _load(golden_dir, "logmel_b2")
+    mel = mel_spectrogram(torch.from_numpy(z["y"]).cuda())
+    ref = torch.from_numpy(z["mel"])
+    assert tuple(mel.shape) == tuple(ref.shape)
+    assert float((mel.cpu() - ref).abs().max()) <= 2e-4            # fp32 direct DFT vs torch.stft, in log units
+    y = (torch.rand(3, 16000 * 3 + 77, generator=torch.Generator().manual_seed(4)) * 2 - 1) * 0.3
+    got = mel_spectrogram(y.cuda()).cpu()
+    want = oracle.mel_spectrogram(y)
+    assert got.shape == want.shape == (3, 80, 1 + (y.shape[1] - 400) // 320)
+    assert float((got - want).abs().max()) <= 2e-4
+    assert float((mel_spectrogram(y[0].cuda()).cpu() - want[0]).abs().max()) <= 2e-4   # 1-D input like the reference's
+    ids = synthetic.make_units(2, 60, seed=3, lengths=[60, 41]).cuda()
+    wavs = decoder(ids, 0.25, 1.0)
+    m = mel_spectrogram(wavs[0])
+    assert m.shape == (1, 80, 1 + (wavs[0].shape[-1] - 400) // 320) and bool(torch.isfinite(m).all())

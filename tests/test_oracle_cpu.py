@@ -151,3 +151,27 @@ def test_length_regulator_all_zero_rule():
     ids = torch.tensor([[5, 9, 0], [7, 0, 0]])
     out, lengths = oracle.length_regulate_ids(ids, torch.zeros(2, 3, dtype=torch.long))
     assert torch.equal(out, ids) and lengths.tolist() == [3, 3]
+
+
+def test_oracle_log_mel_matches_reference_golden(golden_dir):
+    """mel_spectrogram (hifigan/data.py:17-53): the golden is the live reference function run with the restated librosa
+    filter bank injected (librosa is not installed; the bank itself is the unpinned piece)."""
+    z = np.load(os.path.join(golden_dir, "logmel_b2.npz"))
+    mel = oracle.mel_spectrogram(torch.from_numpy(z["y"]))
+    assert tuple(mel.shape) == (2, 80, 20)
+    assert float((mel - torch.from_numpy(z["mel"])).abs().max()) <= 1e-5
+
+
+def test_mel_filter_bank_properties():
+    """Both restatements of librosa.filters.mel (oracle: scalar loops, package: vectorised numpy) agree, every band is a
+    non-negative triangle, and Slaney's area normalisation holds: sum(weights) * (sr / n_fft) ~ 1 per band."""
+    from speech_resynth_b200.features import mel_filter_bank
+
+    a = oracle.librosa_mel_filter_bank()
+    b = torch.from_numpy(mel_filter_bank())
+    assert a.shape == (80, 201) and float((a - b).abs().max()) <= 1e-7
+    assert bool((a >= 0).all()) and bool((a.sum(1) > 0).all())
+    area = a.double().sum(1) * (16000 / 400)
+    assert float((area[5:] - 1).abs().max()) <= 0.15      # discretisation of narrow triangles on a 40 Hz grid
+    peak = a.argmax(1)
+    assert bool((peak[1:] >= peak[:-1]).all())
