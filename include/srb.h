@@ -159,6 +159,10 @@ int srb_hifigan_upsample(const void* x, const void* w_packed, const float* bias,
                          int32_t batch, int32_t rows_in, int32_t c_in, int32_t c_out, int32_t kernel, int32_t stride,
                          float slope, void* stream);
 
+/* Number of time phases D the fused-MRF kernel uses for a channel width (host query, no launch): the packed weights
+ * of its dilation-1 convs depend on it (speech_resynth_b200/packing.py: pack_mrf_conv). */
+int srb_hifigan_mrf_phases(int32_t channels);
+
 /* Whole multi-receptive-field stage for the narrow stages (channels = 16 or 32), fused in one kernel:
  *   out_act = leaky_relu((resblock_3(u) + resblock_7(u) + resblock_11(u)) / 3, slope_next)      (HF:1359-1367, 1475-1480)
  * 18 convolutions with every intermediate kept in shared memory / TMEM.  u_raw, out_act: (B, L, C) bf16.

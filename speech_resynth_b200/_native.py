@@ -52,7 +52,7 @@ _PROTOTYPES = {
     "srb_crop_concat": [_P, _P, _P, _P, _I, _I, _P],
 }
 
-EXPORTED_SYMBOLS = tuple(_PROTOTYPES) + ("srb_last_error",)
+EXPORTED_SYMBOLS = tuple(_PROTOTYPES) + ("srb_last_error", "srb_hifigan_mrf_phases")
 
 
 class NativeLibraryError(RuntimeError):
@@ -83,6 +83,8 @@ def load() -> ctypes.CDLL:
         fn.restype = c_int32
     lib.srb_last_error.argtypes = []
     lib.srb_last_error.restype = c_char_p
+    lib.srb_hifigan_mrf_phases.argtypes = [c_int32]
+    lib.srb_hifigan_mrf_phases.restype = c_int32
     _lib = lib
     return lib
 

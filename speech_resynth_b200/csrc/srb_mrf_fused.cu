@@ -13,6 +13,14 @@
 //   * per-tile mbarriers order MMA issue against the epilogue (a conv on tile m needs tiles m-1..m+1 of its input);
 //   * weights stream through a double buffer with cp.async.bulk, pre-packed on the host in operand layout.
 // HBM traffic: u read once (+ halo), out written once; everything else stays on chip.
+//
+// Phases (template parameter D).  An M = 128, K = 16 MMA costs 39 / 40 / 48 clk at N = 16 / 32 / 64 (measured,
+// tools/probes/umma_rate_probe.cu), so at C = 16 this kernel is bound by its MMA COUNT.  With D = 2 the window is stored
+// as two phase buffers (time row r -> phase r % D, q-row r / D) and an accumulator row holds D consecutive time rows
+// (N = D C columns: column block d' = time row q D + d').  A dilation-1 conv then needs k - 1 + D MMAs of N = D C per
+// 128 q-rows -- input phase e at q-shift s feeds output phase d' through tap c + s D + e - d', the host packs those
+// D taps side by side ("phase matrices") -- instead of D k MMAs of N = C.  Dilated convs map every (tap, output phase)
+// to one input phase and keep N = C MMAs into the column slice of the output phase.  D = 1 is the plain form.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
@@ -60,14 +68,30 @@ __host__ __device__ constexpr int mrf_conv_tap_begin(int j, int q, int which) {
   return base + (2 * q + which) * mrf_kernel_size(j);
 }
 
-template <int C, int R>
+template <int C, int R, int D>
 struct MrfLayout {
-  static constexpr int NM = R / 128;
-  static constexpr int RP = R + 2 * kMrfGuard;
+  static_assert(D == 1 || D == 2, "one or two phases");
+  static constexpr int RQ = R / D;                    // q-rows per window (one accumulator row = D time rows)
+  static constexpr int NM = RQ / 128;
+  static constexpr int RP = RQ + 2 * kMrfGuard;       // q-rows of one (phase, chunk) operand column, with guards
   static constexpr int CH = C / 8;
-  static constexpr int buf_bytes = CH * RP * 16;
-  static constexpr int tap_bytes = C * C * 2;
-  static constexpr int wbuf_bytes = 11 * tap_bytes;
+  static constexpr int NPC = D * CH;                  // (phase, 8-channel chunk) columns of an operand buffer
+  static constexpr int N = D * C;                     // accumulator columns of a tile
+  static constexpr int buf_bytes = NPC * RP * 16;
+  static constexpr int tap_bytes = C * C * 2;         // one tap matrix [C][C]
+  static constexpr int pm_bytes = N * C * 2;          // one phase matrix [D C][C]
+  static constexpr int wbuf_bytes = (10 + D) * pm_bytes;   // largest conv blob: k = 11, dilation 1
+  // bytes of the packed weights of a conv (k taps, dilation dil) and the offset of conv (j, q, which)
+  __host__ __device__ static constexpr int conv_bytes(int k, int dil) {
+    return dil == 1 ? (k - 1 + D) * pm_bytes : k * tap_bytes;
+  }
+  __host__ __device__ static constexpr int conv_offset(int j, int cc) {
+    int off = 0;
+    for (int jj = 0; jj <= j; ++jj)
+      for (int c2 = 0; c2 < (jj < j ? 6 : cc); ++c2)
+        off += conv_bytes(mrf_kernel_size(jj), (c2 & 1) ? 1 : mrf_dilation(c2 >> 1));
+    return off;
+  }
   static constexpr int off_u = 0;
   static constexpr int off_a = buf_bytes;
   static constexpr int off_t = 2 * buf_bytes;
@@ -80,6 +104,7 @@ struct MrfLayout {
   static constexpr int off_tmem = off_cnt + 4 * ((NM + 3) & ~3);
   static constexpr int total = off_tmem + 16;
   static constexpr int tout = R - 2 * kMrfHalo;
+  static_assert(3 * NM * N <= 512, "accumulators exceed tensor memory");
 };
 
 // epilogue teams of four warps (one per TMEM lane quarter); team t post-processes the M tiles m = t (mod NTEAMS).
@@ -90,21 +115,28 @@ struct MrfLayout {
 // independent accumulators, so no ordering between issuers is needed beyond the per-tile barriers.
 template <int C>
 struct MrfTeams {
-  static constexpr int value = C == 16 ? 4 : 3;          // epilogue teams
-#ifdef SRB_MRF_ISSUERS
-  static constexpr int issuers = SRB_MRF_ISSUERS;
+#ifdef SRB_MRF_TEAMS
+  static constexpr int value = C == 16 ? SRB_MRF_TEAMS : 3;
 #else
-  static constexpr int issuers = C == 16 ? 4 : 3;        // MMA issuer warps
+  static constexpr int value = C == 16 ? 4 : 3;          // epilogue teams
+#endif
+#ifdef SRB_MRF_ISSUERS
+  static constexpr int issuers = C == 16 ? SRB_MRF_ISSUERS : 3;
+#else
+  // MMA issuer warps.  Measured at C = 16 with two phases (us per launch, config 2): 1 issuer 2907, 2: 2220, 3: 1995,
+  // 4: 2190, 5: 2362 (four or five epilogue teams make no difference)
+  static constexpr int issuers = 3;
 #endif
   static constexpr int threads = 32 * (1 + issuers) + 128 * value;
 };
 
-template <int C, int R>
+template <int C, int R, int D>
 __global__ void __launch_bounds__(MrfTeams<C>::threads, 1) mrf_fused_kernel(const MrfParams p) {
-  using L = MrfLayout<C, R>;
-  constexpr int NM = L::NM, RP = L::RP, CH = L::CH, KS = C / 16, G = kMrfGuard;
+  using L = MrfLayout<C, R, D>;
+  constexpr int NM = L::NM, RP = L::RP, CH = L::CH, KS = C / 16, G = kMrfGuard, N = L::N, NPC = L::NPC;
   constexpr int NTEAMS = MrfTeams<C>::value, EPI_THREADS = 128 * NTEAMS, NI = MrfTeams<C>::issuers;
-  constexpr uint32_t IDESC = umma_idesc_bf16(128, C);
+  constexpr uint32_t IDESC = umma_idesc_bf16(128, C);      // one output phase (dilated convs, identity)
+  constexpr uint32_t IDESC_N = umma_idesc_bf16(128, N);    // all output phases at once (dilation-1 convs)
   constexpr uint32_t TCOLS = 512;
 
   extern __shared__ __align__(128) uint8_t smem[];
@@ -163,7 +195,7 @@ __global__ void __launch_bounds__(MrfTeams<C>::threads, 1) mrf_fused_kernel(cons
   tc_fence_after();
   pdl_wait();   // setup above read only weights / biases; the up-sampler output is read from here on
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + L::off_tmem);
-  const uint32_t t_dt = tmem_base, t_dx = tmem_base + NM * C, t_f = tmem_base + 2 * NM * C;
+  const uint32_t t_dt = tmem_base, t_dx = tmem_base + NM * N, t_f = tmem_base + 2 * NM * N;
 
   if (warp == 0) {
     // ================= weight producer =================
@@ -176,10 +208,9 @@ __global__ void __launch_bounds__(MrfTeams<C>::threads, 1) mrf_fused_kernel(cons
             const int buf = n_loaded & 1;
             const uint32_t ph = (n_loaded >> 1) & 1;
             mbar_wait(w_free(buf), ph ^ 1u);
-            const uint32_t bytes = k * L::tap_bytes;
+            const uint32_t bytes = L::conv_bytes(k, (cc & 1) ? 1 : mrf_dilation(cc >> 1));
             mbar_expect_tx(w_full(buf), bytes);
-            const int tap0 = mrf_conv_tap_begin(j, cc >> 1, cc & 1);
-            bulk_g2s(s_w + buf * L::wbuf_bytes, p.w + (size_t)tap0 * C * C, bytes, w_full(buf));
+            bulk_g2s(s_w + buf * L::wbuf_bytes, reinterpret_cast<const uint8_t*>(p.w) + L::conv_offset(j, cc), bytes, w_full(buf));
           }
         }
       }
@@ -217,33 +248,59 @@ __global__ void __launch_bounds__(MrfTeams<C>::threads, 1) mrf_fused_kernel(cons
             const int buf = n_conv & 1;
             mbar_wait(w_full(buf), (n_conv >> 1) & 1);
             const uint32_t wb = s_w + buf * L::wbuf_bytes;
-            // descriptors advance in 16-byte units: one row = +1, one K slice (two 8-channel chunks) = +2*RP / +2*C
+            // descriptors advance in 16-byte units: one q-row = +1, one K slice (two 8-channel chunks) = +2*RP (operand) or
+            // +2*rows (weights), one phase of an operand = +CH*RP
             const uint64_t a_desc0 = desc_interleaved(src, RP * 16);
             const uint64_t u_desc0 = desc_interleaved(s_u, RP * 16);
-            const uint64_t w_desc0 = desc_interleaved(wb, C * 16);
+            const uint64_t wn_desc0 = desc_interleaved(wb, N * 16);    // phase matrices [N][C]
+            const uint64_t wc_desc0 = desc_interleaved(wb, C * 16);    // tap matrices [C][C]
             const uint64_t i_desc0 = desc_interleaved(s_ident, C * 16);
+            const int c_tap = (k - 1) / 2;
             for (int m = mi; m < NM; m += NI) {
               if (m > 0) wait_written(m - 1, ev);
               wait_written(m, ev);
               if (m + 1 < NM) wait_written(m + 1, ev);
               tc_fence_after();
-              const uint32_t dacc = (which == 0 ? t_dt : t_dx) + m * C;
+              const uint32_t dacc = (which == 0 ? t_dt : t_dx) + m * N;
               if (cc == 0) {
-                // x := u (identity MMA) for this resblock, before the first conv2 accumulates into it
+                // x := u (identity MMA, phase by phase) for this resblock, before the first conv2 accumulates into it
 #pragma unroll
-                for (int s = 0; s < KS; ++s)
-                  umma_bf16_pred(leader, t_dx + m * C, u_desc0 + (uint64_t)(m * 128 + G + s * 2 * RP),
-                                 i_desc0 + (uint64_t)(s * 2 * C), IDESC, s != 0 ? 1u : 0u);
+                for (int e = 0; e < D; ++e)
+#pragma unroll
+                  for (int s = 0; s < KS; ++s)
+                    umma_bf16_pred(leader, t_dx + m * N + e * C, u_desc0 + (uint64_t)(e * CH * RP + m * 128 + G + s * 2 * RP),
+                                   i_desc0 + (uint64_t)(s * 2 * C), IDESC, s != 0 ? 1u : 0u);
               }
-              uint64_t a_desc = a_desc0 + (uint64_t)(m * 128 + G - ((k - 1) / 2) * dil);
-              uint64_t w_desc = w_desc0;
-              for (int t = 0; t < k; ++t) {
+              const uint64_t a_row = a_desc0 + (uint64_t)(m * 128 + G);
+              if (dil == 1) {
+                // phase matrix pi: input time offset o = pi - c, i.e. input phase e = o mod D at q-shift (o - e) / D
+                for (int pi = 0; pi < k - 1 + D; ++pi) {
+                  const int o = pi - c_tap;
+                  const int e = ((o % D) + D) % D;
+                  const int sh = (o - e) / D;
+                  const uint64_t a_desc = a_row + (uint64_t)(int64_t)(e * CH * RP + sh);
+                  const uint64_t w_desc = wn_desc0 + (uint64_t)(pi * (L::pm_bytes >> 4));
 #pragma unroll
-                for (int s = 0; s < KS; ++s)
-                  umma_bf16_pred(leader, dacc, a_desc + (uint64_t)(s * 2 * RP), w_desc + (uint64_t)(s * 2 * C), IDESC,
-                                 (which == 1 || t != 0 || s != 0) ? 1u : 0u);
-                a_desc += (uint64_t)dil;
-                w_desc += (uint64_t)(L::tap_bytes >> 4);
+                  for (int s = 0; s < KS; ++s)
+                    umma_bf16_pred(leader, dacc, a_desc + (uint64_t)(s * 2 * RP), w_desc + (uint64_t)(s * 2 * N), IDESC_N,
+                                   (which == 1 || pi != 0 || s != 0) ? 1u : 0u);
+                }
+              } else {
+                // dilated conv1: (tap t, output phase d') reads input phase e at q-shift sh into column slice d' C
+                for (int t = 0; t < k; ++t) {
+                  const uint64_t w_desc = wc_desc0 + (uint64_t)(t * (L::tap_bytes >> 4));
+#pragma unroll
+                  for (int dp = 0; dp < D; ++dp) {
+                    const int o = dp + (t - c_tap) * dil;
+                    const int e = ((o % D) + D) % D;
+                    const int sh = (o - e) / D;
+                    const uint64_t a_desc = a_row + (uint64_t)(int64_t)(e * CH * RP + sh);
+#pragma unroll
+                    for (int s = 0; s < KS; ++s)
+                      umma_bf16_pred(leader, dacc + dp * C, a_desc + (uint64_t)(s * 2 * RP), w_desc + (uint64_t)(s * 2 * C), IDESC,
+                                     (t != 0 || s != 0) ? 1u : 0u);
+                  }
+                }
               }
               umma_commit_pred(leader, acc_ready(m));
             }
@@ -268,13 +325,14 @@ __global__ void __launch_bounds__(MrfTeams<C>::threads, 1) mrf_fused_kernel(cons
       const int b = tile / p.tiles_per_b;
       const int t0 = (tile % p.tiles_per_b) * L::tout - kMrfHalo;     // global row of window row 0
       const __nv_bfloat16* ub = p.u + (size_t)b * p.rows * C;
-      // ---- load the raw window into the U operand buffer (rows outside [0, L) are zero)
+      // ---- load the raw window into the U operand buffer (rows outside [0, L) are zero): time row r -> phase r % D,
+      // q-row r / D
       for (int i = etid; i < R * CH; i += EPI_THREADS) {
         const int row = i / CH, ch = i % CH;
         const int gr = t0 + row;
         uint4 v = make_uint4(0, 0, 0, 0);
         if (gr >= 0 && gr < p.rows) v = __ldg(reinterpret_cast<const uint4*>(ub + (size_t)gr * C) + ch);
-        *reinterpret_cast<uint4*>(smem + L::off_u + ch * RP * 16 + (row + G) * 16) = v;
+        *reinterpret_cast<uint4*>(smem + L::off_u + (((row % D) * CH + ch) * RP + (row / D) + G) * 16) = v;
       }
       fence_proxy_async_smem();
       asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");   // every epilogue warp finished writing U
@@ -283,18 +341,18 @@ __global__ void __launch_bounds__(MrfTeams<C>::threads, 1) mrf_fused_kernel(cons
       uint32_t acc_ev = n_tiles_done * 18u;   // events on acc_ready[m]: one per conv
 
       for (int j = 0; j < 3; ++j) {
-        // ---- E0: A = leaky_relu(U) for my tiles
+        // ---- E0: A = leaky_relu(U) for my tiles (all phases of my q-row)
         for (int m = team; m < NM; m += NTEAMS) {
           const int row = m * 128 + quarter * 32 + lane;
 #pragma unroll
-          for (int ch = 0; ch < CH; ++ch) {
-            const uint4 v = *reinterpret_cast<const uint4*>(smem + L::off_u + ch * RP * 16 + (row + G) * 16);
+          for (int pc = 0; pc < NPC; ++pc) {
+            const uint4 v = *reinterpret_cast<const uint4*>(smem + L::off_u + pc * RP * 16 + (row + G) * 16);
             uint4 o;
             o.x = pack_bf16(lrelu(bf16_lo(v.x), p.slope), lrelu(bf16_hi(v.x), p.slope));
             o.y = pack_bf16(lrelu(bf16_lo(v.y), p.slope), lrelu(bf16_hi(v.y), p.slope));
             o.z = pack_bf16(lrelu(bf16_lo(v.z), p.slope), lrelu(bf16_hi(v.z), p.slope));
             o.w = pack_bf16(lrelu(bf16_lo(v.w), p.slope), lrelu(bf16_hi(v.w), p.slope));
-            *reinterpret_cast<uint4*>(smem + L::off_a + ch * RP * 16 + (row + G) * 16) = o;
+            *reinterpret_cast<uint4*>(smem + L::off_a + pc * RP * 16 + (row + G) * 16) = o;
           }
           fence_proxy_async_smem();
           __syncwarp();
@@ -312,77 +370,89 @@ __global__ void __launch_bounds__(MrfTeams<C>::threads, 1) mrf_fused_kernel(cons
             for (int c = 0; c < C; ++c) bsum[c] += bias[c];
           }
           for (int m = team; m < NM; m += NTEAMS) {
-            const int row = m * 128 + quarter * 32 + lane;
-            const int gr = t0 + row;
-            const bool inside = gr >= 0 && gr < p.rows;
+            const int row = m * 128 + quarter * 32 + lane;     // q-row: accumulator column block d is time row row*D + d
+            bool inside[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+              const int gr = t0 + row * D + d;
+              inside[d] = gr >= 0 && gr < p.rows;
+            }
             mbar_wait(acc_ready(m), acc_ev & 1);
             tc_fence_after();
             const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
-            float y[C];
+            float y[N];
             if (which == 0) {
               // conv1 -> T = leaky_relu(acc + b1), zero outside the utterance (the next conv zero-pads there)
-              tmem_ld_f<C>(t_dt + m * C + lane_addr, y);
+              tmem_ld_f<N>(t_dt + m * N + lane_addr, y);
 #pragma unroll
-              for (int ch = 0; ch < CH; ++ch) {
+              for (int pc = 0; pc < NPC; ++pc) {
+                const int d = pc / CH, ch = pc % CH;
                 uint32_t o[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                  const float a0 = lrelu(y[ch * 8 + 2 * e] + bias[ch * 8 + 2 * e], p.slope);
-                  const float a1 = lrelu(y[ch * 8 + 2 * e + 1] + bias[ch * 8 + 2 * e + 1], p.slope);
-                  o[e] = inside ? pack_bf16(a0, a1) : 0u;
+                  const float a0 = lrelu(y[d * C + ch * 8 + 2 * e] + bias[ch * 8 + 2 * e], p.slope);
+                  const float a1 = lrelu(y[d * C + ch * 8 + 2 * e + 1] + bias[ch * 8 + 2 * e + 1], p.slope);
+                  o[e] = inside[d] ? pack_bf16(a0, a1) : 0u;
                 }
-                *reinterpret_cast<uint4*>(smem + L::off_t + ch * RP * 16 + (row + G) * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<uint4*>(smem + L::off_t + pc * RP * 16 + (row + G) * 16) = make_uint4(o[0], o[1], o[2], o[3]);
               }
               fence_proxy_async_smem();
             } else if (q < 2) {
               // conv2 of pairs 0,1: x = acc (u + all conv2 so far) + their biases; A = leaky_relu(x)
-              tmem_ld_f<C>(t_dx + m * C + lane_addr, y);
+              tmem_ld_f<N>(t_dx + m * N + lane_addr, y);
 #pragma unroll
-              for (int ch = 0; ch < CH; ++ch) {
+              for (int pc = 0; pc < NPC; ++pc) {
+                const int d = pc / CH, ch = pc % CH;
                 uint32_t o[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                  const float a0 = lrelu(y[ch * 8 + 2 * e] + bsum[ch * 8 + 2 * e], p.slope);
-                  const float a1 = lrelu(y[ch * 8 + 2 * e + 1] + bsum[ch * 8 + 2 * e + 1], p.slope);
-                  o[e] = inside ? pack_bf16(a0, a1) : 0u;
+                  const float a0 = lrelu(y[d * C + ch * 8 + 2 * e] + bsum[ch * 8 + 2 * e], p.slope);
+                  const float a1 = lrelu(y[d * C + ch * 8 + 2 * e + 1] + bsum[ch * 8 + 2 * e + 1], p.slope);
+                  o[e] = inside[d] ? pack_bf16(a0, a1) : 0u;
                 }
-                *reinterpret_cast<uint4*>(smem + L::off_a + ch * RP * 16 + (row + G) * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<uint4*>(smem + L::off_a + pc * RP * 16 + (row + G) * 16) = make_uint4(o[0], o[1], o[2], o[3]);
               }
               fence_proxy_async_smem();
             } else {
               // last conv2 of resblock j: x_final = acc + biases; F (+)= x_final; after the third resblock write out
-              tmem_ld_f<C>(t_dx + m * C + lane_addr, y);
+              tmem_ld_f<N>(t_dx + m * N + lane_addr, y);
 #pragma unroll
-              for (int c = 0; c < C; ++c) y[c] += bsum[c];
+              for (int n = 0; n < N; ++n) y[n] += bsum[n % C];
               if (j > 0) {
-                float f[C];
-                tmem_ld_f<C>(t_f + m * C + lane_addr, f);
+                float f[N];
+                tmem_ld_f<N>(t_f + m * N + lane_addr, f);
 #pragma unroll
-                for (int c = 0; c < C; ++c) y[c] += f[c];
+                for (int n = 0; n < N; ++n) y[n] += f[n];
               }
               if (j < 2) {
-                if constexpr (C == 32) {
+                if constexpr (N == 32) {
                   uint32_t v[32];
 #pragma unroll
                   for (int c = 0; c < 32; ++c) v[c] = __float_as_uint(y[c]);
-                  tmem_st32(t_f + m * C + lane_addr, v);
+                  tmem_st32(t_f + m * N + lane_addr, v);
                 } else {
                   uint32_t v[16];
 #pragma unroll
                   for (int c = 0; c < 16; ++c) v[c] = __float_as_uint(y[c]);
-                  tmem_st16(t_f + m * C + lane_addr, v);
+                  tmem_st16(t_f + m * N + lane_addr, v);
                 }
                 tmem_st_wait();
-              } else if (inside && row >= kMrfHalo && row < kMrfHalo + L::tout) {
-                __nv_bfloat16* ob = p.out + ((size_t)b * p.rows + gr) * C;
+              } else {
 #pragma unroll
-                for (int ch = 0; ch < CH; ++ch) {
-                  uint32_t o[4];
+                for (int d = 0; d < D; ++d) {
+                  const int wr = row * D + d;          // window time row
+                  if (inside[d] && wr >= kMrfHalo && wr < kMrfHalo + L::tout) {
+                    __nv_bfloat16* ob = p.out + ((size_t)b * p.rows + (t0 + wr)) * C;
 #pragma unroll
-                  for (int e = 0; e < 4; ++e)
-                    o[e] = pack_bf16(lrelu(y[ch * 8 + 2 * e] * (1.f / 3.f), p.slope_next),
-                                     lrelu(y[ch * 8 + 2 * e + 1] * (1.f / 3.f), p.slope_next));
-                  reinterpret_cast<uint4*>(ob)[ch] = make_uint4(o[0], o[1], o[2], o[3]);
+                    for (int ch = 0; ch < CH; ++ch) {
+                      uint32_t o[4];
+#pragma unroll
+                      for (int e = 0; e < 4; ++e)
+                        o[e] = pack_bf16(lrelu(y[d * C + ch * 8 + 2 * e] * (1.f / 3.f), p.slope_next),
+                                         lrelu(y[d * C + ch * 8 + 2 * e + 1] * (1.f / 3.f), p.slope_next));
+                      reinterpret_cast<uint4*>(ob)[ch] = make_uint4(o[0], o[1], o[2], o[3]);
+                    }
+                  }
                 }
               }
             }
@@ -402,13 +472,13 @@ __global__ void __launch_bounds__(MrfTeams<C>::threads, 1) mrf_fused_kernel(cons
   if (warp == 1) tmem_dealloc(tmem_base, TCOLS);
 }
 
-template <int C, int R>
+template <int C, int R, int D>
 static int launch_mrf(const MrfParams& p0, cudaStream_t stream) {
-  using L = MrfLayout<C, R>;
+  using L = MrfLayout<C, R, D>;
   MrfParams p = p0;
   p.tiles_per_b = (p.rows + L::tout - 1) / L::tout;
   p.total_tiles = p.tiles_per_b * p.batch;
-  auto kernel = mrf_fused_kernel<C, R>;
+  auto kernel = mrf_fused_kernel<C, R, D>;
   static bool configured[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -427,6 +497,8 @@ static int launch_mrf(const MrfParams& p0, cudaStream_t stream) {
 
 using namespace srb;
 
+extern "C" int srb_hifigan_mrf_phases(int32_t channels) { return channels == 16 ? 2 : 1; }
+
 extern "C" int srb_hifigan_mrf_fused(const void* u_raw, const void* w_packed, const float* bias, void* out_act,
                                      int32_t batch, int32_t rows, int32_t channels, float slope, float slope_next,
                                      void* stream) {
@@ -442,8 +514,10 @@ extern "C" int srb_hifigan_mrf_fused(const void* u_raw, const void* w_packed, co
   p.slope = slope;
   p.slope_next = slope_next;
   if (batch <= 0 || rows <= 0) return 0;
-  if (channels == 16) return launch_mrf<16, 1280>(p, (cudaStream_t)stream);
-  if (channels == 32) return launch_mrf<32, 640>(p, (cudaStream_t)stream);
+  // weight layout: see srb_hifigan_mrf_phases() -- two phases at C = 16 (MMA-count bound), one at C = 32 (TMEM holds
+  // only two M tiles of N = 64 accumulators, which would break the tile pipelining)
+  if (channels == 16) return launch_mrf<16, 1280, 2>(p, (cudaStream_t)stream);
+  if (channels == 32) return launch_mrf<32, 640, 1>(p, (cudaStream_t)stream);
   set_error("srb_hifigan_mrf_fused: channels must be 16 or 32 (got %d)", channels);
   return -2;
 }

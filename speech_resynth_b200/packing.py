@@ -56,15 +56,48 @@ def pack_operand_taps(w: torch.Tensor) -> torch.Tensor:
     return t.to(torch.bfloat16).contiguous()
 
 
+def mrf_phases(channels: int) -> int:
+    """Time phases the fused-MRF kernel uses for this width (srb_hifigan_mrf_phases): 2 at C = 16, else 1."""
+    from . import _native as nat
+
+    return int(nat.load().srb_hifigan_mrf_phases(int(channels)))
+
+
+def pack_mrf_conv(w: torch.Tensor, dilation: int, phases: int) -> torch.Tensor:
+    """One conv of the fused-MRF kernel, flat bf16 in tcgen05 operand layout.
+
+    Dilated convs (and every conv when phases == 1): the k tap matrices of pack_operand_taps.
+    Dilation-1 convs with D = phases > 1: k - 1 + D "phase matrices" [D*C_out][C_in]; matrix pi (input time offset
+    o = pi - (k-1)/2 relative to the D-row group) holds, in row block d', tap pi - d' (zero when outside [0, k)):
+    out[q D + d'] = sum_tap W[tap] x[q D + d' + tap - (k-1)/2]."""
+    if dilation != 1 or phases == 1:
+        return pack_operand_taps(w).reshape(-1)
+    c_out, c_in, k = w.shape
+    mats = torch.zeros(k - 1 + phases, phases * c_out, c_in, dtype=torch.float32, device=w.device)
+    for pi in range(k - 1 + phases):
+        for d in range(phases):
+            tap = pi - d
+            if 0 <= tap < k:
+                mats[pi, d * c_out:(d + 1) * c_out] = w[:, :, tap].float()
+    # (n, ci) -> chunk ci // 8, row n, lane ci % 8
+    t = mats.reshape(k - 1 + phases, phases * c_out, c_in // 8, 8).permute(0, 2, 1, 3)
+    return t.to(torch.bfloat16).contiguous().reshape(-1)
+
+
 def pack_mrf_weights(sd: Dict[str, torch.Tensor], stage: int, device):
     """All 18 convs of one stage's three resblocks, in the order the fused kernel walks them:
     (resblock k=3,7,11) x (pair 0..2) x (convs1, convs2).  Returns (weights bf16 flat, bias fp32 [18][C])."""
     ws, bs = [], []
+    phases = None
     for j in range(3):
         pre = f"vocoder.resblocks.{stage * 3 + j}."
         for q in range(3):
             for name in ("convs1", "convs2"):
-                ws.append(pack_operand_taps(sd[pre + f"{name}.{q}.weight"].detach().to(device)).reshape(-1))
+                w = sd[pre + f"{name}.{q}.weight"].detach().to(device)
+                if phases is None:
+                    phases = mrf_phases(w.shape[0])
+                dil = RESBLOCK_DILATIONS[q] if name == "convs1" else 1
+                ws.append(pack_mrf_conv(w, dil, phases))
                 bs.append(sd[pre + f"{name}.{q}.bias"].detach().to(device=device, dtype=torch.float32))
     return torch.cat(ws).contiguous(), torch.stack(bs).contiguous()
 

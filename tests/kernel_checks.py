@@ -266,7 +266,8 @@ def _mrf_case(c, rows, batch=2, seed=0):
             b1 = torch.randn(c, generator=gen) * 0.1
             w2 = bf(torch.randn(c, c, k, generator=gen) / math.sqrt(c * k))
             b2 = torch.randn(c, generator=gen) * 0.1
-            ws += [packing.pack_operand_taps(w1).reshape(-1), packing.pack_operand_taps(w2).reshape(-1)]
+            ph = packing.mrf_phases(c)
+            ws += [packing.pack_mrf_conv(w1, dil, ph), packing.pack_mrf_conv(w2, 1, ph)]
             bs += [b1, b2]
             r = x
             t = F.conv1d(F.leaky_relu(x, 0.1), w1.double(), b1.double(), dilation=dil, padding=(k - 1) // 2 * dil)
