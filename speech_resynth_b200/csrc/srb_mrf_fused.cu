@@ -105,6 +105,7 @@ struct MrfLayout {
   static constexpr int total = off_tmem + 16;
   static constexpr int tout = R - 2 * kMrfHalo;
   static_assert(3 * NM * N <= 512, "accumulators exceed tensor memory");
+  static_assert(N == 16 || N == 32, "the epilogue reads an accumulator row with one 16- or 32-column TMEM load");
 };
 
 // epilogue teams of four warps (one per TMEM lane quarter); team t post-processes the M tiles m = t (mod NTEAMS).
@@ -116,12 +117,12 @@ struct MrfLayout {
 template <int C>
 struct MrfTeams {
 #ifdef SRB_MRF_TEAMS
-  static constexpr int value = C == 16 ? SRB_MRF_TEAMS : 3;
+  static constexpr int value = C == 16 ? SRB_MRF_TEAMS : SRB_MRF_TEAMS32;
 #else
   static constexpr int value = C == 16 ? 4 : 3;          // epilogue teams
 #endif
 #ifdef SRB_MRF_ISSUERS
-  static constexpr int issuers = C == 16 ? SRB_MRF_ISSUERS : 3;
+  static constexpr int issuers = C == 16 ? SRB_MRF_ISSUERS : SRB_MRF_ISSUERS32;
 #else
   // MMA issuer warps.  Measured at C = 16 with two phases (us per launch, config 2): 1 issuer 2907, 2: 2220, 3: 1995,
   // 4: 2190, 5: 2362 (four or five epilogue teams make no difference)
