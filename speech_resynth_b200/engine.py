@@ -410,6 +410,26 @@ class ResynthEngine:
             self._launch(plan)
         return plan
 
+    def lengths_async(self, input_ids: torch.Tensor):
+        """Valid-frame counts of a batch on their way to the host, enqueued BEFORE the big graph so that the caller can wait
+        for them (event) while the graph is still running -- the public forward then never drains the GPU between calls.
+        srb_unit_lengths writes straight into pinned host memory (device-accessible under unified addressing): a D2H
+        copy would queue on the copy engine behind the previous call's 41 MB waveform read-back and hold up the graph
+        enqueued after it (measured: +0.8 ms per call).  Returns (pinned int32 tensor, event)."""
+        b, n = input_ids.shape
+        slot = getattr(self, "_len_slot", 0)
+        self._len_slot = slot ^ 1
+        bufs = getattr(self, "_len_bufs", None)
+        if bufs is None or bufs[0].shape[0] < b:
+            bufs = [torch.zeros(max(b, 64), dtype=torch.int32).pin_memory() for _ in range(2)]
+            self._len_bufs = bufs
+        host_buf = bufs[slot]
+        with torch.cuda.device(self.device):
+            nat.call("srb_unit_lengths", P(input_ids.contiguous()), host_buf.data_ptr(), b, n)
+            ev = torch.cuda.Event()
+            ev.record()
+        return host_buf[:b], ev
+
     def sample(self, input_ids: torch.Tensor, dt: float, truncation: Optional[float],
                noise: Optional[torch.Tensor] = None) -> torch.Tensor:
         """ConditionalFlowMatchingModel.sample: (B, N) int64 -> mel (B, N, 80) fp32 (a fresh tensor)."""

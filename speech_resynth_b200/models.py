@@ -335,7 +335,12 @@ class ConditionalFlowMatchingWithHifiGan(PreTrainedModel):
         ids = input_ids.to(self.device)
         if self.config.model_config.predict_duration:
             ids, _ = self.model.sampler().regulate(ids)     # models.py:157-164
-        wav, lengths, _ = self.engine().resynthesize(ids, dt, truncation_value)
-        wav_lengths = self._get_waveform_lengths(lengths.to("cpu", torch.int64)).tolist()
+        eng = self.engine()
+        # the lengths travel to the host ahead of the graph: waiting for them does not wait for the waveforms, so the
+        # next call can be enqueued while this one still runs (the reference syncs once per utterance, models.py:252-256)
+        lengths_host, ready = eng.lengths_async(ids)
+        wav, _, _ = eng.resynthesize(ids, dt, truncation_value)
         wav = wav.clone()  # the engine's buffer is reused by the next call
+        ready.synchronize()
+        wav_lengths = self._get_waveform_lengths(lengths_host.to(torch.int64)).tolist()
         return [wav[i, :n].unsqueeze(0) for i, n in enumerate(wav_lengths)]
