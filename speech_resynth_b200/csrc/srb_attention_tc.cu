@@ -148,8 +148,9 @@ __global__ void __launch_bounds__(448, 1) attn_tc_kernel(const __grid_constant__
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
+#ifdef SRB_TRACE
   int trace_n = 0;
-  (void)trace_n;
+#endif
   if (warp <= 2) ATTN_STAMP(warp);   // kernel entry
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2; ++s) {
@@ -383,7 +384,6 @@ __global__ void __launch_bounds__(448, 1) attn_tc_kernel(const __grid_constant__
       const AttnItem it = get_item(n, item);
       const int len = it.len, nkv = it.nkv;
       const int ob = n & 1;
-      const uint32_t t_o = t_o0 + ob * 128;
       float m = -INFINITY;
       for (int j = 0; j < (it.two_pass ? nkv : 0); ++j, ++t) {
         const int sb = t & 1;

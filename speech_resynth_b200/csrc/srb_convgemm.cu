@@ -212,6 +212,11 @@ static int launch_inst(ConvGemmParams& p, int total_tiles, cudaStream_t stream, 
   // RESNORM: two residual-stream buffers per epilogue warp when the K loop is short (the epilogue, not the MMAs,
   // paces those launches); one when the long K loop (FFN conv2) needs the shared memory for its weight ring
   if (EPI != EPI_GENERIC) p.res_bufs = (EPI == EPI_RESNORM && n_slabs <= 8) ? 2 : 1;   // (GENERIC: residual count, set by the caller)
+  {
+    // SRB_WEIGHTS_EARLY=0 requests the first weight slabs after the dependency wait instead of before it (A/B runs)
+    static const int early = [] { const char* e = getenv("SRB_WEIGHTS_EARLY"); return e ? atoi(e) : 1; }();
+    p.w_early = early;
+  }
   // coalescing / streaming buffers of the epilogue warps + CTA-wide epilogue tables
   const int stage_smem = EpiWarps<BN, EPI>::value * EpiWarps<BN, EPI>::stage_bytes(p.res_bufs) + EpiWarps<BN, EPI>::extra_bytes;
   if (MC == 2) w_stages = 6;

@@ -63,6 +63,7 @@ struct ConvGemmParams {
   int gen_lsu;                                    // GENERIC: 1 = register / LSU epilogue (MMA-bound launches, fused tails)
   int gen_nbuf;                                   // GENERIC TMA epilogue: staging depth (1 or 2) of residual and output blocks
   int l2_keep;                                    // RESNORM: 1 = evict_last policy on the residual stream's TMA transfers
+  int w_early;                                    // 1 = request the first weight slabs before the dependency wait (PDL)
   // epilogue operands
   const float* bias;
   void* out0;                                     // bf16 "activated"/normalised output
@@ -920,8 +921,31 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
   // everything above touched only shared / tensor memory and constant tables; activations come after this point
   if (warp == 0) SRB_TRACE_AT(0, 0, 1);   // prologue done
+  // Weights never depend on a predecessor: the producer requests its first ring of slabs (all of them in the
+  // weight-stationary form) BEFORE waiting for the previous kernel, so they travel while that kernel drains.
+  int w_pre = 0;   // slabs already requested (producer warp only; same order as the main loop below)
+  auto request_first_slabs = [&]() {
+    if (warp != 0 || walker >= total_tiles) return;
+    if constexpr (WS) {
+      // slab s = tap * kchunks + chunk lives in slot s for the whole kernel
+      for (int s = 0; s < w_stages; ++s) {
+        mbar_expect_tx_elect(w_full(s), L::w_bytes_raw);
+        tma_load_2d_elect(w_ring + s * L::w_bytes, &p.tmW, w_full(s), s * KB, ws_n * BN);
+      }
+    } else if constexpr (MC == 0) {
+      const TileCoord tc = decode(walker);
+      for (int sg = p.group_seg_begin[tc.group]; sg < p.group_seg_begin[tc.group + 1] && w_pre < w_stages; ++sg)
+        for (int kc = 0; kc < p.kchunks && w_pre < w_stages; ++kc)
+          for (int t = p.seg_tap_begin[sg]; t < p.seg_tap_begin[sg + 1] && w_pre < w_stages; ++t, ++w_pre) {
+            mbar_expect_tx_elect(w_full(w_pre), L::w_bytes_raw);
+            tma_load_2d_elect(w_ring + w_pre * L::w_bytes, &p.tmW, w_full(w_pre), (t * p.kchunks + kc) * KB, tc.n * BN);
+          }
+    }
+  };
+  if (p.w_early) request_first_slabs();
   pdl_wait();
   if (warp == 0) SRB_TRACE_AT(0, 0, 2);   // dependencies satisfied
+  if (!p.w_early) request_first_slabs();
   if constexpr (EPI == EPI_QKV_ROPE) {
     // clear the norm-bound buffer of the NEXT q|k projection (nobody reads or fills it while this launch runs)
     if (blockIdx.x == 0 && p.aux1 != nullptr)
@@ -934,15 +958,6 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
       int ai = 0, wi = 0;
       uint32_t aph = 0, wph = 0;
       const uint32_t a_tx = static_cast<uint32_t>(p.a_box_rows) * KB * 2;
-      if constexpr (WS) {
-        // slab s = tap * kchunks + chunk lives in slot s for the whole kernel
-        if (walker < total_tiles) {
-          for (int s = 0; s < w_stages; ++s) {
-            mbar_expect_tx_elect(w_full(s), L::w_bytes_raw);
-            tma_load_2d_elect(w_ring + s * L::w_bytes, &p.tmW, w_full(s), s * KB, ws_n * BN);
-          }
-        }
-      }
       for (int tile = walker; tile < total_tiles; tile += n_walkers) {
         const TileCoord tc = decode(tile);
         const int t0 = tc.m * kTileM;
@@ -963,6 +978,12 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
             if (++ai == a_stages) { ai = 0; aph ^= 1u; }
             if constexpr (WS) continue;
             for (int t = tb; t < te; ++t) {
+              if (w_pre > 0) {
+                // requested before the dependency wait
+                --w_pre;
+                if (++wi == w_stages) { wi = 0; wph ^= 1u; }
+                continue;
+              }
               mbar_wait(w_empty(wi), wph ^ 1u);
               if constexpr (MC == 2) {
                 if (mc_rank == 0) mbar_expect_tx_elect(w_full(wi), L::w_bytes_raw);
