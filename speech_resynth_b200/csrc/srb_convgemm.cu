@@ -215,7 +215,7 @@ static int launch_inst(ConvGemmParams& p, int total_tiles, cudaStream_t stream, 
   {
     // SRB_WEIGHTS_EARLY=0 requests the first weight slabs after the dependency wait instead of before it (A/B runs)
     static const int early = [] { const char* e = getenv("SRB_WEIGHTS_EARLY"); return e ? atoi(e) : 1; }();
-    p.w_early = early;
+    p.w_early = (early && !p.w_dynamic) ? 1 : 0;
   }
   // coalescing / streaming buffers of the epilogue warps + CTA-wide epilogue tables
   const int stage_smem = EpiWarps<BN, EPI>::value * EpiWarps<BN, EPI>::stage_bytes(p.res_bufs) + EpiWarps<BN, EPI>::extra_bytes;
@@ -638,6 +638,7 @@ int srb_cfm_v_transposed(const void* xn_bf16, const void* wv_bf16, void* vt_bf16
   d.batch = 1;
   d.epilogue = EPI_GENERIC;
   d.epi = empty_epi();
+  d.epi.w_dynamic = 1;   // the streamed operand is the previous kernel's output: never requested before the dependency wait
   d.epi.out1 = vt_bf16;
   d.epi.out_row_stride = m_pad;
   d.epi.out_batch_stride = 0;

@@ -64,6 +64,7 @@ struct ConvGemmParams {
   int gen_nbuf;                                   // GENERIC TMA epilogue: staging depth (1 or 2) of residual and output blocks
   int l2_keep;                                    // RESNORM: 1 = evict_last policy on the residual stream's TMA transfers
   int w_early;                                    // 1 = request the first weight slabs before the dependency wait (PDL)
+  int w_dynamic;                                  // 1 = the "weight" operand is produced by a predecessor kernel (swapped-operand v^T GEMM)
   // epilogue operands
   const float* bias;
   void* out0;                                     // bf16 "activated"/normalised output
