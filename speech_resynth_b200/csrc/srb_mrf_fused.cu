@@ -126,6 +126,7 @@ struct MrfTeams {
 #else
   // MMA issuer warps.  Measured at C = 16 with two phases (us per launch, config 2): 1 issuer 2907, 2: 2220, 3: 1995,
   // 4: 2190, 5: 2362 (four or five epilogue teams make no difference)
+  // and at C = 32 (teams, issuers): (3,3) 2611, (4,3) 2664, (3,4) 2724, (2,5) 2713, (3,5) 2852, (4,5) 2912
   static constexpr int issuers = 3;
 #endif
   static constexpr int threads = 32 * (1 + issuers) + 128 * value;
