@@ -294,7 +294,8 @@ def gpu_run(args):
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(top_name)   # dram read+write bytes per launch from an ncu --set full capture
+            # dram read+write bytes per launch from an ncu --set full capture of exactly this launch shape (else null)
+            traffic = json.load(open(tpath)).get(f"{top_name}{list(top_tag[:-1])}")
         roofline = {
             "bound": "tensor", "kernel": f"{top_name}{list(top_tag[:-1])}", "achieved": achieved, "peak": pk["bf16_sustained"],
             "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"], "traffic": traffic,
