@@ -289,8 +289,8 @@ def gpu_run(args):
         (top_name, top_tag), top = max(agg.items(), key=lambda kv: kv[1]["ms"])
         avg_s = top["ms"] / top["n"] / 1e3
         achieved = top["flops"] / avg_s / 1e12
-        from oracle import cfm_hifigan_oracle as oracle
-        flops_step = BATCH * (oracle.transformer_flops(FRAMES, 16, hoisted=True) + oracle.vocoder_flops(FRAMES))
+        from speech_resynth_b200 import sharding
+        flops_step = BATCH * (sharding.transformer_flops(FRAMES, 16, hoisted=True) + sharding.vocoder_flops(FRAMES))
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tpath):

@@ -27,10 +27,35 @@ class Bucket:
         return len(self.indices)
 
 
+# ---- cost model: algorithmic FLOPs of the path (multiply-add = 2) --------------------------
+# generator geometry of the shipped vocoder config (HF config defaults + src/hifigan/train.py:36-42)
+_UP_RATES, _UP_KERNELS = (5, 4, 4, 2, 2), (10, 9, 8, 4, 4)
+_PER_FRAME_LINEAR = 19_103_232      # embed + 4 x (qkv, out, both FFN convs) + to_pred, per frame per velocity evaluation
+_HOISTED_COND = 393_216             # the loop-invariant conditioning half of to_embed, computed once per call here
+
+
+def transformer_flops(frames: int, nfe: int, hoisted: bool = True) -> int:
+    """ODE loop over the transformer for one utterance padded to `frames`: NFE N (19 103 232 + 4096 N), attention being
+    the 4096 N term (4 layers x 2 heads x 128 x 4 N); `hoisted` drops the conditioning projection this path runs once."""
+    per_frame = _PER_FRAME_LINEAR + 4096 * frames - (_HOISTED_COND if hoisted else 0)
+    return nfe * frames * per_frame
+
+
+def vocoder_flops(frames: int) -> int:
+    """HiFi-GAN generator on `frames` mel frames: conv_pre, five (transposed conv + three-resblock MRF) stages, conv_post."""
+    total = 2 * 7 * 80 * 512 * frames
+    channels, rows = 512, frames
+    for rate, kernel in zip(_UP_RATES, _UP_KERNELS):
+        out_rows = (rows - 1) * rate - 2 * ((kernel - rate) // 2) + kernel
+        total += 2 * channels * (channels // 2) * kernel * rows          # transposed conv, per input row
+        total += 2 * (3 + 7 + 11) * 6 * (channels // 2) ** 2 * out_rows   # 18 convs of the three resblocks
+        channels, rows = channels // 2, out_rows
+    return total + 2 * 16 * 7 * rows
+
+
 def utterance_cost(frames: int, nfe: int) -> float:
-    """Algorithmic FLOPs of one utterance padded to `frames`:
-    transformer NFE*N*(19.10M - hoisted 0.39M + 4096 N) + vocoder ~320.5M*N."""
-    return nfe * frames * (19_103_232 - 393_216 + 4096 * frames) + 320.5e6 * frames
+    """Algorithmic FLOPs of one utterance padded to `frames`: what the rank assignment balances."""
+    return float(transformer_flops(frames, nfe) + vocoder_flops(frames))
 
 
 def bucket_by_length(lengths: Sequence[int], granularity: int = 64, max_batch: int = 64,

@@ -232,3 +232,15 @@ def test_wav_writer_round_trip(tmp_path, bits):
         assert y.dtype.kind == "f" and (y == x).all()
     else:
         assert y.dtype == "int16" and abs(y.astype("float64") / 32768.0 - x).max() <= 0.5 / 32768 + 1e-9
+
+
+def test_cost_model_matches_the_oracle_flop_count():
+    """The package's own FLOP formulas (rank balancing, bench.py's roofline) against the oracle's and SURVEY.md 8(a)."""
+    from oracle import cfm_hifigan_oracle as oracle
+
+    for n in (1, 40, 250, 500, 3000):
+        assert sharding.vocoder_flops(n) == oracle.vocoder_flops(n)
+        for hoisted in (False, True):
+            assert sharding.transformer_flops(n, 16, hoisted) == oracle.transformer_flops(n, 16, hoisted)
+    assert sharding.vocoder_flops(500) == 160_305_440_256
+    assert sharding.utterance_cost(500, 16) == sharding.transformer_flops(500, 16) + sharding.vocoder_flops(500)
