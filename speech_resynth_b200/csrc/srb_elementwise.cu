@@ -353,36 +353,58 @@ __global__ void __launch_bounds__(128) posconv_norm_kernel(const float* __restri
 
 // ------------------------------------------------------------------------------------------ conv_post + tanh
 // wav[b, t] = tanh(bias + sum_{j<7, c<16} w[j][c] * x[b, t + j - 3, c]);  x already leaky_relu(0.01)'ed.  HF:1480-1482
-__global__ void __launch_bounds__(256) post_tanh_kernel(const uint4* __restrict__ x, const float* __restrict__ w, float bias,
+// 128 threads x 2 consecutive outputs (256 outputs per block): the 8 input rows of an output pair are read once (16
+// conflict-free 16-byte shared loads per pair instead of 28 two-way conflicting ones for two single outputs -- the
+// one-output form was shared-memory-bandwidth bound at 232 us per 64 x 160 080 samples).  Row r of the window sits in
+// slot r + r / 8 so that the stride-2 row pattern of a quarter warp covers eight different 16-byte bank groups.
+constexpr int kPostOutputs = 256;
+__device__ __forceinline__ int post_slot(int r) { return r + (r >> 3); }
+__device__ __forceinline__ void post_unpack(const uint4 u, float* f) {
+  f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+  f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+__global__ void __launch_bounds__(128) post_tanh_kernel(const uint4* __restrict__ x, const float* __restrict__ w, float bias,
                                                         float* __restrict__ wav, int rows) {
   pdl_launch_dependents();
   pdl_wait();
-  __shared__ uint4 tile[(256 + 6) * 2];
-  __shared__ float ws[7 * 16];
-  const int b = blockIdx.y, t0 = blockIdx.x * 256;
+  constexpr int kRows = kPostOutputs + 6;
+  constexpr int kSlots = kRows + kRows / 8 + 1;
+  __shared__ uint4 tile[2][kSlots];
+  __shared__ __align__(16) float ws[7 * 16];
+  const int b = blockIdx.y, t0 = blockIdx.x * kPostOutputs;
   if (threadIdx.x < 112) ws[threadIdx.x] = w[threadIdx.x];
   const uint4* xb = x + (long long)b * rows * 2;
-  for (int i = threadIdx.x; i < (256 + 6) * 2; i += 256) {
-    const int t = t0 - 3 + (i >> 1);
-    tile[i] = (t >= 0 && t < rows) ? __ldg(xb + (long long)t * 2 + (i & 1)) : make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < kRows * 2; i += 128) {
+    const int r = i >> 1, t = t0 - 3 + r;
+    tile[i & 1][post_slot(r)] = (t >= 0 && t < rows) ? __ldg(xb + (long long)t * 2 + (i & 1)) : make_uint4(0, 0, 0, 0);
   }
   __syncthreads();
-  const int t = t0 + threadIdx.x;
+  const int r0 = 2 * threadIdx.x;        // window row of tap 0 of the first output
+  const int t = t0 + r0;
   if (t >= rows) return;
-  float acc = bias;
+  float acc0 = bias, acc1 = bias;
 #pragma unroll
-  for (int j = 0; j < 7; ++j) {
+  for (int k = 0; k < 8; ++k) {
+    float f[16];
+    post_unpack(tile[0][post_slot(r0 + k)], f);
+    post_unpack(tile[1][post_slot(r0 + k)], f + 8);
+    if (k < 7) {
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const uint4 u = tile[(threadIdx.x + j) * 2 + h];
-      const float* wj = ws + j * 16 + h * 8;
-      acc = fmaf(bf16_lo(u.x), wj[0], acc); acc = fmaf(bf16_hi(u.x), wj[1], acc);
-      acc = fmaf(bf16_lo(u.y), wj[2], acc); acc = fmaf(bf16_hi(u.y), wj[3], acc);
-      acc = fmaf(bf16_lo(u.z), wj[4], acc); acc = fmaf(bf16_hi(u.z), wj[5], acc);
-      acc = fmaf(bf16_lo(u.w), wj[6], acc); acc = fmaf(bf16_hi(u.w), wj[7], acc);
+      for (int c = 0; c < 16; ++c) acc0 = fmaf(f[c], ws[k * 16 + c], acc0);
+    }
+    if (k > 0) {
+#pragma unroll
+      for (int c = 0; c < 16; ++c) acc1 = fmaf(f[c], ws[(k - 1) * 16 + c], acc1);
     }
   }
-  wav[(long long)b * rows + t] = tanhf(acc);
+  float* o = wav + (long long)b * rows + t;
+  const float y0 = tanhf(acc0), y1 = tanhf(acc1);
+  if (t + 1 < rows && (reinterpret_cast<uintptr_t>(o) & 7) == 0) {
+    *reinterpret_cast<float2*>(o) = make_float2(y0, y1);
+  } else {
+    o[0] = y0;
+    if (t + 1 < rows) o[1] = y1;
+  }
 }
 
 __global__ void crop_concat_kernel(const float* __restrict__ wav, const int* __restrict__ lengths,
@@ -495,8 +517,8 @@ int srb_cfm_posconv_norm(const float* x0, const float* dw_w, const float* dw_b, 
 int srb_hifigan_post(const void* x_act, const float* w, float bias, float* wav, int32_t batch, int32_t rows,
                      void* stream) {
   if (batch <= 0 || rows <= 0) return 0;
-  dim3 grid((rows + 255) / 256, batch);
-  SRB_CUDA(launch_pdl(post_tanh_kernel, grid, dim3(256), 0, (cudaStream_t)stream, static_cast<const uint4*>(x_act), w, bias, wav, rows));
+  dim3 grid((rows + kPostOutputs - 1) / kPostOutputs, batch);
+  SRB_CUDA(launch_pdl(post_tanh_kernel, grid, dim3(128), 0, (cudaStream_t)stream, static_cast<const uint4*>(x_act), w, bias, wav, rows));
   return after_launch("post_tanh_kernel");
 }
 
