@@ -14,7 +14,10 @@
  *   - activations are channel-last: (batch, rows, channels) with explicit element strides, bf16 unless noted;
  *   - "packed" weights are bf16 [n][k] with k contiguous, k ordered (tap, channel) and the channel count padded to
  *     a multiple of the K block the op uses (see speech_resynth_b200/packing.py for the exact recipe);
- *   - `lengths` is int32[batch]: number of valid (non-pad) rows per utterance.
+ *   - `lengths` is int32[batch]: number of valid (non-pad) rows per utterance;
+ *   - ordering: kernels are launched with programmatic dependent launch; each waits in-kernel for its predecessor on
+ *     the stream before it touches activations, but may read weight / bias / table operands before that, so those
+ *     must stay constant while calls are in flight (environment: SRB_PDL=0, SRB_WEIGHTS_EARLY=0 turn this off).
  */
 #ifndef SRB_H_
 #define SRB_H_
