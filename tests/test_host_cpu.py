@@ -244,3 +244,18 @@ def test_cost_model_matches_the_oracle_flop_count():
             assert sharding.transformer_flops(n, 16, hoisted) == oracle.transformer_flops(n, 16, hoisted)
     assert sharding.vocoder_flops(500) == 160_305_440_256
     assert sharding.utterance_cost(500, 16) == sharding.transformer_flops(500, 16) + sharding.vocoder_flops(500)
+
+
+def test_product_package_never_reaches_for_the_oracle_or_the_reference_tree():
+    """The oracle is test infrastructure: nothing under speech_resynth_b200/ may import it, and nothing there may
+    read /root/reference (absent on the GPU box)."""
+    pkg = os.path.dirname(os.path.abspath(srb.__file__))
+    offenders = []
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if not f.endswith((".py", ".cu", ".cuh", ".h", ".sh")):
+                continue
+            text = open(os.path.join(root, f), encoding="utf-8").read()
+            if re.search(r"^\s*(from|import)\s+oracle\b", text, re.M) or "/root/reference" in text:
+                offenders.append(os.path.relpath(os.path.join(root, f), pkg))
+    assert offenders == []
