@@ -8,6 +8,7 @@ FastSpeech2ConformerHifiGan.forward (HF:1451-1491).
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
 
@@ -229,6 +230,8 @@ class HifiGanGenerator:
         self.w = packed
         self.slope = float(slope)
         self.fuse_mrf = fuse_mrf
+        # SRB_PAIR_UPSAMPLE=0 runs every up-sampler through the polyphase kernel instead (A/B runs)
+        self.pair_upsample = os.environ.get("SRB_PAIR_UPSAMPLE", "1") != "0"
         self.fork = _Fork(packed.w_pre.device, 2)
         self.device = packed.w_pre.device
 
@@ -264,9 +267,17 @@ class HifiGanGenerator:
             rows, c = st["rows"], st["c"]
             fused = self.fuse_mrf and i in w.w_mrf
             # upsampler (HF:1472-1473): raw copy = residual of the three resblocks, activated copy = their input
-            nat.call("srb_hifigan_upsample", P(x_act), P(w.w_up[i]), P(w.b_up[i]), P(st["u_raw"]),
-                     None if fused else P(st["u_act"]), b, rows_in, c_in, c, k, s, self.slope,
-                     flops=2.0 * b * rows_in * k * c_in * c)
+            if i in w.up_pair and self.pair_upsample:
+                # L_out = s L: all s output phases of an input row from one 3-tap conv (packing.upsampler_as_row_group_conv);
+                # (B, rows_in, s c) is the (B, rows, c) result.  FLOPs reported are the transposed conv's own.
+                wp, bp = w.up_pair[i]
+                nat.call("srb_hifigan_conv", P(x_act), None, None, 1, _i32([3]), dil1, P(wp), P(bp), None, None, None,
+                         P(st["u_raw"]), None if fused else P(st["u_act"]), b, rows_in, c_in, s * c, 1.0, self.slope,
+                         flops=2.0 * b * rows_in * k * c_in * c)
+            else:
+                nat.call("srb_hifigan_upsample", P(x_act), P(w.w_up[i]), P(w.b_up[i]), P(st["u_raw"]),
+                         None if fused else P(st["u_act"]), b, rows_in, c_in, c, k, s, self.slope,
+                         flops=2.0 * b * rows_in * k * c_in * c)
             if fused:
                 # narrow stages: the whole MRF block (18 convs + residuals + mean + next leaky_relu) in one kernel
                 slope_next = self.slope if i + 1 < n_stage else 0.01

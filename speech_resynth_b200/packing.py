@@ -48,6 +48,29 @@ def pack_upsampler_weight(w: torch.Tensor, stride: int) -> torch.Tensor:
     return torch.cat(cols, dim=1).to(torch.bfloat16).contiguous()
 
 
+def upsampler_as_row_group_conv(w: torch.Tensor, bias: torch.Tensor, stride: int):
+    """ConvTranspose1d (C_in, C_out, k) with k - 2 pad = stride (HF:1392-1402: (8, 4, 2) and (4, 2, 1)) as an ordinary
+    3-tap Conv1d that produces ALL `stride` output phases of an input row at once:
+        out[stride r + ph, co] = y[r, ph * C_out + co],   y[r] = Wv[:, :, 0] x[r-1] + Wv[:, :, 1] x[r] + Wv[:, :, 2] x[r+1]
+    (zero padding = the transposed conv's skipped out-of-range inputs).  From o = stride i - pad + j: tap j feeds phase ph
+    iff (ph + pad - j) % stride == 0, reading x[r + d] with d = (ph + pad - j) / stride in {-1, 0, 1}.
+    The (B, L, stride C_out) result IS the (B, stride L, C_out) up-sampled tensor (L_out = stride L exactly), so the
+    launch writes whole contiguous rows and issues N = stride C_out MMAs (narrow tiles pay per MMA, DESIGN.md section
+    5.2) at the price of some zero blocks.  Returns (Conv1d weight (stride C_out, C_in, 3), bias (stride C_out,))."""
+    c_in, c_out, k = w.shape
+    pad = (k - stride) // 2
+    assert k - 2 * pad == stride, "row-group form needs L_out = stride * L"
+    wv = torch.zeros(stride * c_out, c_in, 3, dtype=torch.float32, device=w.device)
+    wt = w.float()
+    for ph in range(stride):
+        for j in range(k):
+            if (ph + pad - j) % stride == 0:
+                d = (ph + pad - j) // stride
+                assert -1 <= d <= 1
+                wv[ph * c_out:(ph + 1) * c_out, :, d + 1] = wt[:, :, j].t()
+    return wv, bias.float().repeat(stride).contiguous()
+
+
 def pack_operand_taps(w: torch.Tensor) -> torch.Tensor:
     """Conv1d weight (C_out, C_in, k) -> bf16 [k][C_in/8][C_out][8]: per tap the B operand of the fused-MRF kernel
     in the un-swizzled K-major layout (16-byte K chunks, rows 16 bytes apart)."""
@@ -133,6 +156,9 @@ class PackedVocoder:
     b_pre: torch.Tensor
     w_up: List[torch.Tensor] = field(default_factory=list)
     b_up: List[torch.Tensor] = field(default_factory=list)
+    # stage -> (packed weight, bias) of the up-samplers with L_out = stride L in row-group conv form
+    # (upsampler_as_row_group_conv)
+    up_pair: Dict[int, tuple] = field(default_factory=dict)
     # [stage][resblock j][pair q] -> (w1, b1, w2, b2); for q == 2 the conv2 lives in w_tail instead
     w_c1: List[List[List[torch.Tensor]]] = field(default_factory=list)
     b_c1: List[List[List[torch.Tensor]]] = field(default_factory=list)
@@ -209,6 +235,9 @@ def pack_vocoder(sd: Dict[str, torch.Tensor], device) -> PackedVocoder:
     for i, (s, k) in enumerate(zip(UPSAMPLE_RATES, UPSAMPLE_KERNELS)):
         v.w_up.append(pack_upsampler_weight(f(f"vocoder.upsampler.{i}.weight"), s))
         v.b_up.append(f(f"vocoder.upsampler.{i}.bias").contiguous())
+        if k - 2 * ((k - s) // 2) == s:
+            wv, bv = upsampler_as_row_group_conv(f(f"vocoder.upsampler.{i}.weight"), f(f"vocoder.upsampler.{i}.bias"), s)
+            v.up_pair[i] = (pack_conv_weight(wv, block_k_for(wv.shape[1])), bv)
         c //= 2
         bk = block_k_for(c)
         w1s, b1s, w2s, b2s, tails, tail_b = [], [], [], [], [], None

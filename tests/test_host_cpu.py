@@ -259,3 +259,18 @@ def test_product_package_never_reaches_for_the_oracle_or_the_reference_tree():
             if re.search(r"^\s*(from|import)\s+oracle\b", text, re.M) or "/root/reference" in text:
                 offenders.append(os.path.relpath(os.path.join(root, f), pkg))
     assert offenders == []
+
+
+@pytest.mark.parametrize("c_in,c_out,k,s", [(128, 64, 8, 4), (64, 32, 4, 2), (32, 16, 4, 2)])
+def test_upsampler_as_row_group_conv_reproduces_conv_transpose(c_in, c_out, k, s):
+    """ConvTranspose1d with k - 2 pad = stride == a 3-tap Conv1d producing all output phases per input row (HF:1392-1402)."""
+    g = torch.Generator().manual_seed(3)
+    w = torch.randn(c_in, c_out, k, generator=g, dtype=torch.float64)
+    b = torch.randn(c_out, generator=g, dtype=torch.float64)
+    x = torch.randn(2, c_in, 37, generator=g, dtype=torch.float64)
+    ref = F.conv_transpose1d(x, w, b, stride=s, padding=(k - s) // 2)            # (2, c_out, s * 37)
+    wv, bv = packing.upsampler_as_row_group_conv(w, b, s)
+    y = F.conv1d(x, wv.double(), bv.double(), padding=1)                          # (2, s c_out, 37)
+    got = y.view(2, s, c_out, 37).permute(0, 2, 3, 1).reshape(2, c_out, s * 37)  # [b, co, s r + ph]
+    assert ref.shape == got.shape
+    assert float((ref - got).abs().max()) < 1e-5
