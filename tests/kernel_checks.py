@@ -254,6 +254,38 @@ for _i, (_c, _k, _s) in enumerate(zip((512, 256, 128, 64, 32), packing.UPSAMPLE_
     CHECKS[f"upsample_stage{_i}_c{_c}_k{_k}_s{_s}"] = _fn
 
 
+def _upsample_row_group_case(c_in, k, s, rows_in, batch=2, seed=0):
+    """the production form of the up-samplers with L_out = stride L: srb_hifigan_conv on the weights of
+    packing.upsampler_as_row_group_conv, (B, L, s C_out) output read as (B, s L, C_out), vs conv_transpose1d"""
+    gen = g(seed)
+    c_out = c_in // 2
+    x = bf(torch.randn(batch, rows_in, c_in, generator=gen))
+    w = bf(torch.randn(c_in, c_out, k, generator=gen) / math.sqrt(c_in * k / s))
+    bias = torch.randn(c_out, generator=gen)
+    pad = (k - s) // 2
+    with torch.backends.mkldnn.flags(enabled=False):
+        y = F.conv_transpose1d(x.transpose(1, 2).double(), w.double(), bias.double(), stride=s, padding=pad).transpose(1, 2)
+    assert y.shape[1] == s * rows_in
+    wv, bv = packing.upsampler_as_row_group_conv(w.to(DEV), bias.to(DEV), s)
+    wp = packing.pack_conv_weight(wv, packing.block_k_for(c_in))
+    out_raw = torch.full((batch, s * rows_in, c_out), float("nan"), dtype=torch.bfloat16, device=DEV)
+    out_act = torch.full_like(out_raw, float("nan"))
+    xd = x.to(DEV).to(torch.bfloat16).contiguous()
+    nat.call("srb_hifigan_conv", P(xd), None, None, 1, _i32([3]), _i32([1]), P(wp), P(bv), None, None, None, P(out_raw),
+             P(out_act), batch, rows_in, c_in, s * c_out, 1.0, 0.1)
+    torch.cuda.synchronize()
+    e1 = rel_l2(out_raw.float(), y)
+    e2 = rel_l2(out_act.float(), F.leaky_relu(y, 0.1))
+    return max(e1, e2), BF16_TOL
+
+
+for _i, (_c, _k, _s) in enumerate(zip((512, 256, 128, 64, 32), packing.UPSAMPLE_KERNELS, packing.UPSAMPLE_RATES)):
+    if _k - 2 * ((_k - _s) // 2) == _s:
+        def _fn(c=_c, k=_k, s=_s, i=_i):
+            return _upsample_row_group_case(c, k, s, rows_in=77 + 60 * i)
+        CHECKS[f"upsample_row_group_stage{_i}_c{_c}_k{_k}_s{_s}"] = _fn
+
+
 def _mrf_case(c, rows, batch=2, seed=0):
     """whole fused MRF stage vs a float64 evaluation of HF:1359-1367,1475-1480 on the same bf16-rounded weights"""
     gen = g(seed)
