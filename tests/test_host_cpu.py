@@ -274,3 +274,29 @@ def test_upsampler_as_row_group_conv_reproduces_conv_transpose(c_in, c_out, k, s
     got = y.view(2, s, c_out, 37).permute(0, 2, 3, 1).reshape(2, c_out, s * 37)  # [b, co, s r + ph]
     assert ref.shape == got.shape
     assert float((ref - got).abs().max()) < 1e-5
+
+
+def test_bucketing_and_rank_assignment_properties():
+    """Property test (hypothesis) of the host-side sharding: buckets partition the utterances, are padded to their longest
+    member, respect the batch / frame caps, and every bucket lands on exactly one rank with a balanced load (LPT bound)."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(st.integers(min_value=1, max_value=3000), min_size=1, max_size=200),
+           st.sampled_from([16, 64, 128]), st.sampled_from([1, 8, 64]), st.integers(min_value=1, max_value=8))
+    def check(lengths, granularity, max_batch, world):
+        buckets = sharding.bucket_by_length(lengths, granularity=granularity, max_batch=max_batch)
+        seen = sorted(i for b in buckets for i in b.indices)
+        assert seen == list(range(len(lengths)))
+        for b in buckets:
+            member = [lengths[i] for i in b.indices]
+            assert b.frames == max(member) and 1 <= b.batch <= max_batch
+            assert len({(n + granularity - 1) // granularity for n in member}) == 1
+        plan = sharding.assign_buckets(buckets, world)
+        assert sorted(j for r in plan for j in r) == list(range(len(buckets)))
+        cost = [b.batch * sharding.utterance_cost(b.frames, 16) for b in buckets]
+        load = [sum(cost[j] for j in r) for r in plan]
+        # greedy LPT: no rank exceeds the mean by more than the largest single bucket
+        assert max(load) <= sum(cost) / world + max(cost) + 1e-6
+
+    check()
