@@ -42,6 +42,10 @@ int srb_embed_gather(const float* table, const int64_t* ids, float* out, int64_t
 
 /* valid-frame count per utterance: mask = input_ids.ne(0) (models.py:152); lengths[b] = sum(mask[b]) */
 int srb_unit_lengths(const int64_t* ids, int32_t* lengths, int32_t batch, int32_t frames, void* stream);
+/* same, plus extents[b] = index of the last non-pad id + 1.  The kernels mask by prefix length, the reference by position
+ * (models.py:152, transformer.py:115-127): both agree exactly when lengths[b] == extents[b] (right-padded rows, the
+ * reference's input convention, synthesize.py:39-42); the host raises otherwise.  Either output may be pinned host memory. */
+int srb_unit_extents(const int64_t* ids, int32_t* lengths, int32_t* extents, int32_t batch, int32_t frames, void* stream);
 
 /* ---- time conditioning table: models.py:47-49,179 + norm.py:42 --------------------------------------------
  * For each ODE time t_s (s < nfe): c = SiLU(Linear([t, sin(2*pi*t*w), cos(2*pi*t*w)])) and, for each of the
@@ -53,9 +57,18 @@ int srb_time_cond_table(const float* times, int32_t nfe, const float* four_w, co
 /* rotary table: transformer.py:56-63.  cos/sin[(pos, f)] for pos < rows, f < 64 (fp32, freq = pos * inv_freq[f]) */
 int srb_rotary_table(const float* inv_freq, int32_t rows, float* cos_out, float* sin_out, void* stream);
 
-/* noise truncation + bf16 copy: models.py:168-170.  xt (fp32, in place) = clamp(xt, -tv, tv) when tv > 0;
- * xt_bf16 = bf16(xt).  n = batch*frames*80 */
-int srb_prior_prepare(float* xt, void* xt_bf16, int64_t n, float truncation, void* stream);
+/* noise truncation + bf16 copy: models.py:168-170.  xt (fp32, in place) = torch.clamp(xt, -tv, tv) when has_truncation
+ * (any tv, including 0 and negative values: clamp's min > max rule applies); xt_bf16 = bf16(xt).  n = batch*frames*80 */
+int srb_prior_prepare(float* xt, void* xt_bf16, int64_t n, float truncation, int32_t has_truncation, void* stream);
+
+/* Per-call input staging ahead of the (graph-captured) loop: caller tensors -> the plan's static buffers whose rows are
+ * padded from frames_in to frames (multiple of 8).  ids (B, frames) = ids_in (B, frames_in) right-padded with 0;
+ * xt (B, frames, 80) fp32 = clamp(prior_in (B, frames_in, 80)) (models.py:168-170) with zero pad rows; xt_bf16 = bf16(xt);
+ * [zero_a, +zero_a_bytes) and [zero_b, +zero_b_bytes) are cleared (nullable; the rows of xn beyond B*frames that the v^T
+ * GEMM reads, and the attention norm bounds).  Replaces four framework copy / fill kernels per call. */
+int srb_stage_inputs(const int64_t* ids_in, const float* prior_in, int64_t* ids, float* xt, void* xt_bf16, void* zero_a,
+                     int64_t zero_a_bytes, void* zero_b, int64_t zero_b_bytes, int32_t batch, int32_t frames_in,
+                     int32_t frames, float truncation, int32_t has_truncation, void* stream);
 
 /* Log-mel front end = mel_spectrogram of src/hifigan/data.py:17-53 (n_fft 400, hop 320, hann window, center=False,
  * 80 slaney mel bands 0-8 kHz, log(max(., 1e-5))):  wav (B, samples) fp32 with row pitch wav_stride ->
@@ -91,11 +104,7 @@ int srb_cfm_posconv_norm(const float* x0, const float* dw_w, const float* dw_b, 
 int srb_cfm_qkv_rope(const void* xn_bf16, const void* w_packed, const float* rot_cos, const float* rot_sin,
                      void* qkv_bf16, int32_t batch, int32_t frames, void* stream);
 
-/* key-padding-masked softmax attention, 2 heads x 128 (transformer.py:115-127): o (B, N, 256) bf16 */
-int srb_cfm_attention(const void* qkv_bf16, const int32_t* lengths, void* o_bf16, int32_t batch, int32_t frames,
-                      void* stream);
-
-/* tcgen05 attention path (same math as srb_cfm_attention, transformer.py:109-127):
+/* tcgen05 attention path (to_qkv, rotary, masked softmax attention: transformer.py:109-127):
  *   srb_cfm_qk_rope      : qk (B, N, 512) bf16 = rope(xn @ Wqk^T), Wqk = first 512 rows of to_qkv.weight.  rot_cos /
  *                          rot_sin: (rows, 64) fp32 tables of srb_rotary_table with rows >= max(frames, 32).
  *                          qk_norm2_max (nullable): (B, 2 [q|k], 2 [head], 2 [frequency half]) fp32, zeroed by the
@@ -139,10 +148,12 @@ int srb_cfm_ffn_out_norm(const void* h_bf16, const void* w_packed, const float* 
 
 /* to_pred + Euler update (models.py:183-184), and on the last step the de-normalisation and pad fill
  * (models.py:186-187): xt += dt * (xn @ Wpred^T); xt_bf16 = bf16(xt);
- * if mel != NULL: mel = xt*std + mean, pad rows = log(1e-5) (fp32 and bf16 copies) */
+ * if mel != NULL: mel = xt*std + mean, pad rows = log(1e-5) (fp32 and bf16 copies), both COMPACT (B, mel_rows, 80) with
+ * mel_rows <= frames: the caller's frame count, which is what the vocoder must see (rows mel_rows..frames are the
+ * alignment padding of the loop's buffers and are dropped here) */
 int srb_cfm_pred_euler(const void* xn_bf16, const void* w_packed, float dt, float* xt, void* xt_bf16, float* mel,
-                       void* mel_bf16, float std, float mean, float pad_value, const int32_t* lengths, int32_t batch,
-                       int32_t frames, void* stream);
+                       void* mel_bf16, int32_t mel_rows, float std, float mean, float pad_value, const int32_t* lengths,
+                       int32_t batch, int32_t frames, void* stream);
 
 /* ---- HiFi-GAN generator (HF:1308-1367, 1451-1491) ------------------------------------------------------------
  * "same"-padded dilated Conv1d as an implicit GEMM with a fused epilogue:
@@ -175,14 +186,12 @@ int srb_hifigan_mrf_fused(const void* u_raw, const void* w_packed, const float* 
                           int32_t rows, int32_t channels, float slope, float slope_next, void* stream);
 
 /* conv_post (16 -> 1, k = 7) + tanh (HF:1480-1482); x is the leaky_relu(0.01)'ed stage-5 output (B, L, 16) bf16;
- * w[7][16] fp32 (tap-major), wav (B, L) fp32 */
+ * w[7][16] fp32 (tap-major).  Dense form (lengths == NULL): wav (B, L) fp32.  Ragged form (lengths = int32[B] valid
+ * frames per utterance): utterance b keeps its first n_b = min(L, 320 * lengths[b] + 80) samples
+ * (_get_waveform_lengths, models.py:211-221), stored back to back at wav[sum_{i<b} n_i ...] -- the per-utterance crop
+ * loop of the reference (models.py:252-256) folded into the store; wav must hold sum_b n_b floats. */
 int srb_hifigan_post(const void* x_act, const float* w, float bias, float* wav, int32_t batch, int32_t rows,
-                     void* stream);
-
-/* length-aware copy-out replacing the per-utterance crop loop (models.py:252-256):
- * dst[offsets[b] + i] = wav[b, i] for i < 320*len_b + 80 */
-int srb_crop_concat(const float* wav, const int32_t* lengths, const int64_t* offsets, float* dst, int32_t batch,
-                    int32_t rows, void* stream);
+                     const int32_t* lengths, void* stream);
 
 #ifdef __cplusplus
 }

@@ -94,6 +94,19 @@ def _main():
             "wav_rel_l2_oracle64_vs_ref": max(rel_l2(a, r) for a, r in zip(
                 oracle.resynthesize(sd64, ids, x0.double(), dt, tv), ref_wavs)),
         }
+        # the reference's OWN low-precision mode (bf16 autocast over fp32 weights, train.py:174) on the same inputs: the
+        # yardstick SURVEY.md section 8(c) sets for a bf16 implementation ("<= 3x the reference's own bf16-autocast error")
+        torch.manual_seed(noise_seed)
+        with torch.inference_mode(), torch.autocast("cpu", dtype=torch.bfloat16):
+            ac_mel = ref.model.sample(ids, dt, tv).float()
+        torch.manual_seed(noise_seed)
+        with torch.inference_mode(), torch.autocast("cpu", dtype=torch.bfloat16):
+            ac_wavs = [w.float() for w in ref(ids, dt, tv)]
+        info["bf16_autocast_vs_fp32"] = {
+            "mel_raw": rel_l2(ac_mel[valid], ref_mel[valid]),
+            "mel_normalised": rel_l2((ac_mel[valid] + 5.8843) / 2.2615, (ref_mel[valid] + 5.8843) / 2.2615),
+            "wav": max(rel_l2(a, r) for a, r in zip(ac_wavs, ref_wavs)),
+        }
         assert [w.shape[-1] for w in o_wavs32] == info["wav_lengths"]
         manifest["cases"][name] = dict(batch=b, frames=n, lengths=lengths, dt=dt, truncation=tv,
                                        ids_seed=ids_seed, noise_seed=noise_seed, **info)

@@ -28,28 +28,28 @@ _PROTOTYPES = {
     "srb_device_arch": [],
     "srb_embed_gather": [_P, _P, _P, _L, _I, _I, _P],
     "srb_unit_lengths": [_P, _P, _I, _I, _P],
+    "srb_unit_extents": [_P, _P, _P, _I, _I, _P],
+    "srb_stage_inputs": [_P, _P, _P, _P, _P, _P, _L, _P, _L, _I, _I, _I, _F, _I, _P],
     "srb_time_cond_table": [_P, _I, _P, _P, _P, _P, _I, _P, _P, _P],
     "srb_rotary_table": [_P, _I, _P, _P, _P],
-    "srb_prior_prepare": [_P, _P, _L, _F, _P],
+    "srb_prior_prepare": [_P, _P, _L, _F, _I, _P],
     "srb_log_mel": [_P, _L, _I, _I, _P, _P, _P, _P, _P, _I, _P],
     "srb_duration_predict": [_P, _P, _F, _P, _P, _I, _I, _I, _P],
     "srb_length_regulate": [_P, _P, _P, _I, _I, _I, _I, _P],
     "srb_cfm_embed": [_P, _P, _P, _P, _I, _I, _P],
     "srb_cfm_posconv_norm": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P],
     "srb_cfm_qkv_rope": [_P, _P, _P, _P, _P, _I, _I, _P],
-    "srb_cfm_attention": [_P, _P, _P, _I, _I, _P],
     "srb_cfm_qk_rope": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P],
     "srb_cfm_v_transposed": [_P, _P, _P, _L, _P],
     "srb_cfm_attention_tc": [_P, _I, _P, _L, _P, _P, _P, _I, _I, _P],
     "srb_cfm_attn_out_norm": [_P, _P, _P, _P, _P, _P, _I, _I, _P],
     "srb_cfm_ffn_glu": [_P, _P, _P, _P, _P, _I, _I, _P],
     "srb_cfm_ffn_out_norm": [_P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _P],
-    "srb_cfm_pred_euler": [_P, _P, _F, _P, _P, _P, _P, _F, _F, _F, _P, _I, _I, _P],
+    "srb_cfm_pred_euler": [_P, _P, _F, _P, _P, _P, _P, _I, _F, _F, _F, _P, _I, _I, _P],
     "srb_hifigan_conv": [_P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _P],
     "srb_hifigan_upsample": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P],
     "srb_hifigan_mrf_fused": [_P, _P, _P, _P, _I, _I, _I, _F, _F, _P],
-    "srb_hifigan_post": [_P, _P, _F, _P, _I, _I, _P],
-    "srb_crop_concat": [_P, _P, _P, _P, _I, _I, _P],
+    "srb_hifigan_post": [_P, _P, _F, _P, _I, _I, _P, _P],
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOTYPES) + ("srb_last_error", "srb_hifigan_mrf_phases")

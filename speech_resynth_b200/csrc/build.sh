@@ -16,10 +16,10 @@ else
 fi
 mkdir -p ../../build
 pids=()
-for f in srb_convgemm srb_elementwise srb_attention srb_attention_tc srb_mrf_fused; do
+for f in srb_convgemm srb_elementwise srb_attention_tc srb_mrf_fused; do
   $NVCC $FLAGS $EXTRA -c $f.cu -o $OBJ/$f.o &
   pids+=($!)
 done
 for p in "${pids[@]}"; do wait $p; done
-$NVCC -shared -o $OUT $OBJ/srb_convgemm.o $OBJ/srb_elementwise.o $OBJ/srb_attention.o $OBJ/srb_attention_tc.o $OBJ/srb_mrf_fused.o -lcudart
+$NVCC -shared -o $OUT $OBJ/srb_convgemm.o $OBJ/srb_elementwise.o $OBJ/srb_attention_tc.o $OBJ/srb_mrf_fused.o -lcudart
 echo "built $(realpath $OUT)"

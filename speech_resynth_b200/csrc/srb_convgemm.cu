@@ -733,9 +733,10 @@ int srb_cfm_ffn_out_norm(const void* h_bf16, const void* w_packed, const float* 
 }
 
 int srb_cfm_pred_euler(const void* xn_bf16, const void* w_packed, float dt, float* xt, void* xt_bf16, float* mel,
-                       void* mel_bf16, float std, float mean, float pad_value, const int32_t* lengths, int32_t batch,
-                       int32_t frames, void* stream) {
+                       void* mel_bf16, int32_t mel_rows, float std, float mean, float pad_value, const int32_t* lengths,
+                       int32_t batch, int32_t frames, void* stream) {
   SRB_REQUIRE((mel == nullptr) == (mel_bf16 == nullptr), "srb_cfm_pred_euler: mel and mel_bf16 go together");
+  SRB_REQUIRE(mel == nullptr || (mel_rows > 0 && mel_rows <= frames), "srb_cfm_pred_euler: mel_rows must be in (0, frames]");
   ConvGemmDesc d;
   d.src[0] = act(xn_bf16, batch, frames, 256);
   d.weight = w_packed;
@@ -759,6 +760,7 @@ int srb_cfm_pred_euler(const void* xn_bf16, const void* w_packed, float dt, floa
   d.epi.f3 = pad_value;
   d.epi.aux0 = mel;
   d.epi.aux1 = mel_bf16;
+  d.epi.aux_rows = mel_rows;
   return launch_convgemm(d, (cudaStream_t)stream);
 }
 

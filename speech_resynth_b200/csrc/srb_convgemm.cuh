@@ -80,6 +80,7 @@ struct ConvGemmParams {
   float f0, f1, f2, f3;                           // EULER: dt, std, mean, pad
   void* aux0;                                     // EULER: mel fp32 (or null)
   void* aux1;                                     // EULER: mel bf16
+  int aux_rows;                                   // EULER: rows per utterance of the (compact) mel outputs; rows beyond are not written
 #ifdef SRB_TRACE
   unsigned long long* trace;                      // debug build only: %globaltimer stamps, see SRB_TRACE_AT
 #endif
@@ -750,10 +751,13 @@ __device__ __forceinline__ void euler_chunk(const uint32_t (&v)[N], int c0, floa
 // to_pred (N = 80) + Euler step in fp32 (models.py:183-184); last step also de-normalises and fills pads (:186-187)
 __device__ __forceinline__ void epi_euler(const ConvGemmParams& p, uint32_t tacc, const TileCoord& tc, int q) {
   const bool valid = q < p.group_rows[0];
-  const long long off = (long long)tc.b * p.out_batch_stride + (long long)q * p.out_row_stride;
-  float* xt = static_cast<float*>(p.out1) + off;
-  __nv_bfloat16* xtb = static_cast<__nv_bfloat16*>(p.out0) + off;
-  float* mel = static_cast<float*>(p.aux0);
+  const long long xoff = (long long)tc.b * p.out_batch_stride + (long long)q * p.out_row_stride;
+  float* xt = static_cast<float*>(p.out1) + xoff;
+  __nv_bfloat16* xtb = static_cast<__nv_bfloat16*>(p.out0) + xoff;
+  // the mel outputs are compact: aux_rows (<= frames) rows per utterance, what the vocoder must see
+  const bool has_mel = p.aux0 != nullptr && q < p.aux_rows;
+  const long long off = ((long long)tc.b * p.aux_rows + q) * p.out_row_stride;
+  float* mel = has_mel ? static_cast<float*>(p.aux0) : nullptr;
   __nv_bfloat16* melb = static_cast<__nv_bfloat16*>(p.aux1);
   const bool is_pad = valid && p.lengths != nullptr && q >= p.lengths[tc.b];
   const float dt = p.f0, sd = p.f1, mean = p.f2, padv = p.f3;

@@ -1,5 +1,5 @@
 // HBM-bound pieces of the path: embedding gather, conditioning tables, depthwise positional conv, prior
-// preparation, the 16->1 output conv + tanh and the length-aware copy-out.  CUDA-core kernels, vectorised and
+// preparation, the 16->1 output conv + tanh with its length-aware (cropping) store.  CUDA-core kernels, vectorised and
 // coalesced; none of them is GEMM shaped.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -33,20 +33,38 @@ __global__ void __launch_bounds__(256) embed_gather_kernel(const float4* __restr
   }
 }
 
-__global__ void unit_lengths_kernel(const int64_t* __restrict__ ids, int* __restrict__ lengths, int frames) {
+// lengths[b] = number of non-zero ids; extents[b] (optional) = index of the last non-zero id + 1.  The path masks by
+// prefix length, the reference by position (models.py:152): the two agree exactly when lengths == extents (right-padded
+// rows), which the host checks.
+__global__ void unit_lengths_kernel(const int64_t* __restrict__ ids, int* __restrict__ lengths, int* __restrict__ extents,
+                                    int frames) {
   pdl_launch_dependents();
   pdl_wait();
   const int b = blockIdx.x;
-  int cnt = 0;
-  for (int t = threadIdx.x; t < frames; t += blockDim.x) cnt += ids[(long long)b * frames + t] != 0;
-  __shared__ int s[32];
-  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = cnt;
+  int cnt = 0, ext = 0;
+  for (int t = threadIdx.x; t < frames; t += blockDim.x) {
+    const bool nz = ids[(long long)b * frames + t] != 0;
+    cnt += nz;
+    if (nz) ext = t + 1;
+  }
+  __shared__ int s[32], e[32];
+  for (int o = 16; o > 0; o >>= 1) {
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    ext = max(ext, __shfl_xor_sync(0xffffffffu, ext, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s[threadIdx.x >> 5] = cnt;
+    e[threadIdx.x >> 5] = ext;
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
-    int tot = 0;
-    for (int w = 0; w < (blockDim.x + 31) / 32; ++w) tot += s[w];
+    int tot = 0, mx = 0;
+    for (int w = 0; w < (blockDim.x + 31) / 32; ++w) {
+      tot += s[w];
+      mx = max(mx, e[w]);
+    }
     lengths[b] = tot;
+    if (extents != nullptr) extents[b] = mx;
   }
 }
 
@@ -93,20 +111,65 @@ __global__ void rotary_table_kernel(const float* __restrict__ inv_freq, int rows
   sn[i] = sinf(a);
 }
 
-__global__ void prior_prepare_kernel(float4* __restrict__ xt, uint2* __restrict__ xtb, long long n4, float tv) {
+// torch.clamp(x, -tv, tv) (models.py:169-170), including its min > max rule (the result is max) for a negative tv
+__device__ __forceinline__ float clamp_tv(float v, float tv) { return fminf(fmaxf(v, -tv), tv); }
+
+__global__ void prior_prepare_kernel(float4* __restrict__ xt, uint2* __restrict__ xtb, long long n4, float tv, int has_tv) {
   pdl_launch_dependents();
   pdl_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 v = xt[i];
-    if (tv > 0.f) {
-      v.x = fminf(fmaxf(v.x, -tv), tv);
-      v.y = fminf(fmaxf(v.y, -tv), tv);
-      v.z = fminf(fmaxf(v.z, -tv), tv);
-      v.w = fminf(fmaxf(v.w, -tv), tv);
+    if (has_tv) {
+      v.x = clamp_tv(v.x, tv);
+      v.y = clamp_tv(v.y, tv);
+      v.z = clamp_tv(v.z, tv);
+      v.w = clamp_tv(v.w, tv);
       xt[i] = v;
     }
     xtb[i] = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
   }
+}
+
+// Per-call input staging (one launch ahead of the captured graph): the caller's units (B, n) and prior sample (B, n, 80)
+// go into the plan's static buffers, whose rows are padded to n8 >= n: ids -> (B, n8) with zero (= pad) columns, prior ->
+// fp32 ODE state (B, n8, 80) with zero pad rows, clamped (models.py:169-170), plus its bf16 copy; two small regions the
+// loop relies on being zero (tail rows of the normalised activations, the attention norm bounds) are cleared.
+__global__ void __launch_bounds__(256) stage_inputs_kernel(const int64_t* __restrict__ ids_in, const float4* __restrict__ noise,
+                                                           int64_t* __restrict__ ids, float4* __restrict__ xt,
+                                                           uint2* __restrict__ xtb, uint4* __restrict__ zero_a, long long za16,
+                                                           uint4* __restrict__ zero_b, long long zb16, int batch, int n, int n8,
+                                                           float tv, int has_tv) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n_x = (long long)batch * n8 * 20;   // float4 pieces of the ODE state
+  for (long long i = tid; i < n_x; i += stride) {
+    const long long row = i / 20;
+    const int piece = (int)(i - row * 20);
+    const long long b = row / n8;
+    const int t = (int)(row - b * n8);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t < n) {
+      v = __ldg(noise + (b * n + t) * 20 + piece);
+      if (has_tv) {
+        v.x = clamp_tv(v.x, tv);
+        v.y = clamp_tv(v.y, tv);
+        v.z = clamp_tv(v.z, tv);
+        v.w = clamp_tv(v.w, tv);
+      }
+    }
+    xt[i] = v;
+    xtb[i] = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+  }
+  const long long n_ids = (long long)batch * n8;
+  for (long long i = tid; i < n_ids; i += stride) {
+    const long long b = i / n8;
+    const int t = (int)(i - b * n8);
+    ids[i] = t < n ? ids_in[b * n + t] : 0;
+  }
+  for (long long i = tid; i < za16; i += stride) zero_a[i] = make_uint4(0, 0, 0, 0);
+  for (long long i = tid; i < zb16; i += stride) zero_b[i] = make_uint4(0, 0, 0, 0);
 }
 
 // ------------------------------------------------------------------------------------------ duration prediction
@@ -114,6 +177,9 @@ __global__ void prior_prepare_kernel(float4* __restrict__ xt, uint2* __restrict_
 // (fastspeech/modules.py:87-107).  The Conv1d(768 -> 1, k 3) over embedding rows is linear in the rows, so it is
 // three lookups in a (3, vocab + 1) table of per-unit dot products (dur_table[tap][u] = <W[0, :, tap], E[u]>, built in
 // float64 at pack time) + bias.  One block per utterance; it also sums the durations (the expanded length).
+__device__ __forceinline__ int64_t dur_clamp_id(int64_t id, int vocab_rows) {
+  return id < 0 ? 0 : (id >= vocab_rows ? (int64_t)vocab_rows - 1 : id);
+}
 __global__ void __launch_bounds__(256) duration_predict_kernel(const int64_t* __restrict__ ids, const float* __restrict__ dur_table,
                                                                float bias, int* __restrict__ durations, int* __restrict__ totals,
                                                                int frames, int vocab_rows) {
@@ -124,10 +190,12 @@ __global__ void __launch_bounds__(256) duration_predict_kernel(const int64_t* __
   const int64_t* row = ids + (long long)b * frames;
   int sum = 0;
   for (int n = threadIdx.x; n < frames; n += blockDim.x) {
-    const int64_t u = row[n];
+    const int64_t u = dur_clamp_id(row[n], vocab_rows);
     int d = 0;
     if (u != 0) {
-      const int64_t um = n > 0 ? row[n - 1] : 0, up = n + 1 < frames ? row[n + 1] : 0;   // zero padding of the conv
+      // zero padding of the conv; ids outside [0, vocab_rows) are clamped like the gather kernel does
+      const int64_t um = n > 0 ? dur_clamp_id(row[n - 1], vocab_rows) : 0;
+      const int64_t up = n + 1 < frames ? dur_clamp_id(row[n + 1], vocab_rows) : 0;
       const float x = (dur_table[um] + dur_table[vocab_rows + u]) + (dur_table[2 * vocab_rows + up] + bias);
       const float r = rintf(expf(x) - 1.f);   // torch.round: half to even
       d = r > 0.f ? (r < 1048576.f ? (int)r : 1048576) : 0;
@@ -363,16 +431,30 @@ __device__ __forceinline__ void post_unpack(const uint4 u, float* f) {
   f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
   f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
 }
+// Ragged form (lengths != NULL): utterance b keeps its first n_b = min(rows, 320 * lengths[b] + 80) samples
+// (_get_waveform_lengths, models.py:211-221) and they are stored back to back: wav[sum_{i<b} n_i + t] -- the reference's
+// per-utterance crop loop (models.py:252-256) folded into the store.  Every block sums the (<= a few thousand) preceding
+// lengths itself, so no offset array has to travel to the device.
 __global__ void __launch_bounds__(128) post_tanh_kernel(const uint4* __restrict__ x, const float* __restrict__ w, float bias,
-                                                        float* __restrict__ wav, int rows) {
+                                                        float* __restrict__ wav, int rows, const int* __restrict__ lengths) {
   pdl_launch_dependents();
   pdl_wait();
   constexpr int kRows = kPostOutputs + 6;
   constexpr int kSlots = kRows + kRows / 8 + 1;
   __shared__ uint4 tile[2][kSlots];
   __shared__ __align__(16) float ws[7 * 16];
+  __shared__ long long off_s[4];
   const int b = blockIdx.y, t0 = blockIdx.x * kPostOutputs;
   if (threadIdx.x < 112) ws[threadIdx.x] = w[threadIdx.x];
+  int n_out = rows;
+  if (lengths != nullptr) {
+    n_out = min(rows, 320 * lengths[b] + 80);
+    if (t0 >= n_out) return;   // block-uniform: the whole block is beyond the utterance's end
+    long long part = 0;
+    for (int i = threadIdx.x; i < b; i += 128) part += min(rows, 320 * lengths[i] + 80);
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((threadIdx.x & 31) == 0) off_s[threadIdx.x >> 5] = part;
+  }
   const uint4* xb = x + (long long)b * rows * 2;
   for (int i = threadIdx.x; i < kRows * 2; i += 128) {
     const int r = i >> 1, t = t0 - 3 + r;
@@ -381,7 +463,7 @@ __global__ void __launch_bounds__(128) post_tanh_kernel(const uint4* __restrict_
   __syncthreads();
   const int r0 = 2 * threadIdx.x;        // window row of tap 0 of the first output
   const int t = t0 + r0;
-  if (t >= rows) return;
+  if (t >= n_out) return;
   float acc0 = bias, acc1 = bias;
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
@@ -397,25 +479,14 @@ __global__ void __launch_bounds__(128) post_tanh_kernel(const uint4* __restrict_
       for (int c = 0; c < 16; ++c) acc1 = fmaf(f[c], ws[(k - 1) * 16 + c], acc1);
     }
   }
-  float* o = wav + (long long)b * rows + t;
+  float* o = wav + (lengths != nullptr ? (off_s[0] + off_s[1]) + (off_s[2] + off_s[3]) : (long long)b * rows) + t;
   const float y0 = tanhf(acc0), y1 = tanhf(acc1);
-  if (t + 1 < rows && (reinterpret_cast<uintptr_t>(o) & 7) == 0) {
+  if (t + 1 < n_out && (reinterpret_cast<uintptr_t>(o) & 7) == 0) {
     *reinterpret_cast<float2*>(o) = make_float2(y0, y1);
   } else {
     o[0] = y0;
-    if (t + 1 < rows) o[1] = y1;
+    if (t + 1 < n_out) o[1] = y1;
   }
-}
-
-__global__ void crop_concat_kernel(const float* __restrict__ wav, const int* __restrict__ lengths,
-                                   const int64_t* __restrict__ offsets, float* __restrict__ dst, int rows) {
-  pdl_launch_dependents();
-  pdl_wait();
-  const int b = blockIdx.y;
-  const int n = 320 * lengths[b] + 80;  // models.py:211-221
-  const float* src = wav + (long long)b * rows;
-  float* d = dst + offsets[b];
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n && i < rows; i += gridDim.x * blockDim.x) d[i] = src[i];
 }
 
 }  // namespace srb
@@ -438,7 +509,13 @@ int srb_embed_gather(const float* table, const int64_t* ids, float* out, int64_t
 
 int srb_unit_lengths(const int64_t* ids, int32_t* lengths, int32_t batch, int32_t frames, void* stream) {
   if (batch <= 0) return 0;
-  SRB_CUDA(launch_pdl(unit_lengths_kernel, dim3(batch), dim3(256), 0, (cudaStream_t)stream, ids, lengths, frames));
+  SRB_CUDA(launch_pdl(unit_lengths_kernel, dim3(batch), dim3(256), 0, (cudaStream_t)stream, ids, lengths, (int*)nullptr, frames));
+  return after_launch("unit_lengths_kernel");
+}
+
+int srb_unit_extents(const int64_t* ids, int32_t* lengths, int32_t* extents, int32_t batch, int32_t frames, void* stream) {
+  if (batch <= 0) return 0;
+  SRB_CUDA(launch_pdl(unit_lengths_kernel, dim3(batch), dim3(256), 0, (cudaStream_t)stream, ids, lengths, extents, frames));
   return after_launch("unit_lengths_kernel");
 }
 
@@ -456,14 +533,34 @@ int srb_rotary_table(const float* inv_freq, int32_t rows, float* cos_out, float*
   return after_launch("rotary_table_kernel");
 }
 
-int srb_prior_prepare(float* xt, void* xt_bf16, int64_t n, float truncation, void* stream) {
+int srb_stage_inputs(const int64_t* ids_in, const float* prior_in, int64_t* ids, float* xt, void* xt_bf16, void* zero_a,
+                     int64_t zero_a_bytes, void* zero_b, int64_t zero_b_bytes, int32_t batch, int32_t frames_in,
+                     int32_t frames, float truncation, int32_t has_truncation, void* stream) {
+  SRB_REQUIRE(frames >= frames_in && frames_in > 0 && batch > 0, "srb_stage_inputs: need 0 < frames_in <= frames and batch > 0");
+  SRB_REQUIRE(((uintptr_t)prior_in & 15) == 0 && ((uintptr_t)xt & 15) == 0 && ((uintptr_t)xt_bf16 & 7) == 0,
+              "srb_stage_inputs: prior / state pointers must be 16-byte aligned");
+  SRB_REQUIRE(zero_a_bytes % 16 == 0 && zero_b_bytes % 16 == 0 && ((uintptr_t)zero_a & 15) == 0 && ((uintptr_t)zero_b & 15) == 0,
+              "srb_stage_inputs: cleared regions must be 16-byte aligned multiples of 16 bytes");
+  long long blocks = ((long long)batch * frames * 20 + 255) / 256;
+  const long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  SRB_CUDA(launch_pdl(stage_inputs_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, ids_in,
+                      reinterpret_cast<const float4*>(prior_in), ids, reinterpret_cast<float4*>(xt),
+                      reinterpret_cast<uint2*>(xt_bf16), static_cast<uint4*>(zero_a), (long long)(zero_a ? zero_a_bytes / 16 : 0),
+                      static_cast<uint4*>(zero_b), (long long)(zero_b ? zero_b_bytes / 16 : 0), (int)batch, (int)frames_in,
+                      (int)frames, truncation, (int)has_truncation));
+  return after_launch("stage_inputs_kernel");
+}
+
+int srb_prior_prepare(float* xt, void* xt_bf16, int64_t n, float truncation, int32_t has_truncation, void* stream) {
   SRB_REQUIRE(n % 4 == 0, "srb_prior_prepare: element count must be a multiple of 4");
   if (n <= 0) return 0;
   long long blocks = (n / 4 + 255) / 256;
   const long long cap = (long long)num_sms() * 8;
   if (blocks > cap) blocks = cap;
   SRB_CUDA(launch_pdl(prior_prepare_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream,
-                      reinterpret_cast<float4*>(xt), reinterpret_cast<uint2*>(xt_bf16), (long long)(n / 4), truncation));
+                      reinterpret_cast<float4*>(xt), reinterpret_cast<uint2*>(xt_bf16), (long long)(n / 4), truncation,
+                      (int)has_truncation));
   return after_launch("prior_prepare_kernel");
 }
 
@@ -515,19 +612,12 @@ int srb_cfm_posconv_norm(const float* x0, const float* dw_w, const float* dw_b, 
 }
 
 int srb_hifigan_post(const void* x_act, const float* w, float bias, float* wav, int32_t batch, int32_t rows,
-                     void* stream) {
+                     const int32_t* lengths, void* stream) {
   if (batch <= 0 || rows <= 0) return 0;
   dim3 grid((rows + kPostOutputs - 1) / kPostOutputs, batch);
-  SRB_CUDA(launch_pdl(post_tanh_kernel, grid, dim3(128), 0, (cudaStream_t)stream, static_cast<const uint4*>(x_act), w, bias, wav, rows));
+  SRB_CUDA(launch_pdl(post_tanh_kernel, grid, dim3(128), 0, (cudaStream_t)stream, static_cast<const uint4*>(x_act), w, bias, wav, rows,
+                      lengths));
   return after_launch("post_tanh_kernel");
-}
-
-int srb_crop_concat(const float* wav, const int32_t* lengths, const int64_t* offsets, float* dst, int32_t batch,
-                    int32_t rows, void* stream) {
-  if (batch <= 0) return 0;
-  dim3 grid((rows + 1023) / 1024, batch);
-  SRB_CUDA(launch_pdl(crop_concat_kernel, grid, dim3(256), 0, (cudaStream_t)stream, wav, lengths, offsets, dst, rows));
-  return after_launch("crop_concat_kernel");
 }
 
 }  // extern "C"

@@ -1,16 +1,28 @@
 """Host-side orchestration of the sm_100a kernels: the ODE loop and the HiFi-GAN generator as sequences of C-ABI
-calls on the current stream, captured once per (batch, frames, dt, truncation) bucket into a CUDA graph.
+calls on the current stream.
 
 Mirrors, step for step, the reference call stack:
 ConditionalFlowMatchingModel.sample (src/flow_matching/models.py:132-189) and
 FastSpeech2ConformerHifiGan.forward (HF:1451-1491).
+
+Memory and launch model
+  * ONE arena per device (`Arena`): every workspace of every (batch, frames) shape is carved from offset 0 of the
+    same buffer, so the footprint is that of the largest shape seen, not the sum over shapes.  Shapes run one after
+    the other on one stream, so aliasing them is safe; nothing in a workspace survives a call (the per-call staging
+    kernel re-establishes the few regions the loop needs zeroed).
+  * a shape's FIRST call runs its kernels eagerly (the host enqueues while the GPU still works on the previous
+    call); from its SECOND call on it is a CUDA graph.  Graphs live in an LRU of bounded size; a graph is only valid
+    for the arena generation it was captured in (growing the arena drops them all).
+  * results leave the arena inside the call: the last kernel (conv_post + tanh) is launched after the graph and
+    writes either the plan's dense (B, 320 N + 80) buffer or -- ragged form -- a fresh tensor holding the cropped
+    utterances back to back, which is what the public `forward` hands out.
 """
 from __future__ import annotations
 
-import math
 import os
-from dataclasses import dataclass
-from typing import Dict, List, Optional, Tuple
+from collections import OrderedDict
+from dataclasses import dataclass, field
+from typing import Callable, Dict, List, Optional, Tuple
 
 import torch
 
@@ -35,6 +47,60 @@ def _i32(vals) -> "nat.ctypes.Array":
     import ctypes
 
     return (ctypes.c_int32 * len(vals))(*vals)
+
+
+# ------------------------------------------------------------------------------------------------------ arena
+class Arena:
+    """The device buffer all workspaces are carved from (one per device, shared by every engine on it)."""
+
+    _by_device: Dict[int, "Arena"] = {}
+
+    def __init__(self, device: torch.device):
+        self.device = device
+        self.buf: Optional[torch.Tensor] = None
+        self.generation = 0
+
+    @classmethod
+    def get(cls, device: torch.device) -> "Arena":
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        a = cls._by_device.get(idx)
+        if a is None:
+            a = cls._by_device[idx] = Arena(torch.device("cuda", idx))
+        return a
+
+    @property
+    def nbytes(self) -> int:
+        return 0 if self.buf is None else self.buf.numel()
+
+    def ensure(self, nbytes: int) -> None:
+        """Grow to at least `nbytes`.  Growing invalidates every pointer handed out before (generation += 1): callers
+        compare generations and re-carve / re-capture."""
+        if self.nbytes >= nbytes:
+            return
+        torch.cuda.synchronize(self.device)      # kernels still in flight use the old buffer
+        if self.buf is not None:
+            self.buf = None                      # release before allocating: never hold both
+            torch.cuda.empty_cache()             # ... and hand the old block back to the driver (growth is rare)
+        self.buf = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        self.generation += 1
+
+
+class Carver:
+    """Bump allocation of 1 KB-aligned tensors; with `buf=None` it only measures."""
+
+    def __init__(self, buf: Optional[torch.Tensor], device: torch.device):
+        self.buf, self.device, self.off = buf, device, 0
+
+    def take(self, shape: Tuple[int, ...], dtype: torch.dtype) -> Optional[torch.Tensor]:
+        n = 1
+        for s in shape:
+            n *= int(s)
+        nbytes = n * torch.empty(0, dtype=dtype).element_size()
+        off = self.off
+        self.off = (off + nbytes + 1023) // 1024 * 1024
+        if self.buf is None:
+            return None
+        return self.buf[off: off + nbytes].view(dtype).view(*shape)
 
 
 class _Fork:
@@ -68,6 +134,21 @@ class _Fork:
             main.wait_event(ev)
 
 
+def padded_frames(frames: int) -> int:
+    """Frames are padded to a multiple of 8 inside the sampler (extra rows are ordinary pad frames: masked
+    everywhere, never visible to valid frames, dropped before the vocoder)."""
+    return (frames + 7) // 8 * 8
+
+
+def waveform_rows(frames: int) -> int:
+    """_get_waveform_lengths (models.py:211-221) for the padded frame count: 320*T + 80."""
+    rows = frames
+    for k, s in zip(UPSAMPLE_KERNELS, UPSAMPLE_RATES):
+        rows = (rows - 1) * s - 2 * ((k - s) // 2) + k
+    return rows
+
+
+# ------------------------------------------------------------------------------------------------------ sampler
 class CFMSampler:
     """ODE sampler over the flow-matching transformer velocity field (kernels: srb_cfm_*)."""
 
@@ -84,10 +165,12 @@ class CFMSampler:
     # -- tables -----------------------------------------------------------------------------------------------
     def rotary(self, rows: int) -> Tuple[torch.Tensor, torch.Tensor]:
         if self._rot is None or self._rot[0].shape[0] < rows:
-            n = max(rows, 1024)
+            n = max(rows, 4096)
             cs = torch.empty(n, 64, dtype=torch.float32, device=self.device)
             sn = torch.empty_like(cs)
             nat.call("srb_rotary_table", P(self.w.inv_freq), n, P(cs), P(sn))
+            # captured graphs hold raw pointers into earlier tables: those stay alive
+            self._rot_keep = getattr(self, "_rot_keep", []) + [(cs, sn)]
             self._rot = (cs, sn)
         return self._rot
 
@@ -128,53 +211,78 @@ class CFMSampler:
         return out, dur
 
     # -- workspace --------------------------------------------------------------------------------------------
-    def workspace(self, batch: int, frames: int) -> Dict[str, torch.Tensor]:
-        """`frames` must be a multiple of 8 (see `padded_frames`): the transposed-V operand of the attention kernel
-        is addressed by TMA per utterance and TMA needs 16-byte aligned box origins."""
+    def workspace(self, batch: int, frames: int, mel_rows: Optional[int] = None, carver: Optional[Carver] = None
+                  ) -> Dict[str, object]:
+        """Buffers of one (batch, frames) shape.  `frames` must be a multiple of 8 (see `padded_frames`): the
+        transposed-V operand of the attention kernel is addressed by TMA per utterance and TMA needs 16-byte aligned box
+        origins.  `mel_rows` (<= frames) is the caller's frame count: the mel outputs are compact (batch, mel_rows, 80).
+        With a `carver` the tensors are views of the arena (a measuring carver returns None entries); without one they are
+        stand-alone allocations (tests, tools)."""
         assert frames % 8 == 0, "CFMSampler.workspace: frames must be padded to a multiple of 8"
+        mel_rows = frames if mel_rows is None else mel_rows
+        assert 0 < mel_rows <= frames
         dev, m = self.device, batch * frames
         m_pad = (m + 255) // 256 * 256
-        f32 = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
-        b16 = lambda *s: torch.empty(*s, dtype=torch.bfloat16, device=dev)
-        return dict(
-            ids=torch.zeros(batch, frames, dtype=torch.int64, device=dev),
-            lengths=torch.zeros(batch, dtype=torch.int32, device=dev),
-            cond=f32(m, 256), xt=torch.zeros(batch, frames, 80, dtype=torch.float32, device=dev),
-            xt_b=b16(batch, frames, 80), x0=f32(m, 256), x=f32(m, 256),
-            # xn is also the B operand of the V^T GEMM, read in 256-row tiles: rows >= m stay zero forever
-            xn=torch.zeros(m_pad, 256, dtype=torch.bfloat16, device=dev),
-            qk=b16(m, 512), vt=b16(256, m_pad), o=b16(m, 256), h=b16(m, 896),
-            mel=f32(batch, frames, 80), mel_b=b16(batch, frames, 80),
+        c = carver if carver is not None else Carver(None, dev)
+        if carver is None:
+            take = lambda shape, dtype: torch.empty(*shape, dtype=dtype, device=dev)
+        else:
+            take = c.take
+        f32, b16 = torch.float32, torch.bfloat16
+        ws: Dict[str, object] = dict(
+            frames=frames, mel_rows=mel_rows, batch=batch, qk_calls=0,
+            ids=take((batch, frames), torch.int64), lengths=take((batch,), torch.int32),
+            cond=take((m, 256), f32), xt=take((batch, frames, 80), f32), xt_b=take((batch, frames, 80), b16),
+            x0=take((m, 256), f32), x=take((m, 256), f32),
+            # xn is also the B operand of the V^T GEMM, read in 256-row tiles: rows >= m are cleared by the staging kernel
+            xn=take((m_pad, 256), b16),
+            qk=take((m, 512), b16), vt=take((256, m_pad), b16), o=take((m, 256), b16), h=take((m, 896), b16),
+            mel=take((batch, mel_rows, 80), f32), mel_b=take((batch, mel_rows, 80), b16),
             # max |q|^2, |k|^2 per (utterance, head), recorded by qk_rope, read by the attention kernel; two buffers used
             # alternately by successive layers (each projection clears the other one for its successor)
-            qkmax=torch.zeros(2, batch, 2, 2, 2, dtype=torch.float32, device=dev),
+            qkmax=take((2, batch, 2, 2, 2), f32),
         )
+        return ws
 
     # -- the loop ---------------------------------------------------------------------------------------------
-    def prepare(self, ws: Dict[str, torch.Tensor], truncation: Optional[float]) -> None:
-        """mask/lengths (models.py:152), hoisted conditioning gather (:154,:175-176), prior clamp (:169-170)."""
+    def stage(self, ws: Dict[str, object], input_ids: torch.Tensor, noise: torch.Tensor,
+              truncation: Optional[float]) -> None:
+        """Per-call staging, ahead of the (captured) loop: the caller's ids / prior sample go into the static buffers
+        (rows padded to the workspace's frame count), the prior is clamped (models.py:169-170) and the zero regions the
+        loop relies on are re-established (the arena is shared between shapes)."""
+        b, n = input_ids.shape
+        n8 = ws["frames"]
+        assert b == ws["batch"] and n == ws["mel_rows"] and tuple(noise.shape) == (b, n, 80)
+        assert noise.dtype == torch.float32 and input_ids.dtype == torch.int64
+        xn, m = ws["xn"], b * n8
+        tail = xn[m:]
+        nat.call("srb_stage_inputs", P(input_ids.contiguous()), P(noise.contiguous()), P(ws["ids"]), P(ws["xt"]), P(ws["xt_b"]),
+                 P(tail) if tail.numel() else None, tail.numel() * 2, P(ws["qkmax"]), ws["qkmax"].numel() * 4, b, n, n8,
+                 float(truncation) if truncation is not None else 0.0, 0 if truncation is None else 1)
+        ws["qk_calls"] = 0
+
+    def prepare(self, ws: Dict[str, object]) -> None:
+        """mask/lengths (models.py:152) and the hoisted conditioning gather (:154,:175-176)."""
         b, n = ws["ids"].shape
         nat.call("srb_unit_lengths", P(ws["ids"]), P(ws["lengths"]), b, n)
         nat.call("srb_embed_gather", P(self.w.cond_table), P(ws["ids"]), P(ws["cond"]), b * n,
                  self.w.cond_table.shape[0], 256, nbytes=b * n * (2 * 256 * 4 + 8))
-        tv = float(truncation) if truncation is not None else 0.0
-        nat.call("srb_prior_prepare", P(ws["xt"]), P(ws["xt_b"]), b * n * 80, tv)
-        ws["qkmax"].zero_()
-        self._qk_calls = 0
+        ws["qk_calls"] = 0
 
-    def step(self, ws: Dict[str, torch.Tensor], g_step: torch.Tensor, dt: float, last: bool) -> None:
+    def step(self, ws: Dict[str, object], g_step: torch.Tensor, dt: float, last: bool) -> None:
         """One velocity evaluation + Euler update (models.py:173-184); `last` adds :186-187."""
         b, n = ws["ids"].shape
         w, L = self.w, ws["lengths"]
         cs, sn = self.rotary(n)
         m = b * n
-        nat.call("srb_cfm_embed", P(ws["xt_b"]), P(w.w_embed), P(ws["cond"]), P(ws["x0"]), b, n, flops=2.0 * m * 80 * 256)
+        nat.call("srb_cfm_embed", P(ws["xt_b"]), P(w.w_embed), P(ws["cond"]), P(ws["x0"]), b, n, flops=2.0 * m * 80 * 256,
+                 nbytes=m * (80 * 2 + 256 * 8))
         nat.call("srb_cfm_posconv_norm", P(ws["x0"]), P(w.dw_w), P(w.dw_b), P(g_step[0]), P(L), P(ws["x"]), P(ws["xn"]), b, n,
                  flops=2.0 * m * 31 * 256, nbytes=m * 256 * (4 + 4 + 2))
         for i in range(self.depth):
             m_pad = ws["vt"].shape[1]
-            qk_cur, qk_next = ws["qkmax"][self._qk_calls % 2], ws["qkmax"][(self._qk_calls + 1) % 2]
-            self._qk_calls += 1
+            qk_cur, qk_next = ws["qkmax"][ws["qk_calls"] % 2], ws["qkmax"][(ws["qk_calls"] + 1) % 2]
+            ws["qk_calls"] += 1
             # q|k projection and the transposed-v projection both read xn only: two parallel graph branches
             self.fork.run([
                 lambda: nat.call("srb_cfm_qk_rope", P(ws["xn"]), P(w.w_qkv[i]), P(cs), P(sn), P(ws["qk"]),
@@ -197,32 +305,20 @@ class CFMSampler:
         mel = P(ws["mel"]) if last else None
         mel_b = P(ws["mel_b"]) if last else None
         nat.call("srb_cfm_pred_euler", P(ws["xn"]), P(w.w_pred), float(dt), P(ws["xt"]), P(ws["xt_b"]), mel, mel_b,
-                 self.std, self.mean, pad_value_f32(), P(L), b, n, flops=2.0 * m * 256 * 80)
+                 ws["mel_rows"], self.std, self.mean, pad_value_f32(), P(L), b, n, flops=2.0 * m * 256 * 80,
+                 nbytes=m * (256 * 2 + 80 * (4 + 4 + 2)))
 
-    def run(self, ws: Dict[str, torch.Tensor], dt: float, truncation: Optional[float]) -> None:
-        """ids and the prior sample must already be in ws['ids'] / ws['xt']; result lands in ws['mel'], ws['mel_b']."""
+    def run(self, ws: Dict[str, object], dt: float) -> None:
+        """ids and the (clamped) prior sample must already be staged (`stage`); result lands in ws['mel'], ws['mel_b']."""
         times = ode_times(dt)
         g = self.cond_table(times)
-        self.prepare(ws, truncation)
+        self.prepare(ws)
         nfe = len(times)
         for s in range(nfe):
             self.step(ws, g[s], dt, last=(s == nfe - 1))
 
 
-def padded_frames(frames: int) -> int:
-    """Frames are padded to a multiple of 8 inside the sampler (extra rows are ordinary pad frames: masked
-    everywhere, never visible to valid frames, dropped before the vocoder)."""
-    return (frames + 7) // 8 * 8
-
-
-def waveform_rows(frames: int) -> int:
-    """_get_waveform_lengths (models.py:211-221) for the padded frame count: 320*T + 80."""
-    rows = frames
-    for k, s in zip(UPSAMPLE_KERNELS, UPSAMPLE_RATES):
-        rows = (rows - 1) * s - 2 * ((k - s) // 2) + k
-    return rows
-
-
+# ------------------------------------------------------------------------------------------------------ vocoder
 class HifiGanGenerator:
     """mel (B, T, 80) bf16 -> waveform (B, 320 T + 80) fp32 (kernels: srb_hifigan_*)."""
 
@@ -235,24 +331,35 @@ class HifiGanGenerator:
         self.fork = _Fork(packed.w_pre.device, 2)
         self.device = packed.w_pre.device
 
-    def workspace(self, batch: int, frames: int) -> Dict[str, object]:
+    def workspace(self, batch: int, frames: int, carver: Optional[Carver] = None) -> Dict[str, object]:
+        """Stage tensors of one (batch, frames) shape.  A stage run by the fused MRF kernel needs only the up-sampler
+        output and the stage output; the others add the activated copy and nine conv intermediates."""
         dev = self.device
-        b16 = lambda *s: torch.empty(*s, dtype=torch.bfloat16, device=dev)
-        ws: Dict[str, object] = {"pre": b16(batch, frames, 512)}
+        if carver is None:
+            take = lambda shape: torch.empty(*shape, dtype=torch.bfloat16, device=dev)
+        else:
+            take = lambda shape: carver.take(shape, torch.bfloat16)
+        ws: Dict[str, object] = {"batch": batch, "frames": frames, "pre": take((batch, frames, 512))}
         rows, c = frames, 512
         stages = []
-        for k, s in zip(UPSAMPLE_KERNELS, UPSAMPLE_RATES):
+        for i, (k, s) in enumerate(zip(UPSAMPLE_KERNELS, UPSAMPLE_RATES)):
             rows = (rows - 1) * s - 2 * ((k - s) // 2) + k
             c //= 2
-            st = dict(rows=rows, c=c, u_raw=b16(batch, rows, c), u_act=b16(batch, rows, c), out=b16(batch, rows, c),
-                      t=[b16(batch, rows, c) for _ in range(3)], xr=[b16(batch, rows, c) for _ in range(3)],
-                      xa=[b16(batch, rows, c) for _ in range(3)])
+            st = dict(rows=rows, c=c, u_raw=take((batch, rows, c)), out=take((batch, rows, c)))
+            if not (self.fuse_mrf and i in self.w.w_mrf):
+                st.update(u_act=take((batch, rows, c)), t=[take((batch, rows, c)) for _ in range(3)],
+                          xr=[take((batch, rows, c)) for _ in range(3)], xa=[take((batch, rows, c)) for _ in range(3)])
             stages.append(st)
         ws["stages"] = stages
-        ws["wav"] = torch.empty(batch, rows, dtype=torch.float32, device=dev)
+        ws["rows"] = rows
+        if carver is None:
+            ws["wav"] = torch.empty(batch, rows, dtype=torch.float32, device=dev)
+        else:
+            ws["wav"] = carver.take((batch, rows), torch.float32)
         return ws
 
     def run(self, mel_b: torch.Tensor, ws: Dict[str, object]) -> torch.Tensor:
+        """Everything up to (not including) conv_post: returns the leaky_relu(0.01)'ed last stage (B, 320 T + 80, 16)."""
         b, t, _ = mel_b.shape
         w = self.w
         one = _i32([7])
@@ -314,18 +421,28 @@ class HifiGanGenerator:
                      _i32([1, 1, 1]), P(w.w_tail[i]), P(w.b_tail[i]), P(res[0]), P(res[1]), P(res[2]), None, P(st["out"]),
                      b, rows, c, c, 1.0 / 3.0, slope_next, flops=2.0 * b * rows * sum(RESBLOCK_KERNELS) * c * c)
             x_act, rows_in, c_in = st["out"], rows, c
-        nat.call("srb_hifigan_post", P(x_act), P(w.w_post), w.b_post, P(ws["wav"]), b, rows_in,
-                 flops=2.0 * b * rows_in * 7 * 16, nbytes=b * rows_in * (16 * 2 + 4))
-        return ws["wav"]
+        return x_act
+
+    def post(self, x_act: torch.Tensor, wav: torch.Tensor, lengths: Optional[torch.Tensor] = None) -> None:
+        """conv_post + tanh (HF:1480-1482).  lengths=None: dense (B, rows) output; else ragged (see srb_hifigan_post)."""
+        b, rows, _ = x_act.shape
+        nat.call("srb_hifigan_post", P(x_act), P(self.w.w_post), self.w.b_post, P(wav), b, rows,
+                 P(lengths) if lengths is not None else None, flops=2.0 * b * rows * 7 * 16, nbytes=b * rows * (16 * 2 + 4))
 
 
+# ------------------------------------------------------------------------------------------------------ engine
 @dataclass
 class _Plan:
-    cfm_ws: Dict[str, torch.Tensor]
+    key: Tuple
+    generation: int
+    cfm_ws: Dict[str, object]
     voc_ws: Dict[str, object]
-    graph: Optional[torch.cuda.CUDAGraph]
-    body: object
-    n_launches: int
+    body: Callable[[], None]
+    graph: Optional[torch.cuda.CUDAGraph] = None
+    n_launches: int = 0
+    uses: int = 0
+    x_last: Optional[torch.Tensor] = None     # last stage's activated output (input of conv_post)
+    extra: Dict[str, object] = field(default_factory=dict)
 
 
 def build_sampler(state_dict: Dict[str, torch.Tensor], device, depth: int = 4, mean: float = -5.8843,
@@ -346,112 +463,171 @@ def build_vocoder(state_dict: Dict[str, torch.Tensor], device, slope: float = 0.
 
 
 class ResynthEngine:
-    """units -> waveform for one device.  One CUDA graph per (batch, frames, dt, truncation) bucket."""
+    """units -> waveform for one device.
 
-    def __init__(self, sampler: Optional[CFMSampler], vocoder: Optional[HifiGanGenerator], use_graphs: bool = True):
+    use_graphs: "auto" (default; a shape's first call is eager, later calls replay a CUDA graph), True (capture at the
+    first call), False (always eager).  max_graphs bounds the LRU of captured shapes."""
+
+    def __init__(self, sampler: Optional[CFMSampler], vocoder: Optional[HifiGanGenerator], use_graphs="auto",
+                 max_graphs: int = 48):
         nat.require_blackwell()
         self.sampler = sampler
         self.vocoder = vocoder
         self.device = (sampler or vocoder).device
+        env = os.environ.get("SRB_GRAPHS")
+        if env is not None:
+            use_graphs = {"0": False, "1": True}.get(env, "auto")
         self.use_graphs = use_graphs
-        self._plans: Dict[Tuple, _Plan] = {}
-        self._voc_plans: Dict[Tuple, Tuple] = {}
+        self.max_graphs = max_graphs
+        self.arena = Arena.get(self.device)
+        self._plans: "OrderedDict[Tuple, _Plan]" = OrderedDict()
+        self.stats = {"graphs_captured": 0, "eager_runs": 0, "graph_replays": 0, "plans_built": 0, "plans_evicted": 0}
 
-    def _plan(self, batch: int, frames: int, dt: float, truncation: Optional[float], with_vocoder: bool) -> _Plan:
-        key = (batch, frames, float(dt), truncation, with_vocoder)
-        plan = self._plans.get(key)
-        if plan is not None:
-            return plan
+    # -- memory -----------------------------------------------------------------------------------------------
+    def _layout(self, batch: int, frames: int, with_cfm: bool, with_vocoder: bool, carver: Carver):
         n8 = padded_frames(frames)
-        cfm_ws = self.sampler.workspace(batch, n8)
-        voc_ws = self.vocoder.workspace(batch, frames) if with_vocoder else {}
-        self.sampler.cond_table(ode_times(dt))
-        self.sampler.rotary(n8)
-        if with_vocoder and n8 != frames:
-            # the vocoder must see exactly the caller's frames (pad frames are vocoded, SURVEY.md section 8(e))
-            voc_ws["mel_in"] = torch.empty(batch, frames, 80, dtype=torch.bfloat16, device=self.device)
+        cfm_ws = self.sampler.workspace(batch, n8, mel_rows=frames, carver=carver) if with_cfm else {}
+        voc_ws: Dict[str, object] = {}
+        if with_vocoder:
+            voc_ws = self.vocoder.workspace(batch, frames, carver=carver)
+            if not with_cfm:
+                voc_ws["mel_b"] = carver.take((batch, frames, 80), torch.bfloat16)
+        return cfm_ws, voc_ws
+
+    def workspace_bytes(self, batch: int, frames: int, with_cfm: bool = True, with_vocoder: bool = True) -> int:
+        c = Carver(None, self.device)
+        self._layout(batch, frames, with_cfm, with_vocoder, c)
+        return c.off
+
+    def reserve(self, batch: int, frames: int, with_vocoder: bool = True) -> int:
+        """Size the arena for a (batch, frames) shape up front (a driver that knows its largest bucket calls this once
+        so that no later shape has to grow the arena and drop the captured graphs).  Returns the arena size."""
+        with torch.cuda.device(self.device):
+            self.arena.ensure(self.workspace_bytes(batch, frames, self.sampler is not None, with_vocoder and self.vocoder is not None))
+        return self.arena.nbytes
+
+    # -- plans ------------------------------------------------------------------------------------------------
+    def _plan(self, batch: int, frames: int, dt: Optional[float], with_cfm: bool, with_vocoder: bool) -> _Plan:
+        key = (batch, frames, None if dt is None else float(dt), with_cfm, with_vocoder)
+        plan = self._plans.get(key)
+        if plan is not None and plan.generation == self.arena.generation:
+            self._plans.move_to_end(key)
+            return plan
+        self.arena.ensure(self.workspace_bytes(batch, frames, with_cfm, with_vocoder))
+        # if the arena moved (now or through another engine on this device), older plans point into freed memory
+        for k in [k for k, p in self._plans.items() if p.generation != self.arena.generation]:
+            self._drop(k)
+        cfm_ws, voc_ws = self._layout(batch, frames, with_cfm, with_vocoder, Carver(self.arena.buf, self.device))
+        if with_cfm:
+            self.sampler.cond_table(ode_times(dt))
+            self.sampler.rotary(cfm_ws["frames"])
+        plan = _Plan(key, self.arena.generation, cfm_ws, voc_ws, body=lambda: None)
 
         def body():
-            self.sampler.run(cfm_ws, dt, truncation)
+            if with_cfm:
+                self.sampler.run(cfm_ws, dt)
             if with_vocoder:
-                mel_b = cfm_ws["mel_b"]
-                if n8 != frames:
-                    voc_ws["mel_in"].copy_(mel_b[:, :frames])
-                    mel_b = voc_ws["mel_in"]
-                self.vocoder.run(mel_b, voc_ws)
+                plan.x_last = self.vocoder.run(cfm_ws["mel_b"] if with_cfm else voc_ws["mel_b"], voc_ws)
 
-        graph, n_launches = None, 0
-        if self.use_graphs:
-            # warm-up run outside capture (configures kernel attributes, fills caches), then capture
-            cfm_ws["ids"].zero_()
-            cfm_ws["ids"][:, :frames].fill_(1)
-            # (private generator: the warm-up must not advance the global CUDA RNG, or the first call of a new shape
-            # would draw a different prior than the reference's torch.randn with the same seed)
-            cfm_ws["xt"].normal_(generator=torch.Generator(device=self.device).manual_seed(0))
-            body()
-            torch.cuda.current_stream().synchronize()
+        plan.body = body
+        self._plans[key] = plan
+        self.stats["plans_built"] += 1
+        while len(self._plans) > self.max_graphs:
+            self._drop(next(iter(self._plans)))
+        return plan
+
+    def _drop(self, key) -> None:
+        plan = self._plans.pop(key, None)
+        if plan is not None:
+            if plan.graph is not None:
+                plan.graph.reset()
+            self.stats["plans_evicted"] += 1
+
+    def _launch(self, plan: _Plan) -> None:
+        plan.uses += 1
+        if plan.graph is None and (self.use_graphs is True or (self.use_graphs == "auto" and plan.uses >= 2)):
+            # the previous (eager) call of this shape -- or, with use_graphs=True, the run below -- has configured the
+            # kernels' attributes; capture allocates nothing
+            if plan.uses == 1:
+                plan.body()
+                torch.cuda.current_stream().synchronize()
             graph = torch.cuda.CUDAGraph()
             c0 = nat.launch_count
             with torch.cuda.graph(graph):
-                body()
-            n_launches = nat.launch_count - c0   # recorded, not executed: counted again at every replay
+                plan.body()
+            plan.n_launches = nat.launch_count - c0   # recorded, not executed: counted again at every replay
             nat.launch_count = c0
-        plan = _Plan(cfm_ws, voc_ws, graph, body, n_launches)
-        self._plans[key] = plan
-        return plan
-
-    def _launch(self, plan: _Plan) -> None:
+            plan.graph = graph
+            self.stats["graphs_captured"] += 1
         if plan.graph is not None:
             plan.graph.replay()
             nat.launch_count += plan.n_launches
+            self.stats["graph_replays"] += 1
         else:
             plan.body()
+            self.stats["eager_runs"] += 1
 
-    def _run(self, input_ids, dt, truncation, noise, with_vocoder) -> _Plan:
-        assert input_ids.dim() == 2 and input_ids.dtype == torch.int64
+    def _run(self, input_ids: torch.Tensor, dt: float, truncation: Optional[float], noise: Optional[torch.Tensor],
+             with_vocoder: bool) -> _Plan:
+        assert input_ids.dim() == 2 and input_ids.dtype == torch.int64 and input_ids.is_cuda
         b, n = input_ids.shape
         with torch.cuda.device(self.device):
-            plan = self._plan(b, n, dt, truncation, with_vocoder)
-            plan.cfm_ws["ids"][:, :n].copy_(input_ids, non_blocking=True)
+            plan = self._plan(b, n, dt, True, with_vocoder)
             if noise is None:
                 # same call as the reference (models.py:168) so a seeded run draws the same prior on the same device
                 noise = torch.randn(b, n, 80, device=self.device)
-            plan.cfm_ws["xt"].zero_()
-            plan.cfm_ws["xt"][:, :n].copy_(noise, non_blocking=True)
+            self.sampler.stage(plan.cfm_ws, input_ids, noise, truncation)
             self._launch(plan)
         return plan
 
     def lengths_async(self, input_ids: torch.Tensor):
-        """Valid-frame counts of a batch on their way to the host, enqueued BEFORE the big graph so that the caller can wait
-        for them (event) while the graph is still running -- the public forward then never drains the GPU between calls.
-        srb_unit_lengths writes straight into pinned host memory (device-accessible under unified addressing): a D2H
-        copy would queue on the copy engine behind the previous call's 41 MB waveform read-back and hold up the graph
-        enqueued after it (measured: +0.8 ms per call).  Returns (pinned int32 tensor, event)."""
+        """Valid-frame counts (and extents, see srb_unit_extents) of a batch on their way to the host, enqueued BEFORE the
+        big graph so that the caller can wait for them (event) while the graph is still running -- the public forward
+        then never drains the GPU between calls.  The kernel writes straight into pinned host memory (device-accessible
+        under unified addressing): a D2H copy would queue on the copy engine behind the previous call's waveform
+        read-back and hold up the graph enqueued after it (measured: +0.8 ms per call).
+        Returns (pinned int32 (2, B) tensor [counts; extents], event)."""
         b, n = input_ids.shape
         slot = getattr(self, "_len_slot", 0)
-        self._len_slot = slot ^ 1
+        self._len_slot = (slot + 1) % 4
         bufs = getattr(self, "_len_bufs", None)
-        if bufs is None or bufs[0].shape[0] < b:
-            bufs = [torch.zeros(max(b, 64), dtype=torch.int32).pin_memory() for _ in range(2)]
+        if bufs is None or bufs[0].shape[1] < b:
+            bufs = [torch.zeros(2, max(b, 64), dtype=torch.int32).pin_memory() for _ in range(4)]
             self._len_bufs = bufs
         host_buf = bufs[slot]
         with torch.cuda.device(self.device):
-            nat.call("srb_unit_lengths", P(input_ids.contiguous()), host_buf.data_ptr(), b, n)
+            nat.call("srb_unit_extents", P(input_ids.contiguous()), host_buf[0].data_ptr(), host_buf[1].data_ptr(), b, n)
             ev = torch.cuda.Event()
             ev.record()
-        return host_buf[:b], ev
+        return host_buf[:, :b], ev
 
     def sample(self, input_ids: torch.Tensor, dt: float, truncation: Optional[float],
                noise: Optional[torch.Tensor] = None) -> torch.Tensor:
         """ConditionalFlowMatchingModel.sample: (B, N) int64 -> mel (B, N, 80) fp32 (a fresh tensor)."""
         plan = self._run(input_ids, dt, truncation, noise, with_vocoder=False)
-        return plan.cfm_ws["mel"][:, : input_ids.shape[1]].clone()
+        return plan.cfm_ws["mel"].clone()
 
     def resynthesize(self, input_ids: torch.Tensor, dt: float, truncation: Optional[float],
                      noise: Optional[torch.Tensor] = None):
-        """Returns (wav (B, 320 N + 80) fp32 [plan-owned buffer], lengths (B,) int32 device tensor, mel)."""
+        """Returns (wav (B, 320 N + 80) fp32, lengths (B,) int32 device tensor, mel (B, N, 80)) -- all three are views
+        of the arena, valid until the next call on this device."""
         plan = self._run(input_ids, dt, truncation, noise, with_vocoder=True)
-        return plan.voc_ws["wav"], plan.cfm_ws["lengths"], plan.cfm_ws["mel"][:, : input_ids.shape[1]]
+        with torch.cuda.device(self.device):
+            self.vocoder.post(plan.x_last, plan.voc_ws["wav"])
+        return plan.voc_ws["wav"], plan.cfm_ws["lengths"], plan.cfm_ws["mel"]
+
+    def resynthesize_ragged(self, input_ids: torch.Tensor, dt: float, truncation: Optional[float], total_samples: int,
+                            noise: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """The public forward's form: a 1-D tensor (fresh, or the caller's `out`) holding every utterance cropped to
+        320 len + 80 samples, back to back (the crop loop of models.py:252-256 happens in the last kernel's store).
+        `total_samples` = sum of those lengths (the caller knows the valid-frame counts on the host)."""
+        plan = self._run(input_ids, dt, truncation, noise, with_vocoder=True)
+        with torch.cuda.device(self.device):
+            if out is None:
+                out = torch.empty(total_samples, dtype=torch.float32, device=self.device)
+            assert out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and out.numel() >= total_samples
+            self.vocoder.post(plan.x_last, out, plan.cfm_ws["lengths"])
+        return out
 
     def vocode(self, mel: torch.Tensor) -> torch.Tensor:
         """decoder.vocoder(mel): (B, T, 80) float -> (B, 320 T + 80) fp32 (a fresh tensor)."""
@@ -460,31 +636,11 @@ class ResynthEngine:
             mel = mel.unsqueeze(0)
         b, t, _ = mel.shape
         with torch.cuda.device(self.device):
-            key = (b, t)
-            entry = self._voc_plans.get(key)
-            if entry is None:
-                ws = self.vocoder.workspace(b, t)
-                mel_b = torch.empty(b, t, 80, dtype=torch.bfloat16, device=self.device)
-                graph = None
-                if self.use_graphs:
-                    mel_b.zero_()
-                    self.vocoder.run(mel_b, ws)
-                    torch.cuda.current_stream().synchronize()
-                    graph = torch.cuda.CUDAGraph()
-                    c0 = nat.launch_count
-                    with torch.cuda.graph(graph):
-                        self.vocoder.run(mel_b, ws)
-                    n_launch = nat.launch_count - c0
-                else:
-                    n_launch = 0
-                entry = (ws, mel_b, graph, n_launch)
-                self._voc_plans[key] = entry
-            ws, mel_b, graph, n_launch = entry
-            mel_b.copy_(mel)  # fp32 -> bf16 (the reference's autocast would do the same cast at conv_pre)
-            if graph is not None:
-                graph.replay()
-                nat.launch_count += n_launch
-            else:
-                self.vocoder.run(mel_b, ws)
-            wav = ws["wav"].clone()
+            plan = self._plan(b, t, None, False, True)
+            mel32 = mel.to(device=self.device, dtype=torch.float32).contiguous()
+            # fp32 -> bf16 (the reference's autocast would do the same cast at conv_pre)
+            nat.call("srb_prior_prepare", P(mel32), P(plan.voc_ws["mel_b"]), mel32.numel(), 0.0, 0)
+            self._launch(plan)
+            wav = torch.empty(b, plan.voc_ws["rows"], dtype=torch.float32, device=self.device)
+            self.vocoder.post(plan.x_last, wav)
         return wav[0] if squeeze else wav

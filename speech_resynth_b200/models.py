@@ -105,6 +105,26 @@ def _reset_like_reference(module: nn.Module) -> None:
         module.reset_parameters()
 
 
+def _check_right_padded(counts, extents) -> None:
+    """counts = non-pad ids per row, extents = index of the last non-pad id + 1.  The reference masks per position
+    (input_ids.ne(0), models.py:152); the kernels take a prefix length per utterance.  Both agree for right-padded rows,
+    which is what every caller of the reference passes (synthesize.py:39-42, data.py:132,200)."""
+    if not bool((counts == extents).all()):
+        bad = [i for i, (c, e) in enumerate(zip(counts.tolist(), extents.tolist())) if c != e]
+        raise ValueError(f"input_ids rows {bad[:8]} contain pad ids (0) before their last unit: rows must be right-padded")
+    if int(counts.min()) <= 0:
+        raise ValueError("every row of input_ids needs at least one unit (the reference yields NaN for an all-pad row)")
+
+
+def _param_signature(module: nn.Module):
+    """Changes whenever a parameter / buffer is replaced or written in place (load_state_dict, load_adapter, manual
+    edits): the packed bf16 weights and captured graphs are rebuilt when it does."""
+    try:
+        return tuple((t.data_ptr(), t._version) for t in list(module.parameters()) + list(module.buffers()))
+    except RuntimeError:       # inference tensors carry no version counter
+        return tuple(t.data_ptr() for t in list(module.parameters()) + list(module.buffers()))
+
+
 def _fresh_state(module: nn.Module):
     return {k: v.detach() for k, v in module.state_dict().items()}
 
@@ -136,6 +156,7 @@ class ConditionalFlowMatchingModel(PreTrainedModel):
         self.duration_predictor = ConditionalFlowMatchingDurationPredictor(config.dim_cond_emb) if config.predict_duration else None
         self._sampler = None
         self._engine = None
+        self._sig = None
         self.post_init()
 
     def _init_weights(self, module):
@@ -157,9 +178,11 @@ class ConditionalFlowMatchingModel(PreTrainedModel):
 
     def sampler(self) -> "_engine.CFMSampler":
         dev = self.device
-        if self._sampler is None or self._sampler.device != dev:
+        sig = _param_signature(self)
+        if self._sampler is None or self._sampler.device != dev or self._sig != sig:
             sd = {"model." + k: v for k, v in _fresh_state(self).items()}
             self._sampler = _engine.build_sampler(sd, dev, depth=self.config.depth, mean=self.config.mean, std=self.config.std)
+            self._sig = sig
             self._engine = None
         return self._sampler
 
@@ -237,6 +260,7 @@ class HifiGanVocoder(PreTrainedModel):
         self.register_buffer("scale", torch.ones(config.model_in_dim))
         self._generator = None
         self._engine = None
+        self._sig = None
         self.post_init()
 
     def _init_weights(self, module):
@@ -256,9 +280,11 @@ class HifiGanVocoder(PreTrainedModel):
 
     def generator(self) -> "_engine.HifiGanGenerator":
         dev = self.device
-        if self._generator is None or self._generator.device != dev:
+        sig = _param_signature(self)
+        if self._generator is None or self._generator.device != dev or self._sig != sig:
             sd = {"vocoder." + k: v for k, v in _fresh_state(self).items()}
             self._generator = _engine.build_vocoder(sd, dev, slope=self.config.leaky_relu_slope)
+            self._sig = sig
             self._engine = None
         return self._generator
 
@@ -324,23 +350,51 @@ class ConditionalFlowMatchingWithHifiGan(PreTrainedModel):
         return spectrogram_lengths
 
     @torch.inference_mode()
+    def resynthesize_flat(self, input_ids: torch.LongTensor, dt: float = 0.1, truncation_value: Optional[float] = None,
+                          out: Optional[torch.Tensor] = None):
+        """The work of `forward`, returned as (flat, wav_lengths): `flat` is a fresh 1-D CUDA tensor holding the cropped
+        waveforms back to back (utterance i occupies wav_lengths[i] = 320 len_i + 80 samples).  Batch drivers use this form
+        (one read-back per bucket instead of one per utterance); with `out` (1-D float32 CUDA tensor of at least that
+        many samples) the waveforms are written there instead.
+
+        `input_ids` may live on the host: its valid-frame counts are then taken there and the call never waits for the
+        GPU.  For a CUDA tensor they are read back through pinned memory, enqueued ahead of the kernels (the reference
+        syncs once per utterance, models.py:252-256).  Rows must be right-padded (the reference's input convention,
+        synthesize.py:39-42): the kernels mask by length where the reference masks by position."""
+        dev = self.device
+        eng = self.engine()
+        if self.config.model_config.predict_duration:
+            input_ids, _ = self.model.sampler().regulate(input_ids.to(dev))     # models.py:157-164
+        if not input_ids.is_cuda:
+            nz = input_ids.ne(0)
+            counts = nz.sum(dim=1)
+            n = input_ids.shape[1]
+            extents = (nz * torch.arange(1, n + 1)).amax(dim=1) if n > 0 else counts
+            _check_right_padded(counts, extents)
+            ids = input_ids.to(dev, non_blocking=True)
+            wav_lengths = self._get_waveform_lengths(counts.to(torch.int64)).tolist()
+            flat = eng.resynthesize_ragged(ids, dt, truncation_value, sum(wav_lengths), out=out)
+            return flat, wav_lengths
+        ids = input_ids.to(dev)
+        host, ready = eng.lengths_async(ids)
+        ready.synchronize()     # waits for the length kernel only: it is queued ahead of this call's work
+        _check_right_padded(host[0], host[1])
+        wav_lengths = self._get_waveform_lengths(host[0].to(torch.int64)).tolist()
+        flat = eng.resynthesize_ragged(ids, dt, truncation_value, sum(wav_lengths), out=out)
+        return flat, wav_lengths
+
+    @torch.inference_mode()
     def forward(self, input_ids: torch.LongTensor, dt: float = 0.1, truncation_value: Optional[float] = None
                 ) -> List[torch.FloatTensor]:
         """Same contract as the reference (models.py:223-256): list of B tensors (1, 320 * len_i + 80).
 
         The valid-frame counts come from ``input_ids`` (the reference re-derives them by scanning the mel for the
-        exact pad value, models.py:245-247 -- identical result, see tests) and are read back once instead of once
-        per utterance.
+        exact pad value, models.py:245-247 -- identical result, see tests); the per-utterance crop (models.py:252-256)
+        happens in the last kernel's store, so the returned tensors are views of one fresh buffer.
         """
-        ids = input_ids.to(self.device)
-        if self.config.model_config.predict_duration:
-            ids, _ = self.model.sampler().regulate(ids)     # models.py:157-164
-        eng = self.engine()
-        # the lengths travel to the host ahead of the graph: waiting for them does not wait for the waveforms, so the
-        # next call can be enqueued while this one still runs (the reference syncs once per utterance, models.py:252-256)
-        lengths_host, ready = eng.lengths_async(ids)
-        wav, _, _ = eng.resynthesize(ids, dt, truncation_value)
-        wav = wav.clone()  # the engine's buffer is reused by the next call
-        ready.synchronize()
-        wav_lengths = self._get_waveform_lengths(lengths_host.to(torch.int64)).tolist()
-        return [wav[i, :n].unsqueeze(0) for i, n in enumerate(wav_lengths)]
+        flat, wav_lengths = self.resynthesize_flat(input_ids, dt, truncation_value)
+        outs, off = [], 0
+        for n in wav_lengths:
+            outs.append(flat[off: off + n].unsqueeze(0))
+            off += n
+        return outs

@@ -93,65 +93,199 @@ def assign_buckets(buckets: Sequence[Bucket], world: int, nfe: int = 16) -> List
     return out
 
 
-def pad_bucket(units: Sequence[torch.Tensor], bucket: Bucket) -> torch.Tensor:
+def contiguous_partition(lengths: Sequence[int], world: int, nfe: int = 16,
+                         shares: Optional[Sequence[float]] = None) -> List[List[int]]:
+    """Sort by length (descending) and cut the sorted list into `world` contiguous ranges whose modelled cost follows
+    `shares` (default: equal): rank 0 gets the longest utterances, the last rank the shortest.  Balanced to within one
+    utterance, and every rank's utterances are as homogeneous in length as the input allows (little padding inside
+    its buckets)."""
+    order = sorted(range(len(lengths)), key=lambda i: (-int(lengths[i]), i))
+    cost = [utterance_cost(int(lengths[i]), nfe) for i in order]
+    total = sum(cost)
+    shares = [1.0 / world] * world if shares is None else [s / sum(shares) for s in shares]
+    edges, run = [], 0.0
+    for s in shares:
+        run += s
+        edges.append(run * total)
+    out: List[List[int]] = [[] for _ in range(world)]
+    acc, r = 0.0, 0
+    for i, c in zip(order, cost):
+        # an utterance goes to the rank whose share contains its midpoint
+        while r + 1 < world and acc + 0.5 * c >= edges[r]:
+            r += 1
+        out[r].append(i)
+        acc += c
+    return out
+
+
+def tiles_per_utterance(frames: int) -> int:
+    """128-row GEMM tiles an utterance of `frames` (padded to a multiple of 8) occupies: tiles never span utterances."""
+    return ((frames + 7) // 8 * 8 + 127) // 128
+
+
+def _greedy_buckets(order: Sequence[int], lengths: Sequence[int], tile_budget: int, max_batch: int, max_waste: float,
+                    min_window: int) -> List[Bucket]:
+    buckets: List[Bucket] = []
+    cur: Optional[Bucket] = None
+    for i in order:
+        n = int(lengths[i])
+        if n <= 0:
+            raise ValueError("every utterance needs at least one unit (the reference yields NaN for empty rows)")
+        if cur is not None:
+            full = (cur.batch + 1) * tiles_per_utterance(cur.frames) > tile_budget or cur.batch >= max_batch
+            if full or cur.frames - n > max(min_window, int(max_waste * cur.frames)):
+                cur = None
+        if cur is None:
+            cur = Bucket([], n)
+            buckets.append(cur)
+        cur.indices.append(i)
+    return buckets
+
+
+def bucket_sorted(order: Sequence[int], lengths: Sequence[int], tile_budget: int = 296, max_batch: int = 160,
+                  max_waste: float = 0.12, min_window: int = 64) -> List[Bucket]:
+    """Buckets over utterances already sorted by descending length.  A bucket is padded to its first (longest) member
+    and closes when the next utterance would (a) push it past the tile budget (296 row tiles = two full waves of the
+    148 SMs for the kernels whose tile spans the whole width), (b) exceed `max_batch`, or (c) be padded by more than
+    max(min_window, max_waste * frames) frames.  The budget actually used is the smallest one that needs no more
+    buckets than `tile_budget` does: the same number of buckets, but evenly filled instead of full ones plus a
+    nearly empty straggler (every bucket costs ~1500 kernel launches however small it is)."""
+    order = list(order)
+    best = _greedy_buckets(order, lengths, tile_budget, max_batch, max_waste, min_window)
+    lo, hi = 1, tile_budget
+    while lo < hi:
+        mid = (lo + hi) // 2
+        trial = _greedy_buckets(order, lengths, mid, max_batch, max_waste, min_window)
+        if len(trial) <= len(best):
+            best, hi = trial, mid
+        else:
+            lo = mid + 1
+    return best
+
+
+@dataclass
+class ShardPlan:
+    buckets: List[Bucket]
+    per_rank: List[List[int]]          # bucket ids per rank, in execution order
+    cost: List[float]                  # modelled FLOPs per rank (padded buckets)
+
+    @property
+    def imbalance(self) -> float:
+        """max / mean of the modelled per-rank cost"""
+        mean = sum(self.cost) / max(len(self.cost), 1)
+        return max(self.cost) / mean if mean > 0 else 1.0
+
+
+def bucket_cost(bucket: Bucket, nfe: int = 16) -> float:
+    """Modelled cost of a bucket: the FLOPs of its PADDED shape (pad frames are computed like any other) plus a fixed
+    term for the ~1500 kernel launches every bucket pays however small it is (expressed in FLOPs at the rate the GPU
+    sustains on this path: ~0.7 PFLOP/s x ~3 ms)."""
+    return bucket.batch * utterance_cost(bucket.frames, nfe) + BUCKET_FIXED_FLOPS
+
+
+BUCKET_FIXED_FLOPS = 2.0e12
+
+
+def plan_shards(lengths: Sequence[int], world: int, nfe: int = 16, strategy: str = "contiguous", **bucket_args) -> ShardPlan:
+    """Every rank calls this with the same lengths and gets the same plan.
+    strategy "contiguous": cost-balanced contiguous ranges of the length-sorted list, bucketed per rank (`bucket_sorted`);
+    the range boundaries are refined for a few rounds against the cost of the buckets they produce (padding and the
+    per-bucket fixed cost differ between long and short ranges);
+    strategy "lpt": global buckets by length class (`bucket_by_length`) dealt to ranks longest-processing-time first."""
+    if strategy == "lpt":
+        buckets = bucket_by_length(lengths, **bucket_args)
+        per_rank = assign_buckets(buckets, world, nfe)
+        cost = [sum(bucket_cost(buckets[j], nfe) for j in ids) for ids in per_rank]
+        return ShardPlan(buckets, per_rank, cost)
+    if strategy != "contiguous":
+        raise ValueError(f"unknown sharding strategy {strategy!r}")
+    best: Optional[ShardPlan] = None
+    shares = [1.0] * world
+    for _ in range(8 if world > 1 else 1):
+        buckets, per_rank = [], []
+        for part in contiguous_partition(lengths, world, nfe, shares):
+            mine = bucket_sorted(part, lengths, **bucket_args) if part else []
+            per_rank.append(list(range(len(buckets), len(buckets) + len(mine))))
+            buckets.extend(mine)
+        cost = [sum(bucket_cost(buckets[j], nfe) for j in ids) for ids in per_rank]
+        plan = ShardPlan(buckets, per_rank, cost)
+        if best is None or plan.imbalance < best.imbalance:
+            best = plan
+        mean = sum(cost) / world
+        shares = [s * (mean / c if c > 0 else 1.0) ** 0.7 for s, c in zip(shares, cost)]
+    return best
+
+
+def pad_bucket(units: Sequence[torch.Tensor], bucket: Bucket, pin: bool = False) -> torch.Tensor:
     """Right-pad with 0 (ids are unit + 1, 0 = pad; synthesize.py:39-42) to the bucket's padded length."""
     ids = torch.zeros(bucket.batch, bucket.frames, dtype=torch.int64)
     for row, i in enumerate(bucket.indices):
         u = units[i].reshape(-1).to(torch.int64)
         ids[row, : u.numel()] = u
-    return ids
+    return ids.pin_memory() if pin else ids
 
 
-def resynthesize_sharded(units: Sequence[torch.Tensor], synth: Callable[[torch.Tensor], List[torch.Tensor]],
-                         rank: int = 0, world: int = 1, nfe: int = 16, granularity: int = 64, max_batch: int = 64,
-                         device: Optional[torch.device] = None, group=None) -> Optional[List[torch.Tensor]]:
-    """Run `synth(ids (B, N) int64) -> list of (1, L_i) waveforms` on this rank's buckets and gather on rank 0.
+def resynthesize_sharded(units: Sequence[torch.Tensor], synth: Optional[Callable[[torch.Tensor], List[torch.Tensor]]] = None,
+                         rank: int = 0, world: int = 1, nfe: int = 16, device: Optional[torch.device] = None, group=None,
+                         plan: Optional[ShardPlan] = None, strategy: str = "contiguous",
+                         synth_into: Optional[Callable[[torch.Tensor, torch.Tensor], None]] = None,
+                         on_plan: Optional[Callable[[ShardPlan], None]] = None, stats: Optional[dict] = None,
+                         **bucket_args) -> Optional[List[torch.Tensor]]:
+    """Run this rank's buckets through the local decoder and gather the cropped waveforms on rank 0.
 
-    Every rank passes the same `units` list (length-only metadata is enough to agree on the plan).  Returns the
-    waveforms in the caller's order on rank 0 and None elsewhere.
+    Every rank passes the same `units` list (length-only metadata is enough to agree on the plan).  Either
+    `synth(ids (B, N) int64) -> list of (1, L_i) waveforms` (the decoder's public call), or
+    `synth_into(ids, out)` which writes the bucket's cropped waveforms back to back into the 1-D view `out` of this
+    rank's gather buffer (no per-utterance tensors, no concatenation).  `ids` are host tensors (pinned when a device
+    is given): the decoder takes the valid-frame counts from them without waiting for the GPU.
+    `on_plan(plan)` runs before the first bucket (a driver sizes its arena there).  `stats`, when given, receives
+    `plan`, `buckets_run` and `local_samples`.  Returns the waveforms in the caller's order on rank 0, None elsewhere.
     """
     import torch.distributed as dist
 
     lengths = [int(u.numel()) for u in units]
-    buckets = bucket_by_length(lengths, granularity, max_batch)
-    plan = assign_buckets(buckets, world, nfe)
-    mine = plan[rank]
+    if plan is None:
+        plan = plan_shards(lengths, world, nfe, strategy=strategy, **bucket_args)
+    if on_plan is not None:
+        on_plan(plan)
+    buckets = plan.buckets
     wav_len = [320 * n + 80 for n in lengths]
-
-    local_idx: List[int] = []
-    local_wavs: List[torch.Tensor] = []
-    for j in mine:
-        b = buckets[j]
-        ids = pad_bucket(units, b)
-        if device is not None:
-            ids = ids.to(device)
-        outs = synth(ids)
-        for i, w in zip(b.indices, outs):
-            assert w.shape[-1] == wav_len[i], (w.shape, wav_len[i])
-            local_idx.append(i)
-            local_wavs.append(w.reshape(-1))
-    if world == 1:
-        out: List[Optional[torch.Tensor]] = [None] * len(units)
-        for i, w in zip(local_idx, local_wavs):
-            out[i] = w.unsqueeze(0)
-        return out  # type: ignore[return-value]
-
-    # final gather: every rank knows every rank's utterance list from the shared plan, so only samples move
-    per_rank_idx = [[i for j in plan[r] for i in buckets[j].indices] for r in range(world)]
+    per_rank_idx = [[i for j in plan.per_rank[r] for i in buckets[j].indices] for r in range(world)]
     sizes = [sum(wav_len[i] for i in idx) for idx in per_rank_idx]
     cap = max(max(sizes), 1)
-    dev = local_wavs[0].device if local_wavs else (device or torch.device("cpu"))
-    flat = torch.zeros(cap, dtype=torch.float32, device=dev)
-    if local_wavs:
-        torch.cat(local_wavs, out=flat[: sizes[rank]])
-    gathered = [torch.empty(cap, dtype=torch.float32, device=dev) for _ in range(world)] if rank == 0 else None
-    dist.gather(flat, gathered, dst=0, group=group)
-    if rank != 0:
-        return None
-    out = [None] * len(units)
+    dev = device if device is not None else torch.device("cpu")
+    # this rank's waveforms, back to back in plan order; padded to the largest rank's size for the gather
+    flat = torch.zeros(cap if world > 1 else sizes[rank], dtype=torch.float32, device=dev)
+
+    off = 0
+    for j in plan.per_rank[rank]:
+        b = buckets[j]
+        ids = pad_bucket(units, b, pin=dev.type == "cuda")
+        n_b = sum(wav_len[i] for i in b.indices)
+        if synth_into is not None:
+            synth_into(ids, flat[off: off + n_b])
+        else:
+            outs = synth(ids)
+            o = off
+            for i, w in zip(b.indices, outs):
+                assert w.shape[-1] == wav_len[i], (w.shape, wav_len[i])
+                flat[o: o + wav_len[i]].copy_(w.reshape(-1))
+                o += wav_len[i]
+        off += n_b
+    if stats is not None:
+        stats.update(plan=plan, buckets_run=len(plan.per_rank[rank]), local_samples=sizes[rank])
+
+    if world == 1:
+        gathered = [flat]
+    else:
+        gathered = [torch.empty(cap, dtype=torch.float32, device=dev) for _ in range(world)] if rank == 0 else None
+        dist.gather(flat, gathered, dst=0, group=group)
+        if rank != 0:
+            return None
+    out: List[Optional[torch.Tensor]] = [None] * len(units)
     for r in range(world):
-        off = 0
+        o = 0
         for i in per_rank_idx[r]:
-            out[i] = gathered[r][off: off + wav_len[i]].unsqueeze(0)
-            off += wav_len[i]
+            out[i] = gathered[r][o: o + wav_len[i]].unsqueeze(0)
+            o += wav_len[i]
     return out  # type: ignore[return-value]

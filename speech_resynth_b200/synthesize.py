@@ -6,8 +6,9 @@ wall clock.  Here the same work is pipelined:
 
 * utterances are length-bucketed (``sharding.bucket_by_length``: a bucket is padded to its longest member, exactly what
   ``pad_sequence`` gives the reference, ``synthesize.py:42``) so no bucket pays for another's padding;
-* every bucket's waveforms go device -> pinned host buffer on a second CUDA stream (two buffers in rotation) while the
-  next bucket computes;
+* a bucket's waveforms leave the last kernel already cropped and back to back (``resynthesize_flat``), so they go
+  device -> pinned host buffer as ONE copy on a second CUDA stream (two buffers in rotation) while the next bucket
+  computes; the unit ids stay on the host until the decoder copies them, so it never waits for the GPU;
 * a writer thread turns finished host buffers into RIFF/WAVE files (32-bit float PCM, what ``torchaudio.save`` writes for
   a float32 tensor; 16-bit on request).
 
@@ -110,21 +111,20 @@ def synthesize_units(decoder, units: Sequence[torch.Tensor], out_paths: Sequence
     n_samples = [0] * len(units)
     try:
         for b in buckets:
-            ids = sharding.pad_bucket(units, b).to(device, non_blocking=True)
-            wavs = decoder(ids, dt, truncation_value)               # list of (1, 320 len + 80), fresh storage
+            ids = sharding.pad_bucket(units, b, pin=True)
+            flat, wav_lengths = decoder.resynthesize_flat(ids, dt, truncation_value)   # cropped, back to back, fresh storage
             slot = free_slots.get()                                  # blocks only if both host buffers are still in use
             if writer.error is not None:
                 raise writer.error
             copy_stream.wait_stream(torch.cuda.current_stream(device))
             files, off = [], 0
+            for i, n in zip(b.indices, wav_lengths):
+                files.append((out_paths[i], off, n))
+                n_samples[i] = n
+                off += n
             with torch.cuda.stream(copy_stream):
-                for i, w in zip(b.indices, wavs):
-                    n = w.shape[-1]
-                    w.record_stream(copy_stream)
-                    hosts[slot][off: off + n].copy_(w[0], non_blocking=True)
-                    files.append((out_paths[i], off, n))
-                    n_samples[i] = n
-                    off += n
+                flat.record_stream(copy_stream)
+                hosts[slot][:off].copy_(flat[:off], non_blocking=True)
                 done = torch.cuda.Event()
                 done.record(copy_stream)
             writer.jobs.put((done, hosts[slot], files, slot))

@@ -1,11 +1,13 @@
 """End-to-end parity of the drop-in API on the GPU against (a) the committed golden vectors minted from the live
 reference and (b) the CPU oracle run on the same inputs.
 
-Stated tolerances (relative L2; bf16 tensor-core compute with fp32 accumulation, fp32 ODE state):
-  mel (valid frames, normalised units (mel - mean) / std)  <= 1.0e-2
-  waveform                                                 <= 3.0e-2
-SURVEY.md section 8(c) measured the reference's own bf16-autocast-vs-fp32 deviation at 7.5e-4 (mel, raw units) and
-3.0e-3 (waveform) on a short utterance; the raw-unit mel bound below (5e-3) is the survey's proposed figure.
+Stated tolerances (relative L2; bf16 tensor-core compute with fp32 accumulation, fp32 ODE state) -- about 3x what this
+path measures on a B200 (every comparison appends its measured error to gpurun_out/parity_errors.txt):
+  mel, valid frames, raw units                             <= MEL_TOL_RAW
+  mel, valid frames, normalised units (mel - mean) / std   <= MEL_TOL_NORM
+  waveform                                                 <= WAV_TOL
+and, where the golden manifest carries it, <= 3x the REFERENCE'S OWN bf16-autocast-vs-fp32 error on the same inputs
+(minted by oracle/make_golden.py: 7.5e-4 raw mel, 2.2e-3 normalised mel, 3.5e-3 waveform).
 """
 import json
 import os
@@ -20,12 +22,26 @@ from speech_resynth_b200 import synthetic
 pytestmark = pytest.mark.gpu
 
 MEAN, STD = -5.8843, 2.2615
-MEL_TOL_NORM, MEL_TOL_RAW, WAV_TOL = 1.0e-2, 5.0e-3, 3.0e-2
+MEL_TOL_NORM, MEL_TOL_RAW, WAV_TOL = 3.0e-3, 1.0e-3, 5.0e-3
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def rel_l2(a, b):
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def within(name, err, tol):
+    """assert err <= tol, leaving the measured figure in the test log and in gpurun_out/parity_errors.txt"""
+    line = f"{name}: measured {err:.3e}, tolerance {tol:.1e}"
+    print("[parity]", line)
+    try:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "parity_errors.txt"), "a") as f:
+            f.write(line + "\n")
+    except OSError:
+        pass
+    assert err == err and err <= tol, line
 
 
 @pytest.fixture(scope="module")
@@ -55,13 +71,19 @@ def test_resynthesis_matches_reference_golden(decoder, golden_dir, name):
     assert torch.equal(lengths.cpu().long(), valid.sum(1))
     # pads carry the exact float32 pad constant, like the reference (models.py:187)
     assert bool((mel[~valid] == oracle.pad_value()).all())
-    assert rel_l2(mel[valid], ref_mel[valid]) <= MEL_TOL_RAW
-    assert rel_l2((mel[valid] - MEAN) / STD, (ref_mel[valid] - MEAN) / STD) <= MEL_TOL_NORM
+    ac = info["bf16_autocast_vs_fp32"]      # the reference's own bf16 mode against its fp32 run, same inputs
+    e_raw = rel_l2(mel[valid], ref_mel[valid])
+    e_norm = rel_l2((mel[valid] - MEAN) / STD, (ref_mel[valid] - MEAN) / STD)
+    within(f"{name} mel raw", e_raw, min(MEL_TOL_RAW, 3 * ac["mel_raw"]))
+    within(f"{name} mel normalised", e_norm, min(MEL_TOL_NORM, 3 * ac["mel_normalised"]))
     ref_wavs = np.split(z["wav_flat"], np.cumsum(z["wav_lengths"])[:-1])
+    worst = 0.0
     for b, ref_w in enumerate(ref_wavs):
         n = len(ref_w)
         assert n == 320 * int(valid[b].sum()) + 80
-        assert rel_l2(wav[b, :n], torch.from_numpy(ref_w)) <= WAV_TOL
+        worst = max(worst, rel_l2(wav[b, :n], torch.from_numpy(ref_w)))
+    within(f"{name} waveform", worst, min(WAV_TOL, 3 * ac["wav"]))
+    # the public call on the same seeded prior: ragged output == the dense rows cropped (the crop is in the last kernel)
 
 
 def test_public_call_shapes_and_seeding(decoder, golden_dir):
@@ -87,14 +109,49 @@ def test_sample_matches_oracle_on_fresh_inputs(decoder, state_dict):
     ref = oracle.sample(state_dict, ids, x0, 0.125, 1.0)
     valid = ids.ne(0)
     assert bool((mel[~valid] == oracle.pad_value()).all())
-    assert rel_l2((mel[valid] - MEAN) / STD, (ref[valid] - MEAN) / STD) <= MEL_TOL_NORM
+    within("sample 4x96 NFE 8 mel normalised", rel_l2((mel[valid] - MEAN) / STD, (ref[valid] - MEAN) / STD), MEL_TOL_NORM)
+
+
+def test_public_call_equals_engine_rows_and_accepts_host_ids(decoder):
+    """decoder(ids) hands out the engine's dense rows cropped to 320 len + 80 (the crop happens in the last kernel's
+    store, models.py:252-256), bit for bit, whether the ids arrive on the host or on the device; truncation_value=None
+    and 0.0 are different things (models.py:169-170: None = no clamp, 0.0 = clamp everything to 0)."""
+    ids = synthetic.make_units(5, 77, seed=12, lengths=[77, 76, 40, 2, 1])
+    x0 = torch.randn(5, 77, 80, generator=torch.Generator().manual_seed(8)).cuda()
+    eng = decoder.engine()
+    wav, lens, _ = eng.resynthesize(ids.cuda(), 0.25, 1.0, noise=x0)
+    wav = wav.clone()
+    n_i = [320 * n + 80 for n in lens.cpu().tolist()]
+    flat = eng.resynthesize_ragged(ids.cuda(), 0.25, 1.0, sum(n_i), noise=x0)
+    off = 0
+    for i, n in enumerate(n_i):
+        assert torch.equal(flat[off: off + n], wav[i, :n])
+        off += n
+    for where in ("cpu", "cuda"):
+        torch.manual_seed(4)
+        a = decoder(ids.to(where), 0.25, 1.0)
+        torch.manual_seed(4)
+        ref_noise = torch.randn(5, 77, 80, device="cuda")
+        w2, _, _ = eng.resynthesize(ids.cuda(), 0.25, 1.0, noise=ref_noise)
+        assert [tuple(w.shape) for w in a] == [(1, n) for n in n_i]
+        assert all(torch.equal(a[i][0], w2[i, :n]) for i, n in enumerate(n_i))
+    none_, zero_ = eng.sample(ids.cuda(), 0.5, None, noise=x0), eng.sample(ids.cuda(), 0.5, 0.0, noise=x0)
+    assert not torch.equal(none_, zero_)
+    zeros = eng.sample(ids.cuda(), 0.5, 1.0, noise=torch.zeros_like(x0))
+    assert torch.equal(zero_, zeros)          # clamp(x, -0, 0) == 0: the all-zero prior
+    # rows must be right-padded: the reference masks per position, the kernels by prefix length
+    bad = ids.clone()
+    bad[1, 3] = 0
+    for where in ("cpu", "cuda"):
+        with pytest.raises(ValueError):
+            decoder(bad.to(where), 0.25, 1.0)
 
 
 def test_vocoder_matches_reference_golden(decoder, golden_dir):
     z, _ = _load(golden_dir, "vocoder_b2_t30")
     wav = decoder.vocoder(torch.from_numpy(z["mel"]).cuda())
     assert wav.shape == (2, 320 * 30 + 80)
-    assert rel_l2(wav, torch.from_numpy(z["wav"])) <= WAV_TOL
+    within("vocoder_b2_t30 waveform", rel_l2(wav, torch.from_numpy(z["wav"])), WAV_TOL)
 
 
 def test_velocity_field_matches_reference_golden(decoder, golden_dir, state_dict):
@@ -104,16 +161,16 @@ def test_velocity_field_matches_reference_golden(decoder, golden_dir, state_dict
     xt = torch.from_numpy(z["xt"])
     sampler = decoder.model.sampler()
     ws = sampler.workspace(2, 40)
-    ws["ids"].copy_(ids)
-    ws["xt"].copy_(xt)
+    ws["xn"].zero_()
     times = torch.tensor([float(z["t"])], dtype=torch.float32)
     g = sampler.cond_table(times)
-    sampler.prepare(ws, None)
+    sampler.stage(ws, ids.cuda(), xt.cuda(), None)
+    sampler.prepare(ws)
     sampler.step(ws, g[0], 1.0, last=False)
     torch.cuda.synchronize()
     v = (ws["xt"].cpu() - xt)
     valid = ids.ne(0)
-    assert rel_l2(v[valid], torch.from_numpy(z["v"])[valid]) <= 1.5e-2
+    within("velocity_b2_n40", rel_l2(v[valid], torch.from_numpy(z["v"])[valid]), 6e-3)
 
 
 def test_gather_matches_reference_fingerprint(decoder, golden_dir):
@@ -124,8 +181,10 @@ def test_gather_matches_reference_fingerprint(decoder, golden_dir):
     assert hashlib.sha256(emb.numpy().tobytes()).hexdigest() == info["sha256"]
 
 
-def test_full_size_properties(decoder):
-    """Config-2-sized call (64 x 500 frames, NFE 16): size-independent properties instead of an oracle run.
+def test_full_size_properties(decoder, state_dict):
+    """Config-2-sized call (64 x 500 frames, NFE 16): three rows of the batch against the CPU oracle run on exactly those
+    rows (same prior, same padded length -- the transformer is composition independent and the vocoder sees the same
+    pad frames), plus the size-independent properties on the whole batch.
     Batch-composition independence: an utterance synthesised inside the big batch equals the same utterance
     (same prior) synthesised in a batch of its own padded length, up to bf16 noise."""
     b, n = 64, 500
@@ -144,6 +203,14 @@ def test_full_size_properties(decoder):
         m = valid[i]
         assert rel_l2(mel2[j][m], mel[i][m]) <= 1e-3
     assert rel_l2(wav2[0], wav[0]) <= 1e-2
+    # rows 0 (500 frames), 61 (400) and 62 (123) of the 64 x 500 batch against the oracle
+    ref_mel = oracle.sample(state_dict, ids[sub].cpu(), x0[sub].cpu(), 0.0625, 1.0)
+    ref_wavs = oracle.resynthesize(state_dict, ids[sub].cpu(), x0[sub].cpu(), 0.0625, 1.0)
+    vs = valid[sub].cpu()
+    within("config2 64x500 NFE16 rows vs oracle: mel normalised",
+           rel_l2((mel[sub].cpu()[vs] - MEAN) / STD, (ref_mel[vs] - MEAN) / STD), MEL_TOL_NORM)
+    within("config2 64x500 NFE16 rows vs oracle: waveform",
+           max(rel_l2(wav[i, : r.shape[-1]], r[0]) for i, r in zip(sub, ref_wavs)), WAV_TOL)
 
 
 @pytest.mark.parametrize("b,n,lengths", [(12, 960, [960, 955, 951, 950, 949, 940, 930, 920, 915, 910, 905, 900]),
@@ -166,7 +233,7 @@ def test_graph_replays_are_bit_identical(decoder, b, n, lengths):
         assert torch.equal(wavs[0], w)
 
 
-def test_config3_bucketed_sharded_call_matches_per_bucket_calls(decoder):
+def test_config3_bucketed_sharded_call_matches_per_bucket_calls(decoder, state_dict):
     """BASELINE configs[2], scaled to one GPU: 96 utterances of 2-20 s through sharding.resynthesize_sharded (length
     buckets, caller order restored).  Parity is per bucket: every utterance must equal what
     its own padded bucket gives when synthesised directly with the same prior."""
@@ -181,19 +248,37 @@ def test_config3_bucketed_sharded_call_matches_per_bucket_calls(decoder):
 
     def synth(ids):
         torch.manual_seed(bucket_seed(ids))
-        return [w.clone() for w in decoder(ids, 0.25, 1.0)]
+        return decoder(ids, 0.25, 1.0)
 
-    outs = sharding.resynthesize_sharded(units, synth, rank=0, world=1, nfe=4, device=torch.device("cuda"))
+    stats = {}
+    outs = sharding.resynthesize_sharded(units, synth, rank=0, world=1, nfe=4, device=torch.device("cuda"), stats=stats,
+                                         tile_budget=148)
     assert [o.shape[-1] for o in outs] == [320 * n + 80 for n in lengths]
     assert all(bool(torch.isfinite(o).all()) and float(o.abs().max()) <= 1.0 for o in outs)
-    buckets = sharding.bucket_by_length(lengths)
-    assert sorted(i for b in buckets for i in b.indices) == list(range(96))
-    for b in buckets[:3] + buckets[-2:]:
+    buckets = stats["plan"].buckets
+    assert sorted(i for b in buckets for i in b.indices) == list(range(96)) and len(buckets) >= 4
+    for b in buckets[:2] + buckets[-2:]:
         ids = sharding.pad_bucket(units, b).cuda()
         torch.manual_seed(bucket_seed(ids))
         direct = decoder(ids, 0.25, 1.0)
         for i, w in zip(b.indices, direct):
             assert torch.equal(w, outs[i])
+    # the synth_into form (waveforms written straight into the gather buffer) gives the same samples
+    def synth_into(ids, out):
+        torch.manual_seed(bucket_seed(ids))
+        decoder.resynthesize_flat(ids, 0.25, 1.0, out=out)
+
+    outs2 = sharding.resynthesize_sharded(units, None, rank=0, world=1, nfe=4, device=torch.device("cuda"),
+                                          synth_into=synth_into, tile_budget=148)
+    assert all(torch.equal(a, b) for a, b in zip(outs, outs2))
+    # the shortest bucket against the oracle (same prior: drawn on the device like the decoder does)
+    bk = buckets[-1]
+    ids = sharding.pad_bucket(units, bk)
+    torch.manual_seed(bucket_seed(ids))
+    x0 = torch.randn(bk.batch, bk.frames, 80, device="cuda").cpu()
+    ref = oracle.resynthesize(state_dict, ids, x0, 0.25, 1.0)
+    within("config3 shortest bucket vs oracle: waveform",
+           max(rel_l2(outs[i], r) for i, r in zip(bk.indices, ref)), WAV_TOL)
 
 
 def test_config4_vocoder_alone_properties(decoder, state_dict):
@@ -209,14 +294,14 @@ def test_config4_vocoder_alone_properties(decoder, state_dict):
         alone = decoder.vocoder(mel[i: i + 1].cuda())
         assert rel_l2(alone[0], wav[i]) <= 1e-3
     ref = oracle.hifigan(state_dict, mel[:1].to(torch.bfloat16).float())
-    assert rel_l2(wav[0], ref[0]) <= WAV_TOL
+    within("config4 vocoder 48x500 row 0 vs oracle", rel_l2(wav[0], ref[0]), WAV_TOL)
 
 
 @pytest.mark.parametrize("nfe", [1, 4, 32])
 def test_config5_long_form_step_sweep(decoder, state_dict, nfe):
     """BASELINE configs[4]: 60 s utterances (3000 frames: 24 key tiles per attention row, rotary angles up to 3000 rad)
-    at several ODE step counts.  NFE 1 is checked against the CPU oracle; all of them for the size-independent
-    properties (finite, exact pad constant, waveform length rule, |wav| <= 1)."""
+    at several ODE step counts, every one against the CPU oracle's mel (NFE 1, 4 and 32; the oracle takes ~1 s per step
+    at this size), plus the size-independent properties (finite, exact pad constant, waveform length rule, |wav| <= 1)."""
     lengths = [3000, 2417]
     ids = synthetic.make_units(2, 3000, seed=41, lengths=lengths)
     x0 = torch.randn(2, 3000, 80, generator=torch.Generator().manual_seed(6))
@@ -227,9 +312,8 @@ def test_config5_long_form_step_sweep(decoder, state_dict, nfe):
     assert bool(torch.isfinite(wav).all()) and float(wav.abs().max()) <= 1.0
     valid = ids.ne(0)
     assert bool((mel[~valid] == oracle.pad_value()).all()) and bool(torch.isfinite(mel).all())
-    if nfe == 1:
-        ref = oracle.sample(state_dict, ids, x0, dt, 1.0)
-        assert rel_l2((mel[valid] - MEAN) / STD, (ref[valid] - MEAN) / STD) <= MEL_TOL_NORM
+    ref = oracle.sample(state_dict, ids, x0, dt, 1.0)
+    within(f"config5 2x3000 NFE {nfe} mel normalised", rel_l2((mel[valid] - MEAN) / STD, (ref[valid] - MEAN) / STD), MEL_TOL_NORM)
 
 
 def test_duration_prediction_variant_matches_reference_golden(state_dict, golden_dir):
@@ -253,20 +337,22 @@ def test_duration_prediction_variant_matches_reference_golden(state_dict, golden
     valid = exp_ids.ne(0).cpu()
     ref_mel = torch.from_numpy(z["mel"])
     assert tuple(mel.shape) == tuple(ref_mel.shape)
-    assert rel_l2((mel.cpu()[valid] - MEAN) / STD, (ref_mel[valid] - MEAN) / STD) <= MEL_TOL_NORM
+    within("duration_b3_n48 mel normalised", rel_l2((mel.cpu()[valid] - MEAN) / STD, (ref_mel[valid] - MEAN) / STD), MEL_TOL_NORM)
     outs = m(ids, 0.25, 1.0)                                   # public call: expansion inside, list of waveforms out
     assert [o.shape[-1] for o in outs] == info["wav_lengths"]
     ref_wavs = np.split(z["wav_flat"], np.cumsum(z["wav_lengths"])[:-1])
-    for b, ref_w in enumerate(ref_wavs):
-        assert rel_l2(wav[b, : len(ref_w)], torch.from_numpy(ref_w)) <= WAV_TOL
+    within("duration_b3_n48 waveform", max(rel_l2(wav[b, : len(r)], torch.from_numpy(r)) for b, r in enumerate(ref_wavs)), WAV_TOL)
     # all-zero rule of the length regulator (HF:113-114)
     out, dur = m.model.sampler().regulate(torch.zeros(2, 5, dtype=torch.int64, device="cuda"))
     assert out.shape == (2, 5) and int(dur.sum()) == 0 and int(out.sum()) == 0
 
 
-def test_synthesize_driver_writes_what_the_decoder_returns(decoder, tmp_path):
+def test_synthesize_driver_writes_what_the_decoder_returns(decoder, tmp_path, state_dict):
     """the pipelined batch driver (length buckets, read-back on a second stream, writer
-    thread) must write, for every utterance, exactly the waveform a direct per-bucket decoder call returns."""
+    thread) must write, for every utterance, exactly the waveform a direct per-bucket decoder call returns -- and those
+    files must hold what the ORACLE computes for the same bucket and prior (float32 RIFF/WAVE, rate 16000, mono:
+    what src/flow_matching/synthesize.py:52 writes with torchaudio.save; torchaudio's writer needs torchcodec, absent
+    here, so the container layout is checked through scipy's independent reader)."""
     from scipy.io import wavfile
 
     from speech_resynth_b200 import sharding
@@ -281,11 +367,23 @@ def test_synthesize_driver_writes_what_the_decoder_returns(decoder, tmp_path):
     assert n_samples == [320 * n + 80 for n in lengths]
     # replay the same bucket sequence with the same RNG stream
     torch.manual_seed(77)
-    for b in sharding.bucket_by_length(lengths, max_batch=8):
+    buckets = sharding.bucket_by_length(lengths, max_batch=8)
+    for b in buckets:
         outs = decoder(sharding.pad_bucket(units, b).cuda(), 0.25, 1.0)
         for i, w in zip(b.indices, outs):
             rate, y = wavfile.read(paths[i])
-            assert rate == 16000 and (torch.from_numpy(y) == w[0].cpu()).all()
+            assert rate == 16000 and y.dtype == np.float32 and y.ndim == 1 and (torch.from_numpy(y) == w[0].cpu()).all()
+    # the oracle on the first two buckets, with the prior the driver's RNG stream gave them
+    torch.manual_seed(77)
+    worst = 0.0
+    for b in buckets[:2]:
+        ids = sharding.pad_bucket(units, b)
+        x0 = torch.randn(b.batch, b.frames, 80, device="cuda").cpu()
+        for i, r in zip(b.indices, oracle.resynthesize(state_dict, ids, x0, 0.25, 1.0)):
+            _, y = wavfile.read(paths[i])
+            assert y.shape[0] == r.shape[-1]
+            worst = max(worst, rel_l2(torch.from_numpy(y), r[0]))
+    within("synthesize driver files vs oracle: waveform", worst, WAV_TOL)
 
 
 def test_log_mel_front_end_matches_reference_golden(golden_dir, decoder):

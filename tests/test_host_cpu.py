@@ -161,11 +161,43 @@ def _fake_synth(ids):
     return out
 
 
+def _fake_synth_into(ids, out):
+    off = 0
+    for w in _fake_synth(ids):
+        out[off: off + w.shape[-1]].copy_(w[0])
+        off += w.shape[-1]
+    assert off == out.numel()
+
+
 def test_single_rank_sharded_call_restores_caller_order():
     units = [torch.randint(1, 2001, (n,)) for n in (7, 300, 64, 65, 1)]
-    outs = sharding.resynthesize_sharded(units, _fake_synth, granularity=64)
-    for u, w in zip(units, outs):
-        assert tuple(w.shape) == (1, 320 * u.numel() + 80) and float(w[0, 0]) == float(u.sum())
+    for kw in (dict(strategy="lpt", granularity=64), dict(strategy="contiguous"), dict(strategy="contiguous", max_batch=2)):
+        outs = sharding.resynthesize_sharded(units, _fake_synth, **kw)
+        for u, w in zip(units, outs):
+            assert tuple(w.shape) == (1, 320 * u.numel() + 80) and float(w[0, 0]) == float(u.sum())
+
+
+def test_contiguous_plan_balances_cost_and_keeps_buckets_homogeneous():
+    """BASELINE configs[2] (1024 utterances of 2-20 s, seed 11): cost-balanced contiguous ranges of the sorted list."""
+    g = torch.Generator().manual_seed(11)
+    lengths = torch.randint(100, 1001, (1024,), generator=g).tolist()
+    for world in (1, 2, 4, 8):
+        plan = sharding.plan_shards(lengths, world, nfe=16)
+        assert sorted(i for b in plan.buckets for i in b.indices) == list(range(1024))
+        assert sorted(j for r in plan.per_rank for j in r) == list(range(len(plan.buckets)))
+        for b in plan.buckets:
+            ls = [lengths[i] for i in b.indices]
+            assert b.frames == max(ls) == ls[0] and ls == sorted(ls, reverse=True)
+            assert b.batch * sharding.tiles_per_utterance(b.frames) <= 296 and b.batch <= 160
+            assert b.frames - min(ls) <= max(64, int(0.12 * b.frames))
+        # rank r's utterances are all at least as long as rank r + 1's
+        mins = [min(lengths[i] for j in r for i in plan.buckets[j].indices) for r in plan.per_rank]
+        maxs = [max(lengths[i] for j in r for i in plan.buckets[j].indices) for r in plan.per_rank]
+        assert all(mins[r] >= maxs[r + 1] for r in range(world - 1))
+        assert plan.imbalance < 1.05, (world, plan.imbalance)
+        # padding overhead of the whole plan (padded frames / real frames)
+        padded = sum(b.batch * b.frames for b in plan.buckets)
+        assert padded / sum(lengths) < 1.08
 
 
 def _gloo_worker(rank, world, port, q):
@@ -174,7 +206,10 @@ def _gloo_worker(rank, world, port, q):
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     g = torch.Generator().manual_seed(5)
     units = [torch.randint(1, 2001, (int(n),), generator=g) for n in torch.randint(1, 200, (23,), generator=g)]
-    outs = sharding.resynthesize_sharded(units, _fake_synth, rank=rank, world=world, granularity=32, max_batch=4)
+    outs = sharding.resynthesize_sharded(units, _fake_synth, rank=rank, world=world, strategy="lpt", granularity=32, max_batch=4)
+    outs2 = sharding.resynthesize_sharded(units, None, rank=rank, world=world, max_batch=3, synth_into=_fake_synth_into)
+    if rank == 0:
+        assert all(torch.equal(a, b) for a, b in zip(outs, outs2))
     if rank == 0:
         ok = all(tuple(w.shape) == (1, 320 * u.numel() + 80) and float(w[0, 0]) == float(u.sum())
                  and float(w[0, -1]) == pytest.approx(float(u.sum()) + (320 * u.numel() + 79) * 1e-3, rel=1e-6)
