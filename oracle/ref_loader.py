@@ -16,6 +16,17 @@ import sys
 import types
 
 REFERENCE_ROOT = "/root/reference"
+# the unmodified reference files installed by oracle/install_reference.py (git-ignored, travels to the GPU box):
+# used by bench.py's reference arm when /root/reference itself is not mounted
+INSTALLED_ROOT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+
+
+def reference_root():
+    """Where the reference's `src` package can be imported from: the mounted tree, else the installed copy, else None."""
+    for root in (REFERENCE_ROOT, INSTALLED_ROOT):
+        if os.path.isfile(os.path.join(root, "src", "flow_matching", "models.py")):
+            return root
+    return None
 
 
 def available() -> bool:
@@ -24,8 +35,9 @@ def available() -> bool:
 
 def load_reference():
     """Returns (ConditionalFlowMatchingWithHifiGan, ConditionalFlowMatchingWithHifiGanConfig, ConditionalFlowMatchingConfig)."""
-    if not available():
-        raise RuntimeError("reference tree not present at " + REFERENCE_ROOT)
+    root = reference_root()
+    if root is None:
+        raise RuntimeError("reference tree not present at " + REFERENCE_ROOT + " nor installed under " + INSTALLED_ROOT)
     import transformers  # noqa: F401  (must precede the librosa stub)
     from transformers import FastSpeech2ConformerHifiGan  # noqa: F401
 
@@ -46,8 +58,8 @@ def load_reference():
         einx.multiply = multiply
         sys.modules["einx"] = einx
     sys.dont_write_bytecode = True
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+    if root not in sys.path:
+        sys.path.insert(0, root)
     from src.flow_matching.configs import ConditionalFlowMatchingConfig, ConditionalFlowMatchingWithHifiGanConfig
     from src.flow_matching.models import ConditionalFlowMatchingWithHifiGan
 

@@ -38,7 +38,14 @@ REFERENCE_VOCODER_KWARGS = dict(
 
 
 class ConditionalFlowMatchingConfig(PretrainedConfig):
-    def __init__(self, **kwargs: Any):
+    def __init__(self, *args: Any, **kwargs: Any):
+        """Positional arguments follow the reference's parameter order (configs.py:9-23: vocab_size, dim_in, ...)."""
+        if len(args) > len(_CFM_FIELDS):
+            raise TypeError(f"ConditionalFlowMatchingConfig takes at most {len(_CFM_FIELDS)} positional arguments ({len(args)} given)")
+        for (name, _), value in zip(_CFM_FIELDS, args):
+            if name in kwargs:
+                raise TypeError(f"ConditionalFlowMatchingConfig got multiple values for argument {name!r}")
+            kwargs[name] = value
         for name, default in _CFM_FIELDS:
             setattr(self, name, kwargs.pop(name, default))
         super().__init__(**kwargs)

@@ -130,6 +130,23 @@ def test_polyphase_packing_reproduces_conv_transpose(k, s):
     assert float((out - ref).abs().max()) <= 1e-12
 
 
+def test_config_accepts_the_reference_positional_order():
+    """The reference's config takes its 15 fields positionally (src/flow_matching/configs.py:7-24)."""
+    from speech_resynth_b200.configs import ConditionalFlowMatchingConfig
+
+    c = ConditionalFlowMatchingConfig(1000, 80, 768, 256, 4, 2, 896, 0.0, False, 31, 256, 0.0, -5.0, 2.0, True)
+    assert (c.vocab_size, c.mean, c.std, c.predict_duration, c.depth) == (1000, -5.0, 2.0, True, 4)
+    assert ConditionalFlowMatchingConfig(500, dim_in=80).vocab_size == 500
+    with pytest.raises(TypeError):
+        ConditionalFlowMatchingConfig(500, vocab_size=2000)
+    if os.path.isdir("/root/reference/src/flow_matching"):
+        from oracle import ref_loader
+
+        _, _, ref_cfg = ref_loader.load_reference()
+        assert ref_cfg(1000, 80, 768, 256, 4, 2, 896, 0.0, False, 31, 256, 0.0, -5.0, 2.0, True).to_dict().items() >= {
+            k: getattr(c, k) for k, _ in __import__("speech_resynth_b200.configs", fromlist=["_CFM_FIELDS"])._CFM_FIELDS}.items()
+
+
 # ------------------------------------------------------------------------------------------------ sharding
 def test_buckets_partition_and_pad_like_pad_sequence():
     g = torch.Generator().manual_seed(11)

@@ -50,13 +50,13 @@ if __name__ == "__main__":
     e = eng.ResynthEngine(decoder.model.sampler(), decoder.vocoder.generator(), use_graphs=False)
     sampler = e.sampler
     n8 = eng.padded_frames(n)
-    ws = sampler.workspace(b, n8)
-    ws["ids"][:, :n] = synthetic.make_units(b, n, seed=7).cuda()
-    ws["xt"].normal_()
+    ws = sampler.workspace(b, n8, mel_rows=n)
+    ws["xn"].zero_()
     g = sampler.cond_table(eng.ode_times(0.0625))
     sampler.rotary(n8)
     sampler.fork.enabled = False
-    sampler.prepare(ws, 1.0)
+    sampler.stage(ws, synthetic.make_units(b, n, seed=7).cuda(), torch.randn(b, n, 80, device="cuda"), 1.0)
+    sampler.prepare(ws)
     sampler.step(ws, g[0], 0.0625, last=False)     # warm: fills every buffer with real data
     torch.cuda.synchronize()
     trace = torch.zeros(8 * 3 * 8 * 4, dtype=torch.int64, device="cuda")
@@ -70,7 +70,7 @@ if __name__ == "__main__":
         "ffn_glu": lambda: nat.call("srb_cfm_ffn_glu", P(ws["xn"]), P(w.w_ff1[0]), P(w.b_ff1[0]), P(L), P(ws["h"]), b, n8),
         "ffn_out_norm": lambda: nat.call("srb_cfm_ffn_out_norm", P(ws["h"]), P(w.w_ff2[0]), P(w.b_ff2[0]), P(g[0][2]), 1, P(L), P(ws["x"]), P(ws["xn"]), b, n8),
         "embed": lambda: nat.call("srb_cfm_embed", P(ws["xt_b"]), P(w.w_embed), P(ws["cond"]), P(ws["x0"]), b, n8),
-        "pred_euler": lambda: nat.call("srb_cfm_pred_euler", P(ws["xn"]), P(w.w_pred), 0.0625, P(ws["xt"]), P(ws["xt_b"]), None, None, 2.26, -5.88, -11.5, P(L), b, n8),
+        "pred_euler": lambda: nat.call("srb_cfm_pred_euler", P(ws["xn"]), P(w.w_pred), 0.0625, P(ws["xt"]), P(ws["xt_b"]), None, None, n, 2.26, -5.88, -11.5, P(L), b, n8),
     }
     # attention: raw ordered stamps per role (see ATTN_STAMP in csrc/srb_attention_tc.cu)
     att = torch.zeros(4 * 3 * 256, dtype=torch.int64, device="cuda")
