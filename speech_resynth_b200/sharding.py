@@ -178,12 +178,13 @@ class ShardPlan:
 
 def bucket_cost(bucket: Bucket, nfe: int = 16) -> float:
     """Modelled cost of a bucket: the FLOPs of its PADDED shape (pad frames are computed like any other) plus a fixed
-    term for the ~1500 kernel launches every bucket pays however small it is (expressed in FLOPs at the rate the GPU
-    sustains on this path: ~0.7 PFLOP/s x ~3 ms)."""
+    term for the ~500 kernel launches every bucket pays however small it is.  Measured on a B200
+    (tools/calibrate_buckets.py, profiles/r02_bucket_calibration.jsonl): time = 5.0 ms + 1.17 ms / TFLOP from 2 x 687 to
+    64 x 500 frames, i.e. the fixed part is worth 4.3 TFLOP of marginal work."""
     return bucket.batch * utterance_cost(bucket.frames, nfe) + BUCKET_FIXED_FLOPS
 
 
-BUCKET_FIXED_FLOPS = 2.0e12
+BUCKET_FIXED_FLOPS = 4.3e12
 
 
 def plan_shards(lengths: Sequence[int], world: int, nfe: int = 16, strategy: str = "contiguous", **bucket_args) -> ShardPlan:

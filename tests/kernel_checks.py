@@ -579,18 +579,80 @@ def cfm_pred_euler():
     xt = torch.randn(b, n, 80, generator=g(13))
     xtd = xt.clone().to(DEV)
     xtb = torch.empty(b, n, 80, dtype=torch.bfloat16, device=DEV)
-    mel = torch.empty(b, n, 80, device=DEV)
-    melb = torch.empty(b, n, 80, dtype=torch.bfloat16, device=DEV)
+    # the mel outputs are compact: mel_rows = n - 3 rows per utterance (the caller's frame count), the rest is dropped
+    mr = n - 3
+    mel = torch.full((b, mr + 1, 80), 7.0, device=DEV)[:, :mr].contiguous()
+    melb = torch.empty(b, mr, 80, dtype=torch.bfloat16, device=DEV)
+    guard = torch.full((64,), 7.0, device=DEV)
     pv = oracle.pad_value()
     nat.call("srb_cfm_pred_euler", P(xn.to(DEV).to(torch.bfloat16).contiguous()), P(pk.w_pred), 0.0625, P(xtd), P(xtb),
-             P(mel), P(melb), 2.2615, -5.8843, pv, P(L), b, n)
+             P(mel), P(melb), mr, 2.2615, -5.8843, pv, P(L), b, n)
     w = bf(s["model.to_pred.weight"]).double()
     ref_xt = xt.double() + F.linear(xn.double(), w) * 0.0625
-    ref_mel = ref_xt * 2.2615 + (-5.8843)
-    pad_ok = bool((mel.cpu()[~mask] == pv).all())
-    e = max(rel_l2(xtd, ref_xt), rel_l2(mel.cpu()[mask], ref_mel[mask]), rel_l2(xtb.float(), ref_xt) / 400,
-            rel_l2(melb.float().cpu()[mask], ref_mel[mask]) / 400)
+    ref_mel = (ref_xt * 2.2615 + (-5.8843))[:, :mr]
+    mk = mask[:, :mr]
+    pad_ok = bool((mel.cpu()[~mk] == pv).all()) and bool((guard == 7.0).all())
+    e = max(rel_l2(xtd, ref_xt), rel_l2(mel.cpu()[mk], ref_mel[mk]), rel_l2(xtb.float(), ref_xt) / 400,
+            rel_l2(melb.float().cpu()[mk], ref_mel[mk]) / 400)
     return (e if pad_ok else 1.0), 2e-5
+
+
+@check
+def stage_inputs_bit_exact():
+    """per-call staging: ids / prior padded from n to n8 rows, clamp as torch.clamp, bf16 copy, cleared regions"""
+    b, n, n8 = 3, 37, 40
+    ids = synthetic.make_units(b, n, seed=2, lengths=[37, 20, 1])
+    x = torch.randn(b, n, 80, generator=g(1)) * 2
+    ok = True
+    for tv, has in ((1.0, 1), (0.0, 0), (0.0, 1), (-0.5, 1)):
+        ids_ws = torch.full((b, n8), 9, dtype=torch.int64, device=DEV)
+        xt = torch.full((b, n8, 80), 9.0, device=DEV)
+        xb = torch.full((b, n8, 80), 9.0, dtype=torch.bfloat16, device=DEV)
+        za = torch.full((48,), 9.0, device=DEV)
+        zb = torch.full((16,), 9.0, device=DEV)
+        nat.call("srb_stage_inputs", P(ids.to(DEV)), P(x.to(DEV)), P(ids_ws), P(xt), P(xb), P(za), 32 * 4, P(zb), 16 * 4, b, n, n8, tv, has)
+        ref = torch.zeros(b, n8, 80)
+        ref[:, :n] = torch.clamp(x, -tv, tv) if has else x
+        ref_ids = torch.zeros(b, n8, dtype=torch.int64)
+        ref_ids[:, :n] = ids
+        ok = ok and torch.equal(xt.cpu(), ref) and torch.equal(xb.cpu(), ref.to(torch.bfloat16)) and torch.equal(ids_ws.cpu(), ref_ids)
+        ok = ok and bool((za[:32] == 0).all()) and bool((za[32:] == 9).all()) and bool((zb == 0).all())
+    return (0.0 if ok else 1.0), 0.0
+
+
+@check
+def unit_extents_exact():
+    ids = synthetic.make_units(4, 50, seed=3, lengths=[50, 1, 49, 17])
+    ids[2, 10] = 0                       # an interior pad: count 48, extent 49
+    cnt = torch.empty(4, dtype=torch.int32, device=DEV)
+    ext = torch.empty(4, dtype=torch.int32, device=DEV)
+    nat.call("srb_unit_extents", P(ids.to(DEV)), P(cnt), P(ext), 4, 50)
+    ok = cnt.cpu().tolist() == [50, 1, 48, 17] and ext.cpu().tolist() == [50, 1, 49, 17]
+    return (0.0 if ok else 1.0), 0.0
+
+
+@check
+def hifigan_post_ragged_equals_dense_rows():
+    """conv_post + tanh: the ragged store (utterances cropped to 320 len + 80, back to back) == the dense rows cropped"""
+    s = sd()
+    pk = packing.pack_vocoder(s, DEV)
+    b, rows = 5, 320 * 30 + 80
+    x = (torch.randn(b, rows, 16, generator=g(4)) * 0.5).to(torch.bfloat16).to(DEV)
+    dense = torch.empty(b, rows, device=DEV)
+    nat.call("srb_hifigan_post", P(x), P(pk.w_post), pk.b_post, P(dense), b, rows, None)
+    lens = [30, 7, 29, 1, 30]
+    L = torch.tensor(lens, dtype=torch.int32, device=DEV)
+    total = sum(320 * n + 80 for n in lens)
+    flat = torch.full((total + 8,), 7.0, device=DEV)
+    nat.call("srb_hifigan_post", P(x), P(pk.w_post), pk.b_post, P(flat), b, rows, P(L))
+    ok, off = bool((flat[total:] == 7.0).all()), 0
+    for i, n in enumerate(lens):
+        k = 320 * n + 80
+        ok = ok and torch.equal(flat[off: off + k], dense[i, :k])
+        off += k
+    w = s["vocoder.conv_post.weight"].double()
+    ref = torch.tanh(F.conv1d(x.cpu().double().transpose(1, 2), w, s["vocoder.conv_post.bias"].double(), padding=3))[:, 0]
+    return (rel_l2(dense, ref) if ok else 1.0), 1e-5
 
 
 def run_all(verbose: bool = True) -> List[Tuple[str, float, float, str]]:
