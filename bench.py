@@ -321,12 +321,12 @@ def config3_run(decoder, dev, rank, world, passes: int = 4):
         e1.record()
         torch.cuda.synchronize()
         host_ms = (time.perf_counter() - t0) * 1e3
-        ms = torch.tensor([e0.elapsed_time(e1), host_ms], device=dev)
+        ms = torch.tensor([e0.elapsed_time(e1), host_ms, e0.elapsed_time(stats["local_done"])], device=dev)
         allms = [torch.zeros_like(ms) for _ in range(world)] if world > 1 else [ms]
         if world > 1:
             dist.all_gather(allms, ms)
         dev_ms = [float(m[0]) for m in allms]
-        rec.append({"ms": max(dev_ms), "ms_per_rank": dev_ms, "host_ms_per_rank": [float(m[1]) for m in allms],
+        rec.append({"ms": max(dev_ms), "local_ms_per_rank": [float(m[2]) for m in allms], "host_ms_per_rank": [float(m[1]) for m in allms],
                     "graphs_captured": eng.stats["graphs_captured"] - s0["graphs_captured"],
                     "eager_runs": eng.stats["eager_runs"] - s0["eager_runs"],
                     "graph_replays": eng.stats["graph_replays"] - s0["graph_replays"]})
@@ -337,7 +337,7 @@ def config3_run(decoder, dev, rank, world, passes: int = 4):
     secs = audio_seconds(lengths)
     steady = min(r["ms"] for r in rec[2:]) if len(rec) > 2 else rec[-1]["ms"]
     best = min(rec[2:], key=lambda r: r["ms"]) if len(rec) > 2 else rec[-1]
-    mean_t = sum(best["ms_per_rank"]) / world
+    mean_t = sum(best["local_ms_per_rank"]) / world
     flops = sum(sharding.transformer_flops(n, 16) + sharding.vocoder_flops(n) for n in lengths)
     padded_flops = sum(b.batch * (sharding.transformer_flops(b.frames, 16) + sharding.vocoder_flops(b.frames)) for b in plan.buckets)
     return {
@@ -348,7 +348,7 @@ def config3_run(decoder, dev, rank, world, passes: int = 4):
         "cold_value": secs / (rec[0]["ms"] / 1e3), "passes": rec,
         "buckets": len(plan.buckets), "buckets_per_rank": [len(r) for r in plan.per_rank],
         "bucket_shapes_rank0": [[b.batch, b.frames] for b in mine][:12],
-        "load": {"model_max_over_mean": plan.imbalance, "measured_max_over_mean": max(best["ms_per_rank"]) / mean_t},
+        "load": {"model_max_over_mean": plan.imbalance, "measured_max_over_mean": max(best["local_ms_per_rank"]) / mean_t},
         "algorithmic_tflop": flops / 1e12, "padded_tflop": padded_flops / 1e12,
         "achieved_tflops_per_gpu": flops / (steady / 1e3) / 1e12 / world,
         "arena_gb": eng.arena.nbytes / 2 ** 30,

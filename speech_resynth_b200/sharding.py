@@ -240,7 +240,7 @@ def resynthesize_sharded(units: Sequence[torch.Tensor], synth: Optional[Callable
     rank's gather buffer (no per-utterance tensors, no concatenation).  `ids` are host tensors (pinned when a device
     is given): the decoder takes the valid-frame counts from them without waiting for the GPU.
     `on_plan(plan)` runs before the first bucket (a driver sizes its arena there).  `stats`, when given, receives
-    `plan`, `buckets_run` and `local_samples`.  Returns the waveforms in the caller's order on rank 0, None elsewhere.
+    `plan`, `buckets_run`, `local_samples` and (CUDA) `local_done`, an event recorded after this rank's last bucket, before the gather.  Returns the waveforms in the caller's order on rank 0, None elsewhere.
     """
     import torch.distributed as dist
 
@@ -275,6 +275,11 @@ def resynthesize_sharded(units: Sequence[torch.Tensor], synth: Optional[Callable
         off += n_b
     if stats is not None:
         stats.update(plan=plan, buckets_run=len(plan.per_rank[rank]), local_samples=sizes[rank])
+        if dev.type == "cuda":
+            # this rank's own work ends here (the gather below waits for the slowest rank): lets a driver measure the load balance
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            stats["local_done"] = ev
 
     if world == 1:
         gathered = [flat]

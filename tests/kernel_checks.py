@@ -336,7 +336,7 @@ def post_tanh():
     b = 0.05
     y = torch.tanh(F.conv1d(x.transpose(1, 2).double(), w.double(), torch.tensor([b]).double(), padding=3)).squeeze(1)
     wav = torch.empty(2, 1000, device=DEV)
-    nat.call("srb_hifigan_post", P(x.to(DEV).to(torch.bfloat16).contiguous()), P(w[0].t().contiguous().to(DEV)), b, P(wav), 2, 1000)
+    nat.call("srb_hifigan_post", P(x.to(DEV).to(torch.bfloat16).contiguous()), P(w[0].t().contiguous().to(DEV)), b, P(wav), 2, 1000, None)
     return rel_l2(wav, y), F32_TOL
 
 
