@@ -100,9 +100,12 @@ int srb_cfm_embed(const void* xt_bf16, const void* w_packed, const float* cond_p
 int srb_cfm_posconv_norm(const float* x0, const float* dw_w, const float* dw_b, const float* g, const int32_t* lengths,
                          float* x, void* xn_bf16, int32_t batch, int32_t frames, void* stream);
 
-/* to_qkv + rotary on q,k (transformer.py:109-113): qkv (B, N, 768) bf16 = rope(xn @ Wqkv^T) */
+/* to_qkv + rotary on q,k (transformer.py:109-113): qkv (B, N, 768) bf16 = [rope(q) | rope(k) | v] = xn @ Wqkv^T.
+ * rot_cos / rot_sin: (rows, 64) fp32 tables of srb_rotary_table with rows >= max(frames, 32).  qk_norm2_max /
+ * qk_norm2_clear (both nullable): the norm bounds described at srb_cfm_qk_rope below. */
 int srb_cfm_qkv_rope(const void* xn_bf16, const void* w_packed, const float* rot_cos, const float* rot_sin,
-                     void* qkv_bf16, int32_t batch, int32_t frames, void* stream);
+                     void* qkv_bf16, float* qk_norm2_max, float* qk_norm2_clear, int32_t batch, int32_t frames,
+                     void* stream);
 
 /* tcgen05 attention path (to_qkv, rotary, masked softmax attention: transformer.py:109-127):
  *   srb_cfm_qk_rope      : qk (B, N, 512) bf16 = rope(xn @ Wqk^T), Wqk = first 512 rows of to_qkv.weight.  rot_cos /
@@ -127,7 +130,6 @@ int srb_cfm_qk_rope(const void* xn_bf16, const void* w_packed, const float* rot_
 int srb_cfm_v_transposed(const void* xn_bf16, const void* wv_bf16, void* vt_bf16, int64_t m_pad, void* stream);
 int srb_cfm_attention_tc(const void* qk_bf16, int32_t ld, const void* vt_bf16, int64_t m_pad, const int32_t* lengths,
                          const float* qk_norm2_max, void* o_bf16, int32_t batch, int32_t frames, void* stream);
-
 /* to_out + residual (transformer.py:129-130,203) fused with the following AdaptiveRMSNorm:
  *   x += o @ Wout^T ; xn = bf16(adanorm(x, g)) * mask */
 int srb_cfm_attn_out_norm(const void* o_bf16, const void* w_packed, const float* g, const int32_t* lengths, float* x,

@@ -575,7 +575,9 @@ int srb_cfm_embed(const void* xt_bf16, const void* w_packed, const float* cond_p
 }
 
 int srb_cfm_qkv_rope(const void* xn_bf16, const void* w_packed, const float* rot_cos, const float* rot_sin,
-                     void* qkv_bf16, int32_t batch, int32_t frames, void* stream) {
+                     void* qkv_bf16, float* qk_norm2_max, float* qk_norm2_clear, int32_t batch, int32_t frames,
+                     void* stream) {
+  SRB_REQUIRE(qk_norm2_clear == nullptr || qk_norm2_clear != qk_norm2_max, "srb_cfm_qkv_rope: the buffer to clear must differ from the one to fill");
   ConvGemmDesc d;
   d.src[0] = act(xn_bf16, batch, frames, 256);
   d.weight = w_packed;
@@ -591,6 +593,8 @@ int srb_cfm_qkv_rope(const void* xn_bf16, const void* w_packed, const float* rot
   d.epi.vec0 = rot_cos;
   d.epi.vec1 = rot_sin;
   d.epi.out0 = qkv_bf16;
+  d.epi.aux0 = qk_norm2_max;
+  d.epi.aux1 = qk_norm2_clear;
   d.epi.out_row_stride = 768;
   d.epi.out_batch_stride = (long long)frames * 768;
   return launch_convgemm(d, (cudaStream_t)stream);

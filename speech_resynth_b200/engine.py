@@ -236,12 +236,13 @@ class CFMSampler:
             x0=take((m, 256), f32), x=take((m, 256), f32),
             # xn is also the B operand of the V^T GEMM, read in 256-row tiles: rows >= m are cleared by the staging kernel
             xn=take((m_pad, 256), b16),
-            qk=take((m, 512), b16), vt=take((256, m_pad), b16), o=take((m, 256), b16), h=take((m, 896), b16),
+            o=take((m, 256), b16), h=take((m, 896), b16),
             mel=take((batch, mel_rows, 80), f32), mel_b=take((batch, mel_rows, 80), b16),
             # max |q|^2, |k|^2 per (utterance, head), recorded by qk_rope, read by the attention kernel; two buffers used
             # alternately by successive layers (each projection clears the other one for its successor)
             qkmax=take((2, batch, 2, 2, 2), f32),
         )
+        ws["qk"], ws["vt"] = take((m, 512), b16), take((256, m_pad), b16)
         return ws
 
     # -- the loop ---------------------------------------------------------------------------------------------
@@ -280,9 +281,9 @@ class CFMSampler:
         nat.call("srb_cfm_posconv_norm", P(ws["x0"]), P(w.dw_w), P(w.dw_b), P(g_step[0]), P(L), P(ws["x"]), P(ws["xn"]), b, n,
                  flops=2.0 * m * 31 * 256, nbytes=m * 256 * (4 + 4 + 2))
         for i in range(self.depth):
-            m_pad = ws["vt"].shape[1]
             qk_cur, qk_next = ws["qkmax"][ws["qk_calls"] % 2], ws["qkmax"][(ws["qk_calls"] + 1) % 2]
             ws["qk_calls"] += 1
+            m_pad = ws["vt"].shape[1]
             # q|k projection and the transposed-v projection both read xn only: two parallel graph branches
             self.fork.run([
                 lambda: nat.call("srb_cfm_qk_rope", P(ws["xn"]), P(w.w_qkv[i]), P(cs), P(sn), P(ws["qk"]),

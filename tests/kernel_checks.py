@@ -397,7 +397,7 @@ def cfm_qkv_rope():
     sampler_sn = torch.empty(1024, 64, device=DEV)
     nat.call("srb_rotary_table", P(pk.inv_freq), 1024, P(sampler_cs), P(sampler_sn))
     qkv = torch.empty(b, n, 768, dtype=torch.bfloat16, device=DEV)
-    nat.call("srb_cfm_qkv_rope", P(xn.to(DEV).to(torch.bfloat16).contiguous()), P(pk.w_qkv[1]), P(sampler_cs), P(sampler_sn), P(qkv), b, n)
+    nat.call("srb_cfm_qkv_rope", P(xn.to(DEV).to(torch.bfloat16).contiguous()), P(pk.w_qkv[1]), P(sampler_cs), P(sampler_sn), P(qkv), None, None, b, n)
     w = bf(s["model.transformer.layers.1.2.to_qkv.weight"]).double()
     r = F.linear(xn.double(), w)
     q, k, v = r.chunk(3, dim=-1)
@@ -420,7 +420,8 @@ def _attention_tc_case(bounds: str, scale: float = 1.0):
     """tcgen05 attention (q|k buffer + transposed v) against the float64 softmax-attention definition.
     bounds: "none" -> two-pass path; "given" -> exact norm bounds (single pass when they allow it)"""
     worst = 0.0
-    for b, n, lengths in ((3, 200, (200, 131, 64)), (2, 504, (500, 1)), (1, 136, (129,)), (2, 1024, (1024, 700))):
+    for b, n, lengths in ((3, 200, (200, 131, 64)), (2, 504, (500, 1)), (1, 136, (129,)), (2, 1024, (1024, 700)), (1, 128, (77,)),
+                          (2, 1160, (1160, 385)), (1, 2200, (2100,))):
         L = torch.tensor(lengths, dtype=torch.int32, device=DEV)
         qkv = torch.randn(b, n, 768, generator=g(6 + n))
         qkv[..., :512] *= scale
@@ -443,6 +444,33 @@ def _attention_tc_case(bounds: str, scale: float = 1.0):
         ref = torch.einsum("bhij,bhjd->bhid", sc.softmax(-1), v).permute(0, 2, 1, 3).reshape(b, n, 256)
         worst = max(worst, rel_l2(o.float(), ref))
     return worst, 1e-2
+
+
+@check
+def cfm_qkv_rope_records_norm_bounds():
+    """fused projection: q | k rotated, v plain, norm bounds recorded / the other buffer cleared"""
+    s = sd()
+    pk = packing.pack_cfm(s, DEV)
+    b, n = 2, 150
+    xn_host = bf(torch.randn(b, n, 256, generator=g(5)))
+    xn = xn_host.to(DEV).to(torch.bfloat16).contiguous()
+    cs = torch.empty(1024, 64, device=DEV)
+    sn = torch.empty(1024, 64, device=DEV)
+    nat.call("srb_rotary_table", P(pk.inv_freq), 1024, P(cs), P(sn))
+    qkv = torch.empty(b, n, 768, dtype=torch.bfloat16, device=DEV)
+    nb = torch.zeros(b, 2, 2, 2, device=DEV)
+    nb_other = torch.full((b, 2, 2, 2), 7.0, device=DEV)
+    nat.call("srb_cfm_qkv_rope", P(xn), P(pk.w_qkv[1]), P(cs), P(sn), P(qkv), P(nb), P(nb_other), b, n)
+    w = bf(s["model.transformer.layers.1.2.to_qkv.weight"]).double()
+    q, k, v = F.linear(xn_host.double(), w).chunk(3, dim=-1)
+    rot = oracle.rotary_table(s["model.transformer.rotary_emb.inv_freq"], n).double()
+    hd = lambda z: z.reshape(b, n, 2, 128).permute(0, 2, 1, 3)
+    un = lambda z: z.permute(0, 2, 1, 3).reshape(b, n, 256)
+    q, k = un(oracle.apply_rotary(rot, hd(q))), un(oracle.apply_rotary(rot, hd(k)))
+    e1 = rel_l2(qkv.float(), torch.cat([q, k, v], dim=-1))
+    e3 = rel_l2(nb, _norm_bounds(torch.cat([q, k], dim=-1)))
+    cleared = bool((nb_other == 0).all())
+    return (max(e1, e3 * 100) if cleared else 1.0), BF16_TOL
 
 
 @check
