@@ -128,6 +128,12 @@ int srb_cfm_qk_rope(const void* xn_bf16, const void* w_packed, const float* rot_
                     void* qk_bf16, float* qk_norm2_max, float* qk_norm2_clear, int32_t batch, int32_t frames,
                     void* stream);
 int srb_cfm_v_transposed(const void* xn_bf16, const void* wv_bf16, void* vt_bf16, int64_t m_pad, void* stream);
+/* the two projections above as ONE launch (the whole to_qkv GEMM, N = 768): w_packed = all 768 rows of to_qkv.weight;
+ * q | k with rotary into qk (B, N, 512) and the norm bounds as srb_cfm_qk_rope, v stored transposed into vt [256][m_pad]
+ * by the epilogue (columns beyond batch * frames are not written: srb_cfm_attention_tc never reads them) */
+int srb_cfm_qk_rope_vt(const void* xn_bf16, const void* w_packed, const float* rot_cos, const float* rot_sin, void* qk_bf16,
+                       void* vt_bf16, int64_t m_pad, float* qk_norm2_max, float* qk_norm2_clear, int32_t batch,
+                       int32_t frames, void* stream);
 int srb_cfm_attention_tc(const void* qk_bf16, int32_t ld, const void* vt_bf16, int64_t m_pad, const int32_t* lengths,
                          const float* qk_norm2_max, void* o_bf16, int32_t batch, int32_t frames, void* stream);
 /* to_out + residual (transformer.py:129-130,203) fused with the following AdaptiveRMSNorm:

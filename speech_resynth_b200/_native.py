@@ -41,6 +41,7 @@ _PROTOTYPES = {
     "srb_cfm_qkv_rope": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P],
     "srb_cfm_qk_rope": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P],
     "srb_cfm_v_transposed": [_P, _P, _P, _L, _P],
+    "srb_cfm_qk_rope_vt": [_P, _P, _P, _P, _P, _P, _L, _P, _P, _I, _I, _P],
     "srb_cfm_attention_tc": [_P, _I, _P, _L, _P, _P, _P, _I, _I, _P],
     "srb_cfm_attn_out_norm": [_P, _P, _P, _P, _P, _P, _I, _I, _P],
     "srb_cfm_ffn_glu": [_P, _P, _P, _P, _P, _I, _I, _P],

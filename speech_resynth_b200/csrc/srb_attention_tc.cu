@@ -510,7 +510,8 @@ extern "C" int srb_cfm_attention_tc(const void* qk_bf16, int32_t ld, const void*
     SRB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(q|k) failed: %d", (int)r);
   }
   {
-    cuuint64_t dims[2] = {(cuuint64_t)m_pad, 256};
+    // the map ends at the last utterance's last frame: columns beyond (never written by a fused projection) read as zero
+    cuuint64_t dims[2] = {(cuuint64_t)batch * (cuuint64_t)frames, 256};
     cuuint64_t strides[1] = {(cuuint64_t)m_pad * 2};
     cuuint32_t box[2] = {64, 128};
     cuuint32_t estr[2] = {1, 1};

@@ -600,6 +600,51 @@ int srb_cfm_qkv_rope(const void* xn_bf16, const void* w_packed, const float* rot
   return launch_convgemm(d, (cudaStream_t)stream);
 }
 
+int srb_cfm_qk_rope_vt(const void* xn_bf16, const void* w_packed, const float* rot_cos, const float* rot_sin, void* qk_bf16,
+                       void* vt_bf16, int64_t m_pad, float* qk_norm2_max, float* qk_norm2_clear, int32_t batch,
+                       int32_t frames, void* stream) {
+  SRB_REQUIRE(qk_norm2_clear == nullptr || qk_norm2_clear != qk_norm2_max, "srb_cfm_qk_rope_vt: the buffer to clear must differ from the one to fill");
+  SRB_REQUIRE(frames % 8 == 0 && m_pad % 8 == 0 && m_pad >= (int64_t)batch * frames,
+              "srb_cfm_qk_rope_vt: frames and m_pad must be multiples of 8 and m_pad >= batch * frames");
+  SRB_REQUIRE((reinterpret_cast<uintptr_t>(vt_bf16) & 15) == 0, "srb_cfm_qk_rope_vt: v^T pointer not 16-byte aligned");
+  // the whole to_qkv GEMM (N = 768) in one launch: tiles 0 / 1 = q / k with rotary into the (B, N, 512) buffer, tile 2 = v
+  // stored transposed
+  ConvGemmDesc d;
+  d.src[0] = act(xn_bf16, batch, frames, 256);
+  d.weight = w_packed;
+  d.n_total = 768;
+  d.block_n = 256;
+  d.block_k = 64;
+  d.channels = 256;
+  d.group_tap_begin[1] = 1;
+  d.group_rows[0] = frames;
+  d.batch = batch;
+  d.epilogue = EPI_QKV_ROPE;
+  d.epi = empty_epi();
+  d.epi.vec0 = rot_cos;
+  d.epi.vec1 = rot_sin;
+  d.epi.out0 = qk_bf16;
+  d.epi.aux0 = qk_norm2_max;
+  d.epi.aux1 = qk_norm2_clear;
+  d.epi.out_row_stride = 512;
+  d.epi.out_batch_stride = (long long)frames * 512;
+  d.epi.vt_out = vt_bf16;
+  {
+    auto enc = get_encode();
+    SRB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[3] = {(cuuint64_t)frames, (cuuint64_t)batch, 256};
+    cuuint64_t strides[2] = {(cuuint64_t)frames * 2, (cuuint64_t)m_pad * 2};
+    cuuint32_t box[3] = {32, 1, 32};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&d.epi.tmVt, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, vt_bf16, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SRB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(v^T store) failed: %d (frames=%d batch=%d m_pad=%lld)", (int)r, frames,
+                batch, (long long)m_pad);
+  }
+  return launch_convgemm(d, (cudaStream_t)stream);
+}
+
 int srb_cfm_qk_rope(const void* xn_bf16, const void* w_packed, const float* rot_cos, const float* rot_sin,
                     void* qk_bf16, float* qk_norm2_max, float* qk_norm2_clear, int32_t batch, int32_t frames, void* stream) {
   SRB_REQUIRE(qk_norm2_clear == nullptr || qk_norm2_clear != qk_norm2_max, "srb_cfm_qk_rope: the buffer to clear must differ from the one to fill");

@@ -35,6 +35,10 @@ struct ConvGemmParams {
   // epilogue I/O through TMA (RESNORM, QKV_ROPE): 3-D maps (columns, rows, batch) with a 32-column x 32-row box --
   // one epilogue warp's block.  tmR: fp32 residual, tmO1: fp32 output stream, tmO0: bf16 output.
   CUtensorMap tmR, tmO1, tmO0;
+  // QKV_ROPE with a transposed V: 3-D view (frames, batch, 256) of V^T [256][m_pad] (element (q, b, d) at d * m_pad +
+  // b * frames + q), box (32 keys, 1, 32 d): rows beyond an utterance's frames are clipped by the map
+  CUtensorMap tmVt;
+  void* vt_out;                                   // non-null: tile n == 2 (V) is stored transposed through tmVt
   // GENERIC: bf16 residuals (same geometry as the output) and, per tap group, the raw / activated outputs: a group of
   // a polyphase transposed conv writes rows q * row_mul + phase, which is a plain 3-D view with a row_mul-fold pitch
   CUtensorMap tmRes[3];
@@ -657,6 +661,35 @@ __device__ __forceinline__ void epi_qkv_rope(const ConvGemmParams& p, uint32_t t
     }
     ++blk;
   };
+  if (tc.n == 2 && p.vt_out != nullptr) {
+    // V stored TRANSPOSED ([d][utterance * frames + key], keys contiguous) for the attention kernel's K-major P V product:
+    // a thread holds one key's 32 d-values per chunk and writes them as one bf16 each into a [32 d][32 keys] block
+    // (64-byte rows, the tensor map's 64-byte swizzle; the 32 lanes of a warp fill one row per store: conflict free),
+    // which leaves as one TMA store per chunk.  Replaces a separate swapped-operand GEMM launch.
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t v[32];
+      tmem_ld32(tcol + c * 32, v);
+      tmem_ld_wait();
+      if (w.lane == 0) bulk_wait_read<1>();   // the block stored from this half two blocks ago has been read
+      __syncwarp();
+      uint8_t* hb = w.stage + (blk & 1) * 2048;
+      const int piece = w.lane >> 3, within = (w.lane & 7) * 2;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const __nv_bfloat16 h = __float2bfloat16_rn(__uint_as_float(v[j]));
+        *reinterpret_cast<__nv_bfloat16*>(hb + j * 64 + ((piece ^ ((j >> 1) & 3)) << 4) + within) = h;
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (w.lane == 0) {
+        tma_store_3d(&p.tmVt, stage_s + (blk & 1) * 2048, w.row0, tc.b, half * 128 + c * 32);
+        bulk_commit();
+      }
+      ++blk;
+    }
+    return;
+  }
   if (tc.n == 2) {
 #pragma unroll
     for (int c = 0; c < 4; ++c) {

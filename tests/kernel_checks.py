@@ -525,6 +525,37 @@ def _qk_rope_vt_case(b, n, m_pad):
 
 
 @check
+def cfm_qk_rope_vt_fused():
+    """the whole to_qkv GEMM in one launch: q | k rotated into (B, N, 512), v transposed by the epilogue; bit-equal to the
+    two-launch form (same MMAs, same roundings) on ragged frame counts, untouched beyond batch * frames"""
+    s = sd()
+    pk = packing.pack_cfm(s, DEV)
+    worst = 0.0
+    for b, n in ((2, 152), (3, 504), (1, 40)):
+        m_pad = (b * n + 255) // 256 * 256 + 256
+        xn = torch.zeros(m_pad, 256, dtype=torch.bfloat16, device=DEV)
+        xn[: b * n] = bf(torch.randn(b * n, 256, generator=g(5 + n))).to(DEV).to(torch.bfloat16)
+        cs = torch.empty(1024, 64, device=DEV)
+        sn = torch.empty(1024, 64, device=DEV)
+        nat.call("srb_rotary_table", P(pk.inv_freq), 1024, P(cs), P(sn))
+        wq = pk.w_qkv[2]
+        qk1 = torch.empty(b, n, 512, dtype=torch.bfloat16, device=DEV)
+        vt1 = torch.full((256, m_pad), 5.0, dtype=torch.bfloat16, device=DEV)
+        nb1, nc1 = torch.zeros(b, 2, 2, 2, device=DEV), torch.full((b, 2, 2, 2), 7.0, device=DEV)
+        nat.call("srb_cfm_qk_rope", P(xn), P(wq), P(cs), P(sn), P(qk1), P(nb1), P(nc1), b, n)
+        nat.call("srb_cfm_v_transposed", P(xn), P(wq[512:]), P(vt1), m_pad)
+        qk2 = torch.empty(b, n, 512, dtype=torch.bfloat16, device=DEV)
+        vt2 = torch.full((256, m_pad), 5.0, dtype=torch.bfloat16, device=DEV)
+        nb2, nc2 = torch.zeros(b, 2, 2, 2, device=DEV), torch.full((b, 2, 2, 2), 7.0, device=DEV)
+        nat.call("srb_cfm_qk_rope_vt", P(xn), P(wq), P(cs), P(sn), P(qk2), P(vt2), m_pad, P(nb2), P(nc2), b, n)
+        torch.cuda.synchronize()
+        ok = torch.equal(qk1, qk2) and torch.equal(vt1[:, : b * n], vt2[:, : b * n]) and torch.equal(nb1, nb2)
+        ok = ok and bool((nc2 == 0).all()) and bool((vt2[:, b * n:] == 5.0).all())
+        worst = max(worst, 0.0 if ok else 1.0)
+    return worst, 0.0
+
+
+@check
 def cfm_qk_rope_and_v_transposed():
     return _qk_rope_vt_case(2, 150, 512)
 
