@@ -170,11 +170,15 @@ struct ConvGemmDesc {
 
 // cluster mode of the wide (BN = 256) tiles: 0 = single CTA, 1 = weight-slab multicast, 2 = CTA-pair MMA
 // (cta_group::2).  SRB_CLUSTER_MODE overrides the default.
+// Default 1 since round 2: three alternating same-box runs at config 2 (profiles/r02_cluster_mode_ab.txt) gave 28.68 /
+// 28.65 / 28.58 ms per step with multicast against 28.68 / 29.14 / 28.79 without, and 29.02 +- 0.04 against 29.31 +- 0.02
+// end to end -- 1 %, from the C = 256 vocoder convs and the FFN GEMM; the per-op table shows the K = 256 launches
+// (q|k projection: 24.4 vs 22.6 us) paying for their cluster start-up, which is why mode 2 (pair MMA: 29.5 ms) loses.
 static int cluster_mode() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("SRB_CLUSTER_MODE");
-    v = e ? atoi(e) : 0;
+    v = e ? atoi(e) : 1;
     if (v < 0 || v > 2) v = 0;
   }
   return v;
