@@ -97,12 +97,15 @@ __device__ __forceinline__ void srb_trace_at(const ConvGemmParams& p, int role, 
   if (p.trace != nullptr && blockIdx.x < 8 && tile_it < 8) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    p.trace[((blockIdx.x * 3 + role) * 8 + tile_it) * 4 + k] = t;
+    p.trace[((blockIdx.x * 7 + role) * 8 + tile_it) * 4 + k] = t;
   }
 }
 #define SRB_TRACE_AT(role, it, k) do { if (lane == 0) srb_trace_at(p, role, it, k); } while (0)
+// inside epi_resnorm (roles 3..6), first epilogue warp only
+#define SRB_TRACE_EPI(role, it, k) do { if (w.lane == 0 && half == 0 && quarter == 2) srb_trace_at(p, role, it, k); } while (0)
 #else
 #define SRB_TRACE_AT(role, it, k) do { } while (0)
+#define SRB_TRACE_EPI(role, it, k) do { } while (0)
 #endif
 
 template <int BN>
@@ -513,6 +516,7 @@ __device__ __forceinline__ void epi_resnorm(const ConvGemmParams& p, uint32_t ta
     const int s = rs.seq;
     const int bi = nb == 2 ? (s & 1) : 0;
     mbar_wait(rs.bar + 8u * bi, nb == 2 ? ((s >> 1) & 1) : (s & 1));
+    SRB_TRACE_EPI(3, s >> 2, c);   // residual chunk c is in shared memory
     uint4 rr[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) rr[j] = *stage_slot<8>(rs.gen + bi * 4096, w.lane, j);
@@ -557,6 +561,7 @@ __device__ __forceinline__ void epi_resnorm(const ConvGemmParams& p, uint32_t ta
         issue_load(s + 1, 0);
       }
     }
+    SRB_TRACE_EPI(4, s >> 2, c);   // fp32 block c stored
     ++rs.seq;
     if (p.norm_mode != 0) tmem_st32(tcol + c * 32, v);  // stash y for the second pass
   }
@@ -567,6 +572,7 @@ __device__ __forceinline__ void epi_resnorm(const ConvGemmParams& p, uint32_t ta
     pair_barrier(quarter);
     sumsq += red[(half ^ 1) * 128 + row_in_tile];
   }
+  SRB_TRACE_EPI(6, (rs.seq >> 2) - 1, 1);   // row norms exchanged
   float inv;
   if (p.norm_mode == 1) inv = 1.f / fmaxf(sqrtf(sumsq), 1e-12f);           // F.normalize (norm.py:41)
   else inv = rsqrtf(sumsq * (1.f / 256.f) + 1.1920928955078125e-07f);      // nn.RMSNorm eps = finfo(fp32).eps
@@ -601,6 +607,7 @@ __device__ __forceinline__ void epi_resnorm(const ConvGemmParams& p, uint32_t ta
       tma_store_3d(&p.tmO0, st_stage + (c & 1) * 2048, half * COLS + c * 32, w.row0, tc.b);
       bulk_commit();
     }
+    SRB_TRACE_EPI(5, (rs.seq >> 2) - 1, c);   // bf16 block c stored
   }
   if (nb != 2 && w.lane == 0) {
     bulk_wait_read<0>();
@@ -756,59 +763,74 @@ __device__ __forceinline__ void epi_qkv_rope(const ConvGemmParams& p, uint32_t t
   }
 }
 
+// One N-column chunk (N = 32 or 16) of the Euler epilogue for a warp's 32 rows.  With thread <-> row every 16-byte access
+// of a warp touched 32 different lines of the 320-byte xt rows (11 us of epilogue per 128 x 80 tile in the in-kernel
+// timeline); the chunk now travels through the warp's staging buffer like the GLU output: coalesced loads of the
+// 32 x (N x 4 B) block, own-row reads, coalesced stores of xt / its bf16 copy / the two mel outputs.
 template <int N>
-__device__ __forceinline__ void euler_chunk(const uint32_t (&v)[N], int c0, float* xt, __nv_bfloat16* xtb, float* mel,
-                                            __nv_bfloat16* melb, long long off, bool is_pad, float dt, float sd,
-                                            float mean, float padv) {
+__device__ __forceinline__ void euler_chunk(const ConvGemmParams& p, uint32_t tacc, int c0, const EpiWarp& w, float* xt,
+                                            __nv_bfloat16* xtb, int vrows, float* mel, __nv_bfloat16* melb, int mrows,
+                                            bool is_pad) {
+  constexpr int P = N / 4;   // 16-byte pieces of fp32 per chunk row
+  const float dt = p.f0, sd = p.f1, mean = p.f2, padv = p.f3;
+  uint4 t[P], xin[P];
+  gather_issue<P>(xt + c0, 320, vrows, w.lane, t);
+  uint32_t v[N];
+  if constexpr (N == 32) tmem_ld32(tacc + c0, v);
+  else tmem_ld16(tacc + c0, v);
+  tmem_ld_wait();
+  gather_finish<P>(w, t, xin);
+  uint4 xo[P], xb[P / 2];
+  uint32_t* xbw = reinterpret_cast<uint32_t*>(xb);
 #pragma unroll
-  for (int j = 0; j < N; j += 4) {
-    float4 x = *reinterpret_cast<const float4*>(xt + c0 + j);
-    x.x += dt * __uint_as_float(v[j]);
-    x.y += dt * __uint_as_float(v[j + 1]);
-    x.z += dt * __uint_as_float(v[j + 2]);
-    x.w += dt * __uint_as_float(v[j + 3]);
-    *reinterpret_cast<float4*>(xt + c0 + j) = x;
-    *reinterpret_cast<uint2*>(xtb + c0 + j) = make_uint2(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w));
-    if (mel) {
+  for (int j = 0; j < P; ++j) {
+    float4 x;
+    x.x = __uint_as_float(xin[j].x) + dt * __uint_as_float(v[4 * j + 0]);
+    x.y = __uint_as_float(xin[j].y) + dt * __uint_as_float(v[4 * j + 1]);
+    x.z = __uint_as_float(xin[j].z) + dt * __uint_as_float(v[4 * j + 2]);
+    x.w = __uint_as_float(xin[j].w) + dt * __uint_as_float(v[4 * j + 3]);
+    xo[j] = make_uint4(__float_as_uint(x.x), __float_as_uint(x.y), __float_as_uint(x.z), __float_as_uint(x.w));
+    xbw[2 * j] = pack_bf16(x.x, x.y);
+    xbw[2 * j + 1] = pack_bf16(x.z, x.w);
+  }
+  scatter_store<P>(w, xo, xt + c0, 320, vrows);
+  scatter_store<P / 2>(w, xb, xtb + c0, 160, vrows);
+  if (mel != nullptr) {
+    uint4 mo[P], mb[P / 2];
+    uint32_t* mbw = reinterpret_cast<uint32_t*>(mb);
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
       float4 m;
-      m.x = is_pad ? padv : x.x * sd + mean;
-      m.y = is_pad ? padv : x.y * sd + mean;
-      m.z = is_pad ? padv : x.z * sd + mean;
-      m.w = is_pad ? padv : x.w * sd + mean;
-      *reinterpret_cast<float4*>(mel + off + c0 + j) = m;
-      *reinterpret_cast<uint2*>(melb + off + c0 + j) = make_uint2(pack_bf16(m.x, m.y), pack_bf16(m.z, m.w));
+      m.x = is_pad ? padv : __uint_as_float(xo[j].x) * sd + mean;
+      m.y = is_pad ? padv : __uint_as_float(xo[j].y) * sd + mean;
+      m.z = is_pad ? padv : __uint_as_float(xo[j].z) * sd + mean;
+      m.w = is_pad ? padv : __uint_as_float(xo[j].w) * sd + mean;
+      mo[j] = make_uint4(__float_as_uint(m.x), __float_as_uint(m.y), __float_as_uint(m.z), __float_as_uint(m.w));
+      mbw[2 * j] = pack_bf16(m.x, m.y);
+      mbw[2 * j + 1] = pack_bf16(m.z, m.w);
     }
+    scatter_store<P>(w, mo, mel + c0, 320, mrows);
+    scatter_store<P / 2>(w, mb, melb + c0, 160, mrows);
   }
 }
 
 // to_pred (N = 80) + Euler step in fp32 (models.py:183-184); last step also de-normalises and fills pads (:186-187)
-__device__ __forceinline__ void epi_euler(const ConvGemmParams& p, uint32_t tacc, const TileCoord& tc, int q) {
-  const bool valid = q < p.group_rows[0];
-  const long long xoff = (long long)tc.b * p.out_batch_stride + (long long)q * p.out_row_stride;
+__device__ __forceinline__ void epi_euler(const ConvGemmParams& p, uint32_t tacc, const TileCoord& tc, int q, const EpiWarp& w) {
+  const int rows = p.group_rows[0];
+  const int vrows = clamp_rows(rows, w.row0);
+  const long long xoff = (long long)tc.b * p.out_batch_stride + (long long)w.row0 * p.out_row_stride;
   float* xt = static_cast<float*>(p.out1) + xoff;
   __nv_bfloat16* xtb = static_cast<__nv_bfloat16*>(p.out0) + xoff;
   // the mel outputs are compact: aux_rows (<= frames) rows per utterance, what the vocoder must see
-  const bool has_mel = p.aux0 != nullptr && q < p.aux_rows;
-  const long long off = ((long long)tc.b * p.aux_rows + q) * p.out_row_stride;
-  float* mel = has_mel ? static_cast<float*>(p.aux0) : nullptr;
-  __nv_bfloat16* melb = static_cast<__nv_bfloat16*>(p.aux1);
-  const bool is_pad = valid && p.lengths != nullptr && q >= p.lengths[tc.b];
-  const float dt = p.f0, sd = p.f1, mean = p.f2, padv = p.f3;
-  {
-    uint32_t v[32];
-    tmem_ld32(tacc, v);
-    tmem_ld_wait();
-    if (valid) euler_chunk<32>(v, 0, xt, xtb, mel, melb, off, is_pad, dt, sd, mean, padv);
-    tmem_ld32(tacc + 32, v);
-    tmem_ld_wait();
-    if (valid) euler_chunk<32>(v, 32, xt, xtb, mel, melb, off, is_pad, dt, sd, mean, padv);
-  }
-  {
-    uint32_t v[16];
-    tmem_ld16(tacc + 64, v);
-    tmem_ld_wait();
-    if (valid) euler_chunk<16>(v, 64, xt, xtb, mel, melb, off, is_pad, dt, sd, mean, padv);
-  }
+  const bool has_mel = p.aux0 != nullptr;
+  const int mrows = has_mel ? clamp_rows(p.aux_rows < rows ? p.aux_rows : rows, w.row0) : 0;
+  const long long off = ((long long)tc.b * p.aux_rows + w.row0) * p.out_row_stride;
+  float* mel = has_mel ? static_cast<float*>(p.aux0) + off : nullptr;
+  __nv_bfloat16* melb = has_mel ? static_cast<__nv_bfloat16*>(p.aux1) + off : nullptr;
+  const bool is_pad = q < rows && p.lengths != nullptr && q >= p.lengths[tc.b];
+  euler_chunk<32>(p, tacc, 0, w, xt, xtb, vrows, mel, melb, mrows, is_pad);
+  euler_chunk<32>(p, tacc, 32, w, xt, xtb, vrows, mel, melb, mrows, is_pad);
+  euler_chunk<16>(p, tacc, 64, w, xt, xtb, vrows, mel, melb, mrows, is_pad);
 }
 
 // ---------------------------------------------------------------------------------------------- kernel
@@ -826,6 +848,7 @@ struct EpiWarps {
     return EPI == EPI_RESNORM ? (res_bufs == 2 ? 3 * 4096 : 4096)
            : EPI == EPI_QKV_ROPE ? 5120
            : EPI == EPI_GENERIC ? (res_bufs < 0 ? 2048 : ((res_bufs * (BN < 32 ? BN : 32) * 64 + 1023) & ~1023))
+           : EPI == EPI_EULER ? 4096      // 32 rows x 128 B: one fp32 chunk of the staged Euler update
                                 : 2048;
   }
   // CTA-wide extra: the rotary offset table (cos | sin of positions 0..31)
@@ -1186,7 +1209,7 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
       else if constexpr (EPI == EPI_GLU) epi_glu<NHALF>(p, tacc, tc, q, half, ew);
       else if constexpr (EPI == EPI_RESNORM) epi_resnorm<NHALF>(p, tacc, tc, q, half, red, lane_base + lane, quarter, ew, rs, issue_load);
       else if constexpr (EPI == EPI_QKV_ROPE) epi_qkv_rope<NHALF>(p, tacc, tc, half, ew, extra_base, rope_row);
-      else epi_euler(p, tacc, tc, q);
+      else epi_euler(p, tacc, tc, q, ew);
       tc_fence_before();
       __syncwarp();
       if (warp == 2) SRB_TRACE_AT(2, it, 2);   // epilogue of the tile done

@@ -337,18 +337,33 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
         "l"(reinterpret_cast<unsigned long long&>(c)));
   return d;
 }
-// erf(x), |abs error| <= 1.5e-7 (Abramowitz & Stegun 7.1.26 carried to fp32 with fast exp / reciprocal)
-__device__ __forceinline__ float erf_as(float x) {
-  const float ax = fabsf(x);
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.f));
+// erf(x), |abs error| <= 1.5e-7 (Abramowitz & Stegun 7.1.26 carried to fp32 with the approximate reciprocal and
+// exponential units: 1 ulp each, far below the formula's own error).  The IEEE reciprocal (__frcp_rn) this used before
+// is a software routine -- a CALL per output, ~40 % of the kernel's instructions together with the unfused tail.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// exact (erf) GELU: 0.5 a (1 + erf(a / sqrt 2))
+__device__ __forceinline__ float gelu_exact(float a) {
+  const float z = a * 0.70710678118654752440f;
+  const float az = fabsf(z);
+  const float t = rcp_approx(fmaf(0.3275911f, az, 1.f));
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
-  const float r = 1.f - poly * t * __expf(-ax * ax);
-  return copysignf(r, x);
+  const float e = ex2_approx(az * az * -1.4426950408889634f);   // exp(-z^2)
+  const float erf_abs = fmaf(-(poly * t), e, 1.f);
+  const float ha = 0.5f * a;
+  return fmaf(ha, copysignf(erf_abs, z), ha);
 }
-__device__ __forceinline__ float gelu_exact(float a) { return 0.5f * a * (1.f + erf_as(a * 0.70710678118654752440f)); }
 
 template <int ROWS>
 __global__ void __launch_bounds__(128) posconv_norm_kernel(const float* __restrict__ x0, const float* __restrict__ dw_w,
@@ -427,10 +442,6 @@ __global__ void __launch_bounds__(128) posconv_norm_kernel(const float* __restri
 // slot r + r / 8 so that the stride-2 row pattern of a quarter warp covers eight different 16-byte bank groups.
 constexpr int kPostOutputs = 256;
 __device__ __forceinline__ int post_slot(int r) { return r + (r >> 3); }
-__device__ __forceinline__ void post_unpack(const uint4 u, float* f) {
-  f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
-  f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
-}
 // Ragged form (lengths != NULL): utterance b keeps its first n_b = min(rows, 320 * lengths[b] + 80) samples
 // (_get_waveform_lengths, models.py:211-221) and they are stored back to back: wav[sum_{i<b} n_i + t] -- the reference's
 // per-utterance crop loop (models.py:252-256) folded into the store.  Every block sums the (<= a few thousand) preceding
@@ -464,21 +475,31 @@ __global__ void __launch_bounds__(128) post_tanh_kernel(const uint4* __restrict_
   const int r0 = 2 * threadIdx.x;        // window row of tap 0 of the first output
   const int t = t0 + r0;
   if (t >= n_out) return;
-  float acc0 = bias, acc1 = bias;
+  // channel pairs as packed fp32 FMAs: 8 fma.rn.f32x2 per (row, output) instead of 16 scalar ones; the weights of tap
+  // k serve output 0 now and output 1 at the next row
+  float2 a0 = make_float2(bias, 0.f), a1 = make_float2(bias, 0.f);
+  float2 wprev[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    float f[16];
-    post_unpack(tile[0][post_slot(r0 + k)], f);
-    post_unpack(tile[1][post_slot(r0 + k)], f + 8);
-    if (k < 7) {
-#pragma unroll
-      for (int c = 0; c < 16; ++c) acc0 = fmaf(f[c], ws[k * 16 + c], acc0);
-    }
+    const uint4 u0 = tile[0][post_slot(r0 + k)], u1 = tile[1][post_slot(r0 + k)];
+    float2 f[8];
+    f[0] = make_float2(bf16_lo(u0.x), bf16_hi(u0.x)); f[1] = make_float2(bf16_lo(u0.y), bf16_hi(u0.y));
+    f[2] = make_float2(bf16_lo(u0.z), bf16_hi(u0.z)); f[3] = make_float2(bf16_lo(u0.w), bf16_hi(u0.w));
+    f[4] = make_float2(bf16_lo(u1.x), bf16_hi(u1.x)); f[5] = make_float2(bf16_lo(u1.y), bf16_hi(u1.y));
+    f[6] = make_float2(bf16_lo(u1.z), bf16_hi(u1.z)); f[7] = make_float2(bf16_lo(u1.w), bf16_hi(u1.w));
     if (k > 0) {
 #pragma unroll
-      for (int c = 0; c < 16; ++c) acc1 = fmaf(f[c], ws[(k - 1) * 16 + c], acc1);
+      for (int c = 0; c < 8; ++c) a1 = ffma2(f[c], wprev[c], a1);
+    }
+    if (k < 7) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        wprev[c] = *reinterpret_cast<const float2*>(ws + k * 16 + 2 * c);
+        a0 = ffma2(f[c], wprev[c], a0);
+      }
     }
   }
+  const float acc0 = a0.x + a0.y, acc1 = a1.x + a1.y;
   float* o = wav + (lengths != nullptr ? (off_s[0] + off_s[1]) + (off_s[2] + off_s[3]) : (long long)b * rows) + t;
   const float y0 = tanhf(acc0), y1 = tanhf(acc1);
   if (t + 1 < n_out && (reinterpret_cast<uintptr_t>(o) & 7) == 0) {
@@ -593,20 +614,11 @@ int srb_log_mel(const float* wav, int64_t wav_stride, int32_t batch, int32_t sam
 int srb_cfm_posconv_norm(const float* x0, const float* dw_w, const float* dw_b, const float* g, const int32_t* lengths,
                          float* x, void* xn_bf16, int32_t batch, int32_t frames, void* stream) {
   if (batch <= 0 || frames <= 0) return 0;
-  static int rows_sel = -1;
-  if (rows_sel < 0) {
-    const char* e = getenv("SRB_POSCONV_ROWS");   // A/B knob: 8 (more resident blocks, default: 41.8 vs 45.4 us) or 16 (fewer window loads)
-    rows_sel = (e && atoi(e) == 16) ? 16 : 8;
-  }
-  if (rows_sel == 8) {
-    dim3 grid((frames + 7) / 8, batch);
-    SRB_CUDA(launch_pdl(posconv_norm_kernel<8>, grid, dim3(128), 0, (cudaStream_t)stream, x0, dw_w, dw_b, g, lengths, x,
-                        static_cast<__nv_bfloat16*>(xn_bf16), frames));
-    return after_launch("posconv_norm_kernel");
-  }
-  constexpr int ROWS = 16;
-  dim3 grid((frames + ROWS - 1) / ROWS, batch);
-  SRB_CUDA(launch_pdl(posconv_norm_kernel<ROWS>, grid, dim3(128), 0, (cudaStream_t)stream, x0, dw_w, dw_b, g, lengths, x,
+  // (A "marching" form -- one block sliding the register window down 16..128 rows, so x0 is read once instead of 4.75
+  // times -- measured 47.7-50.3 us against 46.4 us for this one at 64 x 504 with a flushed L2: the launch is bound by
+  // its instruction count (GELU), not by the window reloads.)
+  dim3 grid((frames + 7) / 8, batch);
+  SRB_CUDA(launch_pdl(posconv_norm_kernel<8>, grid, dim3(128), 0, (cudaStream_t)stream, x0, dw_w, dw_b, g, lengths, x,
                       static_cast<__nv_bfloat16*>(xn_bf16), frames));
   return after_launch("posconv_norm_kernel");
 }

@@ -24,6 +24,8 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <stdlib.h>
+
 #include "../../include/srb.h"
 #include "srb_common.h"
 #include "srb_ptx.cuh"
@@ -31,6 +33,7 @@
 namespace srb {
 
 struct MrfParams {
+  int u_ahead;               // 1: the raw window of the NEXT work item is fetched while this one is processed (A/B knob SRB_MRF_AHEAD)
   const __nv_bfloat16* u;    // (B, L, C) raw up-sampler output
   __nv_bfloat16* out;        // (B, L, C)
   const __nv_bfloat16* w;    // packed weights, conv order (resblock j, pair q, conv1 then conv2), operand layout
@@ -42,8 +45,6 @@ struct MrfParams {
 #endif
 };
 
-// debug-only timeline (tools/trace_mrf.py): ordered wall-clock stamps per role; the epilogue warp also records clock64 so
-// the SM clock during the launch can be read off (cycles / nanoseconds)
 #ifdef SRB_TRACE
 #define MRF_STAMP(role)                                                                      \
   do {                                                                                       \
@@ -51,7 +52,6 @@ struct MrfParams {
       unsigned long long t_;                                                                 \
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                 \
       p.trace[(role) * 256 + trace_n++] = t_;                                                \
-      if ((role) == 1) p.trace[512 + trace_n - 1] = clock64();                               \
     }                                                                                        \
   } while (0)
 #else
@@ -111,17 +111,21 @@ struct MrfLayout {
         off += conv_bytes(mrf_kernel_size(jj), (c2 & 1) ? 1 : mrf_dilation(c2 >> 1));
     return off;
   }
+  // the raw window is double buffered (next window's rows arrive while this one is processed) and needs no guard rows:
+  // only the identity MMA and the E0 pass read it, both at shift 0
+  static constexpr int u_bytes = NPC * RQ * 16;
   static constexpr int off_u = 0;
-  static constexpr int off_a = buf_bytes;
-  static constexpr int off_t = 2 * buf_bytes;
-  static constexpr int off_w = 3 * buf_bytes;
+  static constexpr int off_a = 2 * u_bytes;
+  static constexpr int off_t = off_a + buf_bytes;
+  static constexpr int off_w = off_t + buf_bytes;
   static constexpr int off_ident = off_w + 2 * wbuf_bytes;
   static constexpr int off_bias = off_ident + tap_bytes;
   static constexpr int off_bar = off_bias + 18 * C * 4;
-  static constexpr int n_bars = NM + 4 + 1;
+  static constexpr int n_bars = NM + 4 + 4;
   static constexpr int off_cnt = off_bar + 8 * n_bars;     // uint32 written[NM]: monotonic arrival counters
   static constexpr int off_tmem = off_cnt + 4 * ((NM + 3) & ~3);
   static constexpr int total = off_tmem + 16;
+  static_assert(total <= 232448, "shared memory layout exceeds the 227 KB a CTA can have");
   static constexpr int tout = R - 2 * kMrfHalo;
   static_assert(3 * NM * N <= 512, "accumulators exceed tensor memory");
   static_assert(N == 16 || N == 32, "the epilogue reads an accumulator row with one 16- or 32-column TMEM load");
@@ -154,7 +158,7 @@ struct MrfTeams {
 template <int C, int R, int D>
 __global__ void __launch_bounds__(MrfTeams<C>::threads, 1) mrf_fused_kernel(const MrfParams p) {
   using L = MrfLayout<C, R, D>;
-  constexpr int NM = L::NM, RP = L::RP, CH = L::CH, KS = C / 16, G = kMrfGuard, N = L::N, NPC = L::NPC;
+  constexpr int NM = L::NM, RP = L::RP, RQ = L::RQ, CH = L::CH, KS = C / 16, G = kMrfGuard, N = L::N, NPC = L::NPC;
   constexpr int NTEAMS = MrfTeams<C>::value, EPI_THREADS = 128 * NTEAMS, NI = MrfTeams<C>::issuers;
   constexpr uint32_t IDESC = umma_idesc_bf16(128, C);      // one output phase (dilated convs, identity)
   constexpr uint32_t IDESC_N = umma_idesc_bf16(128, N);    // all output phases at once (dilation-1 convs)
@@ -174,7 +178,8 @@ __global__ void __launch_bounds__(MrfTeams<C>::threads, 1) mrf_fused_kernel(cons
   auto written_cnt = [&](int m) { return cnt0 + 4u * m; };
   auto w_full = [&](int b) { return bar0 + 8u * (NM + b); };
   auto w_free = [&](int b) { return bar0 + 8u * (NM + 2 + b); };
-  const uint32_t u_ready = bar0 + 8u * (NM + 4);
+  auto u_ready = [&](int b) { return bar0 + 8u * (NM + 4 + b); };   // raw window b (of two) is in shared memory
+  auto u_free = [&](int b) { return bar0 + 8u * (NM + 6 + b); };    // ... and no longer needed
   const uint32_t tmem_slot = sbase + L::off_tmem;
 
   const int tid = threadIdx.x, lane = tid & 31;
@@ -193,7 +198,10 @@ __global__ void __launch_bounds__(MrfTeams<C>::threads, 1) mrf_fused_kernel(cons
       mbar_init(w_full(b), 1);
       mbar_init(w_free(b), NI);
     }
-    mbar_init(u_ready, 4 * NTEAMS);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(u_ready(b), 32);   // one cp.async arrival per lane of the producer warp
+      mbar_init(u_free(b), 1);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -201,9 +209,9 @@ __global__ void __launch_bounds__(MrfTeams<C>::threads, 1) mrf_fused_kernel(cons
     tmem_relinquish();
   }
   {
-    // zero all three operand buffers once (guards stay zero forever; interiors are rewritten per tile)
-    uint4* z = reinterpret_cast<uint4*>(smem);
-    for (int i = tid; i < 3 * L::buf_bytes / 16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+    // zero the two operand buffers once (guards stay zero forever; interiors are rewritten per tile)
+    uint4* z = reinterpret_cast<uint4*>(smem + L::off_a);
+    for (int i = tid; i < 2 * L::buf_bytes / 16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
     // identity weight in operand layout: element (n, k) at chunk (k/8), row n, lane k%8
     __nv_bfloat16* id = reinterpret_cast<__nv_bfloat16*>(smem + L::off_ident);
     for (int i = tid; i < C * C; i += blockDim.x) {
@@ -222,19 +230,58 @@ __global__ void __launch_bounds__(MrfTeams<C>::threads, 1) mrf_fused_kernel(cons
   const uint32_t t_dt = tmem_base, t_dx = tmem_base + NM * N, t_f = tmem_base + 2 * NM * N;
 
   if (warp == 0) {
-    // ================= weight producer =================
-    if (lane == 0) {
+    // ================= weight / raw-window producer =================
+    // The raw window (R rows x C channels of u; rows outside [0, L) zero) goes straight into operand layout with 16-byte
+    // cp.async copies of the whole warp -- time row r -> phase r % D, q-row r / D -- and the window of the NEXT work item
+    // is requested while this one is processed (double buffer).  Before, the epilogue warps loaded it at the start of
+    // every window with nothing else running: 3.2-3.9 us of a 39 us window (tools/trace_mrf.py).  (A TMA tile copy of the
+    // same rows -- 5-D view, 16-byte inner box -- was correct but slower: 2 560 sixteen-byte requests per window queue in
+    // the copy engine ahead of the weight blobs.)
+    {
       uint32_t n_loaded = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      auto request_window = [&](int tile, int buf) {
+        const int b = tile / p.tiles_per_b;
+        const int t0 = (tile % p.tiles_per_b) * L::tout - kMrfHalo;
+        const __nv_bfloat16* ub_g = p.u + (size_t)b * p.rows * C;
+        const uint32_t dst0 = s_u + buf * L::u_bytes;
+        for (int i = lane; i < R * CH; i += 32) {
+          const int row = i / CH, ch = i % CH;
+          const int gr = t0 + row;
+          const bool ok = gr >= 0 && gr < p.rows;
+          const void* src = ok ? static_cast<const void*>(ub_g + (size_t)gr * C + ch * 8) : static_cast<const void*>(p.u);
+          cp_async_16(dst0 + (((row % D) * CH + ch) * RQ + (row / D)) * 16, src, ok ? 16u : 0u);
+        }
+        cp_async_mbar_arrive_noinc(u_ready(buf));
+      };
+      if (static_cast<int>(blockIdx.x) < p.total_tiles) request_window(blockIdx.x, 0);
+      int wl = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++wl) {
+        const bool has_next = tile + static_cast<int>(gridDim.x) < p.total_tiles;
+        if (!p.u_ahead && wl >= 1) {
+          // (A/B form: fetch a window only once the previous one is finished, as the epilogue-warp loader did)
+          mbar_wait(u_free((wl - 1) & 1), ((wl - 1) >> 1) & 1);
+          request_window(tile, wl & 1);
+        }
         for (int j = 0; j < 3; ++j) {
           const int k = mrf_kernel_size(j);
           for (int cc = 0; cc < 6; ++cc, ++n_loaded) {
-            const int buf = n_loaded & 1;
-            const uint32_t ph = (n_loaded >> 1) & 1;
-            mbar_wait(w_free(buf), ph ^ 1u);
-            const uint32_t bytes = L::conv_bytes(k, (cc & 1) ? 1 : mrf_dilation(cc >> 1));
-            mbar_expect_tx(w_full(buf), bytes);
-            bulk_g2s(s_w + buf * L::wbuf_bytes, reinterpret_cast<const uint8_t*>(p.w) + L::conv_offset(j, cc), bytes, w_full(buf));
+            if (j == 0 && cc == 2 && p.u_ahead && has_next) {
+              // next window's raw rows, into the buffer window wl - 1 used.  Requested here -- not at the top of the window,
+              // where waiting for the end of window wl - 1 would keep the weights of this window's first convs from being
+              // requested ahead -- the loop is now two convs into window wl, so the wait below never blocks.
+              const int nb = (wl + 1) & 1;
+              if (wl >= 1) mbar_wait(u_free(nb), (((wl + 1) >> 1) - 1) & 1);
+              request_window(tile + gridDim.x, nb);
+            }
+            if (lane == 0) {
+              const int buf = n_loaded & 1;
+              const uint32_t ph = (n_loaded >> 1) & 1;
+              mbar_wait(w_free(buf), ph ^ 1u);
+              const uint32_t bytes = L::conv_bytes(k, (cc & 1) ? 1 : mrf_dilation(cc >> 1));
+              mbar_expect_tx(w_full(buf), bytes);
+              bulk_g2s(s_w + buf * L::wbuf_bytes, reinterpret_cast<const uint8_t*>(p.w) + L::conv_offset(j, cc), bytes, w_full(buf));
+            }
+            __syncwarp();
           }
         }
       }
@@ -258,7 +305,9 @@ __global__ void __launch_bounds__(MrfTeams<C>::threads, 1) mrf_fused_kernel(cons
         } while (v < target);
       };
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++n_tiles_done) {
-        mbar_wait(u_ready, n_tiles_done & 1);
+        const uint32_t s_uc = s_u + (n_tiles_done & 1u) * L::u_bytes;   // this window's raw rows
+        mbar_wait(u_ready(n_tiles_done & 1), (n_tiles_done >> 1) & 1);
+        fence_proxy_async_smem();   // the rows were written by cp.async (generic proxy), the MMAs read them through the async proxy
         tc_fence_after();
         if (mi == 0) MRF_STAMP(0);   // window's raw rows are in shared memory
         // events on a tile per window: per resblock 7 (E0 operand init, then conv1/conv2 of 3 pairs) => 21
@@ -276,7 +325,7 @@ __global__ void __launch_bounds__(MrfTeams<C>::threads, 1) mrf_fused_kernel(cons
             // descriptors advance in 16-byte units: one q-row = +1, one K slice (two 8-channel chunks) = +2*RP (operand) or
             // +2*rows (weights), one phase of an operand = +CH*RP
             const uint64_t a_desc0 = desc_interleaved(src, RP * 16);
-            const uint64_t u_desc0 = desc_interleaved(s_u, RP * 16);
+            const uint64_t u_desc0 = desc_interleaved(s_uc, RQ * 16);
             const uint64_t wn_desc0 = desc_interleaved(wb, N * 16);    // phase matrices [N][C]
             const uint64_t wc_desc0 = desc_interleaved(wb, C * 16);    // tap matrices [C][C]
             const uint64_t i_desc0 = desc_interleaved(s_ident, C * 16);
@@ -293,7 +342,7 @@ __global__ void __launch_bounds__(MrfTeams<C>::threads, 1) mrf_fused_kernel(cons
                 for (int e = 0; e < D; ++e)
 #pragma unroll
                   for (int s = 0; s < KS; ++s)
-                    umma_bf16_pred(leader, t_dx + m * N + e * C, u_desc0 + (uint64_t)(e * CH * RP + m * 128 + G + s * 2 * RP),
+                    umma_bf16_pred(leader, t_dx + m * N + e * C, u_desc0 + (uint64_t)(e * CH * RQ + m * 128 + s * 2 * RQ),
                                    i_desc0 + (uint64_t)(s * 2 * C), IDESC, s != 0 ? 1u : 0u);
               }
               const uint64_t a_row = a_desc0 + (uint64_t)(m * 128 + G);
@@ -350,20 +399,10 @@ __global__ void __launch_bounds__(MrfTeams<C>::threads, 1) mrf_fused_kernel(cons
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++n_tiles_done) {
       const int b = tile / p.tiles_per_b;
       const int t0 = (tile % p.tiles_per_b) * L::tout - kMrfHalo;     // global row of window row 0
-      const __nv_bfloat16* ub = p.u + (size_t)b * p.rows * C;
       if (ew == 0) MRF_STAMP(1);   // window start
-      // ---- load the raw window into the U operand buffer (rows outside [0, L) are zero): time row r -> phase r % D,
-      // q-row r / D
-      for (int i = etid; i < R * CH; i += EPI_THREADS) {
-        const int row = i / CH, ch = i % CH;
-        const int gr = t0 + row;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (gr >= 0 && gr < p.rows) v = __ldg(reinterpret_cast<const uint4*>(ub + (size_t)gr * C) + ch);
-        *reinterpret_cast<uint4*>(smem + L::off_u + (((row % D) * CH + ch) * RP + (row / D) + G) * 16) = v;
-      }
-      fence_proxy_async_smem();
-      asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");   // every epilogue warp finished writing U
-      if (lane == 0) mbar_arrive(u_ready);
+      const int ub = n_tiles_done & 1;
+      uint8_t* u_buf = smem + L::off_u + ub * L::u_bytes;
+      mbar_wait(u_ready(ub), (n_tiles_done >> 1) & 1);   // the window's raw rows are in shared memory
       if (ew == 0) MRF_STAMP(1);   // raw rows loaded
 
       uint32_t acc_ev = n_tiles_done * 18u;   // events on acc_ready[m]: one per conv
@@ -374,7 +413,7 @@ __global__ void __launch_bounds__(MrfTeams<C>::threads, 1) mrf_fused_kernel(cons
           const int row = m * 128 + quarter * 32 + lane;
 #pragma unroll
           for (int pc = 0; pc < NPC; ++pc) {
-            const uint4 v = *reinterpret_cast<const uint4*>(smem + L::off_u + pc * RP * 16 + (row + G) * 16);
+            const uint4 v = *reinterpret_cast<const uint4*>(u_buf + (pc * RQ + row) * 16);
             uint4 o;
             o.x = pack_bf16(lrelu(bf16_lo(v.x), p.slope), lrelu(bf16_hi(v.x), p.slope));
             o.y = pack_bf16(lrelu(bf16_lo(v.y), p.slope), lrelu(bf16_hi(v.y), p.slope));
@@ -491,8 +530,9 @@ __global__ void __launch_bounds__(MrfTeams<C>::threads, 1) mrf_fused_kernel(cons
           if (ew == 0) MRF_STAMP(1);   // team 0 finished the epilogues of conv (j, cc)
         }
       }
-      // all eight warps must be done reading U / writing before the next window overwrites the buffers
+      // all epilogue warps must be done reading U / writing before the next window overwrites the buffers
       asm volatile("bar.sync 2, %0;" ::"n"(EPI_THREADS) : "memory");
+      if (etid == 0) mbar_arrive(u_free(ub));   // (the MMAs that read it completed before the last epilogues)
     }
   }
 
@@ -507,6 +547,8 @@ static int launch_mrf(const MrfParams& p0, cudaStream_t stream) {
   MrfParams p = p0;
   p.tiles_per_b = (p.rows + L::tout - 1) / L::tout;
   p.total_tiles = p.tiles_per_b * p.batch;
+  static const int ahead = [] { const char* e = getenv("SRB_MRF_AHEAD"); return e ? atoi(e) : 1; }();
+  p.u_ahead = ahead;
   auto kernel = mrf_fused_kernel<C, R, D>;
   static bool configured[64] = {false};
   int dev = 0;

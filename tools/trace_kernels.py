@@ -24,7 +24,7 @@ P = nat.ptr
 
 
 def dump(trace, title):
-    t = trace.cpu().view(8, 3, 8, 4).tolist()
+    t = trace.cpu().view(8, 7, 8, 4).tolist()
     print("==", title)
     for cta in (0, 1, 147 % 8):
         t0 = t[cta][0][0][0]
@@ -37,6 +37,10 @@ def dump(trace, title):
                 break
             print(f"   tile {it}: mma free {rel(t[cta][1][it][0])} box {rel(t[cta][1][it][1])} issued {rel(t[cta][1][it][2])} | "
                   f"epi ready {rel(t[cta][2][it][0])} acc {rel(t[cta][2][it][1])} done {rel(t[cta][2][it][2])}")
+            if t[cta][3][it][0]:
+                # RESNORM epilogue of warp 2, per 32-column chunk: residual arrived / fp32 block stored / bf16 block stored
+                print("       resid " + " ".join(rel(v) for v in t[cta][3][it]) + " | fp32 " + " ".join(rel(v) for v in t[cta][4][it]) +
+                      " | bf16 " + " ".join(rel(v) for v in t[cta][5][it]) + f" | acc0 {rel(t[cta][6][it][0])} norm {rel(t[cta][6][it][1])}")
 
 
 if __name__ == "__main__":
@@ -59,7 +63,7 @@ if __name__ == "__main__":
     sampler.prepare(ws)
     sampler.step(ws, g[0], 0.0625, last=False)     # warm: fills every buffer with real data
     torch.cuda.synchronize()
-    trace = torch.zeros(8 * 3 * 8 * 4, dtype=torch.int64, device="cuda")
+    trace = torch.zeros(8 * 7 * 8 * 4, dtype=torch.int64, device="cuda")
     w, L = sampler.w, ws["lengths"]
     cs, sn = sampler.rotary(n8)
     m = b * n8
