@@ -144,9 +144,11 @@ int srb_cfm_attn_out_norm(const void* o_bf16, const void* w_packed, const float*
 /* FeedForward conv1 (k=3) + SIGLU + pad mask (fastspeech/modules.py:58-69):
  *   h (B, N, 896) bf16 = mask * silu(gate) * value, (value | gate) = conv1(xn) + b.
  *   w_packed [1792][768] with rows permuted so every 256-row block holds 128 value rows then their 128 gate rows;
- *   bias_packed[1792] in the same row order. */
+ *   bias_packed[1792] in the same row order.
+ *   pad_separated != 0 asserts that every utterance ends in at least one pad row (lengths[b] < frames; pad rows of
+ *   xn are zero): the rows are then processed as one sequence, row tiles spanning utterances (same results). */
 int srb_cfm_ffn_glu(const void* xn_bf16, const void* w_packed, const float* bias_packed, const int32_t* lengths,
-                    void* h_bf16, int32_t batch, int32_t frames, void* stream);
+                    void* h_bf16, int32_t batch, int32_t frames, int32_t pad_separated, void* stream);
 
 /* FeedForward conv2 (k=3) + bias + residual (fastspeech/modules.py:71-73, transformer.py:206) fused with the NEXT
  * norm: norm_mode 1 = AdaptiveRMSNorm with g (next layer), 2 = final nn.RMSNorm (transformer.py:208; g = weight,

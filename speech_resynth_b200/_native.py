@@ -44,7 +44,7 @@ _PROTOTYPES = {
     "srb_cfm_qk_rope_vt": [_P, _P, _P, _P, _P, _P, _L, _P, _P, _I, _I, _P],
     "srb_cfm_attention_tc": [_P, _I, _P, _L, _P, _P, _P, _I, _I, _P],
     "srb_cfm_attn_out_norm": [_P, _P, _P, _P, _P, _P, _I, _I, _P],
-    "srb_cfm_ffn_glu": [_P, _P, _P, _P, _P, _I, _I, _P],
+    "srb_cfm_ffn_glu": [_P, _P, _P, _P, _P, _I, _I, _I, _P],
     "srb_cfm_ffn_out_norm": [_P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _P],
     "srb_cfm_pred_euler": [_P, _P, _F, _P, _P, _P, _P, _I, _F, _F, _F, _P, _I, _I, _P],
     "srb_hifigan_conv": [_P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _P],

@@ -729,10 +729,16 @@ int srb_cfm_attn_out_norm(const void* o_bf16, const void* w_packed, const float*
 }
 
 int srb_cfm_ffn_glu(const void* xn_bf16, const void* w_packed, const float* bias_packed, const int32_t* lengths,
-                    void* h_bf16, int32_t batch, int32_t frames, void* stream) {
+                    void* h_bf16, int32_t batch, int32_t frames, int32_t pad_separated, void* stream) {
   SRB_REQUIRE(lengths != nullptr, "srb_cfm_ffn_glu: lengths required");
+  // pad_separated: every utterance ends in at least one pad row (lengths[b] < frames for all b).  Pad rows of xn are zero,
+  // so the (B, frames) rows can then be convolved as ONE sequence of B * frames rows -- the zero row between two
+  // utterances is exactly the conv's zero padding -- and row tiles need not stop at utterance ends: 252 x 7 tiles
+  // instead of 64 x 4 x 7 = 1 792 at 64 x 504 frames, i.e. 12 rounds of the 148 SMs instead of 12.1 -> 13.
+  static const int flat_on = [] { const char* e = getenv("SRB_GLU_FLAT"); return e ? atoi(e) : 1; }();   // A/B knob
+  const bool flat = flat_on && pad_separated != 0 && batch > 1 && (long long)batch * frames < (1ll << 30);
   ConvGemmDesc d;
-  d.src[0] = act(xn_bf16, batch, frames, 256);
+  d.src[0] = flat ? act(xn_bf16, 1, batch * frames, 256) : act(xn_bf16, batch, frames, 256);
   d.weight = w_packed;
   d.n_total = 1792;
   d.block_n = 256;
@@ -741,12 +747,13 @@ int srb_cfm_ffn_glu(const void* xn_bf16, const void* w_packed, const float* bias
   int ntap = 0;
   same_conv_taps(d, 0, 3, 1, ntap);
   d.group_tap_begin[1] = ntap;
-  d.group_rows[0] = frames;
-  d.batch = batch;
+  d.group_rows[0] = flat ? batch * frames : frames;
+  d.batch = flat ? 1 : batch;
   d.epilogue = EPI_GLU;
   d.epi = empty_epi();
   d.epi.bias = bias_packed;
   d.epi.lengths = lengths;
+  d.epi.flat_frames = flat ? frames : 0;
   d.epi.out0 = h_bf16;
   d.epi.out_row_stride = 896;
   d.epi.out_batch_stride = (long long)frames * 896;

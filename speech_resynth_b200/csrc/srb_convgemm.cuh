@@ -85,6 +85,8 @@ struct ConvGemmParams {
   void* aux0;                                     // EULER: mel fp32 (or null)
   void* aux1;                                     // EULER: mel bf16
   int aux_rows;                                   // EULER: rows per utterance of the (compact) mel outputs; rows beyond are not written
+  int flat_frames;                                // GLU: > 0 = the launch sees ONE sequence of batch * flat_frames rows (row tiles span
+                                                  // utterances, which a zero pad row separates); lengths are looked up per row
 #ifdef SRB_TRACE
   unsigned long long* trace;                      // debug build only: %globaltimer stamps, see SRB_TRACE_AT
 #endif
@@ -438,7 +440,15 @@ __device__ __forceinline__ void epi_glu(const ConvGemmParams& p, uint32_t tacc, 
                                         const EpiWarp& w) {
   constexpr int COLS = 128 / NHALF;
   const int vrows = clamp_rows(p.group_rows[0], w.row0);
-  const bool keep = q < p.group_rows[0] && q < p.lengths[tc.b];
+  bool keep = false;
+  if (q < p.group_rows[0]) {
+    if (p.flat_frames > 0) {
+      const int b = q / p.flat_frames;
+      keep = q - b * p.flat_frames < p.lengths[b];
+    } else {
+      keep = q < p.lengths[tc.b];
+    }
+  }
   __nv_bfloat16* out = static_cast<__nv_bfloat16*>(p.out0) + (long long)tc.b * p.out_batch_stride +
                        (long long)w.row0 * p.out_row_stride + tc.n * 128;
   const float* bias = p.bias + tc.n * 256;
@@ -838,7 +848,12 @@ template <int BN, int EPI>
 struct EpiWarps {
   // eight epilogue warps (two column halves per TMEM lane quarter) for the wide tiles, four otherwise
   // (sixteen for the FFN GLU tile, whose SiLU epilogue is transcendental-bound and needs the extra latency hiding)
-  static constexpr int value = EPI == EPI_GLU ? 16 : ((BN >= 128 && EPI != EPI_EULER) ? 8 : 4);
+  // (eight warps for the BN = 64 tiles too -- -DSRB_EPI_WARPS_MIN_BN=64 -- measured at config 2: k = 11 convs 254 -> 239 us,
+  // but k = 7 180 -> 210, k = 3 152 -> 177 and the fused tail 509 -> 666: the second resident CTA is worth more)
+#ifndef SRB_EPI_WARPS_MIN_BN
+#define SRB_EPI_WARPS_MIN_BN 128
+#endif
+  static constexpr int value = EPI == EPI_GLU ? 16 : ((BN >= SRB_EPI_WARPS_MIN_BN && EPI != EPI_EULER) ? 8 : 4);
   // staging bytes per epilogue warp: bf16 output blocks are 2 KB (4 pieces per row); RESNORM adds `res_bufs` 4 KB
   // buffers for the asynchronous fp32 residual stream (they double as the fp32 output stage)
   // (multiples of 1024: the TMA-staged blocks need their swizzle alignment)

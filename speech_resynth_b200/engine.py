@@ -305,7 +305,9 @@ class CFMSampler:
                      flops=4.0 * m * n * 256)
             nat.call("srb_cfm_attn_out_norm", P(ws["o"]), P(w.w_out[i]), P(g_step[2 * i + 1]), P(L), P(ws["x"]), P(ws["xn"]), b, n,
                      flops=2.0 * m * 256 * 256)
+            # every utterance ends in a pad row whenever the caller's frame count is not a multiple of 8 (lengths <= mel_rows < n)
             nat.call("srb_cfm_ffn_glu", P(ws["xn"]), P(w.w_ff1[i]), P(w.b_ff1[i]), P(L), P(ws["h"]), b, n,
+                     1 if ws["mel_rows"] < n else 0,
                      flops=2.0 * m * 768 * 1792)
             if i + 1 < self.depth:
                 g_next, mode = g_step[2 * i + 2], 1

@@ -586,20 +586,38 @@ def cfm_attn_out_norm():
     return max(e1 * 400, e2), BF16_TOL   # x is fp32 (bound 1.5e-5), xn carries the bf16 rounding
 
 
-@check
-def cfm_ffn_glu():
+def _ffn_glu_case(lengths, frames, pad_separated):
     s = sd()
     pk = packing.pack_cfm(s, DEV)
-    ids, mask, L = _cfm_inputs()
+    ids, mask, L = _cfm_inputs(batch=len(lengths), frames=frames, lengths=lengths)
     b, n = ids.shape
     xn = bf(torch.randn(b, n, 256, generator=g(9))) * mask[..., None]
     h = torch.empty(b, n, 896, dtype=torch.bfloat16, device=DEV)
-    nat.call("srb_cfm_ffn_glu", P(xn.to(DEV).to(torch.bfloat16).contiguous()), P(pk.w_ff1[0]), P(pk.b_ff1[0]), P(L), P(h), b, n)
+    nat.call("srb_cfm_ffn_glu", P(xn.to(DEV).to(torch.bfloat16).contiguous()), P(pk.w_ff1[0]), P(pk.b_ff1[0]), P(L), P(h), b, n,
+             pad_separated)
     w = bf(s["model.transformer.layers.0.4.conv1.weight"]).double()
     y = F.conv1d(xn.double().transpose(1, 2), w, s["model.transformer.layers.0.4.conv1.bias"].double(), padding=1)
     val, gate = y.chunk(2, dim=1)
     ref = (F.silu(gate) * val).transpose(1, 2) * mask[..., None]
+    return h, ref
+
+
+@check
+def cfm_ffn_glu():
+    h, ref = _ffn_glu_case((150, 97), 150, 0)
     return rel_l2(h.float(), ref), BF16_TOL
+
+
+@check
+def cfm_ffn_glu_rows_as_one_sequence():
+    """pad-separated utterances convolved as one sequence (row tiles span utterances): same values as the per-utterance
+    tiling, bit for bit, and within the bf16 tolerance of the float64 evaluation"""
+    lengths = (151, 97, 1, 150)
+    h_flat, ref = _ffn_glu_case(lengths, 152, 1)
+    h_tile, _ = _ffn_glu_case(lengths, 152, 0)
+    if not torch.equal(h_flat, h_tile):
+        return float("inf"), BF16_TOL
+    return rel_l2(h_flat.float(), ref), BF16_TOL
 
 
 @check

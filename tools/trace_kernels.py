@@ -71,7 +71,7 @@ if __name__ == "__main__":
         "qk_rope": lambda: nat.call("srb_cfm_qk_rope", P(ws["xn"]), P(w.w_qkv[0]), P(cs), P(sn), P(ws["qk"]), P(ws["qkmax"][0]), None, b, n8),
         "v_transposed": lambda: nat.call("srb_cfm_v_transposed", P(ws["xn"]), P(w.w_qkv[0][512:]), P(ws["vt"]), ws["vt"].shape[1]),
         "attn_out_norm": lambda: nat.call("srb_cfm_attn_out_norm", P(ws["o"]), P(w.w_out[0]), P(g[0][1]), P(L), P(ws["x"]), P(ws["xn"]), b, n8),
-        "ffn_glu": lambda: nat.call("srb_cfm_ffn_glu", P(ws["xn"]), P(w.w_ff1[0]), P(w.b_ff1[0]), P(L), P(ws["h"]), b, n8),
+        "ffn_glu": lambda: nat.call("srb_cfm_ffn_glu", P(ws["xn"]), P(w.w_ff1[0]), P(w.b_ff1[0]), P(L), P(ws["h"]), b, n8, 1),
         "ffn_out_norm": lambda: nat.call("srb_cfm_ffn_out_norm", P(ws["h"]), P(w.w_ff2[0]), P(w.b_ff2[0]), P(g[0][2]), 1, P(L), P(ws["x"]), P(ws["xn"]), b, n8),
         "embed": lambda: nat.call("srb_cfm_embed", P(ws["xt_b"]), P(w.w_embed), P(ws["cond"]), P(ws["x0"]), b, n8),
         "pred_euler": lambda: nat.call("srb_cfm_pred_euler", P(ws["xn"]), P(w.w_pred), 0.0625, P(ws["xt"]), P(ws["xt_b"]), None, None, n, 2.26, -5.88, -11.5, P(L), b, n8),
