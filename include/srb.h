@@ -31,6 +31,13 @@ extern "C" {
 #define SRB_VERSION 100
 
 int srb_version(void);
+/* 1 = the product library (libsrb.so: plain bf16 activations).  3 = the tight-precision build of the same sources
+ * (libsrb_tight.so, -DSRB_SPLIT): every bf16 ACTIVATION tensor named below is stored with three column blocks
+ * [hi | lo | hi] (hi = bf16(x), lo = bf16(x - hi); 3 C columns for a logical width C, blocks C columns apart) and every
+ * GEMM weight must be packed as [Wh | Wh | Wl] along K, so the unchanged bf16 tensor-core loop accumulates
+ * xh Wh + xl Wh + xh Wl in fp32: results within ~1e-5 of the reference's fp32 path ("tight in fp32/TF32",
+ * BASELINE.json north_star).  fp32 tensors are unaffected.  Entries without a tight form return an error there. */
+int srb_split_factor(void);
 const char* srb_last_error(void);
 /* compute capability major*10+minor of the current device, or negative error */
 int srb_device_arch(void);
@@ -202,6 +209,16 @@ int srb_hifigan_mrf_fused(const void* u_raw, const void* w_packed, const float* 
  * loop of the reference (models.py:252-256) folded into the store; wav must hold sum_b n_b floats. */
 int srb_hifigan_post(const void* x_act, const float* w, float bias, float* wav, int32_t batch, int32_t rows,
                      const int32_t* lengths, void* stream);
+
+/* ---- reference-style forms (fp32 CUDA-core arithmetic; the tight-precision engine and tests) ---------------------
+ * Key-padding-masked softmax attention, 2 heads x 128, online softmax in fp32 (transformer.py:115-127):
+ *   qkv (B, N, 768) bf16 = [q | k | v] after rotary (srb_cfm_qkv_rope), o (B, N, 256) bf16. */
+int srb_cfm_attention_simt(const void* qkv_bf16, const int32_t* lengths, void* o_bf16, int32_t batch, int32_t frames,
+                           void* stream);
+/* out = leaky_relu((x0 + x1 + x2) * scale, slope) over (rows, channels) bf16 tensors: the MRF mean (HF:1475-1480) when
+ * the fused tail of srb_hifigan_conv is not used. */
+int srb_hifigan_mean3(const void* x0, const void* x1, const void* x2, void* out, int64_t rows, int32_t channels, float scale,
+                      float slope, void* stream);
 
 #ifdef __cplusplus
 }

@@ -16,6 +16,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsrb.so")
 if os.environ.get("SRB_DEBUG_LIB"):   # tools/trace_kernels.py: instrumented build of the same sources
     LIB_PATH = os.environ["SRB_DEBUG_LIB"]
+# the same sources built with -DSRB_SPLIT: tight-precision mode (bf16 operands split into hi + lo, see include/srb.h)
+TIGHT_LIB_PATH = os.path.join(_HERE, "libsrb_tight.so")
 
 _P = c_void_p
 _I = c_int32
@@ -51,6 +53,9 @@ _PROTOTYPES = {
     "srb_hifigan_upsample": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P],
     "srb_hifigan_mrf_fused": [_P, _P, _P, _P, _I, _I, _I, _F, _F, _P],
     "srb_hifigan_post": [_P, _P, _F, _P, _I, _I, _P, _P],
+    "srb_cfm_attention_simt": [_P, _P, _P, _I, _I, _P],
+    "srb_hifigan_mean3": [_P, _P, _P, _P, _L, _I, _F, _F, _P],
+    "srb_split_factor": [],
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOTYPES) + ("srb_last_error", "srb_hifigan_mrf_phases")
@@ -60,24 +65,25 @@ class NativeLibraryError(RuntimeError):
     pass
 
 
-_lib: Optional[ctypes.CDLL] = None
+_libs: dict = {}
 launch_count = 0  # kernels launched through this binding (bench.py reports it as gpu_launches)
 # when set to a list, every call appends (name, shape_tag, start_event, end_event): per-op device timing for
 # bench.py's roofline line and tools/profile_ops.py (never enabled on the product path)
 profile_log: Optional[list] = None
 
 
-def load() -> ctypes.CDLL:
-    """Load libsrb.so and declare prototypes.  Raises NativeLibraryError when it is absent."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
+def load(tight: bool = False) -> ctypes.CDLL:
+    """Load libsrb.so (or, tight=True, libsrb_tight.so) and declare prototypes.  Raises NativeLibraryError when absent."""
+    lib = _libs.get(tight)
+    if lib is not None:
+        return lib
+    path = TIGHT_LIB_PATH if tight else LIB_PATH
+    if not os.path.exists(path):
         raise NativeLibraryError(
-            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(speech_resynth_b200 has no CPU or PyTorch fallback)"
         )
-    lib = ctypes.CDLL(LIB_PATH)
+    lib = ctypes.CDLL(path)
     for name, argtypes in _PROTOTYPES.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
@@ -86,12 +92,15 @@ def load() -> ctypes.CDLL:
     lib.srb_last_error.restype = c_char_p
     lib.srb_hifigan_mrf_phases.argtypes = [c_int32]
     lib.srb_hifigan_mrf_phases.restype = c_int32
-    _lib = lib
+    want = 3 if tight else 1
+    if lib.srb_split_factor() != want:
+        raise NativeLibraryError(f"{path} reports split factor {lib.srb_split_factor()}, expected {want}")
+    _libs[tight] = lib
     return lib
 
 
-def last_error() -> str:
-    return load().srb_last_error().decode("utf-8", "replace")
+def last_error(tight: bool = False) -> str:
+    return load(tight).srb_last_error().decode("utf-8", "replace")
 
 
 def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -105,17 +114,18 @@ def stream_ptr() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
-def call(name: str, *args, flops: float = 0.0, nbytes: float = 0.0) -> None:
+def call(name: str, *args, flops: float = 0.0, nbytes: float = 0.0, tight: bool = False) -> None:
     """Invoke an entry point on the current torch stream; non-zero status -> RuntimeError with the C-side text.
-    `flops` / `nbytes` are the op's algorithmic work (used only by the profiling log)."""
+    `flops` / `nbytes` are the op's algorithmic work (used only by the profiling log); tight=True calls the
+    tight-precision build of the same entry point."""
     global launch_count
-    lib = load()
+    lib = load(tight)
     if profile_log is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
     rc = getattr(lib, name)(*args, stream_ptr())
     if rc != 0:
-        raise RuntimeError(f"{name} failed ({rc}): {last_error()}")
+        raise RuntimeError(f"{name} failed ({rc}): {last_error(tight)}")
     if profile_log is not None:
         ev1.record()
         profile_log.append((name, tuple(a for a in args if isinstance(a, int) and 0 <= a < (1 << 24)), ev0, ev1, flops, nbytes))

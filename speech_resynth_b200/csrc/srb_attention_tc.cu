@@ -493,6 +493,7 @@ using namespace srb;
 extern "C" int srb_cfm_attention_tc(const void* qk_bf16, int32_t ld, const void* vt_bf16, int64_t m_pad,
                                     const int32_t* lengths, const float* qk_norm2_max, void* o_bf16, int32_t batch,
                                     int32_t frames, void* stream) {
+  SRB_REQUIRE(kSplit == 1, "srb_cfm_attention_tc: not available in the tight-precision build");
   if (batch <= 0 || frames <= 0) return 0;
   auto enc = attn_get_encode();
   SRB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");

@@ -329,7 +329,7 @@ static int launch_convgemm(const ConvGemmDesc& d, cudaStream_t stream) {
   const int n_taps = d.group_tap_begin[d.n_groups];
   SRB_REQUIRE(n_taps >= 1 && n_taps <= kMaxTaps, "bad tap count %d", n_taps);
   p.batch = d.batch;
-  p.kchunks = (d.channels + kb - 1) / kb;
+  p.kchunks = (d.channels * kSplit + kb - 1) / kb;
   p.n_groups = d.n_groups;
   p.n_tiles = d.n_total / bn;
   p.row_mul = d.row_mul;
@@ -403,11 +403,18 @@ static int launch_convgemm(const ConvGemmDesc& d, cudaStream_t stream) {
       if (rc) return rc;
     }
     if (p.out0 != nullptr) {
-      rc = make_io_map(&p.tmO0, p.out0, 2, (int)p.out_row_stride, rows, d.batch, p.out_row_stride, p.out_batch_stride);
+      rc = make_io_map(&p.tmO0, p.out0, 2, (int)p.out_row_stride * kSplit, rows, d.batch, p.out_row_stride * kSplit,
+                       p.out_batch_stride * kSplit);
       if (rc) return rc;
     }
   }
-  if (d.epilogue == EPI_GENERIC) {
+  if (d.epilogue == EPI_GENERIC && kSplit != 1) {
+    // split build: always the register / LSU epilogue (it writes the three column blocks and reads residuals as hi + lo)
+    p.n_res = 0;
+    p.gen_lsu = 1;
+    p.gen_nbuf = 1;
+    p.res_bufs = -1;
+  } else if (d.epilogue == EPI_GENERIC) {
     // residuals first (packed), then per tap group the raw / activated output views (row = q * row_mul + row_add)
     const int cw = bn < 32 ? bn : 32;
     int n_res = 0;
@@ -517,12 +524,13 @@ static ConvGemmParams empty_epi() {
 
 static ActView act(const void* ptr, int batch, int rows, int channels) {
   ActView a;
+  // (split build: a bf16 activation tensor of logical width `channels` is stored as [hi | lo | hi], kSplit * channels wide)
   a.ptr = ptr;
-  a.channels = channels;
+  a.channels = channels * kSplit;
   a.rows = rows;
   a.batch = batch;
-  a.row_stride = channels;
-  a.batch_stride = (long long)rows * channels;
+  a.row_stride = channels * kSplit;
+  a.batch_stride = (long long)rows * channels * kSplit;
   return a;
 }
 
@@ -544,6 +552,7 @@ using namespace srb;
 extern "C" {
 
 int srb_version(void) { return SRB_VERSION; }
+int srb_split_factor(void) { return kSplit; }
 const char* srb_last_error(void) { return g_err; }
 
 int srb_device_arch(void) {
@@ -607,6 +616,7 @@ int srb_cfm_qkv_rope(const void* xn_bf16, const void* w_packed, const float* rot
 int srb_cfm_qk_rope_vt(const void* xn_bf16, const void* w_packed, const float* rot_cos, const float* rot_sin, void* qk_bf16,
                        void* vt_bf16, int64_t m_pad, float* qk_norm2_max, float* qk_norm2_clear, int32_t batch,
                        int32_t frames, void* stream) {
+  SRB_REQUIRE(kSplit == 1, "srb_cfm_qk_rope_vt: not available in the tight-precision build");
   SRB_REQUIRE(qk_norm2_clear == nullptr || qk_norm2_clear != qk_norm2_max, "srb_cfm_qk_rope_vt: the buffer to clear must differ from the one to fill");
   SRB_REQUIRE(frames % 8 == 0 && m_pad % 8 == 0 && m_pad >= (int64_t)batch * frames,
               "srb_cfm_qk_rope_vt: frames and m_pad must be multiples of 8 and m_pad >= batch * frames");
@@ -651,6 +661,7 @@ int srb_cfm_qk_rope_vt(const void* xn_bf16, const void* w_packed, const float* r
 
 int srb_cfm_qk_rope(const void* xn_bf16, const void* w_packed, const float* rot_cos, const float* rot_sin,
                     void* qk_bf16, float* qk_norm2_max, float* qk_norm2_clear, int32_t batch, int32_t frames, void* stream) {
+  SRB_REQUIRE(kSplit == 1, "srb_cfm_qk_rope: not available in the tight-precision build");
   SRB_REQUIRE(qk_norm2_clear == nullptr || qk_norm2_clear != qk_norm2_max, "srb_cfm_qk_rope: the buffer to clear must differ from the one to fill");
   // q and k only (first 512 rows of to_qkv.weight); v is produced transposed by srb_cfm_v_transposed
   ConvGemmDesc d;
@@ -676,6 +687,7 @@ int srb_cfm_qk_rope(const void* xn_bf16, const void* w_packed, const float* rot_
 }
 
 int srb_cfm_v_transposed(const void* xn_bf16, const void* wv_bf16, void* vt_bf16, int64_t m_pad, void* stream) {
+  SRB_REQUIRE(kSplit == 1, "srb_cfm_v_transposed: not available in the tight-precision build");
   // V^T[d][row] = sum_c Wv[d][c] * xn[row][c]: the same GEMM core with the operand roles swapped (the weight
   // matrix is the "activation" tile, the activations are the K-major B operand), so V comes out keys-contiguous.
   SRB_REQUIRE(m_pad > 0 && m_pad % 256 == 0, "srb_cfm_v_transposed: m_pad must be a positive multiple of 256");

@@ -16,6 +16,9 @@
 // the epilogue of tile i overlaps the MMAs of tile i+1; persistent over tiles.
 #pragma once
 #include <cuda.h>
+
+#include <type_traits>
+
 #include "srb_ptx.cuh"
 
 namespace srb {
@@ -236,18 +239,25 @@ __device__ __forceinline__ void epi_generic_lsu(const ConvGemmParams& p, uint32_
   constexpr int P = CW / 8;   // 16-byte pieces of bf16 per chunk row
   const float sc = p.scale, sl = p.slope;
   if (p.row_mul == 1) {
-    // contiguous output rows: coalesced path
+    // contiguous output rows: coalesced path.  (Split build: bf16 tensors are kSplit times as wide -- [hi | lo | hi]
+    // blocks, out_row_stride / res_row_stride columns apart; residuals are read as hi + lo.)
     const int vrows = clamp_rows(p.group_rows[tc.group], w.row0);
     const long long row0 = (long long)w.row0 + p.group_row_add[tc.group];
-    const long long obase = (long long)tc.b * p.out_batch_stride + row0 * p.out_row_stride + (long long)tc.n * BN;
-    const long long rbase = (long long)tc.b * p.res_batch_stride + row0 * p.res_row_stride + (long long)tc.n * BN;
+    const long long obase = ((long long)tc.b * p.out_batch_stride + row0 * p.out_row_stride) * kSplit + (long long)tc.n * BN;
+    const long long rbase = ((long long)tc.b * p.res_batch_stride + row0 * p.res_row_stride) * kSplit + (long long)tc.n * BN;
+    const long long opitch = p.out_row_stride * 2 * kSplit, rpitch = p.res_row_stride * 2 * kSplit;
+    constexpr int NRP = kSplit == 3 ? 2 : 1;   // parts of a residual tensor
 #pragma unroll 1
     for (int c0 = half * COLS; c0 < (half + 1) * COLS; c0 += CW) {
-      uint4 rt[3][P];
+      uint4 rt[3][NRP][P];
 #pragma unroll
       for (int r = 0; r < 3; ++r)
-        if (p.res[r])
-          gather_issue<P>(static_cast<const __nv_bfloat16*>(p.res[r]) + rbase + c0, p.res_row_stride * 2, vrows, w.lane, rt[r]);
+        if (p.res[r]) {
+#pragma unroll
+          for (int h = 0; h < NRP; ++h)
+            gather_issue<P>(static_cast<const __nv_bfloat16*>(p.res[r]) + rbase + h * p.res_row_stride + c0, rpitch, vrows, w.lane,
+                            rt[r][h]);
+        }
       float y[CW];
       tmem_ld_f<CW>(tacc + c0, y);
       if (p.bias) {
@@ -261,45 +271,51 @@ __device__ __forceinline__ void epi_generic_lsu(const ConvGemmParams& p, uint32_
 #pragma unroll
       for (int r = 0; r < 3; ++r) {
         if (p.res[r]) {
-          uint4 rv[P];
-          gather_finish<P>(w, rt[r], rv);
 #pragma unroll
-          for (int j = 0; j < P; ++j) {
-            const uint4 u = rv[j];
-            y[8 * j + 0] += bf16_lo(u.x); y[8 * j + 1] += bf16_hi(u.x);
-            y[8 * j + 2] += bf16_lo(u.y); y[8 * j + 3] += bf16_hi(u.y);
-            y[8 * j + 4] += bf16_lo(u.z); y[8 * j + 5] += bf16_hi(u.z);
-            y[8 * j + 6] += bf16_lo(u.w); y[8 * j + 7] += bf16_hi(u.w);
+          for (int h = 0; h < NRP; ++h) {
+            uint4 rv[P];
+            gather_finish<P>(w, rt[r][h], rv);
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+              const uint4 u = rv[j];
+              y[8 * j + 0] += bf16_lo(u.x); y[8 * j + 1] += bf16_hi(u.x);
+              y[8 * j + 2] += bf16_lo(u.y); y[8 * j + 3] += bf16_hi(u.y);
+              y[8 * j + 4] += bf16_lo(u.z); y[8 * j + 5] += bf16_hi(u.z);
+              y[8 * j + 6] += bf16_lo(u.w); y[8 * j + 7] += bf16_hi(u.w);
+            }
           }
         }
       }
 #pragma unroll
       for (int j = 0; j < CW; ++j) y[j] *= sc;
-      if (p.out1) {
-        uint4 o[P];
+      // store one bf16 output tensor: hi (and, split build, the rounding rest and hi again)
+      auto put = [&](void* base, auto act_tag) {
+        constexpr bool act = decltype(act_tag)::value;
+        uint4 o[P], ol[P];
+        uint32_t* ow = reinterpret_cast<uint32_t*>(o);
+        uint32_t* lw = reinterpret_cast<uint32_t*>(ol);
 #pragma unroll
-        for (int j = 0; j < P; ++j)
-          o[j] = make_uint4(pack_bf16(y[8 * j], y[8 * j + 1]), pack_bf16(y[8 * j + 2], y[8 * j + 3]),
-                            pack_bf16(y[8 * j + 4], y[8 * j + 5]), pack_bf16(y[8 * j + 6], y[8 * j + 7]));
-        scatter_store<P>(w, o, static_cast<__nv_bfloat16*>(p.out1) + obase + c0, p.out_row_stride * 2, vrows);
-      }
-      if (p.out0) {
-        uint4 o[P];
-#pragma unroll
-        for (int j = 0; j < P; ++j)
-          o[j] = make_uint4(pack_bf16(lrelu(y[8 * j], sl), lrelu(y[8 * j + 1], sl)),
-                            pack_bf16(lrelu(y[8 * j + 2], sl), lrelu(y[8 * j + 3], sl)),
-                            pack_bf16(lrelu(y[8 * j + 4], sl), lrelu(y[8 * j + 5], sl)),
-                            pack_bf16(lrelu(y[8 * j + 6], sl), lrelu(y[8 * j + 7], sl)));
-        scatter_store<P>(w, o, static_cast<__nv_bfloat16*>(p.out0) + obase + c0, p.out_row_stride * 2, vrows);
-      }
+        for (int j = 0; j < CW / 2; ++j) {
+          const float a = act ? lrelu(y[2 * j], sl) : y[2 * j], b2 = act ? lrelu(y[2 * j + 1], sl) : y[2 * j + 1];
+          ow[j] = pack_bf16(a, b2);
+          if constexpr (kSplit == 3) lw[j] = pack_bf16_rest(a, b2, ow[j]);
+        }
+        __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(base) + obase + c0;
+        scatter_store<P>(w, o, ob, opitch, vrows);
+        if constexpr (kSplit == 3) {
+          scatter_store<P>(w, ol, ob + p.out_row_stride, opitch, vrows);
+          scatter_store<P>(w, o, ob + 2 * p.out_row_stride, opitch, vrows);
+        }
+      };
+      if (p.out1) put(p.out1, std::false_type{});
+      if (p.out0) put(p.out0, std::true_type{});
     }
     return;
   }
   // strided output rows (polyphase transposed conv: row = q * stride + phase): per-row stores, no residuals
   const bool valid = q < p.group_rows[tc.group];
   const long long orow = (long long)q * p.row_mul + p.group_row_add[tc.group];
-  const long long obase = (long long)tc.b * p.out_batch_stride + orow * p.out_row_stride + (long long)tc.n * BN;
+  const long long obase = ((long long)tc.b * p.out_batch_stride + orow * p.out_row_stride) * kSplit + (long long)tc.n * BN;
 #pragma unroll 1
   for (int c0 = half * COLS; c0 < (half + 1) * COLS; c0 += CW) {
     float y[CW];
@@ -315,22 +331,29 @@ __device__ __forceinline__ void epi_generic_lsu(const ConvGemmParams& p, uint32_
       }
 #pragma unroll
       for (int j = 0; j < CW; ++j) y[j] *= sc;
-      if (p.out1) {
-        uint4* o4 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out1) + obase + c0);
+      auto put = [&](void* base, auto act_tag) {
+        constexpr bool act = decltype(act_tag)::value;
+        uint4 o[P], ol[P];
+        uint32_t* ow = reinterpret_cast<uint32_t*>(o);
+        uint32_t* lw = reinterpret_cast<uint32_t*>(ol);
 #pragma unroll
-        for (int j = 0; j < P; ++j)
-          o4[j] = make_uint4(pack_bf16(y[8 * j], y[8 * j + 1]), pack_bf16(y[8 * j + 2], y[8 * j + 3]),
-                             pack_bf16(y[8 * j + 4], y[8 * j + 5]), pack_bf16(y[8 * j + 6], y[8 * j + 7]));
-      }
-      if (p.out0) {
-        uint4* o4 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out0) + obase + c0);
+        for (int j = 0; j < CW / 2; ++j) {
+          const float a = act ? lrelu(y[2 * j], sl) : y[2 * j], b2 = act ? lrelu(y[2 * j + 1], sl) : y[2 * j + 1];
+          ow[j] = pack_bf16(a, b2);
+          if constexpr (kSplit == 3) lw[j] = pack_bf16_rest(a, b2, ow[j]);
+        }
+        __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(base) + obase + c0;
 #pragma unroll
-        for (int j = 0; j < P; ++j)
-          o4[j] = make_uint4(pack_bf16(lrelu(y[8 * j], sl), lrelu(y[8 * j + 1], sl)),
-                             pack_bf16(lrelu(y[8 * j + 2], sl), lrelu(y[8 * j + 3], sl)),
-                             pack_bf16(lrelu(y[8 * j + 4], sl), lrelu(y[8 * j + 5], sl)),
-                             pack_bf16(lrelu(y[8 * j + 6], sl), lrelu(y[8 * j + 7], sl)));
-      }
+        for (int j = 0; j < P; ++j) {
+          reinterpret_cast<uint4*>(ob)[j] = o[j];
+          if constexpr (kSplit == 3) {
+            reinterpret_cast<uint4*>(ob + p.out_row_stride)[j] = ol[j];
+            reinterpret_cast<uint4*>(ob + 2 * p.out_row_stride)[j] = o[j];
+          }
+        }
+      };
+      if (p.out1) put(p.out1, std::false_type{});
+      if (p.out0) put(p.out0, std::true_type{});
     }
   }
 }
@@ -449,8 +472,8 @@ __device__ __forceinline__ void epi_glu(const ConvGemmParams& p, uint32_t tacc, 
       keep = q < p.lengths[tc.b];
     }
   }
-  __nv_bfloat16* out = static_cast<__nv_bfloat16*>(p.out0) + (long long)tc.b * p.out_batch_stride +
-                       (long long)w.row0 * p.out_row_stride + tc.n * 128;
+  __nv_bfloat16* out = static_cast<__nv_bfloat16*>(p.out0) +
+                       ((long long)tc.b * p.out_batch_stride + (long long)w.row0 * p.out_row_stride) * kSplit + tc.n * 128;
   const float* bias = p.bias + tc.n * 256;
 #pragma unroll 1
   for (int c0 = half * COLS; c0 < (half + 1) * COLS; c0 += 32) {
@@ -458,20 +481,31 @@ __device__ __forceinline__ void epi_glu(const ConvGemmParams& p, uint32_t tacc, 
     tmem_ld32(tacc + c0, v);
     tmem_ld32(tacc + 128 + c0, g);
     tmem_ld_wait();
-    uint4 o[4];
+    uint4 o[4], ol[4];
     uint32_t* ow = reinterpret_cast<uint32_t*>(o);
+    uint32_t* lw = reinterpret_cast<uint32_t*>(ol);
+    // (the tanh.approx form of SiLU is good to ~5e-4, below one bf16 rounding; the split build takes exp / divide)
+    auto act = [](float x) { return kSplit == 3 ? silu(x) : silu_tanh(x); };
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + c0) + j);
       const float4 bg = __ldg(reinterpret_cast<const float4*>(bias + 128 + c0) + j);
-      const float h0 = silu_tanh(__uint_as_float(g[4 * j + 0]) + bg.x) * (__uint_as_float(v[4 * j + 0]) + bv.x);
-      const float h1 = silu_tanh(__uint_as_float(g[4 * j + 1]) + bg.y) * (__uint_as_float(v[4 * j + 1]) + bv.y);
-      const float h2 = silu_tanh(__uint_as_float(g[4 * j + 2]) + bg.z) * (__uint_as_float(v[4 * j + 2]) + bv.z);
-      const float h3 = silu_tanh(__uint_as_float(g[4 * j + 3]) + bg.w) * (__uint_as_float(v[4 * j + 3]) + bv.w);
+      const float h0 = act(__uint_as_float(g[4 * j + 0]) + bg.x) * (__uint_as_float(v[4 * j + 0]) + bv.x);
+      const float h1 = act(__uint_as_float(g[4 * j + 1]) + bg.y) * (__uint_as_float(v[4 * j + 1]) + bv.y);
+      const float h2 = act(__uint_as_float(g[4 * j + 2]) + bg.z) * (__uint_as_float(v[4 * j + 2]) + bv.z);
+      const float h3 = act(__uint_as_float(g[4 * j + 3]) + bg.w) * (__uint_as_float(v[4 * j + 3]) + bv.w);
       ow[2 * j] = keep ? pack_bf16(h0, h1) : 0u;       // pads are zeroed before conv2 (fastspeech/modules.py:69)
       ow[2 * j + 1] = keep ? pack_bf16(h2, h3) : 0u;
+      if constexpr (kSplit == 3) {
+        lw[2 * j] = keep ? pack_bf16_rest(h0, h1, ow[2 * j]) : 0u;
+        lw[2 * j + 1] = keep ? pack_bf16_rest(h2, h3, ow[2 * j + 1]) : 0u;
+      }
     }
-    scatter_store<4>(w, o, out + c0, p.out_row_stride * 2, vrows);
+    scatter_store<4>(w, o, out + c0, p.out_row_stride * 2 * kSplit, vrows);
+    if constexpr (kSplit == 3) {
+      scatter_store<4>(w, ol, out + p.out_row_stride + c0, p.out_row_stride * 2 * kSplit, vrows);
+      scatter_store<4>(w, o, out + 2 * p.out_row_stride + c0, p.out_row_stride * 2 * kSplit, vrows);
+    }
   }
 }
 
@@ -594,14 +628,38 @@ __device__ __forceinline__ void epi_resnorm(const ConvGemmParams& p, uint32_t ta
     uint32_t v[32];
     tmem_ld32(tcol + c * 32, v);
     tmem_ld_wait();
-    uint4 o[4];
+    uint4 o[4], ol[4];
     uint32_t* ow = reinterpret_cast<uint32_t*>(o);
+    uint32_t* lw = reinterpret_cast<uint32_t*>(ol);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float4 g = __ldg(reinterpret_cast<const float4*>(gv + c * 32 + 4 * j));
+      const float n0 = __uint_as_float(v[4 * j]) * inv * g.x, n1 = __uint_as_float(v[4 * j + 1]) * inv * g.y;
+      const float n2 = __uint_as_float(v[4 * j + 2]) * inv * g.z, n3 = __uint_as_float(v[4 * j + 3]) * inv * g.w;
       // select (not multiply) so a non-finite pad row can never leak into the conv taps of valid frames
-      ow[2 * j] = keep ? pack_bf16(__uint_as_float(v[4 * j]) * inv * g.x, __uint_as_float(v[4 * j + 1]) * inv * g.y) : 0u;
-      ow[2 * j + 1] = keep ? pack_bf16(__uint_as_float(v[4 * j + 2]) * inv * g.z, __uint_as_float(v[4 * j + 3]) * inv * g.w) : 0u;
+      ow[2 * j] = keep ? pack_bf16(n0, n1) : 0u;
+      ow[2 * j + 1] = keep ? pack_bf16(n2, n3) : 0u;
+      if constexpr (kSplit == 3) {
+        lw[2 * j] = keep ? pack_bf16_rest(n0, n1, ow[2 * j]) : 0u;
+        lw[2 * j + 1] = keep ? pack_bf16_rest(n2, n3, ow[2 * j + 1]) : 0u;
+      }
+    }
+    if constexpr (kSplit == 3) {
+      // split build: three blocks per chunk (hi | rest | hi, 256 columns apart), one after the other through the stage
+#pragma unroll
+      for (int part = 0; part < 3; ++part) {
+        if (w.lane == 0) bulk_wait_read<0>();
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) *stage_slot<4>(st_gen, w.lane, j) = part == 1 ? ol[j] : o[j];
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (w.lane == 0) {
+          tma_store_3d(&p.tmO0, st_stage, part * 256 + half * COLS + c * 32, w.row0, tc.b);
+          bulk_commit();
+        }
+      }
+      continue;
     }
     if (w.lane == 0) {
       if (c < 2) bulk_wait_read<0>();   // fp32 blocks (and, in place, the whole buffer) have been read
@@ -664,7 +722,7 @@ __device__ __forceinline__ void epi_qkv_rope(const ConvGemmParams& p, uint32_t t
   const uint32_t stage_s = smem_u32(w.stage);
   // output blocks (32 rows x 64 B = 2 KB, 64-byte swizzle) alternate between the two halves of the 4 KB stage
   int blk = 0;
-  auto put_block = [&](const uint4 (&o)[4], int col) {
+  auto put_one = [&](const uint4 (&o)[4], int col) {
     if (w.lane == 0) bulk_wait_read<1>();   // the block stored from this half two blocks ago has been read
     __syncwarp();
     uint8_t* hb = w.stage + (blk & 1) * 2048;
@@ -677,6 +735,22 @@ __device__ __forceinline__ void epi_qkv_rope(const ConvGemmParams& p, uint32_t t
       bulk_commit();
     }
     ++blk;
+  };
+  // `f` holds the 32 fp32 values of this lane's row; split build: [hi | rest | hi] blocks out_row_stride columns apart
+  auto put_block = [&](const float (&f)[32], int col) {
+    uint4 o[4], ol[4];
+    uint32_t* ow = reinterpret_cast<uint32_t*>(o);
+    uint32_t* lw = reinterpret_cast<uint32_t*>(ol);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      ow[j] = pack_bf16(f[2 * j], f[2 * j + 1]);
+      if constexpr (kSplit == 3) lw[j] = pack_bf16_rest(f[2 * j], f[2 * j + 1], ow[j]);
+    }
+    put_one(o, col);
+    if constexpr (kSplit == 3) {
+      put_one(ol, col + (int)p.out_row_stride);
+      put_one(o, col + 2 * (int)p.out_row_stride);
+    }
   };
   if (tc.n == 2 && p.vt_out != nullptr) {
     // V stored TRANSPOSED ([d][utterance * frames + key], keys contiguous) for the attention kernel's K-major P V product:
@@ -713,14 +787,10 @@ __device__ __forceinline__ void epi_qkv_rope(const ConvGemmParams& p, uint32_t t
       uint32_t v[32];
       tmem_ld32(tcol + c * 32, v);
       tmem_ld_wait();
-      uint4 o[4];
+      float f[32];
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        o[j] = make_uint4(pack_bf16(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1])),
-                          pack_bf16(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
-                          pack_bf16(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
-                          pack_bf16(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
-      put_block(o, col0 + c * 32);
+      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+      put_block(f, col0 + c * 32);
     }
     return;
   }
@@ -738,9 +808,7 @@ __device__ __forceinline__ void epi_qkv_rope(const ConvGemmParams& p, uint32_t t
     tmem_ld32(tcol + f * 32, lo);
     tmem_ld32(tcol + 64 + f * 32, hi);
     tmem_ld_wait();
-    uint4 olo[4], ohi[4];
-    uint32_t* wl = reinterpret_cast<uint32_t*>(olo);
-    uint32_t* wh = reinterpret_cast<uint32_t*>(ohi);
+    float flo[32], fhi[32];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int piece = f * 8 + j;
@@ -756,13 +824,13 @@ __device__ __forceinline__ void epi_qkv_rope(const ConvGemmParams& p, uint32_t t
       const float b0 = __uint_as_float(hi[4 * j]), b1 = __uint_as_float(hi[4 * j + 1]);
       const float b2 = __uint_as_float(hi[4 * j + 2]), b3 = __uint_as_float(hi[4 * j + 3]);
       norm2 += (a0 * a0 + b0 * b0) + (a1 * a1 + b1 * b1) + (a2 * a2 + b2 * b2) + (a3 * a3 + b3 * b3);
-      wl[2 * j] = pack_bf16(a0 * cx - b0 * sx, a1 * cy - b1 * sy);
-      wl[2 * j + 1] = pack_bf16(a2 * cz - b2 * sz, a3 * cw - b3 * sw);
-      wh[2 * j] = pack_bf16(b0 * cx + a0 * sx, b1 * cy + a1 * sy);
-      wh[2 * j + 1] = pack_bf16(b2 * cz + a2 * sz, b3 * cw + a3 * sw);
+      flo[4 * j] = a0 * cx - b0 * sx; flo[4 * j + 1] = a1 * cy - b1 * sy;
+      flo[4 * j + 2] = a2 * cz - b2 * sz; flo[4 * j + 3] = a3 * cw - b3 * sw;
+      fhi[4 * j] = b0 * cx + a0 * sx; fhi[4 * j + 1] = b1 * cy + a1 * sy;
+      fhi[4 * j + 2] = b2 * cz + a2 * sz; fhi[4 * j + 3] = b3 * cw + a3 * sw;
     }
-    put_block(olo, col0 + f * 32);
-    put_block(ohi, col0 + 64 + f * 32);
+    put_block(flo, col0 + f * 32);
+    put_block(fhi, col0 + 64 + f * 32);
     if (p.aux0 != nullptr) {
       // per-(utterance, q|k, head, f) maximum of the partial squared row norms for the attention kernel's single-pass
       // test (max_f0 + max_f1 bounds the maximum of the sum); non-negative floats order like their bit patterns, rows
@@ -790,8 +858,29 @@ __device__ __forceinline__ void euler_chunk(const ConvGemmParams& p, uint32_t ta
   else tmem_ld16(tacc + c0, v);
   tmem_ld_wait();
   gather_finish<P>(w, t, xin);
-  uint4 xo[P], xb[P / 2];
-  uint32_t* xbw = reinterpret_cast<uint32_t*>(xb);
+  // bf16 copies (split build: [hi | rest | hi], 80 columns apart, rows of 3 x 80 values)
+  auto put_bf16 = [&](const uint4 (&f32v)[P], __nv_bfloat16* dst, int rows) {
+    uint4 hb[P / 2], lb[P / 2];
+    uint32_t* hw = reinterpret_cast<uint32_t*>(hb);
+    uint32_t* lw = reinterpret_cast<uint32_t*>(lb);
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      const float a = __uint_as_float(f32v[j].x), b2 = __uint_as_float(f32v[j].y);
+      const float c2 = __uint_as_float(f32v[j].z), d2 = __uint_as_float(f32v[j].w);
+      hw[2 * j] = pack_bf16(a, b2);
+      hw[2 * j + 1] = pack_bf16(c2, d2);
+      if constexpr (kSplit == 3) {
+        lw[2 * j] = pack_bf16_rest(a, b2, hw[2 * j]);
+        lw[2 * j + 1] = pack_bf16_rest(c2, d2, hw[2 * j + 1]);
+      }
+    }
+    scatter_store<P / 2>(w, hb, dst + c0, 160 * kSplit, rows);
+    if constexpr (kSplit == 3) {
+      scatter_store<P / 2>(w, lb, dst + 80 + c0, 160 * kSplit, rows);
+      scatter_store<P / 2>(w, hb, dst + 160 + c0, 160 * kSplit, rows);
+    }
+  };
+  uint4 xo[P];
 #pragma unroll
   for (int j = 0; j < P; ++j) {
     float4 x;
@@ -800,14 +889,11 @@ __device__ __forceinline__ void euler_chunk(const ConvGemmParams& p, uint32_t ta
     x.z = __uint_as_float(xin[j].z) + dt * __uint_as_float(v[4 * j + 2]);
     x.w = __uint_as_float(xin[j].w) + dt * __uint_as_float(v[4 * j + 3]);
     xo[j] = make_uint4(__float_as_uint(x.x), __float_as_uint(x.y), __float_as_uint(x.z), __float_as_uint(x.w));
-    xbw[2 * j] = pack_bf16(x.x, x.y);
-    xbw[2 * j + 1] = pack_bf16(x.z, x.w);
   }
   scatter_store<P>(w, xo, xt + c0, 320, vrows);
-  scatter_store<P / 2>(w, xb, xtb + c0, 160, vrows);
+  put_bf16(xo, xtb, vrows);
   if (mel != nullptr) {
-    uint4 mo[P], mb[P / 2];
-    uint32_t* mbw = reinterpret_cast<uint32_t*>(mb);
+    uint4 mo[P];
 #pragma unroll
     for (int j = 0; j < P; ++j) {
       float4 m;
@@ -816,11 +902,9 @@ __device__ __forceinline__ void euler_chunk(const ConvGemmParams& p, uint32_t ta
       m.z = is_pad ? padv : __uint_as_float(xo[j].z) * sd + mean;
       m.w = is_pad ? padv : __uint_as_float(xo[j].w) * sd + mean;
       mo[j] = make_uint4(__float_as_uint(m.x), __float_as_uint(m.y), __float_as_uint(m.z), __float_as_uint(m.w));
-      mbw[2 * j] = pack_bf16(m.x, m.y);
-      mbw[2 * j + 1] = pack_bf16(m.z, m.w);
     }
     scatter_store<P>(w, mo, mel + c0, 320, mrows);
-    scatter_store<P / 2>(w, mb, melb + c0, 160, mrows);
+    put_bf16(mo, melb, mrows);
   }
 }
 
@@ -830,13 +914,13 @@ __device__ __forceinline__ void epi_euler(const ConvGemmParams& p, uint32_t tacc
   const int vrows = clamp_rows(rows, w.row0);
   const long long xoff = (long long)tc.b * p.out_batch_stride + (long long)w.row0 * p.out_row_stride;
   float* xt = static_cast<float*>(p.out1) + xoff;
-  __nv_bfloat16* xtb = static_cast<__nv_bfloat16*>(p.out0) + xoff;
+  __nv_bfloat16* xtb = static_cast<__nv_bfloat16*>(p.out0) + xoff * kSplit;
   // the mel outputs are compact: aux_rows (<= frames) rows per utterance, what the vocoder must see
   const bool has_mel = p.aux0 != nullptr;
   const int mrows = has_mel ? clamp_rows(p.aux_rows < rows ? p.aux_rows : rows, w.row0) : 0;
   const long long off = ((long long)tc.b * p.aux_rows + w.row0) * p.out_row_stride;
   float* mel = has_mel ? static_cast<float*>(p.aux0) + off : nullptr;
-  __nv_bfloat16* melb = has_mel ? static_cast<__nv_bfloat16*>(p.aux1) + off : nullptr;
+  __nv_bfloat16* melb = has_mel ? static_cast<__nv_bfloat16*>(p.aux1) + off * kSplit : nullptr;
   const bool is_pad = q < rows && p.lengths != nullptr && q >= p.lengths[tc.b];
   euler_chunk<32>(p, tacc, 0, w, xt, xtb, vrows, mel, melb, mrows, is_pad);
   euler_chunk<32>(p, tacc, 32, w, xt, xtb, vrows, mel, melb, mrows, is_pad);

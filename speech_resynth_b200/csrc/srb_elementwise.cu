@@ -114,6 +114,20 @@ __global__ void rotary_table_kernel(const float* __restrict__ inv_freq, int rows
 // torch.clamp(x, -tv, tv) (models.py:169-170), including its min > max rule (the result is max) for a negative tv
 __device__ __forceinline__ float clamp_tv(float v, float tv) { return fminf(fmaxf(v, -tv), tv); }
 
+// bf16 copy of piece i (4 values) of an array of 80-value rows; split build: [hi | rest | hi] blocks of 80 columns
+__device__ __forceinline__ void put_bf16x4(uint2* __restrict__ dst, long long i, float4 v) {
+  const uint2 h = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+  if constexpr (kSplit == 1) {
+    dst[i] = h;
+  } else {
+    const long long row = i / 20;
+    uint2* d = dst + row * (20 * kSplit) + (i - row * 20);
+    d[0] = h;
+    d[20] = make_uint2(pack_bf16_rest(v.x, v.y, h.x), pack_bf16_rest(v.z, v.w, h.y));
+    d[40] = h;
+  }
+}
+
 __global__ void prior_prepare_kernel(float4* __restrict__ xt, uint2* __restrict__ xtb, long long n4, float tv, int has_tv) {
   pdl_launch_dependents();
   pdl_wait();
@@ -126,7 +140,7 @@ __global__ void prior_prepare_kernel(float4* __restrict__ xt, uint2* __restrict_
       v.w = clamp_tv(v.w, tv);
       xt[i] = v;
     }
-    xtb[i] = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+    put_bf16x4(xtb, i, v);
   }
 }
 
@@ -160,7 +174,7 @@ __global__ void __launch_bounds__(256) stage_inputs_kernel(const int64_t* __rest
       }
     }
     xt[i] = v;
-    xtb[i] = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+    put_bf16x4(xtb, i, v);
   }
   const long long n_ids = (long long)batch * n8;
   for (long long i = tid; i < n_ids; i += stride) {
@@ -430,7 +444,16 @@ __global__ void __launch_bounds__(128) posconv_norm_kernel(const float* __restri
     const long long o = ((long long)b * frames + t) * 128 + cp;
     reinterpret_cast<float2*>(x)[o] = acc[r];
     const float inv = inv_s[r];
-    reinterpret_cast<uint32_t*>(xn)[o] = t < len ? pack_bf16(acc[r].x * inv * gc.x, acc[r].y * inv * gc.y) : 0u;
+    const float n0 = acc[r].x * inv * gc.x, n1 = acc[r].y * inv * gc.y;
+    const uint32_t hi = t < len ? pack_bf16(n0, n1) : 0u;
+    if constexpr (kSplit == 1) {
+      reinterpret_cast<uint32_t*>(xn)[o] = hi;
+    } else {
+      uint32_t* d = reinterpret_cast<uint32_t*>(xn) + ((long long)b * frames + t) * (128 * kSplit) + cp;
+      d[0] = hi;
+      d[128] = t < len ? pack_bf16_rest(n0, n1, hi) : 0u;
+      d[256] = hi;
+    }
   }
 }
 
@@ -453,6 +476,7 @@ __global__ void __launch_bounds__(128) post_tanh_kernel(const uint4* __restrict_
   constexpr int kRows = kPostOutputs + 6;
   constexpr int kSlots = kRows + kRows / 8 + 1;
   __shared__ uint4 tile[2][kSlots];
+  __shared__ uint4 tile_lo[kSplit == 3 ? 2 : 1][kSplit == 3 ? kSlots : 1];   // split build only
   __shared__ __align__(16) float ws[7 * 16];
   __shared__ long long off_s[4];
   const int b = blockIdx.y, t0 = blockIdx.x * kPostOutputs;
@@ -466,10 +490,12 @@ __global__ void __launch_bounds__(128) post_tanh_kernel(const uint4* __restrict_
     for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
     if ((threadIdx.x & 31) == 0) off_s[threadIdx.x >> 5] = part;
   }
-  const uint4* xb = x + (long long)b * rows * 2;
+  const uint4* xb = x + (long long)b * rows * 2 * kSplit;
   for (int i = threadIdx.x; i < kRows * 2; i += 128) {
     const int r = i >> 1, t = t0 - 3 + r;
-    tile[i & 1][post_slot(r)] = (t >= 0 && t < rows) ? __ldg(xb + (long long)t * 2 + (i & 1)) : make_uint4(0, 0, 0, 0);
+    tile[i & 1][post_slot(r)] = (t >= 0 && t < rows) ? __ldg(xb + (long long)t * 2 * kSplit + (i & 1)) : make_uint4(0, 0, 0, 0);
+    if constexpr (kSplit == 3)   // the rounding rests, 16 columns (two 16-byte pieces) further on
+      tile_lo[i & 1][post_slot(r)] = (t >= 0 && t < rows) ? __ldg(xb + (long long)t * 2 * kSplit + 2 + (i & 1)) : make_uint4(0, 0, 0, 0);
   }
   __syncthreads();
   const int r0 = 2 * threadIdx.x;        // window row of tap 0 of the first output
@@ -487,6 +513,13 @@ __global__ void __launch_bounds__(128) post_tanh_kernel(const uint4* __restrict_
     f[2] = make_float2(bf16_lo(u0.z), bf16_hi(u0.z)); f[3] = make_float2(bf16_lo(u0.w), bf16_hi(u0.w));
     f[4] = make_float2(bf16_lo(u1.x), bf16_hi(u1.x)); f[5] = make_float2(bf16_lo(u1.y), bf16_hi(u1.y));
     f[6] = make_float2(bf16_lo(u1.z), bf16_hi(u1.z)); f[7] = make_float2(bf16_lo(u1.w), bf16_hi(u1.w));
+    if constexpr (kSplit == 3) {
+      const uint4 l0 = tile_lo[0][post_slot(r0 + k)], l1 = tile_lo[1][post_slot(r0 + k)];
+      f[0].x += bf16_lo(l0.x); f[0].y += bf16_hi(l0.x); f[1].x += bf16_lo(l0.y); f[1].y += bf16_hi(l0.y);
+      f[2].x += bf16_lo(l0.z); f[2].y += bf16_hi(l0.z); f[3].x += bf16_lo(l0.w); f[3].y += bf16_hi(l0.w);
+      f[4].x += bf16_lo(l1.x); f[4].y += bf16_hi(l1.x); f[5].x += bf16_lo(l1.y); f[5].y += bf16_hi(l1.y);
+      f[6].x += bf16_lo(l1.z); f[6].y += bf16_hi(l1.z); f[7].x += bf16_lo(l1.w); f[7].y += bf16_hi(l1.w);
+    }
     if (k > 0) {
 #pragma unroll
       for (int c = 0; c < 8; ++c) a1 = ffma2(f[c], wprev[c], a1);
@@ -507,6 +540,116 @@ __global__ void __launch_bounds__(128) post_tanh_kernel(const uint4* __restrict_
   } else {
     o[0] = y0;
     if (t + 1 < n_out) o[1] = y1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ reference-style ops
+// fp32 CUDA-core forms used by the tight-precision build (and by tests): no tensor cores, no approximations beyond
+// expf.  They read / write bf16 tensors in the build's activation format (plain bf16, or [hi | lo | hi] split).
+__device__ __forceinline__ float load_act(const __nv_bfloat16* row, int logical_width, int c) {
+  float v = __bfloat162float(row[c]);
+  if constexpr (kSplit == 3) v += __bfloat162float(row[logical_width + c]);
+  return v;
+}
+__device__ __forceinline__ void store_act(__nv_bfloat16* row, int logical_width, int c, float v) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  row[c] = h;
+  if constexpr (kSplit == 3) {
+    row[logical_width + c] = __float2bfloat16_rn(v - __bfloat162float(h));
+    row[2 * logical_width + c] = h;
+  }
+}
+
+// Key-padding-masked softmax attention, 2 heads x 128 (transformer.py:115-127), online softmax in fp32.
+// qkv (B, N, 768) = [q | k | v] after rotary, o (B, N, 256).  Block = 4 warps x 4 query rows of one (utterance, head);
+// a lane owns one key of the current 32-key tile for the scores and four output dimensions for P V.
+__global__ void __launch_bounds__(128) attention_simt_kernel(const __nv_bfloat16* __restrict__ qkv, const int* __restrict__ lengths,
+                                                             __nv_bfloat16* __restrict__ o, int frames) {
+  constexpr int D = 128, KT = 32, QR = 16;
+  __shared__ float ks[KT][D + 1];
+  __shared__ float vs[KT][D + 1];
+  __shared__ float qs[QR][D];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.z, h = blockIdx.y, t0 = blockIdx.x * QR;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int len = min(lengths[b], frames);
+  const long long pitch = 768 * kSplit;
+  const __nv_bfloat16* base = qkv + (long long)b * frames * pitch;
+  for (int i = threadIdx.x; i < QR * D; i += 128) {
+    const int r = i / D, d = i % D, t = t0 + r;
+    qs[r][d] = t < frames ? load_act(base + (long long)t * pitch, 768, h * D + d) : 0.f;
+  }
+  float m[4], l[4], acc[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    m[r] = -INFINITY;
+    l[r] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[r][i] = 0.f;
+  }
+  const float scale = 0.08838834764831845f;   // 1 / sqrt(128)
+  for (int j0 = 0; j0 < len; j0 += KT) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < KT * D; i += 128) {
+      const int j = i / D, d = i % D, t = j0 + j;
+      const bool ok = t < len;
+      ks[j][d] = ok ? load_act(base + (long long)t * pitch, 768, 256 + h * D + d) : 0.f;
+      vs[j][d] = ok ? load_act(base + (long long)t * pitch, 768, 512 + h * D + d) : 0.f;
+    }
+    __syncthreads();
+    const bool key_ok = j0 + lane < len;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const float* q = qs[warp * 4 + r];
+      float sc = 0.f;
+#pragma unroll 8
+      for (int d = 0; d < D; ++d) sc = fmaf(q[d], ks[lane][d], sc);
+      sc = key_ok ? sc * scale : -INFINITY;
+      float mx = sc;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+      const float m_new = fmaxf(m[r], mx);        // finite: every tile holds at least one valid key
+      const float corr = expf(m[r] - m_new);      // exp(-inf) = 0 on the first tile
+      const float pr = key_ok ? expf(sc - m_new) : 0.f;
+      float ps = pr;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, off);
+      l[r] = l[r] * corr + ps;
+      m[r] = m_new;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[r][i] *= corr;
+      for (int j = 0; j < KT; ++j) {
+        const float pj = __shfl_sync(0xffffffffu, pr, j);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[r][i] = fmaf(pj, vs[j][lane + 32 * i], acc[r][i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int t = t0 + warp * 4 + r;
+    if (t >= frames) continue;
+    __nv_bfloat16* orow = o + ((long long)b * frames + t) * (256 * kSplit);
+    const float inv = 1.f / l[r];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) store_act(orow, 256, h * D + lane + 32 * i, acc[r][i] * inv);
+  }
+}
+
+// out = leaky_relu((x0 + x1 + x2) * scale, slope): the MRF mean (HF:1475-1480) when the fused tail is not used
+__global__ void __launch_bounds__(256) mean3_act_kernel(const __nv_bfloat16* __restrict__ x0, const __nv_bfloat16* __restrict__ x1,
+                                                        const __nv_bfloat16* __restrict__ x2, __nv_bfloat16* __restrict__ out,
+                                                        long long rows, int c, float scale, float slope) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long n = rows * c;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / c;
+    const int col = (int)(i - row * c);
+    const long long off = row * c * kSplit;
+    const float v = (load_act(x0 + off, c, col) + load_act(x1 + off, c, col) + load_act(x2 + off, c, col)) * scale;
+    store_act(out + off, c, col, v > 0.f ? v : v * slope);
   }
 }
 
@@ -630,6 +773,26 @@ int srb_hifigan_post(const void* x_act, const float* w, float bias, float* wav, 
   SRB_CUDA(launch_pdl(post_tanh_kernel, grid, dim3(128), 0, (cudaStream_t)stream, static_cast<const uint4*>(x_act), w, bias, wav, rows,
                       lengths));
   return after_launch("post_tanh_kernel");
+}
+
+int srb_cfm_attention_simt(const void* qkv_bf16, const int32_t* lengths, void* o_bf16, int32_t batch, int32_t frames, void* stream) {
+  if (batch <= 0 || frames <= 0) return 0;
+  SRB_REQUIRE(lengths != nullptr, "srb_cfm_attention_simt: lengths required");
+  dim3 grid((frames + 15) / 16, 2, batch);
+  SRB_CUDA(launch_pdl(attention_simt_kernel, grid, dim3(128), 0, (cudaStream_t)stream, static_cast<const __nv_bfloat16*>(qkv_bf16),
+                      lengths, static_cast<__nv_bfloat16*>(o_bf16), frames));
+  return after_launch("attention_simt_kernel");
+}
+
+int srb_hifigan_mean3(const void* x0, const void* x1, const void* x2, void* out, int64_t rows, int32_t channels, float scale,
+                      float slope, void* stream) {
+  if (rows <= 0 || channels <= 0) return 0;
+  long long blocks = (rows * channels + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  SRB_CUDA(launch_pdl(mean3_act_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream,
+                      static_cast<const __nv_bfloat16*>(x0), static_cast<const __nv_bfloat16*>(x1),
+                      static_cast<const __nv_bfloat16*>(x2), static_cast<__nv_bfloat16*>(out), (long long)rows, channels, scale, slope));
+  return after_launch("mean3_act_kernel");
 }
 
 }  // extern "C"

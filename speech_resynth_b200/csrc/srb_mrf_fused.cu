@@ -531,6 +531,7 @@ extern "C" int srb_hifigan_mrf_phases(int32_t channels) { return channels == 16 
 extern "C" int srb_hifigan_mrf_fused(const void* u_raw, const void* w_packed, const float* bias, void* out_act,
                                      int32_t batch, int32_t rows, int32_t channels, float slope, float slope_next,
                                      void* stream) {
+  SRB_REQUIRE(kSplit == 1, "srb_hifigan_mrf_fused: not available in the tight-precision build");
   MrfParams p;
   p.u = static_cast<const __nv_bfloat16*>(u_raw);
   p.out = static_cast<__nv_bfloat16*>(out_act);

@@ -392,8 +392,22 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// ---- operand splitting (the tight-precision build, -DSRB_SPLIT: libsrb_tight.so) ------------------------------------
+// Every bf16 activation tensor of logical width C is stored with 3 C columns [hi | lo | hi], hi = bf16(x),
+// lo = bf16(x - hi), and every GEMM weight as [Wh | Wh | Wl] along K, so the unchanged bf16 tensor-core loop computes
+// xh Wh + xl Wh + xh Wl = x W up to the dropped xl Wl term (2^-18) with fp32 accumulation: fp32-grade results from
+// kind::f16 MMAs.  kSplit is the column multiplier of such tensors (1 in the product build: nothing changes there).
+#ifdef SRB_SPLIT
+constexpr int kSplit = 3;
+#else
+constexpr int kSplit = 1;
+#endif
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+// bf16 pair of what the rounding to `hi` = pack_bf16(a, b) left over
+__device__ __forceinline__ uint32_t pack_bf16_rest(float a, float b, uint32_t hi) {
+  return pack_bf16(a - bf16_lo(hi), b - bf16_hi(hi));
+}
 __device__ __forceinline__ float lrelu(float x, float slope) { return x > 0.f ? x : x * slope; }
 __device__ __forceinline__ float silu(float x) { return x / (1.f + __expf(-x)); }
 // MUFU.EX2 + MUFU.RCP form (relative error ~2 ulp of fp32; the result is rounded to bf16 right after)

@@ -152,9 +152,13 @@ def waveform_rows(frames: int) -> int:
 class CFMSampler:
     """ODE sampler over the flow-matching transformer velocity field (kernels: srb_cfm_*)."""
 
-    def __init__(self, packed: PackedCFM, depth: int, mean: float, std: float):
+    def __init__(self, packed: PackedCFM, depth: int, mean: float, std: float, tight: bool = False):
         self.w = packed
         self.depth = depth
+        # tight=True: the tight-precision library (include/srb.h: srb_split_factor) -- bf16 activations travel as
+        # [hi | lo | hi] (three times as wide), weights are packed [Wh | Wh | Wl], attention runs in fp32 on CUDA cores
+        self.tight = tight
+        self.split = 3 if tight else 1
         self.mean = float(mean)
         self.std = float(std)
         self.device = packed.w_embed.device
@@ -167,13 +171,16 @@ class CFMSampler:
         # fused launch (27.6 us) is no shorter than they are together, so the split stays the default
         self.fused_qkv = os.environ.get("SRB_FUSED_QKV", "0") == "1"
 
+    def call(self, name: str, *args, **kw) -> None:
+        nat.call(name, *args, tight=self.tight, **kw)
+
     # -- tables -----------------------------------------------------------------------------------------------
     def rotary(self, rows: int) -> Tuple[torch.Tensor, torch.Tensor]:
         if self._rot is None or self._rot[0].shape[0] < rows:
             n = max(rows, 4096)
             cs = torch.empty(n, 64, dtype=torch.float32, device=self.device)
             sn = torch.empty_like(cs)
-            nat.call("srb_rotary_table", P(self.w.inv_freq), n, P(cs), P(sn))
+            self.call("srb_rotary_table", P(self.w.inv_freq), n, P(cs), P(sn))
             # captured graphs hold raw pointers into earlier tables: those stay alive
             self._rot_keep = getattr(self, "_rot_keep", []) + [(cs, sn)]
             self._rot = (cs, sn)
@@ -188,7 +195,7 @@ class CFMSampler:
             t_dev = times.to(self.device)
             temb = torch.empty(nfe, 256, dtype=torch.float32, device=self.device)
             g = torch.empty(nfe, 2 * self.depth, 256, dtype=torch.float32, device=self.device)
-            nat.call("srb_time_cond_table", P(t_dev), nfe, P(self.w.four_w), P(self.w.lin_w), P(self.w.lin_b),
+            self.call("srb_time_cond_table", P(t_dev), nfe, P(self.w.four_w), P(self.w.lin_w), P(self.w.lin_b),
                      P(self.w.gamma_w), 2 * self.depth, P(temb), P(g))
             torch.cuda.current_stream().synchronize()  # t_dev must outlive the launch
             self._cond_cache[key] = g
@@ -206,13 +213,13 @@ class CFMSampler:
         b, n = ids.shape
         dur = torch.empty(b, n, dtype=torch.int32, device=self.device)
         tot = torch.empty(b, dtype=torch.int32, device=self.device)
-        nat.call("srb_duration_predict", P(ids), P(self.w.dur_table), self.w.dur_bias, P(dur), P(tot), b, n,
+        self.call("srb_duration_predict", P(ids), P(self.w.dur_table), self.w.dur_bias, P(dur), P(tot), b, n,
                  self.w.dur_table.shape[1])
         totals = tot.cpu()
         all_one = int(totals.sum()) == 0          # the regulator's all-zero rule (HF:113-114)
         n_out = n if all_one else int(totals.max())
         out = torch.empty(b, n_out, dtype=torch.int64, device=self.device)
-        nat.call("srb_length_regulate", P(ids), P(dur), P(out), b, n, n_out, 1 if all_one else 0)
+        self.call("srb_length_regulate", P(ids), P(dur), P(out), b, n, n_out, 1 if all_one else 0)
         return out, dur
 
     # -- workspace --------------------------------------------------------------------------------------------
@@ -234,20 +241,24 @@ class CFMSampler:
         else:
             take = c.take
         f32, b16 = torch.float32, torch.bfloat16
+        S = self.split      # bf16 activation tensors are S times as wide in the tight-precision format
         ws: Dict[str, object] = dict(
             frames=frames, mel_rows=mel_rows, batch=batch, qk_calls=0,
             ids=take((batch, frames), torch.int64), lengths=take((batch,), torch.int32),
-            cond=take((m, 256), f32), xt=take((batch, frames, 80), f32), xt_b=take((batch, frames, 80), b16),
+            cond=take((m, 256), f32), xt=take((batch, frames, 80), f32), xt_b=take((batch, frames, 80 * S), b16),
             x0=take((m, 256), f32), x=take((m, 256), f32),
             # xn is also the B operand of the V^T GEMM, read in 256-row tiles: rows >= m are cleared by the staging kernel
-            xn=take((m_pad, 256), b16),
-            o=take((m, 256), b16), h=take((m, 896), b16),
-            mel=take((batch, mel_rows, 80), f32), mel_b=take((batch, mel_rows, 80), b16),
+            xn=take((m_pad, 256 * S), b16),
+            o=take((m, 256 * S), b16), h=take((m, 896 * S), b16),
+            mel=take((batch, mel_rows, 80), f32), mel_b=take((batch, mel_rows, 80 * S), b16),
             # max |q|^2, |k|^2 per (utterance, head), recorded by qk_rope, read by the attention kernel; two buffers used
             # alternately by successive layers (each projection clears the other one for its successor)
             qkmax=take((2, batch, 2, 2, 2), f32),
         )
-        ws["qk"], ws["vt"] = take((m, 512), b16), take((256, m_pad), b16)
+        if self.tight:
+            ws["qkv"] = take((m, 768 * S), b16)      # [q | k | v] after rotary, read by the fp32 attention kernel
+        else:
+            ws["qk"], ws["vt"] = take((m, 512), b16), take((256, m_pad), b16)
         return ws
 
     # -- the loop ---------------------------------------------------------------------------------------------
@@ -262,7 +273,7 @@ class CFMSampler:
         assert noise.dtype == torch.float32 and input_ids.dtype == torch.int64
         xn, m = ws["xn"], b * n8
         tail = xn[m:]
-        nat.call("srb_stage_inputs", P(input_ids.contiguous()), P(noise.contiguous()), P(ws["ids"]), P(ws["xt"]), P(ws["xt_b"]),
+        self.call("srb_stage_inputs", P(input_ids.contiguous()), P(noise.contiguous()), P(ws["ids"]), P(ws["xt"]), P(ws["xt_b"]),
                  P(tail) if tail.numel() else None, tail.numel() * 2, P(ws["qkmax"]), ws["qkmax"].numel() * 4, b, n, n8,
                  float(truncation) if truncation is not None else 0.0, 0 if truncation is None else 1)
         ws["qk_calls"] = 0
@@ -270,8 +281,8 @@ class CFMSampler:
     def prepare(self, ws: Dict[str, object]) -> None:
         """mask/lengths (models.py:152) and the hoisted conditioning gather (:154,:175-176)."""
         b, n = ws["ids"].shape
-        nat.call("srb_unit_lengths", P(ws["ids"]), P(ws["lengths"]), b, n)
-        nat.call("srb_embed_gather", P(self.w.cond_table), P(ws["ids"]), P(ws["cond"]), b * n,
+        self.call("srb_unit_lengths", P(ws["ids"]), P(ws["lengths"]), b, n)
+        self.call("srb_embed_gather", P(self.w.cond_table), P(ws["ids"]), P(ws["cond"]), b * n,
                  self.w.cond_table.shape[0], 256, nbytes=b * n * (2 * 256 * 4 + 8))
         ws["qk_calls"] = 0
 
@@ -281,43 +292,50 @@ class CFMSampler:
         w, L = self.w, ws["lengths"]
         cs, sn = self.rotary(n)
         m = b * n
-        nat.call("srb_cfm_embed", P(ws["xt_b"]), P(w.w_embed), P(ws["cond"]), P(ws["x0"]), b, n, flops=2.0 * m * 80 * 256,
+        self.call("srb_cfm_embed", P(ws["xt_b"]), P(w.w_embed), P(ws["cond"]), P(ws["x0"]), b, n, flops=2.0 * m * 80 * 256,
                  nbytes=m * (80 * 2 + 256 * 8))
-        nat.call("srb_cfm_posconv_norm", P(ws["x0"]), P(w.dw_w), P(w.dw_b), P(g_step[0]), P(L), P(ws["x"]), P(ws["xn"]), b, n,
+        self.call("srb_cfm_posconv_norm", P(ws["x0"]), P(w.dw_w), P(w.dw_b), P(g_step[0]), P(L), P(ws["x"]), P(ws["xn"]), b, n,
                  flops=2.0 * m * 31 * 256, nbytes=m * 256 * (4 + 4 + 2))
         for i in range(self.depth):
             qk_cur, qk_next = ws["qkmax"][ws["qk_calls"] % 2], ws["qkmax"][(ws["qk_calls"] + 1) % 2]
             ws["qk_calls"] += 1
-            m_pad = ws["vt"].shape[1]
-            if self.fused_qkv:
+            if self.tight:
+                # reference-style chain: one q|k|v projection with rotary, then fp32 softmax attention on CUDA cores
+                self.call("srb_cfm_qkv_rope", P(ws["xn"]), P(w.w_qkv[i]), P(cs), P(sn), P(ws["qkv"]), None, None, b, n,
+                          flops=2.0 * m * 256 * 768)
+                self.call("srb_cfm_attention_simt", P(ws["qkv"]), P(L), P(ws["o"]), b, n, flops=4.0 * m * n * 256)
+            elif self.fused_qkv:
+                m_pad = ws["vt"].shape[1]
                 # the whole to_qkv GEMM in one launch: q | k with rotary, v stored transposed by the epilogue
-                nat.call("srb_cfm_qk_rope_vt", P(ws["xn"]), P(w.w_qkv[i]), P(cs), P(sn), P(ws["qk"]), P(ws["vt"]), m_pad,
+                self.call("srb_cfm_qk_rope_vt", P(ws["xn"]), P(w.w_qkv[i]), P(cs), P(sn), P(ws["qk"]), P(ws["vt"]), m_pad,
                          P(qk_cur), P(qk_next), b, n, flops=2.0 * m * 256 * 768)
             else:
                 # q|k projection and the transposed-v projection both read xn only: two parallel graph branches
+                m_pad = ws["vt"].shape[1]
                 self.fork.run([
-                    lambda: nat.call("srb_cfm_qk_rope", P(ws["xn"]), P(w.w_qkv[i]), P(cs), P(sn), P(ws["qk"]),
+                    lambda: self.call("srb_cfm_qk_rope", P(ws["xn"]), P(w.w_qkv[i]), P(cs), P(sn), P(ws["qk"]),
                                      P(qk_cur), P(qk_next), b, n, flops=2.0 * m * 256 * 512),
-                    lambda: nat.call("srb_cfm_v_transposed", P(ws["xn"]), P(w.w_qkv[i][512:]), P(ws["vt"]), m_pad,
+                    lambda: self.call("srb_cfm_v_transposed", P(ws["xn"]), P(w.w_qkv[i][512:]), P(ws["vt"]), m_pad,
                                      flops=2.0 * m * 256 * 256),
                 ])
-            nat.call("srb_cfm_attention_tc", P(ws["qk"]), 512, P(ws["vt"]), m_pad, P(L), P(qk_cur), P(ws["o"]), b, n,
-                     flops=4.0 * m * n * 256)
-            nat.call("srb_cfm_attn_out_norm", P(ws["o"]), P(w.w_out[i]), P(g_step[2 * i + 1]), P(L), P(ws["x"]), P(ws["xn"]), b, n,
+            if not self.tight:
+                self.call("srb_cfm_attention_tc", P(ws["qk"]), 512, P(ws["vt"]), ws["vt"].shape[1], P(L), P(qk_cur), P(ws["o"]), b, n,
+                          flops=4.0 * m * n * 256)
+            self.call("srb_cfm_attn_out_norm", P(ws["o"]), P(w.w_out[i]), P(g_step[2 * i + 1]), P(L), P(ws["x"]), P(ws["xn"]), b, n,
                      flops=2.0 * m * 256 * 256)
             # every utterance ends in a pad row whenever the caller's frame count is not a multiple of 8 (lengths <= mel_rows < n)
-            nat.call("srb_cfm_ffn_glu", P(ws["xn"]), P(w.w_ff1[i]), P(w.b_ff1[i]), P(L), P(ws["h"]), b, n,
+            self.call("srb_cfm_ffn_glu", P(ws["xn"]), P(w.w_ff1[i]), P(w.b_ff1[i]), P(L), P(ws["h"]), b, n,
                      1 if ws["mel_rows"] < n else 0,
                      flops=2.0 * m * 768 * 1792)
             if i + 1 < self.depth:
                 g_next, mode = g_step[2 * i + 2], 1
             else:
                 g_next, mode = w.final_norm_w, 2
-            nat.call("srb_cfm_ffn_out_norm", P(ws["h"]), P(w.w_ff2[i]), P(w.b_ff2[i]), P(g_next), mode, P(L), P(ws["x"]),
+            self.call("srb_cfm_ffn_out_norm", P(ws["h"]), P(w.w_ff2[i]), P(w.b_ff2[i]), P(g_next), mode, P(L), P(ws["x"]),
                      P(ws["xn"]), b, n, flops=2.0 * m * 2688 * 256)
         mel = P(ws["mel"]) if last else None
         mel_b = P(ws["mel_b"]) if last else None
-        nat.call("srb_cfm_pred_euler", P(ws["xn"]), P(w.w_pred), float(dt), P(ws["xt"]), P(ws["xt_b"]), mel, mel_b,
+        self.call("srb_cfm_pred_euler", P(ws["xn"]), P(w.w_pred), float(dt), P(ws["xt"]), P(ws["xt_b"]), mel, mel_b,
                  ws["mel_rows"], self.std, self.mean, pad_value_f32(), P(L), b, n, flops=2.0 * m * 256 * 80,
                  nbytes=m * (256 * 2 + 80 * (4 + 4 + 2)))
 
@@ -335,23 +353,30 @@ class CFMSampler:
 class HifiGanGenerator:
     """mel (B, T, 80) bf16 -> waveform (B, 320 T + 80) fp32 (kernels: srb_hifigan_*)."""
 
-    def __init__(self, packed: PackedVocoder, slope: float = 0.1, fuse_mrf: bool = True):
+    def __init__(self, packed: PackedVocoder, slope: float = 0.1, fuse_mrf: bool = True, tight: bool = False):
         self.w = packed
         self.slope = float(slope)
-        self.fuse_mrf = fuse_mrf
+        # tight=True: the tight-precision library (see CFMSampler); every stage runs conv by conv there
+        self.tight = tight
+        self.split = 3 if tight else 1
+        self.fuse_mrf = fuse_mrf and not tight
         # SRB_PAIR_UPSAMPLE=0 runs every up-sampler through the polyphase kernel instead (A/B runs)
-        self.pair_upsample = os.environ.get("SRB_PAIR_UPSAMPLE", "1") != "0"
+        self.pair_upsample = os.environ.get("SRB_PAIR_UPSAMPLE", "1") != "0" and not tight
         self.fork = _Fork(packed.w_pre.device, 2)
         self.device = packed.w_pre.device
+
+    def call(self, name: str, *args, **kw) -> None:
+        nat.call(name, *args, tight=self.tight, **kw)
 
     def workspace(self, batch: int, frames: int, carver: Optional[Carver] = None) -> Dict[str, object]:
         """Stage tensors of one (batch, frames) shape.  A stage run by the fused MRF kernel needs only the up-sampler
         output and the stage output; the others add the activated copy and nine conv intermediates."""
-        dev = self.device
+        dev, S = self.device, self.split
+        # (bf16 activation tensors are S times as wide in the tight-precision format)
         if carver is None:
-            take = lambda shape: torch.empty(*shape, dtype=torch.bfloat16, device=dev)
+            take = lambda shape: torch.empty(*shape[:-1], shape[-1] * S, dtype=torch.bfloat16, device=dev)
         else:
-            take = lambda shape: carver.take(shape, torch.bfloat16)
+            take = lambda shape: carver.take((*shape[:-1], shape[-1] * S), torch.bfloat16)
         ws: Dict[str, object] = {"batch": batch, "frames": frames, "pre": take((batch, frames, 512))}
         rows, c = frames, 512
         stages = []
@@ -374,11 +399,12 @@ class HifiGanGenerator:
     def run(self, mel_b: torch.Tensor, ws: Dict[str, object]) -> torch.Tensor:
         """Everything up to (not including) conv_post: returns the leaky_relu(0.01)'ed last stage (B, 320 T + 80, 16)."""
         b, t, _ = mel_b.shape
+        assert mel_b.shape[2] == 80 * self.split
         w = self.w
         one = _i32([7])
         dil1 = _i32([1])
         # conv_pre (HF:1470); its only consumer is leaky_relu -> upsampler, so only the activated copy is stored
-        nat.call("srb_hifigan_conv", P(mel_b), None, None, 1, one, dil1, P(w.w_pre), P(w.b_pre), None, None, None, None,
+        self.call("srb_hifigan_conv", P(mel_b), None, None, 1, one, dil1, P(w.w_pre), P(w.b_pre), None, None, None, None,
                  P(ws["pre"]), b, t, 80, 512, 1.0, self.slope, flops=2.0 * b * t * 7 * 80 * 512)
         x_act, rows_in, c_in = ws["pre"], t, 512
         n_stage = len(UPSAMPLE_RATES)
@@ -391,17 +417,17 @@ class HifiGanGenerator:
                 # L_out = s L: all s output phases of an input row from one 3-tap conv (packing.upsampler_as_row_group_conv);
                 # (B, rows_in, s c) is the (B, rows, c) result.  FLOPs reported are the transposed conv's own.
                 wp, bp = w.up_pair[i]
-                nat.call("srb_hifigan_conv", P(x_act), None, None, 1, _i32([3]), dil1, P(wp), P(bp), None, None, None,
+                self.call("srb_hifigan_conv", P(x_act), None, None, 1, _i32([3]), dil1, P(wp), P(bp), None, None, None,
                          P(st["u_raw"]), None if fused else P(st["u_act"]), b, rows_in, c_in, s * c, 1.0, self.slope,
                          flops=2.0 * b * rows_in * k * c_in * c)
             else:
-                nat.call("srb_hifigan_upsample", P(x_act), P(w.w_up[i]), P(w.b_up[i]), P(st["u_raw"]),
+                self.call("srb_hifigan_upsample", P(x_act), P(w.w_up[i]), P(w.b_up[i]), P(st["u_raw"]),
                          None if fused else P(st["u_act"]), b, rows_in, c_in, c, k, s, self.slope,
                          flops=2.0 * b * rows_in * k * c_in * c)
             if fused:
                 # narrow stages: the whole MRF block (18 convs + residuals + mean + next leaky_relu) in one kernel
                 slope_next = self.slope if i + 1 < n_stage else 0.01
-                nat.call("srb_hifigan_mrf_fused", P(st["u_raw"]), P(w.w_mrf[i]), P(w.b_mrf[i]), P(st["out"]), b, rows, c,
+                self.call("srb_hifigan_mrf_fused", P(st["u_raw"]), P(w.w_mrf[i]), P(w.b_mrf[i]), P(st["out"]), b, rows, c,
                          self.slope, slope_next, flops=252.0 * c * c * b * rows)
                 x_act, rows_in, c_in = st["out"], rows, c
                 continue
@@ -412,14 +438,14 @@ class HifiGanGenerator:
                 xr, xa = st["u_raw"], st["u_act"]
                 for q, dil in enumerate(RESBLOCK_DILATIONS):
                     # conv1 with dilation (HF:1361-1363), output only needed activated
-                    nat.call("srb_hifigan_conv", P(xa), None, None, 1, kk, _i32([dil]), P(w.w_c1[i][j][q]),
+                    self.call("srb_hifigan_conv", P(xa), None, None, 1, kk, _i32([dil]), P(w.w_c1[i][j][q]),
                              P(w.b_c1[i][j][q]), None, None, None, None, P(st["t"][j]), b, rows, c, c, 1.0, self.slope,
                              flops=2.0 * b * rows * rk * c * c)
-                    if q < 2:
+                    if q < 2 or self.tight:
                         # conv2 + residual (HF:1364-1366): raw (next residual) and activated (next conv1 input)
-                        nat.call("srb_hifigan_conv", P(st["t"][j]), None, None, 1, kk, dil1, P(w.w_c2[i][j][q]),
-                                 P(w.b_c2[i][j][q]), P(xr), None, None, P(st["xr"][j]), P(st["xa"][j]), b, rows, c, c,
-                                 1.0, self.slope, flops=2.0 * b * rows * rk * c * c)
+                        self.call("srb_hifigan_conv", P(st["t"][j]), None, None, 1, kk, dil1, P(w.w_c2[i][j][q]),
+                                 P(w.b_c2[i][j][q]), P(xr), None, None, P(st["xr"][j]), P(st["xa"][j]) if q < 2 else None,
+                                 b, rows, c, c, 1.0, self.slope, flops=2.0 * b * rows * rk * c * c)
                         xr, xa = st["xr"][j], st["xa"][j]
                 res[j] = xr
 
@@ -430,7 +456,12 @@ class HifiGanGenerator:
             # fused MRF tail: the three last conv2's + their residuals + mean (HF:1475-1478) + the next leaky_relu
             # (slope 0.1 before an upsampler, torch default 0.01 before conv_post, HF:1480)
             slope_next = self.slope if i + 1 < n_stage else 0.01
-            nat.call("srb_hifigan_conv", P(st["t"][0]), P(st["t"][1]), P(st["t"][2]), 3, _i32(list(RESBLOCK_KERNELS)),
+            if self.tight:
+                # every resblock finished conv by conv above: the MRF mean + next leaky_relu as its own kernel
+                self.call("srb_hifigan_mean3", P(res[0]), P(res[1]), P(res[2]), P(st["out"]), b * rows, c, 1.0 / 3.0, slope_next)
+                x_act, rows_in, c_in = st["out"], rows, c
+                continue
+            self.call("srb_hifigan_conv", P(st["t"][0]), P(st["t"][1]), P(st["t"][2]), 3, _i32(list(RESBLOCK_KERNELS)),
                      _i32([1, 1, 1]), P(w.w_tail[i]), P(w.b_tail[i]), P(res[0]), P(res[1]), P(res[2]), None, P(st["out"]),
                      b, rows, c, c, 1.0 / 3.0, slope_next, flops=2.0 * b * rows * sum(RESBLOCK_KERNELS) * c * c)
             x_act, rows_in, c_in = st["out"], rows, c
@@ -438,8 +469,8 @@ class HifiGanGenerator:
 
     def post(self, x_act: torch.Tensor, wav: torch.Tensor, lengths: Optional[torch.Tensor] = None) -> None:
         """conv_post + tanh (HF:1480-1482).  lengths=None: dense (B, rows) output; else ragged (see srb_hifigan_post)."""
-        b, rows, _ = x_act.shape
-        nat.call("srb_hifigan_post", P(x_act), P(self.w.w_post), self.w.b_post, P(wav), b, rows,
+        b, rows, _ = x_act.shape      # (B, rows, 16 * split)
+        self.call("srb_hifigan_post", P(x_act), P(self.w.w_post), self.w.b_post, P(wav), b, rows,
                  P(lengths) if lengths is not None else None, flops=2.0 * b * rows * 7 * 16, nbytes=b * rows * (16 * 2 + 4))
 
 
@@ -459,20 +490,20 @@ class _Plan:
 
 
 def build_sampler(state_dict: Dict[str, torch.Tensor], device, depth: int = 4, mean: float = -5.8843,
-                  std: float = 2.2615) -> CFMSampler:
-    """state_dict uses the top-level key names ("model.*")."""
+                  std: float = 2.2615, tight: bool = False) -> CFMSampler:
+    """state_dict uses the top-level key names ("model.*").  tight=True: the tight-precision library."""
     nat.require_blackwell()
     device = torch.device(device)
     with torch.cuda.device(device):
-        return CFMSampler(pack_cfm(state_dict, device, depth=depth), depth, mean, std)
+        return CFMSampler(pack_cfm(state_dict, device, depth=depth, split=tight), depth, mean, std, tight=tight)
 
 
-def build_vocoder(state_dict: Dict[str, torch.Tensor], device, slope: float = 0.1) -> HifiGanGenerator:
-    """state_dict uses the top-level key names ("vocoder.*")."""
+def build_vocoder(state_dict: Dict[str, torch.Tensor], device, slope: float = 0.1, tight: bool = False) -> HifiGanGenerator:
+    """state_dict uses the top-level key names ("vocoder.*").  tight=True: the tight-precision library."""
     nat.require_blackwell()
     device = torch.device(device)
     with torch.cuda.device(device):
-        return HifiGanGenerator(pack_vocoder(state_dict, device), slope)
+        return HifiGanGenerator(pack_vocoder(state_dict, device, split=tight), slope, tight=tight)
 
 
 class ResynthEngine:
@@ -487,6 +518,8 @@ class ResynthEngine:
         self.sampler = sampler
         self.vocoder = vocoder
         self.device = (sampler or vocoder).device
+        self.tight = (sampler or vocoder).tight
+        assert sampler is None or vocoder is None or sampler.tight == vocoder.tight, "sampler and vocoder precision modes differ"
         env = os.environ.get("SRB_GRAPHS")
         if env is not None:
             use_graphs = {"0": False, "1": True}.get(env, "auto")
@@ -504,7 +537,7 @@ class ResynthEngine:
         if with_vocoder:
             voc_ws = self.vocoder.workspace(batch, frames, carver=carver)
             if not with_cfm:
-                voc_ws["mel_b"] = carver.take((batch, frames, 80), torch.bfloat16)
+                voc_ws["mel_b"] = carver.take((batch, frames, 80 * self.vocoder.split), torch.bfloat16)
         return cfm_ws, voc_ws
 
     def workspace_bytes(self, batch: int, frames: int, with_cfm: bool = True, with_vocoder: bool = True) -> int:
@@ -609,7 +642,8 @@ class ResynthEngine:
             self._len_bufs = bufs
         host_buf = bufs[slot]
         with torch.cuda.device(self.device):
-            nat.call("srb_unit_extents", P(input_ids.contiguous()), host_buf[0].data_ptr(), host_buf[1].data_ptr(), b, n)
+            nat.call("srb_unit_extents", P(input_ids.contiguous()), host_buf[0].data_ptr(), host_buf[1].data_ptr(), b, n,
+                     tight=self.tight)
             ev = torch.cuda.Event()
             ev.record()
         return host_buf[:, :b], ev
@@ -652,7 +686,7 @@ class ResynthEngine:
             plan = self._plan(b, t, None, False, True)
             mel32 = mel.to(device=self.device, dtype=torch.float32).contiguous()
             # fp32 -> bf16 (the reference's autocast would do the same cast at conv_pre)
-            nat.call("srb_prior_prepare", P(mel32), P(plan.voc_ws["mel_b"]), mel32.numel(), 0.0, 0)
+            nat.call("srb_prior_prepare", P(mel32), P(plan.voc_ws["mel_b"]), mel32.numel(), 0.0, 0, tight=self.tight)
             self._launch(plan)
             wav = torch.empty(b, plan.voc_ws["rows"], dtype=torch.float32, device=self.device)
             self.vocoder.post(plan.x_last, wav)

@@ -9,6 +9,7 @@ checkpoint loads unchanged.  None of these modules has a PyTorch ``forward``: in
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional
 
 import torch
@@ -129,7 +130,37 @@ def _fresh_state(module: nn.Module):
     return {k: v.detach() for k, v in module.state_dict().items()}
 
 
-class ConditionalFlowMatchingModel(PreTrainedModel):
+def _default_precision() -> str:
+    p = os.environ.get("SRB_PRECISION", "bf16")
+    if p not in ("bf16", "tight"):
+        raise ValueError(f"SRB_PRECISION must be 'bf16' or 'tight', got {p!r}")
+    return p
+
+
+class _PrecisionMixin:
+    """precision = "bf16" (default: the product kernels, bf16 tensor-core operands, parity ~1e-3) or "tight" (the same
+    kernels over split bf16 operands hi + lo with fp32 accumulation and fp32 CUDA-core attention: parity ~1e-5 against the
+    reference's fp32 path, at several times the cost -- BASELINE.json north_star: "tight in fp32/TF32, looser in bf16")."""
+
+    _precision: Optional[str] = None
+
+    @property
+    def precision(self) -> str:
+        return self._precision or _default_precision()
+
+    def set_precision(self, precision: str) -> "_PrecisionMixin":
+        if precision not in ("bf16", "tight"):
+            raise ValueError(f"precision must be 'bf16' or 'tight', got {precision!r}")
+        if precision != self.precision:
+            self._precision = precision
+            self.refresh()
+        for child in (getattr(self, "model", None), getattr(self, "vocoder", None)):
+            if isinstance(child, _PrecisionMixin):
+                child.set_precision(precision)
+        return self
+
+
+class ConditionalFlowMatchingModel(_PrecisionMixin, PreTrainedModel):
     """Parameter layout of the reference model (models.py:41-71); ``sample`` runs on the GPU kernels."""
 
     config_class = ConditionalFlowMatchingConfig
@@ -181,7 +212,8 @@ class ConditionalFlowMatchingModel(PreTrainedModel):
         sig = _param_signature(self)
         if self._sampler is None or self._sampler.device != dev or self._sig != sig:
             sd = {"model." + k: v for k, v in _fresh_state(self).items()}
-            self._sampler = _engine.build_sampler(sd, dev, depth=self.config.depth, mean=self.config.mean, std=self.config.std)
+            self._sampler = _engine.build_sampler(sd, dev, depth=self.config.depth, mean=self.config.mean, std=self.config.std,
+                                                  tight=self.precision == "tight")
             self._sig = sig
             self._engine = None
         return self._sampler
@@ -231,7 +263,7 @@ class _HifiGanResidualBlock(_ParamsOnly):  # HF:1308-1339
             nn.Conv1d(channels, channels, kernel_size, padding=(kernel_size - 1) // 2) for _ in dilation)
 
 
-class HifiGanVocoder(PreTrainedModel):
+class HifiGanVocoder(_PrecisionMixin, PreTrainedModel):
     """Parameter layout of transformers' FastSpeech2ConformerHifiGan (HF:1376-1416); call = mel -> waveform."""
 
     config_class = FastSpeech2ConformerHifiGanConfig
@@ -283,7 +315,7 @@ class HifiGanVocoder(PreTrainedModel):
         sig = _param_signature(self)
         if self._generator is None or self._generator.device != dev or self._sig != sig:
             sd = {"vocoder." + k: v for k, v in _fresh_state(self).items()}
-            self._generator = _engine.build_vocoder(sd, dev, slope=self.config.leaky_relu_slope)
+            self._generator = _engine.build_vocoder(sd, dev, slope=self.config.leaky_relu_slope, tight=self.precision == "tight")
             self._sig = sig
             self._engine = None
         return self._generator
@@ -297,7 +329,7 @@ class HifiGanVocoder(PreTrainedModel):
         return self._engine.vocode(spectrogram.to(self.device))
 
 
-class ConditionalFlowMatchingWithHifiGan(PreTrainedModel):
+class ConditionalFlowMatchingWithHifiGan(_PrecisionMixin, PreTrainedModel):
     """units -> list of waveforms; the reference's public entry point (models.py:192-256)."""
 
     config_class = ConditionalFlowMatchingWithHifiGanConfig

@@ -23,6 +23,16 @@ def block_k_for(c_in: int) -> int:
     return 64 if c_in >= 64 else (32 if c_in >= 32 else 16)
 
 
+def split_operand(w: torch.Tensor, dim: int) -> torch.Tensor:
+    """Tight-precision (split) packing of a GEMM weight along its input-channel dimension `dim`: [Wh | Wh | Wl] with
+    Wh = bf16(W), Wl = bf16(W - Wh).  Activations travel as [xh | xl | xh] (include/srb.h: srb_split_factor), so the
+    bf16 tensor-core loop accumulates xh Wh + xl Wh + xh Wl in fp32.  Returned in fp32 (every value is a bf16 number)."""
+    w = w.float()
+    hi = w.to(torch.bfloat16).float()
+    lo = (w - hi).to(torch.bfloat16).float()
+    return torch.cat([hi, hi, lo], dim=dim)
+
+
 def pack_conv_weight(w: torch.Tensor, block_k: int) -> torch.Tensor:
     """Conv1d weight (C_out, C_in, k) -> bf16 [C_out][k * C_in_pad], k-major then channel, channels zero-padded."""
     c_out, c_in, k = w.shape
@@ -32,7 +42,7 @@ def pack_conv_weight(w: torch.Tensor, block_k: int) -> torch.Tensor:
     return p.reshape(c_out, k * c_pad).to(torch.bfloat16).contiguous()
 
 
-def pack_upsampler_weight(w: torch.Tensor, stride: int) -> torch.Tensor:
+def pack_upsampler_weight(w: torch.Tensor, stride: int, split: bool = False) -> torch.Tensor:
     """ConvTranspose1d weight (C_in, C_out, k) -> polyphase bf16 [C_out][k * C_in].
 
     Phase r (output rows q*stride + r) uses taps j = j0 + m*stride, j0 = (r + pad) % stride, in increasing m
@@ -44,7 +54,8 @@ def pack_upsampler_weight(w: torch.Tensor, stride: int) -> torch.Tensor:
     for r in range(stride):
         j0 = (r + pad) % stride
         for j in range(j0, k, stride):
-            cols.append(w[:, :, j].float().t())  # (C_out, C_in)
+            tap = w[:, :, j].float().t()  # (C_out, C_in)
+            cols.append(split_operand(tap, 1) if split else tap)
     return torch.cat(cols, dim=1).to(torch.bfloat16).contiguous()
 
 
@@ -182,16 +193,20 @@ def glu_row_permutation(inter: int = 896, device=None) -> torch.Tensor:
     return torch.cat(idx).to(device)
 
 
-def pack_cfm(sd: Dict[str, torch.Tensor], device, depth: int = 4, dim_in: int = 80) -> PackedCFM:
+def pack_cfm(sd: Dict[str, torch.Tensor], device, depth: int = 4, dim_in: int = 80, split: bool = False) -> PackedCFM:
+    """split=True packs the GEMM weights for the tight-precision library (split_operand)."""
     f = lambda k: sd[k].detach().to(device=device, dtype=torch.float32)
+    sp = (lambda w, dim=1: split_operand(w, dim)) if split else (lambda w, dim=1: w)
     w_emb = f("model.to_embed.weight")
     emb = f("model.to_cond_emb.weight").contiguous()
     hidden = w_emb.shape[0]
     inter = sd["model.transformer.layers.0.4.conv2.weight"].shape[1]
     # hoisted loop-invariant conditioning projection, in fp64 then rounded once to fp32
     cond_table = (emb.double() @ w_emb[:, dim_in:].double().t() + f("model.to_embed.bias").double()).float().contiguous()
-    w_x = torch.zeros(hidden, 128, dtype=torch.float32, device=device)
-    w_x[:, :dim_in] = w_emb[:, :dim_in]
+    w_in = sp(w_emb[:, :dim_in])                       # (hidden, 80) or, split, (hidden, 240)
+    k_pad = (w_in.shape[1] + 63) // 64 * 64
+    w_x = torch.zeros(hidden, k_pad, dtype=torch.float32, device=device)
+    w_x[:, :w_in.shape[1]] = w_in
     gam = []
     for i in range(depth):
         gam.append(f(f"model.transformer.layers.{i}.1.to_weight.weight"))
@@ -208,7 +223,7 @@ def pack_cfm(sd: Dict[str, torch.Tensor], device, depth: int = 4, dim_in: int = 
         gamma_w=torch.stack(gam).contiguous(),
         inv_freq=f("model.transformer.rotary_emb.inv_freq").contiguous(),
         final_norm_w=f("model.transformer.final_norm.weight").contiguous(),
-        w_pred=f("model.to_pred.weight").to(torch.bfloat16).contiguous(),
+        w_pred=sp(f("model.to_pred.weight")).to(torch.bfloat16).contiguous(),
     )
     if "model.duration_predictor.conv.weight" in sd:
         # conv over embedding rows = three table lookups (fastspeech/modules.py:86,103); fp64 product, rounded once
@@ -218,24 +233,27 @@ def pack_cfm(sd: Dict[str, torch.Tensor], device, depth: int = 4, dim_in: int = 
     perm = glu_row_permutation(inter, device)
     for i in range(depth):
         pre = f"model.transformer.layers.{i}."
-        p.w_qkv.append(f(pre + "2.to_qkv.weight").to(torch.bfloat16).contiguous())
-        p.w_out.append(f(pre + "2.to_out.weight").to(torch.bfloat16).contiguous())
+        p.w_qkv.append(sp(f(pre + "2.to_qkv.weight")).to(torch.bfloat16).contiguous())
+        p.w_out.append(sp(f(pre + "2.to_out.weight")).to(torch.bfloat16).contiguous())
         w1 = f(pre + "4.conv1.weight")[perm]
-        p.w_ff1.append(pack_conv_weight(w1, 64))
+        p.w_ff1.append(pack_conv_weight(sp(w1), 64))
         p.b_ff1.append(f(pre + "4.conv1.bias")[perm].contiguous())
-        p.w_ff2.append(pack_conv_weight(f(pre + "4.conv2.weight"), 64))
+        p.w_ff2.append(pack_conv_weight(sp(f(pre + "4.conv2.weight")), 64))
         p.b_ff2.append(f(pre + "4.conv2.bias").contiguous())
     return p
 
 
-def pack_vocoder(sd: Dict[str, torch.Tensor], device) -> PackedVocoder:
+def pack_vocoder(sd: Dict[str, torch.Tensor], device, split: bool = False) -> PackedVocoder:
+    """split=True packs for the tight-precision library: split GEMM weights, no fused-MRF / row-group forms (that
+    library runs every stage through the plain conv and polyphase kernels)."""
     f = lambda k: sd[k].detach().to(device=device, dtype=torch.float32)
-    v = PackedVocoder(w_pre=pack_conv_weight(f("vocoder.conv_pre.weight"), 64), b_pre=f("vocoder.conv_pre.bias").contiguous())
+    sp = (lambda w: split_operand(w, 1)) if split else (lambda w: w)
+    v = PackedVocoder(w_pre=pack_conv_weight(sp(f("vocoder.conv_pre.weight")), 64), b_pre=f("vocoder.conv_pre.bias").contiguous())
     c = 512
     for i, (s, k) in enumerate(zip(UPSAMPLE_RATES, UPSAMPLE_KERNELS)):
-        v.w_up.append(pack_upsampler_weight(f(f"vocoder.upsampler.{i}.weight"), s))
+        v.w_up.append(pack_upsampler_weight(f(f"vocoder.upsampler.{i}.weight"), s, split=split))
         v.b_up.append(f(f"vocoder.upsampler.{i}.bias").contiguous())
-        if k - 2 * ((k - s) // 2) == s:
+        if k - 2 * ((k - s) // 2) == s and not split:
             wv, bv = upsampler_as_row_group_conv(f(f"vocoder.upsampler.{i}.weight"), f(f"vocoder.upsampler.{i}.bias"), s)
             v.up_pair[i] = (pack_conv_weight(wv, block_k_for(wv.shape[1])), bv)
         c //= 2
@@ -243,10 +261,11 @@ def pack_vocoder(sd: Dict[str, torch.Tensor], device) -> PackedVocoder:
         w1s, b1s, w2s, b2s, tails, tail_b = [], [], [], [], [], None
         for j in range(len(RESBLOCK_KERNELS)):
             pre = f"vocoder.resblocks.{i * 3 + j}."
-            w1s.append([pack_conv_weight(f(pre + f"convs1.{q}.weight"), bk) for q in range(3)])
+            w1s.append([pack_conv_weight(sp(f(pre + f"convs1.{q}.weight")), bk) for q in range(3)])
             b1s.append([f(pre + f"convs1.{q}.bias").contiguous() for q in range(3)])
-            w2s.append([pack_conv_weight(f(pre + f"convs2.{q}.weight"), bk) for q in range(2)])
-            b2s.append([f(pre + f"convs2.{q}.bias").contiguous() for q in range(2)])
+            # (split: all three conv2's individually -- the tight engine does not use the fused tail)
+            w2s.append([pack_conv_weight(sp(f(pre + f"convs2.{q}.weight")), bk) for q in range(3 if split else 2)])
+            b2s.append([f(pre + f"convs2.{q}.bias").contiguous() for q in range(3 if split else 2)])
             tails.append(pack_conv_weight(f(pre + "convs2.2.weight"), bk))
             tb = f(pre + "convs2.2.bias")
             tail_b = tb if tail_b is None else tail_b + tb
@@ -256,7 +275,7 @@ def pack_vocoder(sd: Dict[str, torch.Tensor], device) -> PackedVocoder:
         v.b_c2.append(b2s)
         v.w_tail.append(torch.cat(tails, dim=1).contiguous())
         v.b_tail.append(tail_b.contiguous())
-        if c in FUSED_MRF_CHANNELS:
+        if c in FUSED_MRF_CHANNELS and not split:
             v.w_mrf[i], v.b_mrf[i] = pack_mrf_weights(sd, i, device)
     v.w_post = f("vocoder.conv_post.weight")[0].t().contiguous()  # (7, 16)
     v.b_post = float(sd["vocoder.conv_post.bias"].detach().float().reshape(-1)[0])

@@ -261,10 +261,14 @@ def test_library_exports_every_symbol_declared_in_the_header():
     assert declared == set(_native.EXPORTED_SYMBOLS)
     if not os.path.exists(_native.LIB_PATH):
         pytest.skip("libsrb.so not built (run __graft_entry__.build())")
-    lib = ctypes.CDLL(_native.LIB_PATH)
-    for name in declared:
-        assert hasattr(lib, name), name
-    assert lib.srb_version() == 100
+    # the product library and the tight-precision build of the same sources (include/srb.h: srb_split_factor)
+    for path, split in ((_native.LIB_PATH, 1), (_native.TIGHT_LIB_PATH, 3)):
+        assert os.path.exists(path), path
+        lib = ctypes.CDLL(path)
+        for name in declared:
+            assert hasattr(lib, name), (path, name)
+        assert lib.srb_version() == 100
+        assert lib.srb_split_factor() == split
 
 
 # ------------------------------------------------------------------------------------------------ synthesize driver
@@ -352,3 +356,32 @@ def test_bucketing_and_rank_assignment_properties():
         assert max(load) <= sum(cost) / world + max(cost) + 1e-6
 
     check()
+
+
+# ------------------------------------------------------------------------------------------------ tight-precision packing
+def test_split_operand_packing_recovers_fp32_products():
+    """The tight-precision format (include/srb.h: srb_split_factor): activations [xh | xl | xh], weights [Wh | Wh | Wl]
+    along K, every value a bf16 number -- a bf16 GEMM with fp32 accumulation over them gives x W up to the dropped
+    xl Wl term (~2^-17 relative), against ~2^-8 for plain bf16 operands."""
+    from speech_resynth_b200.packing import pack_conv_weight, split_operand
+
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(37, 48, generator=g)
+    w = torch.randn(24, 48, generator=g)
+    xh = x.to(torch.bfloat16).float()
+    xl = (x - xh).to(torch.bfloat16).float()
+    xs = torch.cat([xh, xl, xh], dim=1)
+    ws = split_operand(w, 1)
+    assert ws.shape == (24, 144) and torch.equal(ws, ws.to(torch.bfloat16).float())
+    ref = x.double() @ w.double().t()
+    tight = xs.double() @ ws.double().t()
+    plain = xh.double() @ w.to(torch.bfloat16).double().t()
+    e_tight = float((tight - ref).norm() / ref.norm())
+    e_plain = float((plain - ref).norm() / ref.norm())
+    assert e_tight < 2e-5 and e_plain > 1e-3, (e_tight, e_plain)
+    # conv weights: the split runs along input channels, then the usual tap-major packing with channel padding
+    cw = torch.randn(8, 20, 3, generator=g)
+    p = pack_conv_weight(split_operand(cw, 1), 64)
+    assert p.shape == (8, 3 * 64) and p.dtype == torch.bfloat16
+    assert torch.equal(p[:, 64:124].float(), split_operand(cw[:, :, 1], 1))
+    assert bool((p[:, 60:64] == 0).all())
