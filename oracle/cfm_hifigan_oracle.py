@@ -320,8 +320,10 @@ def resynthesize(sd: Dict[str, Tensor], ids: Tensor, x0: Tensor, dt: float = 0.1
 
 # --------------------------------------------------------------------------------------
 # Log-mel front end (src/hifigan/data.py:17-53); the mel filter bank is third-party (librosa, not installed here):
-# restated from librosa.filters.mel's published definition (Slaney scale, area normalisation) -- PARITY UNPINNED for the
-# filter bank itself; the rest of the function is pinned by running the live reference with this bank injected.
+# restated from librosa.filters.mel's published definition (Slaney scale, area normalisation) and pinned against the two
+# librosa-compatible banks that are installed (transformers.audio_utils.mel_filter_bank slaney/slaney: 9e-10,
+# torchaudio.functional.melscale_fbanks: 6e-8; tests/test_oracle_cpu.py) -- not against librosa's own output, the one
+# remaining caveat; the rest of the function is pinned by running the live reference with this bank injected.
 # --------------------------------------------------------------------------------------
 def librosa_mel_filter_bank(sr: int = 16000, n_fft: int = 400, n_mels: int = 80, fmin: float = 0.0,
                             fmax: float = 8000.0) -> Tensor:

@@ -202,7 +202,7 @@ def _main():
     print("duration_b3_n48", json.dumps(info))
 
     # log-mel front end (hifigan/data.py:17-53): the LIVE reference function with the restated librosa filter bank injected
-    # (librosa itself is not installed: the bank is the one unpinned piece, see the oracle header)
+    # (librosa itself is not installed: the bank is pinned against transformers' and torchaudio's librosa-compatible banks instead, see the oracle header)
     import sys as _sys
 
     _sys.modules["librosa.filters"].mel = lambda **kw: oracle.librosa_mel_filter_bank(

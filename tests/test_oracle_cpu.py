@@ -175,3 +175,26 @@ def test_mel_filter_bank_properties():
     assert float((area[5:] - 1).abs().max()) <= 0.15      # discretisation of narrow triangles on a 40 Hz grid
     peak = a.argmax(1)
     assert bool((peak[1:] >= peak[:-1]).all())
+
+
+def test_mel_filter_bank_matches_third_party_librosa_compatible_banks():
+    """librosa (the reference's source of the bank, hifigan/data.py:6,33) is not installed here, so the restated bank is
+    pinned against the two librosa-compatible implementations that are: transformers.audio_utils.mel_filter_bank
+    (norm="slaney", mel_scale="slaney": the form HF's own feature extractors use in place of librosa.filters.mel; transformers
+    is a pinned dependency of the reference) and, when importable, torchaudio.functional.melscale_fbanks."""
+    from transformers.audio_utils import mel_filter_bank as hf_bank
+
+    from speech_resynth_b200.features import mel_filter_bank
+
+    ours = np.asarray(oracle.librosa_mel_filter_bank(), dtype=np.float64)            # (80, 201)
+    hf = hf_bank(num_frequency_bins=201, num_mel_filters=80, min_frequency=0.0, max_frequency=8000.0, sampling_rate=16000,
+                 norm="slaney", mel_scale="slaney").T
+    assert ours.shape == hf.shape == (80, 201)
+    assert float(np.abs(ours - hf).max()) <= 1e-8 * 1.0 + 1e-8
+    assert float(np.abs(np.asarray(mel_filter_bank(), dtype=np.float64) - hf).max()) <= 1e-7
+    try:
+        import torchaudio
+    except Exception:
+        return
+    ta = torchaudio.functional.melscale_fbanks(201, 0.0, 8000.0, 80, 16000, norm="slaney", mel_scale="slaney").T.double().numpy()
+    assert float(np.abs(ours - ta).max()) <= 2e-7
