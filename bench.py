@@ -280,7 +280,7 @@ def make_config3_units():
     return lengths, units
 
 
-def config3_run(decoder, dev, rank, world, passes: int = 4):
+def config3_run(decoder, dev, rank, world, passes: int = 4, bucket_args=None):
     """BASELINE configs[2] through the product API: sharding.resynthesize_sharded over the same 1024 utterances (seed 11,
     100-1000 frames, NFE 16) at every world size -- STRONG scaling.  Pass 1 is cold (every bucket shape runs eagerly),
     pass 2 captures the graphs, later passes replay them; the headline is the best later pass, the others are listed."""
@@ -290,7 +290,7 @@ def config3_run(decoder, dev, rank, world, passes: int = 4):
 
     lengths, units = make_config3_units()
     eng = decoder.engine()
-    plan = sharding.plan_shards(lengths, world, nfe=16)
+    plan = sharding.plan_shards(lengths, world, nfe=16, **(bucket_args or {}))
     mine = [plan.buckets[j] for j in plan.per_rank[rank]]
     big = max(mine, key=lambda b: eng.workspace_bytes(b.batch, b.frames))
     eng.reserve(big.batch, big.frames)
@@ -346,6 +346,7 @@ def config3_run(decoder, dev, rank, world, passes: int = 4):
                     "decoder.resynthesize_flat (host ids in, cropped waveforms gathered on rank 0); strong scaling",
         "n_gpus": world, "audio_seconds": secs, "value": secs / (steady / 1e3), "unit": UNIT, "ms": steady,
         "cold_value": secs / (rec[0]["ms"] / 1e3), "passes": rec,
+        "bucket_args": bucket_args or "defaults of sharding.bucket_sorted",
         "buckets": len(plan.buckets), "buckets_per_rank": [len(r) for r in plan.per_rank],
         "bucket_shapes_rank0": [[b.batch, b.frames] for b in mine][:12],
         "load": {"model_max_over_mean": plan.imbalance, "measured_max_over_mean": max(best["local_ms_per_rank"]) / mean_t},
@@ -373,6 +374,11 @@ def gpu_run(args):
     decoder = srb.ConditionalFlowMatchingWithHifiGan(srb.reference_config()).eval()
     decoder.load_state_dict(synthetic.make_state_dict(0), strict=True)
     decoder = decoder.to(dev)
+    if args.precision == "tight":
+        # tight-precision mode (libsrb_tight.so: split bf16 operands, fp32 attention): a verification mode; this line
+        # records what it costs at the headline shape (no configs[2] record)
+        decoder.set_precision("tight")
+        args.no_config3 = True
     engine = decoder.engine()
 
     if args.config == 4:
@@ -454,7 +460,11 @@ def gpu_run(args):
         agg = op_profile(engine, ids_dev, x0)
     c3 = None
     if not args.no_config3:
-        c3 = config3_run(decoder, dev, rank, world)
+        ba = None
+        if args.c3_buckets:
+            tb, mb, mw = args.c3_buckets.split(",")
+            ba = dict(tile_budget=int(tb), max_batch=int(mb), max_waste=float(mw))
+        c3 = config3_run(decoder, dev, rank, world, bucket_args=ba)
 
     out = None
     if rank == 0:
@@ -483,7 +493,8 @@ def gpu_run(args):
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic", "config": workload_config(world), "clocks": clk,
+            "dtype": "bf16" if args.precision == "bf16" else "bf16 hi+lo split operands, fp32 accumulation (tight mode)",
+            "data": "synthetic", "config": dict(workload_config(world), precision=args.precision), "clocks": clk,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": ids_host.numel() * 8,
                     "d2h_bytes_per_step": BATCH * rows * 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "roofline": roofline, "hbm_rooflines": hbm_rooflines(agg, pk), "cpu_baseline": cpu,
@@ -657,6 +668,10 @@ def main():
     ap.add_argument("--config", type=int, default=2, choices=[2, 4, 5], help="BASELINE.json configs[] (1-based): 2 = headline "
                     "(with the configs[2] sharded record inside), 4 = vocoder alone, 5 = NFE sweep at 60 s")
     ap.add_argument("--no-config3", action="store_true", help="skip the configs[2] sharded record of the default run")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "tight"], help="tight = the tight-precision library (fp32-grade "
+                    "results, several times slower); the line then says so in `dtype` and `config.precision`")
+    ap.add_argument("--c3-buckets", default=None, help="A/B knob for the configs[2] record: 'tile_budget,max_batch,max_waste' "
+                    "passed to sharding.plan_shards instead of its defaults")
     ap.add_argument("--ops", default=None, help="write the per-op device-time table (csv) here")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -84,6 +84,34 @@ int srb_stage_inputs(const int64_t* ids_in, const float* prior_in, int64_t* ids,
 int srb_log_mel(const float* wav, int64_t wav_stride, int32_t batch, int32_t samples, const float* window, const float* tw_cos,
                 const float* tw_sin, const float* mel_basis, float* out, int32_t frames, void* stream);
 
+/* ---- unit quantiser: the k-means half of the upstream unit encoder (src/flow_matching/utils/textless.py:9-21 ->
+ * textless SpeechEncoder: units = kmeans_model.predict(dense features), optional de-duplication) ----------------------
+ * The codebook is the decoder's own embedding table without its pad row (utils/textless.py:33-35:
+ * to_cond_emb.weight = [0; kmeans.cluster_centers_]), so units = argmin_j |x - c_j|^2 = argmax_j (x . c_j - |c_j|^2 / 2).
+ *   srb_kmeans_assign: feats (rows, dim) fp32 -> units (rows) int64 = nearest centroid + id_offset (1 = the decoder's
+ *     input ids, 0 = sklearn's labels).  Ties go to the smallest index (numpy / sklearn argmin).  The score GEMM runs on the
+ *     tensor cores over SPLIT bf16 operands (fp32-grade products, see srb_split_factor) in both libraries:
+ *       centroids_packed (n_padded, k_pad) bf16 = [Ch | Ch | Cl] per row, k_pad = 3 dim rounded up to 64, zero filled,
+ *       n_padded = centroid count rounded up to 256;  neg_half_norm2 (n_padded) fp32 = -|c_j|^2 / 2, -inf for padding rows;
+ *       split_ws (rows, 3 dim) bf16 and keys_ws (rows) u64 are caller-provided scratch.  dim % 8 == 0.
+ *     It is the three launches below in sequence.
+ *   srb_split_bf16: out (rows, 3 width) bf16 = [bf16(x) | bf16(x - bf16(x)) | bf16(x)]; keys_to_clear (rows u64, or NULL) zeroed.
+ *   srb_kmeans_scores_argmax: the GEMM with the arg-max epilogue: keys[row] = max_j ((ordered score bits << 32) | ~j).
+ *   srb_kmeans_decode: units[row] = column of keys[row] + id_offset; with lengths (rows = batch * frames) positions at or
+ *     beyond lengths[b] become 0, the pad id (srb_kmeans_assign passes its lengths / frames through; NULL = no padding).
+ *   srb_unique_consecutive: torch.unique_consecutive(return_counts=True) per utterance over its first lengths[b] ids
+ *     (lengths NULL = all `frames`): out_ids / out_counts (batch, frames) right-padded with 0, out_lengths[b] = runs. */
+int srb_kmeans_assign(const float* feats, const void* centroids_packed, const float* neg_half_norm2, void* split_ws,
+                      uint64_t* keys_ws, int64_t* units, int64_t rows, int32_t dim, int32_t n_padded, int32_t id_offset,
+                      const int32_t* lengths, int32_t frames, void* stream);
+int srb_split_bf16(const float* x, void* out_bf16, int64_t rows, int32_t width, uint64_t* keys_to_clear, void* stream);
+int srb_kmeans_scores_argmax(const void* feats_split_bf16, const void* centroids_packed, const float* neg_half_norm2,
+                             void* keys_u64, int64_t rows, int32_t dim, int32_t n_padded, void* stream);
+int srb_kmeans_decode(const uint64_t* keys, int64_t* units, int64_t rows, int32_t id_offset, const int32_t* lengths,
+                      int32_t frames, void* stream);
+int srb_unique_consecutive(const int64_t* ids, const int32_t* lengths, int64_t* out_ids, int32_t* out_counts,
+                           int32_t* out_lengths, int32_t batch, int32_t frames, void* stream);
+
 /* Duration-prediction variant (models.py:157-164; fastspeech/modules.py:76-107; transformers length_regulator HF:88-134):
  *   srb_duration_predict : durations[b, n] = clamp(round(exp(conv_k3(E[ids])[b, n]) - 1), 0), 0 at pads; totals[b] = sum.
  *                          dur_table (3, vocab_rows) fp32 = per-unit dot products of the Conv1d(768 -> 1, k 3) taps with the

@@ -56,6 +56,11 @@ _PROTOTYPES = {
     "srb_cfm_attention_simt": [_P, _P, _P, _I, _I, _P],
     "srb_hifigan_mean3": [_P, _P, _P, _P, _L, _I, _F, _F, _P],
     "srb_split_factor": [],
+    "srb_kmeans_assign": [_P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _P, _I, _P],
+    "srb_split_bf16": [_P, _P, _L, _I, _P, _P],
+    "srb_kmeans_scores_argmax": [_P, _P, _P, _P, _L, _I, _I, _P],
+    "srb_kmeans_decode": [_P, _P, _L, _I, _P, _I, _P],
+    "srb_unique_consecutive": [_P, _P, _P, _P, _P, _I, _I, _P],
 }
 
 EXPORTED_SYMBOLS = tuple(_PROTOTYPES) + ("srb_last_error", "srb_hifigan_mrf_phases")

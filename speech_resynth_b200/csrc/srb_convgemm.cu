@@ -450,7 +450,8 @@ static int launch_convgemm(const ConvGemmDesc& d, cudaStream_t stream) {
   }
   // weight multicast across 2-CTA clusters for the wide tiles (needs an even number of row tiles)
   const int row_tiles = d.batch * p.m_tiles[0];
-  const int mode = (bn == 256 && kb == 64 && d.n_groups == 1 && row_tiles % 2 == 0 && row_tiles >= 2) ? cluster_mode() : 0;
+  const int mode = (bn == 256 && kb == 64 && d.n_groups == 1 && row_tiles % 2 == 0 && row_tiles >= 2 && d.epilogue != EPI_ARGMAX)
+                       ? cluster_mode() : 0;
   if (mode != 0) {
     rc = make_weight_map(&p.tmWh, d.weight, k_total, d.n_total, kb, bn / 2);
     if (rc) return rc;
@@ -498,6 +499,7 @@ static int launch_convgemm(const ConvGemmDesc& d, cudaStream_t stream) {
   SRB_DISPATCH(256, 64, EPI_RESNORM)
   SRB_DISPATCH(256, 64, EPI_QKV_ROPE)
   SRB_DISPATCH(80, 64, EPI_EULER)
+  SRB_DISPATCH(256, 64, EPI_ARGMAX)
 #undef SRB_DISPATCH
   set_error("no convgemm instantiation for block_n=%d block_k=%d epilogue=%d", bn, kb, d.epilogue);
   return -4;
@@ -834,6 +836,52 @@ int srb_cfm_pred_euler(const void* xn_bf16, const void* w_packed, float dt, floa
   d.epi.aux1 = mel_bf16;
   d.epi.aux_rows = mel_rows;
   return launch_convgemm(d, (cudaStream_t)stream);
+}
+
+int srb_kmeans_scores_argmax(const void* feats_split_bf16, const void* centroids_packed, const float* neg_half_norm2,
+                             void* keys_u64, int64_t rows, int32_t dim, int32_t n_padded, void* stream) {
+  // x . c_j - |c_j|^2 / 2 over split bf16 operands ([xh | xl | xh] against [Ch | Ch | Cl]: fp32-grade products from the bf16
+  // tensor-core loop, see srb_split_factor) with the argmax folded into the epilogue.  The operands are in split form in
+  // BOTH libraries (the caller splits explicitly), so this view is built by hand instead of through act().
+  SRB_REQUIRE(dim > 0 && dim % 8 == 0, "srb_kmeans_assign: the feature width must be a positive multiple of 8");
+  SRB_REQUIRE(n_padded > 0 && n_padded % 256 == 0, "srb_kmeans_assign: the padded centroid count must be a multiple of 256");
+  SRB_REQUIRE(rows > 0 && rows < (1ll << 31), "srb_kmeans_assign: bad row count");
+  ConvGemmDesc d;
+  ActView a;
+  a.ptr = feats_split_bf16;
+  a.channels = 3 * dim;
+  a.rows = (int)rows;
+  a.batch = 1;
+  a.row_stride = 3 * dim;
+  a.batch_stride = (long long)rows * 3 * dim;
+  d.src[0] = a;
+  d.weight = centroids_packed;
+  d.n_total = n_padded;
+  d.block_n = 256;
+  d.block_k = 64;
+  SRB_REQUIRE((3 * dim) % kSplit == 0, "srb_kmeans_assign: width not divisible by the library's split factor");
+  d.channels = 3 * dim / kSplit;      // launch_convgemm multiplies by kSplit again
+  d.group_tap_begin[1] = 1;
+  d.group_rows[0] = (int)rows;
+  d.batch = 1;
+  d.epilogue = EPI_ARGMAX;
+  d.epi = empty_epi();
+  d.epi.bias = neg_half_norm2;
+  d.epi.out1 = keys_u64;
+  d.epi.out_row_stride = 1;
+  d.epi.out_batch_stride = rows;
+  return launch_convgemm(d, (cudaStream_t)stream);
+}
+
+int srb_kmeans_assign(const float* feats, const void* centroids_packed, const float* neg_half_norm2, void* split_ws,
+                      uint64_t* keys_ws, int64_t* units, int64_t rows, int32_t dim, int32_t n_padded, int32_t id_offset,
+                      const int32_t* lengths, int32_t frames, void* stream) {
+  if (rows <= 0) return 0;
+  int rc = srb_split_bf16(feats, split_ws, rows, dim, keys_ws, stream);
+  if (rc) return rc;
+  rc = srb_kmeans_scores_argmax(split_ws, centroids_packed, neg_half_norm2, keys_ws, rows, dim, n_padded, stream);
+  if (rc) return rc;
+  return srb_kmeans_decode(keys_ws, units, rows, id_offset, lengths, frames, stream);
 }
 
 int srb_hifigan_conv(const void* x0, const void* x1, const void* x2, int32_t n_src, const int32_t* kernel,

@@ -29,7 +29,7 @@ constexpr int kMaxSrc = 3;
 constexpr int kMaxSegs = 8;
 constexpr int kTileM = 128;
 
-enum Epilogue : int { EPI_GENERIC = 0, EPI_GLU = 1, EPI_RESNORM = 2, EPI_QKV_ROPE = 3, EPI_EULER = 4 };
+enum Epilogue : int { EPI_GENERIC = 0, EPI_GLU = 1, EPI_RESNORM = 2, EPI_QKV_ROPE = 3, EPI_EULER = 4, EPI_ARGMAX = 5 };
 
 struct ConvGemmParams {
   CUtensorMap tmA[kMaxSrc];
@@ -927,6 +927,43 @@ __device__ __forceinline__ void epi_euler(const ConvGemmParams& p, uint32_t tacc
   euler_chunk<16>(p, tacc, 64, w, xt, xtb, vrows, mel, melb, mrows, is_pad);
 }
 
+// Nearest-centroid assignment (the k-means unit quantiser on the input side of the path, utils/textless.py:9-21 ->
+// sklearn KMeans.predict): score[row][j] = acc + bias[j] with bias[j] = -|c_j|^2 / 2 (-inf for padding columns), so
+// argmax_j score = argmin_j |x - c_j|^2.  A thread scans its row's columns of this tile, then the best (score, column)
+// pairs of the two column halves and of all N tiles are merged by ONE 64-bit atomicMax per (row, warp) on
+// keys[row] = (order-preserving bits of the score << 32) | (0xFFFFFFFF - column): equal scores resolve to the SMALLEST
+// column, numpy / sklearn argmin's first-occurrence rule.  `out1` = keys (u64 per row, zeroed by the caller).
+template <int NHALF>
+__device__ __forceinline__ void epi_argmax(const ConvGemmParams& p, uint32_t tacc, const TileCoord& tc, int q, int half) {
+  constexpr int COLS = 256 / NHALF;
+  float best = -INFINITY;
+  int best_col = 0;
+  const int col0 = tc.n * 256 + half * COLS;
+  const float* bias = p.bias + col0;
+#pragma unroll 1
+  for (int c0 = 0; c0 < COLS; c0 += 32) {
+    uint32_t v[32];
+    tmem_ld32(tacc + half * COLS + c0, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c0) + j);
+      const float s0 = __uint_as_float(v[4 * j]) + b4.x, s1 = __uint_as_float(v[4 * j + 1]) + b4.y;
+      const float s2 = __uint_as_float(v[4 * j + 2]) + b4.z, s3 = __uint_as_float(v[4 * j + 3]) + b4.w;
+      if (s0 > best) { best = s0; best_col = col0 + c0 + 4 * j; }
+      if (s1 > best) { best = s1; best_col = col0 + c0 + 4 * j + 1; }
+      if (s2 > best) { best = s2; best_col = col0 + c0 + 4 * j + 2; }
+      if (s3 > best) { best = s3; best_col = col0 + c0 + 4 * j + 3; }
+    }
+  }
+  if (q < p.group_rows[0] && best > -INFINITY) {
+    uint32_t u = __float_as_uint(best);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);   // unsigned order == float order
+    const unsigned long long key = (static_cast<unsigned long long>(u) << 32) | (0xFFFFFFFFu - static_cast<uint32_t>(best_col));
+    atomicMax(static_cast<unsigned long long*>(p.out1) + (long long)tc.b * p.out_batch_stride + q, key);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- kernel
 template <int BN, int EPI>
 struct EpiWarps {
@@ -1308,6 +1345,7 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
       else if constexpr (EPI == EPI_GLU) epi_glu<NHALF>(p, tacc, tc, q, half, ew);
       else if constexpr (EPI == EPI_RESNORM) epi_resnorm<NHALF>(p, tacc, tc, q, half, red, lane_base + lane, quarter, ew, rs, issue_load);
       else if constexpr (EPI == EPI_QKV_ROPE) epi_qkv_rope<NHALF>(p, tacc, tc, half, ew, extra_base, rope_row);
+      else if constexpr (EPI == EPI_ARGMAX) epi_argmax<NHALF>(p, tacc, tc, q, half);
       else epi_euler(p, tacc, tc, q, ew);
       tc_fence_before();
       __syncwarp();

@@ -653,6 +653,90 @@ __global__ void __launch_bounds__(256) mean3_act_kernel(const __nv_bfloat16* __r
   }
 }
 
+
+// ------------------------------------------------------------------------------------------ unit quantiser (input side)
+// Split copy of fp32 rows for the tight GEMM form: out row = [bf16(x) | bf16(x - bf16(x)) | bf16(x)], 3 * width bf16
+// (include/srb.h: srb_split_factor); also clears the per-row argmax keys of srb_kmeans_assign.
+__global__ void __launch_bounds__(256) split_rows_kernel(const float4* __restrict__ x, uint2* __restrict__ out, long long rows,
+                                                         int w4, unsigned long long* __restrict__ keys) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long n = rows * w4, stride = (long long)gridDim.x * blockDim.x;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (long long i = tid; i < n; i += stride) {
+    const long long row = i / w4;
+    const int piece = (int)(i - row * w4);
+    const float4 v = __ldg(x + i);
+    const uint2 h = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+    uint2* d = out + row * (3ll * w4) + piece;
+    d[0] = h;
+    d[w4] = make_uint2(pack_bf16_rest(v.x, v.y, h.x), pack_bf16_rest(v.z, v.w, h.y));
+    d[2 * w4] = h;
+  }
+  if (keys != nullptr)
+    for (long long i = tid; i < rows; i += stride) keys[i] = 0ull;
+}
+
+// keys[row] = (ordered score bits << 32) | (0xFFFFFFFF - column)  ->  units[row] = column + id_offset
+// (rows = batch * frames with per-utterance lengths: positions at or beyond lengths[b] become 0, the pad id)
+__global__ void __launch_bounds__(256) kmeans_decode_kernel(const unsigned long long* __restrict__ keys, int64_t* __restrict__ units,
+                                                            long long rows, int id_offset, const int* __restrict__ lengths, int frames) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (long long)gridDim.x * blockDim.x) {
+    const bool pad = lengths != nullptr && (int)(i % frames) >= lengths[i / frames];
+    units[i] = pad ? 0 : (int64_t)(0xFFFFFFFFu - (uint32_t)(keys[i] & 0xFFFFFFFFull)) + id_offset;
+  }
+}
+
+// torch.unique_consecutive(return_counts=True) per utterance (textless SpeechEncoder's `deduplicate`): runs of equal ids
+// within the first lengths[b] entries of a row collapse to one id + its run length; outputs are right-padded with 0.
+// One block per utterance: chunked scan of the "starts a run" flags (same scheme as length_regulate_kernel).
+__global__ void __launch_bounds__(256) unique_consecutive_kernel(const int64_t* __restrict__ ids, const int* __restrict__ lengths,
+                                                                 int64_t* __restrict__ out_ids, int* __restrict__ out_counts,
+                                                                 int* __restrict__ out_len, int frames) {
+  __shared__ int warp_tot[8];
+  __shared__ int carry_s;
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t* row = ids + (long long)b * frames;
+  int64_t* orow = out_ids + (long long)b * frames;
+  int* crow = out_counts + (long long)b * frames;
+  const int len = lengths != nullptr ? min(lengths[b], frames) : frames;
+  for (int n = threadIdx.x; n < frames; n += blockDim.x) {
+    orow[n] = 0;
+    crow[n] = 0;
+  }
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < len; base += blockDim.x) {
+    const int n = base + threadIdx.x;
+    const int start = (n < len && (n == 0 || row[n] != row[n - 1])) ? 1 : 0;
+    int incl = start;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    int off = carry_s;
+    for (int w = 0; w < warp; ++w) off += warp_tot[w];
+    if (start) {
+      // this thread opens run number off + incl - 1: its length is the distance to the next run start (or to len)
+      int e = n + 1;
+      const int64_t u = row[n];
+      while (e < len && row[e] == u) ++e;
+      orow[off + incl - 1] = u;
+      crow[off + incl - 1] = e - n;
+    }
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry_s = off + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out_len[b] = carry_s;
+}
+
 }  // namespace srb
 
 using namespace srb;
@@ -793,6 +877,39 @@ int srb_hifigan_mean3(const void* x0, const void* x1, const void* x2, void* out,
                       static_cast<const __nv_bfloat16*>(x0), static_cast<const __nv_bfloat16*>(x1),
                       static_cast<const __nv_bfloat16*>(x2), static_cast<__nv_bfloat16*>(out), (long long)rows, channels, scale, slope));
   return after_launch("mean3_act_kernel");
+}
+
+int srb_split_bf16(const float* x, void* out_bf16, int64_t rows, int32_t width, uint64_t* keys_to_clear, void* stream) {
+  if (rows <= 0 || width <= 0) return 0;
+  SRB_REQUIRE(width % 4 == 0, "srb_split_bf16: width must be a multiple of 4");
+  long long blocks = (rows * (width / 4) + 255) / 256;
+  const long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  SRB_CUDA(launch_pdl(split_rows_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream,
+                      reinterpret_cast<const float4*>(x), reinterpret_cast<uint2*>(out_bf16), (long long)rows, (int)(width / 4),
+                      reinterpret_cast<unsigned long long*>(keys_to_clear)));
+  return after_launch("split_rows_kernel");
+}
+
+int srb_kmeans_decode(const uint64_t* keys, int64_t* units, int64_t rows, int32_t id_offset, const int32_t* lengths,
+                      int32_t frames, void* stream) {
+  if (rows <= 0) return 0;
+  SRB_REQUIRE(lengths == nullptr || (frames > 0 && rows % frames == 0), "srb_kmeans_decode: rows must be batch * frames when lengths are given");
+  long long blocks = (rows + 255) / 256;
+  const long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  SRB_CUDA(launch_pdl(kmeans_decode_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream,
+                      reinterpret_cast<const unsigned long long*>(keys), units, (long long)rows, (int)id_offset, lengths,
+                      (int)(lengths != nullptr ? frames : 1)));
+  return after_launch("kmeans_decode_kernel");
+}
+
+int srb_unique_consecutive(const int64_t* ids, const int32_t* lengths, int64_t* out_ids, int32_t* out_counts, int32_t* out_lengths,
+                           int32_t batch, int32_t frames, void* stream) {
+  if (batch <= 0 || frames <= 0) return 0;
+  SRB_CUDA(launch_pdl(unique_consecutive_kernel, dim3(batch), dim3(256), 0, (cudaStream_t)stream, ids, lengths, out_ids, out_counts,
+                      out_lengths, (int)frames));
+  return after_launch("unique_consecutive_kernel");
 }
 
 }  // extern "C"

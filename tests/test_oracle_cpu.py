@@ -198,3 +198,38 @@ def test_mel_filter_bank_matches_third_party_librosa_compatible_banks():
         return
     ta = torchaudio.functional.melscale_fbanks(201, 0.0, 8000.0, 80, 16000, norm="slaney", mel_scale="slaney").T.double().numpy()
     assert float(np.abs(ours - ta).max()) <= 2e-7
+
+
+# ------------------------------------------------------------------------------------------------ unit quantiser oracle
+def test_kmeans_oracle_matches_sklearn_golden_and_live_predict(golden_dir):
+    """oracle/kmeans_oracle.py against scikit-learn's own KMeans.predict -- the call textlesslib's quantiser makes
+    (utils/textless.py:9-21): the committed golden, then a live predict on a fresh codebook."""
+    from oracle import kmeans_oracle as ko
+
+    z = np.load(os.path.join(golden_dir, "kmeans_k300_d64.npz"))
+    assert np.array_equal(ko.assign(z["feats"], z["centroids"]), z["labels"])
+    assert float(ko.margins(z["feats"], z["centroids"]).min()) > 1e-4      # the golden has no near-ties
+    from sklearn.cluster import KMeans
+
+    rng = np.random.default_rng(1)
+    train = rng.normal(size=(500, 16)).astype(np.float32)
+    km = KMeans(n_clusters=40, n_init=1, max_iter=3, random_state=0).fit(train)
+    x = rng.normal(size=(700, 16)).astype(np.float32)
+    got, ref = ko.assign(x, km.cluster_centers_), km.predict(x)
+    decisive = ko.margins(x, km.cluster_centers_) > 1e-5
+    assert np.array_equal(got[decisive], ref[decisive]) and decisive.mean() > 0.99
+
+
+def test_kmeans_oracle_deduplication_follows_torch_unique_consecutive(golden_dir):
+    from oracle import kmeans_oracle as ko
+
+    z = np.load(os.path.join(golden_dir, "kmeans_k300_d64.npz"))
+    lengths = z["lengths"].tolist()
+    ids, counts, n_out = ko.encode(z["feats"], lengths, z["centroids"], deduplicate=True)
+    for b, n in enumerate(lengths):
+        u, c = torch.unique_consecutive(torch.from_numpy(z["labels"][b, :n] + 1), return_counts=True)
+        assert n_out[b] == len(u) and np.array_equal(ids[b, : len(u)], u.numpy()) and np.array_equal(counts[b, : len(u)], c.numpy())
+        assert not ids[b, len(u):].any() and not counts[b, len(u):].any() and counts[b].sum() == n
+    assert n_out[0] < lengths[0]           # the golden really has runs
+    u, c = ko.unique_consecutive(np.array([], dtype=np.int64))
+    assert len(u) == 0 and len(c) == 0
