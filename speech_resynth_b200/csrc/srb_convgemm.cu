@@ -242,7 +242,17 @@ static int launch_inst(ConvGemmParams& p, int total_tiles, cudaStream_t stream, 
   while (a_stages * a_bytes + w_stages * w_stage_bytes + stage_smem > 222 * 1024 && w_stages > 2 && !WS) --w_stages;
   p.w_stages = w_stages;
   // alignment slack + rings + 2 KB bookkeeping block (barriers, TMEM slot, norm exchange) + epilogue staging / tables
-  SRB_REQUIRE(8 * (2 * (a_stages + w_stages) + 4) + 16 + 1024 + 128 <= 2048, "too many pipeline stages for the bookkeeping block");
+  SRB_REQUIRE(8 * (2 * (a_stages + w_stages) + 4) + 16 + 1024 + 384 <= 2048, "too many pipeline stages for the bookkeeping block");
+  {
+    // RESNORM with ONE residual buffer per warp (the long-K launches: FFN conv2): the last tile of a CTA takes its remaining
+    // residual chunks at once into the idle weight ring (3 x 4 KB per epilogue warp) instead of paying one L2 latency per
+    // chunk in its exposed epilogue.  Same-box A/B at config 2: ffn_out_norm 51.8 / 51.9 -> 49.7 / 49.6 us per launch
+    // (857 -> 894 TFLOP/s); the two-buffer launches (attn_out_norm) gained nothing (28.5 / 28.9 vs 28.8 / 28.8) and keep
+    // their stream.  SRB_RES_TAIL=0 switches it off, =2 also enables it for the two-buffer launches (A/B knob).
+    static const int tail_on = [] { const char* e = getenv("SRB_RES_TAIL"); return e ? atoi(e) : 1; }();
+    p.res_tail = (EPI == EPI_RESNORM && MC != 2 && tail_on && (p.res_bufs == 1 || tail_on == 2) && !p.w_dynamic &&
+                  (long long)w_stages * w_stage_bytes >= (long long)EpiWarps<BN, EPI>::value * 3 * 4096) ? 1 : 0;
+  }
   const int smem = 1024 + a_stages * a_bytes + w_stages * w_stage_bytes + 2048 + stage_smem;
   static int configured_smem[64] = {0};
   int dev = 0;

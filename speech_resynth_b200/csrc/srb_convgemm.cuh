@@ -70,6 +70,8 @@ struct ConvGemmParams {
   int gen_lsu;                                    // GENERIC: 1 = register / LSU epilogue (MMA-bound launches, fused tails)
   int gen_nbuf;                                   // GENERIC TMA epilogue: staging depth (1 or 2) of residual and output blocks
   int l2_keep;                                    // RESNORM: 1 = evict_last policy on the residual stream's TMA transfers
+  int res_tail;                                   // RESNORM: 1 = the CTA's LAST tile takes its remaining residual chunks all at once
+                                                  // into the (by then idle) weight ring instead of one latency after the other
   int w_early;                                    // 1 = request the first weight slabs before the dependency wait (PDL)
   int w_dynamic;                                  // 1 = the "weight" operand is produced by a predecessor kernel (swapped-operand v^T GEMM)
   // epilogue operands
@@ -541,6 +543,13 @@ struct ResStream {
   uint8_t* gen;        // generic pointer to `buf`
   int nb;
   int seq;             // chunks consumed so far
+  // Last tile of the CTA (see ConvGemmParams::res_tail): once that tile's MMAs are complete nothing uses the weight ring
+  // any more, so the chunks the stream has not requested yet (all but the first `nb`) are requested at once into this
+  // warp's 3 x 4 KB slice of it, each with its own single-use mbarrier; they are staged for the store in place.
+  uint32_t tail_buf;   // shared address of the slice (1024-byte aligned)
+  uint8_t* tail_gen;   // generic pointer to it
+  uint32_t tail_bar;   // 3 mbarriers
+  int tail;            // 1 while the current tile is served that way
 };
 
 template <int NHALF, typename IssueLoad>
@@ -559,13 +568,16 @@ __device__ __forceinline__ void epi_resnorm(const ConvGemmParams& p, uint32_t ta
   for (int c = 0; c < NCHUNK; ++c) {
     const int s = rs.seq;
     const int bi = nb == 2 ? (s & 1) : 0;
-    mbar_wait(rs.bar + 8u * bi, nb == 2 ? ((s >> 1) & 1) : (s & 1));
+    const bool from_tail = rs.tail && c >= nb;          // chunk c of the CTA's last tile sits in the weight-ring slice
+    if (from_tail) mbar_wait(rs.tail_bar + 8u * (c - nb), 0u);
+    else mbar_wait(rs.bar + 8u * bi, nb == 2 ? ((s >> 1) & 1) : (s & 1));
     SRB_TRACE_EPI(3, s >> 2, c);   // residual chunk c is in shared memory
+    uint8_t* src_gen = from_tail ? rs.tail_gen + (c - nb) * 4096 : rs.gen + bi * 4096;
     uint4 rr[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) rr[j] = *stage_slot<8>(rs.gen + bi * 4096, w.lane, j);
+    for (int j = 0; j < 8; ++j) rr[j] = *stage_slot<8>(src_gen, w.lane, j);
     __syncwarp();   // every lane has its row
-    if (nb == 2) issue_load(s + 2, bi);
+    if (nb == 2 && !rs.tail) issue_load(s + 2, bi);
     uint32_t v[32];
     tmem_ld32(tcol + c * 32, v);
     tmem_ld_wait();
@@ -586,21 +598,26 @@ __device__ __forceinline__ void epi_resnorm(const ConvGemmParams& p, uint32_t ta
       v[4 * j + 2] = __float_as_uint(y.z); v[4 * j + 3] = __float_as_uint(y.w);
       yo[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     }
+    // store stage of this chunk: the separate stage (nb == 2), the load buffer itself (nb == 1), or -- a chunk that came
+    // through the weight-ring slice -- its own slot there (used once, so nothing to wait for)
+    const bool own_slot = from_tail && nb != 2;
+    const uint32_t o_stage = own_slot ? rs.tail_buf + (c - nb) * 4096 : st_stage;
+    uint8_t* o_gen = own_slot ? src_gen : st_gen;
     if (nb == 2) {
       if (w.lane == 0) bulk_wait_read<0>();   // the previous block has left the store stage
       __syncwarp();
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) *stage_slot<8>(st_gen, w.lane, j) = yo[j];
+    for (int j = 0; j < 8; ++j) *stage_slot<8>(o_gen, w.lane, j) = yo[j];
     fence_proxy_async_smem();
     __syncwarp();
     if (w.lane == 0) {
-      if (p.l2_keep) tma_store_3d_hint(&p.tmO1, st_stage, half * COLS + c * 32, w.row0, tc.b, kL2EvictLast);
-      else tma_store_3d(&p.tmO1, st_stage, half * COLS + c * 32, w.row0, tc.b);
+      if (p.l2_keep) tma_store_3d_hint(&p.tmO1, o_stage, half * COLS + c * 32, w.row0, tc.b, kL2EvictLast);
+      else tma_store_3d(&p.tmO1, o_stage, half * COLS + c * 32, w.row0, tc.b);
       bulk_commit();
       // in place: the buffer takes the next chunk once the store has read it; the last chunk of a tile waits until
       // the bf16 pass below has used the buffer as its stage
-      if (nb != 2 && (c < NCHUNK - 1 || p.norm_mode == 0)) {
+      if (nb != 2 && !rs.tail && (c < NCHUNK - 1 || p.norm_mode == 0)) {
         bulk_wait_read<0>();
         issue_load(s + 1, 0);
       }
@@ -677,7 +694,7 @@ __device__ __forceinline__ void epi_resnorm(const ConvGemmParams& p, uint32_t ta
     }
     SRB_TRACE_EPI(5, (rs.seq >> 2) - 1, c);   // bf16 block c stored
   }
-  if (nb != 2 && w.lane == 0) {
+  if (nb != 2 && !rs.tail && w.lane == 0) {
     bulk_wait_read<0>();
     issue_load(rs.seq, 0);
   }
@@ -1044,11 +1061,12 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t red_off = (bar_base - smem_base) + 8 * (n_ring_bars + 4) + 16;
   float* red = reinterpret_cast<float*>(smem_gen + red_off);  // [2][128]
-  const uint32_t epi_bar = smem_base + ((red_off + 1024 + 15) & ~15u);               // EW x 2 residual-stream mbarriers
+  const uint32_t epi_bar = smem_base + ((red_off + 1024 + 15) & ~15u);               // EW x 2 residual-stream mbarriers, then
+                                                                                     // (RESNORM) EW x 3 single-use ones of the last tile
   // the bookkeeping block (ring barriers, TMEM slot, `red`, epilogue barriers) is 2 KB; bar_base is 1024-aligned
   // (written as an explicitly aligned offset: with the plain sum the compiler lost the 1024-byte alignment of the
   // staging areas and spent ~50 % more integer instructions on every swizzled slot address)
-  uint8_t* stage_base = smem_gen + ((red_off + 1024 + 128 + 1023) & ~1023u);         // EW warp-private staging areas
+  uint8_t* stage_base = smem_gen + ((red_off + 1024 + 384 + 1023) & ~1023u);         // EW warp-private staging areas
   const int stage_bytes = EpiWarps<BN, EPI>::stage_bytes(p.res_bufs);
   uint8_t* extra_base = stage_base + EW * stage_bytes;                               // CTA-wide epilogue tables
 
@@ -1089,7 +1107,7 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
       mbar_init(tempty_bar(b), MC == 2 ? 2 * EW : EW);
     }
     if constexpr (EPI == EPI_RESNORM || EPI == EPI_GENERIC) {
-      for (int i = 0; i < 2 * EW; ++i) mbar_init(epi_bar + 8u * i, 1);
+      for (int i = 0; i < (EPI == EPI_RESNORM ? 5 : 2) * EW; ++i) mbar_init(epi_bar + 8u * i, 1);
     }
     if constexpr (EPI == EPI_RESNORM) {
       tma_prefetch_desc(&p.tmR);
@@ -1273,6 +1291,10 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
     rs.bar = epi_bar + 16u * (warp - 2);
     rs.nb = p.res_bufs;
     rs.seq = 0;
+    rs.tail_buf = w_ring + (warp - 2) * (3 * 4096);
+    rs.tail_gen = smem_gen + (rs.tail_buf - smem_base);
+    rs.tail_bar = epi_bar + 16u * EW + 24u * (warp - 2);
+    rs.tail = 0;
     auto issue_load = [&](int s, int bi) {
       if constexpr (EPI == EPI_RESNORM) {
         const int tile = walker + (s >> 2) * n_walkers;
@@ -1337,6 +1359,24 @@ convgemm_kernel(const __grid_constant__ ConvGemmParams p, int total_tiles) {
       mbar_wait(tfull_bar(buf), bphase);
       tc_fence_after();
       if (warp == 2) SRB_TRACE_AT(2, it, 1);   // accumulator complete
+      if constexpr (EPI == EPI_RESNORM && MC != 2) {
+        // CTA's last tile: its MMAs are complete, so the weight ring is idle from here on (no tile follows, and with
+        // multicast every slab a peer writes into this ring has been consumed by the MMAs just completed): request the
+        // residual chunks the stream has not asked for yet all at once into this warp's slice of it
+        if (p.res_tail && tile + n_walkers >= total_tiles) {
+          rs.tail = 1;
+          if (lane == 0) {
+            for (int c = rs.nb; c < 4; ++c) {
+              const uint32_t bar = rs.tail_bar + 8u * (c - rs.nb), dst = rs.tail_buf + (c - rs.nb) * 4096;
+              mbar_expect_tx(bar, 4096);
+              if (p.l2_keep)
+                tma_load_3d_hint(dst, &p.tmR, bar, half * (256 / NHALF) + c * 32, tc.m * kTileM + lane_base, tc.b, kL2EvictLast);
+              else
+                tma_load_3d(dst, &p.tmR, bar, half * (256 / NHALF) + c * 32, tc.m * kTileM + lane_base, tc.b);
+            }
+          }
+        }
+      }
       const uint32_t tacc = tmem_base + (static_cast<uint32_t>(lane_base) << 16) + buf * TBUF;
       if constexpr (EPI == EPI_GENERIC) {
         if (p.gen_lsu) epi_generic_lsu<BN, NHALF>(p, tacc, tc, q, half, ew);
