@@ -492,6 +492,7 @@ static int launch_convgemm(const ConvGemmDesc& d, cudaStream_t stream) {
   if (bn == BN_ && kb == KB_ && d.epilogue == EPI_) return launch_inst<BN_, KB_, EPI_, 0, 1>(p, row_tiles, stream, n_slabs);
       SRB_DISPATCH_WS(256, 64, EPI_QKV_ROPE)
       SRB_DISPATCH_WS(64, 64, EPI_GENERIC)
+      SRB_DISPATCH_WS(32, 32, EPI_GENERIC)    // the C = 32 -> 2 x 16 row-group up-sampler: 6 KB of weights per 8 KB activation box
 #undef SRB_DISPATCH_WS
     }
   }
