@@ -204,6 +204,11 @@ static int launch_inst(ConvGemmParams& p, int total_tiles, cudaStream_t stream, 
   int a_stages, w_stages;
   if (L::w_bytes >= 32 * 1024) { a_stages = 3; w_stages = 4; }        // wide tiles: one CTA per SM
   else if (L::w_bytes >= 8 * 1024) { a_stages = 2; w_stages = 4; }    // two CTAs per SM
+  if (EPI == EPI_GENERIC && BN == 128) {
+    // A/B knob: ring depth of the C = 128 vocoder convs ("a,w"), e.g. 2,3 so that two different launches fit one SM
+    static const char* e = getenv("SRB_GEN128_STAGES");
+    if (e) { a_stages = atoi(e); const char* c = strchr(e, ','); if (c) w_stages = atoi(c + 1); }
+  }
   else { a_stages = 2; w_stages = 6; }
   {
     // experiment knobs (profiling only)
@@ -229,6 +234,10 @@ static int launch_inst(ConvGemmParams& p, int total_tiles, cudaStream_t stream, 
     // every slab resident; the activation ring takes what is left (at most 4 boxes)
     w_stages = n_slabs;
     a_stages = L::w_bytes >= 32 * 1024 ? 4 : 3;
+    if (EPI == EPI_GENERIC) {
+      static const int ws_a = [] { const char* e = getenv("SRB_WS_A_STAGES"); return e ? atoi(e) : 0; }();   // A/B knob
+      if (ws_a >= 2) a_stages = ws_a;
+    }
     while (a_stages > 2 && a_stages * a_bytes + w_stages * w_stage_bytes + stage_smem > 220 * 1024) --a_stages;
     // narrow tiles: prefer two resident CTAs (their epilogues overlap) over a third activation box
     if (a_stages == 3 && 3 * a_bytes + w_stages * w_stage_bytes + stage_smem > 108 * 1024 &&
@@ -277,6 +286,12 @@ static int launch_inst(ConvGemmParams& p, int total_tiles, cudaStream_t stream, 
   occ = occ < by_threads ? occ : by_threads;
   occ = occ < by_tmem ? occ : by_tmem;
   occ = occ < 1 ? 1 : occ;
+  if (WS && EPI == EPI_GENERIC) {
+    // A/B knob: cap the resident CTAs per SM of the weight-stationary vocoder convs (co-residency with the kernels of the
+    // other resblock chains running as parallel graph branches)
+    static const int cap = [] { const char* e = getenv("SRB_WS_OCC"); return e ? atoi(e) : 0; }();
+    if (cap > 0 && occ > cap) occ = cap;
+  }
   int grid = num_sms() * occ;
   if constexpr (MC) {
     // 2-CTA clusters; `total_tiles` counts PAIRS of row tiles here

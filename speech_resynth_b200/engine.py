@@ -110,7 +110,8 @@ class _Fork:
     def __init__(self, device, n: int):
         with torch.cuda.device(device):
             self.side = [torch.cuda.Stream(device=device) for _ in range(n)]
-        self.enabled = True
+        # SRB_FORK: bit 0 = the sampler's q|k / v^T branches, bit 1 = the vocoder's three resblock chains (A/B knob, default 3)
+        self.enabled = bool(int(os.environ.get("SRB_FORK", "3")) & (1 if n == 1 else 2))
 
     def run(self, branches) -> None:
         """branches: list of callables; branch 0 runs on the current stream, the others on side streams."""
@@ -291,7 +292,7 @@ class CFMSampler:
         b, n = ws["ids"].shape
         w, L = self.w, ws["lengths"]
         cs, sn = self.rotary(n)
-        m = b * n
+        m = b * ws["mel_rows"]      # algorithmic work (profiling log only): the caller's frames, not the 8-row padding
         self.call("srb_cfm_embed", P(ws["xt_b"]), P(w.w_embed), P(ws["cond"]), P(ws["x0"]), b, n, flops=2.0 * m * 80 * 256,
                  nbytes=m * (80 * 2 + 256 * 8))
         self.call("srb_cfm_posconv_norm", P(ws["x0"]), P(w.dw_w), P(w.dw_b), P(g_step[0]), P(L), P(ws["x"]), P(ws["xn"]), b, n,
@@ -303,7 +304,7 @@ class CFMSampler:
                 # reference-style chain: one q|k|v projection with rotary, then fp32 softmax attention on CUDA cores
                 self.call("srb_cfm_qkv_rope", P(ws["xn"]), P(w.w_qkv[i]), P(cs), P(sn), P(ws["qkv"]), None, None, b, n,
                           flops=2.0 * m * 256 * 768)
-                self.call("srb_cfm_attention_simt", P(ws["qkv"]), P(L), P(ws["o"]), b, n, flops=4.0 * m * n * 256)
+                self.call("srb_cfm_attention_simt", P(ws["qkv"]), P(L), P(ws["o"]), b, n, flops=4.0 * m * ws["mel_rows"] * 256)
             elif self.fused_qkv:
                 m_pad = ws["vt"].shape[1]
                 # the whole to_qkv GEMM in one launch: q | k with rotary, v stored transposed by the epilogue
@@ -320,7 +321,7 @@ class CFMSampler:
                 ])
             if not self.tight:
                 self.call("srb_cfm_attention_tc", P(ws["qk"]), 512, P(ws["vt"]), ws["vt"].shape[1], P(L), P(qk_cur), P(ws["o"]), b, n,
-                          flops=4.0 * m * n * 256)
+                          flops=4.0 * m * ws["mel_rows"] * 256)
             self.call("srb_cfm_attn_out_norm", P(ws["o"]), P(w.w_out[i]), P(g_step[2 * i + 1]), P(L), P(ws["x"]), P(ws["xn"]), b, n,
                      flops=2.0 * m * 256 * 256)
             # every utterance ends in a pad row whenever the caller's frame count is not a multiple of 8 (lengths <= mel_rows < n)

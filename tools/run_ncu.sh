@@ -12,6 +12,8 @@ ncu --set full --clock-control none -k regex:"convgemm_kernel" -s 4 -c 12 \
     -o /tmp/ncu/convgemm_step -f python tools/ncu_hbm_kernels.py 1 > gpurun_out/r02_ncu_convgemm.log 2>&1
 ncu --set full --clock-control none -k regex:"attn_tc_kernel|mrf_fused" -c 4 \
     -o /tmp/ncu/attn_mrf -f python tools/ncu_hbm_kernels.py 1 > gpurun_out/r02_ncu_attn_mrf.log 2>&1
+ncu --set full --clock-control none -k regex:"convgemm_kernel|split_rows|kmeans_decode" -c 3 \
+    -o /tmp/ncu/units -f python tools/time_units.py > gpurun_out/r02_ncu_units.log 2>&1
 python tools/ncu_summary.py "round 2, config-2 shape (64 x 500 units), ncu --set full --clock-control none; cold-cache, serialised launches" \
-    /tmp/ncu/hbm_kernels.ncu-rep /tmp/ncu/convgemm_step.ncu-rep /tmp/ncu/attn_mrf.ncu-rep > gpurun_out/r02_ncu_summary.csv
+    /tmp/ncu/hbm_kernels.ncu-rep /tmp/ncu/convgemm_step.ncu-rep /tmp/ncu/attn_mrf.ncu-rep /tmp/ncu/units.ncu-rep > gpurun_out/r02_ncu_summary.csv
 wc -l gpurun_out/r02_ncu_summary.csv gpurun_out/r02_ncu_launches.csv
