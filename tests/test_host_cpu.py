@@ -211,7 +211,10 @@ def test_contiguous_plan_balances_cost_and_keeps_buckets_homogeneous():
         mins = [min(lengths[i] for j in r for i in plan.buckets[j].indices) for r in plan.per_rank]
         maxs = [max(lengths[i] for j in r for i in plan.buckets[j].indices) for r in plan.per_rank]
         assert all(mins[r] >= maxs[r + 1] for r in range(world - 1))
-        assert plan.imbalance < 1.05, (world, plan.imbalance)
+        assert plan.imbalance < 1.03, (world, plan.imbalance)    # 8 ranks: 1.050 before the boundary search, 1.027 with it
+        # every rank derives the same plan from the lengths alone (the search is deterministic)
+        again = sharding.plan_shards(lengths, world, nfe=16)
+        assert [b.indices for b in again.buckets] == [b.indices for b in plan.buckets] and again.per_rank == plan.per_rank
         # padding overhead of the whole plan (padded frames / real frames)
         padded = sum(b.batch * b.frames for b in plan.buckets)
         assert padded / sum(lengths) < 1.08
