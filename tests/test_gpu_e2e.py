@@ -316,6 +316,36 @@ def test_config5_long_form_step_sweep(decoder, state_dict, nfe):
     within(f"config5 2x3000 NFE {nfe} mel normalised", rel_l2((mel[valid] - MEAN) / STD, (ref[valid] - MEAN) / STD), MEL_TOL_NORM)
 
 
+def test_extreme_shapes_long_utterance_and_wide_batch(decoder, state_dict):
+    """Edges of the shape space: (a) one two-minute utterance whose frame count is odd and exceeds the initial rotary table
+    (6001 frames: the table regrows, 48 key tiles per attention row, 1.9 M output samples in one row); (b) a wide batch of
+    very short utterances (300 x 16 frames, lengths 1..16: every tile is mostly padding, batch > any tile-count constant).
+    Mel against the CPU oracle (all of (a); a ragged sample of rows of (b)), plus the size-independent properties."""
+    ids = synthetic.make_units(1, 6001, seed=43, lengths=[6001])
+    x0 = torch.randn(1, 6001, 80, generator=torch.Generator().manual_seed(9))
+    wav, lens, mel = decoder.engine().resynthesize(ids.cuda(), 1.0, 1.0, noise=x0.cuda())
+    wav, mel = wav.clone().cpu(), mel.clone().cpu()
+    assert lens.cpu().tolist() == [6001] and wav.shape == (1, 320 * 6001 + 80)
+    assert bool(torch.isfinite(wav).all()) and float(wav.abs().max()) <= 1.0
+    ref = oracle.sample(state_dict, ids, x0, 1.0, 1.0)
+    within("1x6001 NFE 1 mel normalised", rel_l2((mel - MEAN) / STD, (ref - MEAN) / STD), MEL_TOL_NORM)
+
+    lengths = [(7 * i) % 16 + 1 for i in range(300)]
+    ids = synthetic.make_units(300, 16, seed=44, lengths=lengths)
+    x0 = torch.randn(300, 16, 80, generator=torch.Generator().manual_seed(10))
+    outs = decoder.engine().resynthesize(ids.cuda(), 0.5, 1.0, noise=x0.cuda())
+    wav, lens, mel = outs[0].clone().cpu(), outs[1].cpu().tolist(), outs[2].clone().cpu()
+    assert lens == lengths and wav.shape == (300, 320 * 16 + 80) and bool(torch.isfinite(wav).all())
+    valid = ids.ne(0)
+    assert bool((mel[~valid] == oracle.pad_value()).all())
+    sub = [0, 1, 15, 16, 150, 299]
+    ref = oracle.sample(state_dict, ids[sub], x0[sub], 0.5, 1.0)
+    vs = valid[sub]
+    within("300x16 NFE 2 mel normalised (6 rows)", rel_l2((mel[sub][vs] - MEAN) / STD, (ref[vs] - MEAN) / STD), MEL_TOL_NORM)
+    ref_w = oracle.resynthesize(state_dict, ids[sub[:3]], x0[sub[:3]], 0.5, 1.0)
+    within("300x16 NFE 2 waveform (3 rows)", max(rel_l2(wav[i, : r.shape[-1]], r[0]) for i, r in zip(sub[:3], ref_w)), WAV_TOL)
+
+
 def test_duration_prediction_variant_matches_reference_golden(state_dict, golden_dir):
     """SURVEY.md section 8(f) N1 -- the second shipped config (predict_duration): integer durations and the expanded
     sequence bit exact against the live reference, mel / waveforms within the bf16 tolerances."""
