@@ -174,14 +174,20 @@ struct ConvGemmDesc {
 // 28.65 / 28.58 ms per step with multicast against 28.68 / 29.14 / 28.79 without, and 29.02 +- 0.04 against 29.31 +- 0.02
 // end to end -- 1 %, from the C = 256 vocoder convs and the FFN GEMM; the per-op table shows the K = 256 launches
 // (q|k projection: 24.4 vs 22.6 us) paying for their cluster start-up, which is why mode 2 (pair MMA: 29.5 ms) loses.
-static int cluster_mode() {
-  static int v = -1;
-  if (v < 0) {
+// Per launch kind since the end of round 2: the same table (profiles/r02_ops_cluster_mode*.csv) and an isolated, L2-flushed
+// timing of the FFN conv2 launch (52.2 us single CTA, 55.5 us multicast) show that only the GLU GEMM and the C = 256
+// vocoder convs gain from multicast; the RESNORM launches lose 2-3 us each and the q|k projection loses its
+// weight-stationary form (24.4 vs 22.6 us).  So: multicast for GLU / GENERIC, single CTA for RESNORM / QKV_ROPE.
+// An explicit SRB_CLUSTER_MODE applies to every eligible launch as before.
+static int cluster_mode(int epilogue) {
+  static int v = -2;
+  if (v == -2) {
     const char* e = getenv("SRB_CLUSTER_MODE");
-    v = e ? atoi(e) : 1;
-    if (v < 0 || v > 2) v = 0;
+    v = e ? atoi(e) : -1;
+    if (v < -1 || v > 2) v = 0;
   }
-  return v;
+  if (v >= 0) return v;
+  return (epilogue == EPI_GLU || epilogue == EPI_GENERIC) ? 1 : 0;
 }
 
 // SRB_WEIGHT_STATIONARY is a bit mask for A/B measurements: 1 = transformer linears, 2 = vocoder convs (default 3)
@@ -476,7 +482,7 @@ static int launch_convgemm(const ConvGemmDesc& d, cudaStream_t stream) {
   // weight multicast across 2-CTA clusters for the wide tiles (needs an even number of row tiles)
   const int row_tiles = d.batch * p.m_tiles[0];
   const int mode = (bn == 256 && kb == 64 && d.n_groups == 1 && row_tiles % 2 == 0 && row_tiles >= 2 && d.epilogue != EPI_ARGMAX)
-                       ? cluster_mode() : 0;
+                       ? cluster_mode(d.epilogue) : 0;
   if (mode != 0) {
     rc = make_weight_map(&p.tmWh, d.weight, k_total, d.n_total, kb, bn / 2);
     if (rc) return rc;
