@@ -388,3 +388,28 @@ def test_split_operand_packing_recovers_fp32_products():
     assert p.shape == (8, 3 * 64) and p.dtype == torch.bfloat16
     assert torch.equal(p[:, 64:124].float(), split_operand(cw[:, :, 1], 1))
     assert bool((p[:, 60:64] == 0).all())
+
+
+def test_centroid_packing_for_the_unit_quantiser():
+    """units.pack_centroids: split rows [Ch | Ch | Cl] padded to 64 columns, codebook padded to 256 rows that can never win
+    (bias -inf), bias = -|c|^2 / 2 -- so argmax_j (x . c_j + bias_j) over the packed operands is KMeans.predict's argmin."""
+    import numpy as np
+
+    from oracle import kmeans_oracle as ko
+    from speech_resynth_b200.packing import split_operand
+    from speech_resynth_b200.units import pack_centroids
+
+    g = torch.Generator().manual_seed(3)
+    c = torch.randn(300, 24, generator=g)
+    packed, bias = pack_centroids(c)
+    assert packed.shape == (512, 128) and packed.dtype == torch.bfloat16 and bias.shape == (512,)
+    assert torch.equal(packed[:300, :72].float(), split_operand(c, 1)) and not bool(packed[:300, 72:].any()) and not bool(packed[300:].any())
+    assert bool(torch.isinf(bias[300:]).all()) and bool((bias[300:] < 0).all())
+    assert torch.allclose(bias[:300], -0.5 * c.pow(2).sum(1), rtol=1e-6)
+    x = torch.randn(50, 24, generator=g)
+    xh = x.to(torch.bfloat16).float()
+    xs = torch.cat([xh, (x - xh).to(torch.bfloat16).float(), xh], dim=1)
+    scores = xs.double() @ packed[:, :72].double().t() + bias.double()
+    assert np.array_equal(scores.argmax(1).numpy(), ko.assign(x.numpy(), c.numpy()))
+    with pytest.raises(ValueError):
+        pack_centroids(torch.randn(10, 20))        # width not a multiple of 8
