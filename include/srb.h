@@ -211,6 +211,16 @@ int srb_hifigan_conv(const void* x0, const void* x1, const void* x2, int32_t n_s
                      const void* res1, const void* res2, void* out_raw, void* out_act, int32_t batch, int32_t rows,
                      int32_t c_in, int32_t c_out, float scale, float slope, void* stream);
 
+/* Same launch with residuals that carry a leaky_relu: res_slope > 0 says res* hold bf16(leaky_relu(r, res_slope)) instead
+ * of bf16(r), and the epilogue adds the raw r recovered from them (negative values divided by res_slope: as accurate as a
+ * bf16 copy of r itself).  The resblock chains then keep ONE copy of every tensor -- the activated one the next conv reads
+ * -- instead of a raw and an activated one: a third less HBM traffic for the memory-bound convs.  res_slope = 0 is
+ * srb_hifigan_conv. */
+int srb_hifigan_conv_res_act(const void* x0, const void* x1, const void* x2, int32_t n_src, const int32_t* kernel,
+                             const int32_t* dilation, const void* w_packed, const float* bias, const void* res0,
+                             const void* res1, const void* res2, float res_slope, void* out_raw, void* out_act, int32_t batch,
+                             int32_t rows, int32_t c_in, int32_t c_out, float scale, float slope, void* stream);
+
 /* ConvTranspose1d (HF:1392-1402,1473) in polyphase form: for phase r < stride, output rows q*stride + r are a
  * 2-3 tap conv of the input.  x (B, L_in, c_in) bf16 (already leaky-relu'ed by its producer);
  * out rows L_out = (L_in-1)*stride - 2*pad + k; writes raw and lrelu(slope) copies. */

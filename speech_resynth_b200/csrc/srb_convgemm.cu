@@ -553,6 +553,7 @@ static ConvGemmParams empty_epi() {
   memset(&e, 0, sizeof(e));
   e.scale = 1.f;
   e.slope = 1.f;
+  e.res_unact = 1.f;
   return e;
 }
 
@@ -920,7 +921,16 @@ int srb_hifigan_conv(const void* x0, const void* x1, const void* x2, int32_t n_s
                      const int32_t* dilation, const void* w_packed, const float* bias, const void* res0,
                      const void* res1, const void* res2, void* out_raw, void* out_act, int32_t batch, int32_t rows,
                      int32_t c_in, int32_t c_out, float scale, float slope, void* stream) {
+  return srb_hifigan_conv_res_act(x0, x1, x2, n_src, kernel, dilation, w_packed, bias, res0, res1, res2, 0.f, out_raw, out_act,
+                                  batch, rows, c_in, c_out, scale, slope, stream);
+}
+
+int srb_hifigan_conv_res_act(const void* x0, const void* x1, const void* x2, int32_t n_src, const int32_t* kernel,
+                             const int32_t* dilation, const void* w_packed, const float* bias, const void* res0,
+                             const void* res1, const void* res2, float res_slope, void* out_raw, void* out_act, int32_t batch,
+                             int32_t rows, int32_t c_in, int32_t c_out, float scale, float slope, void* stream) {
   SRB_REQUIRE(n_src >= 1 && n_src <= 3, "srb_hifigan_conv: n_src must be 1..3");
+  SRB_REQUIRE(res_slope >= 0.f && (res_slope == 0.f || kSplit == 1), "srb_hifigan_conv_res_act: bad residual slope (the tight-precision build takes raw residuals only)");
   const void* xs[3] = {x0, x1, x2};
   ConvGemmDesc d;
   d.n_src = n_src;
@@ -953,6 +963,7 @@ int srb_hifigan_conv(const void* x0, const void* x1, const void* x2, int32_t n_s
   d.epi.out_batch_stride = (long long)rows * c_out;
   d.epi.scale = scale;
   d.epi.slope = slope;
+  d.epi.res_unact = res_slope > 0.f ? 1.f / res_slope : 1.f;
   return launch_convgemm(d, (cudaStream_t)stream);
 }
 

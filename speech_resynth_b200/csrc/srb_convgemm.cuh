@@ -85,6 +85,8 @@ struct ConvGemmParams {
   const float* vec0;
   const float* vec1;
   float scale, slope;
+  float res_unact;                                // GENERIC: negative residual values are multiplied by this (1 = residuals are raw;
+                                                  // 1 / slope = they carry a leaky_relu(slope) and the raw value is recovered here)
   int norm_mode;                                  // RESNORM: 0 none, 1 adaptive (L2), 2 rms
   float f0, f1, f2, f3;                           // EULER: dt, std, mean, pad
   void* aux0;                                     // EULER: mel fp32 (or null)
@@ -231,6 +233,11 @@ __device__ __forceinline__ int clamp_rows(int total, int row0) {
   return v < 0 ? 0 : (v > 32 ? 32 : v);
 }
 
+// residual value as stored -> raw value (see ConvGemmParams::res_unact): the activated copy of a tensor carries the same
+// information as the raw one (leaky_relu with a non-zero slope is invertible, and bf16(slope * y) / slope is y to within the
+// same 2^-9 a bf16 copy of y itself has), so the resblock chains keep ONE copy and the consumer undoes the activation
+__device__ __forceinline__ float unact(float v, float k) { return v < 0.f ? v * k : v; }
+
 // Register / LSU form of the GENERIC epilogue (kept for launches with two or three residual tensors -- the fused MRF
 // tails, whose long MMA phase hides it: their TMA staging would take the shared memory of two weight-ring stages).
 template <int BN, int NHALF>
@@ -240,6 +247,7 @@ __device__ __forceinline__ void epi_generic_lsu(const ConvGemmParams& p, uint32_
   constexpr int COLS = BN / NHALF;
   constexpr int P = CW / 8;   // 16-byte pieces of bf16 per chunk row
   const float sc = p.scale, sl = p.slope;
+  const float ru = kSplit == 1 ? p.res_unact : 1.f;   // (the split build's residuals are always raw hi + lo pairs)
   if (p.row_mul == 1) {
     // contiguous output rows: coalesced path.  (Split build: bf16 tensors are kSplit times as wide -- [hi | lo | hi]
     // blocks, out_row_stride / res_row_stride columns apart; residuals are read as hi + lo.)
@@ -280,10 +288,10 @@ __device__ __forceinline__ void epi_generic_lsu(const ConvGemmParams& p, uint32_
 #pragma unroll
             for (int j = 0; j < P; ++j) {
               const uint4 u = rv[j];
-              y[8 * j + 0] += bf16_lo(u.x); y[8 * j + 1] += bf16_hi(u.x);
-              y[8 * j + 2] += bf16_lo(u.y); y[8 * j + 3] += bf16_hi(u.y);
-              y[8 * j + 4] += bf16_lo(u.z); y[8 * j + 5] += bf16_hi(u.z);
-              y[8 * j + 6] += bf16_lo(u.w); y[8 * j + 7] += bf16_hi(u.w);
+              y[8 * j + 0] += unact(bf16_lo(u.x), ru); y[8 * j + 1] += unact(bf16_hi(u.x), ru);
+              y[8 * j + 2] += unact(bf16_lo(u.y), ru); y[8 * j + 3] += unact(bf16_hi(u.y), ru);
+              y[8 * j + 4] += unact(bf16_lo(u.z), ru); y[8 * j + 5] += unact(bf16_hi(u.z), ru);
+              y[8 * j + 6] += unact(bf16_lo(u.w), ru); y[8 * j + 7] += unact(bf16_hi(u.w), ru);
             }
           }
         }
@@ -381,7 +389,7 @@ __device__ __forceinline__ void epi_generic(const ConvGemmParams& p, uint32_t ta
   constexpr int COLS = BN / NHALF;
   constexpr int P = CW / 8;             // 16-byte pieces of bf16 per block row
   constexpr int BLK = CW * 64;          // bytes of a 32-row block
-  const float sc = p.scale, sl = p.slope;
+  const float sc = p.scale, sl = p.slope, ru = p.res_unact;
   const int n_res = gs.n_res, nbuf = gs.nbuf;
   const uint32_t out_stage = gs.buf + nbuf * n_res * BLK;
   uint8_t* out_gen = gs.gen + nbuf * n_res * BLK;
@@ -426,10 +434,10 @@ __device__ __forceinline__ void epi_generic(const ConvGemmParams& p, uint32_t ta
 #pragma unroll
         for (int j = 0; j < P; ++j) {
           const uint4 u = *stage_slot<P>(const_cast<uint8_t*>(rb), w.lane, j);
-          y[8 * j + 0] += bf16_lo(u.x); y[8 * j + 1] += bf16_hi(u.x);
-          y[8 * j + 2] += bf16_lo(u.y); y[8 * j + 3] += bf16_hi(u.y);
-          y[8 * j + 4] += bf16_lo(u.z); y[8 * j + 5] += bf16_hi(u.z);
-          y[8 * j + 6] += bf16_lo(u.w); y[8 * j + 7] += bf16_hi(u.w);
+          y[8 * j + 0] += unact(bf16_lo(u.x), ru); y[8 * j + 1] += unact(bf16_hi(u.x), ru);
+          y[8 * j + 2] += unact(bf16_lo(u.y), ru); y[8 * j + 3] += unact(bf16_hi(u.y), ru);
+          y[8 * j + 4] += unact(bf16_lo(u.z), ru); y[8 * j + 5] += unact(bf16_hi(u.z), ru);
+          y[8 * j + 6] += unact(bf16_lo(u.w), ru); y[8 * j + 7] += unact(bf16_hi(u.w), ru);
         }
       }
       __syncwarp();   // every lane has its rows: the buffer takes the chunk after next (the next one when single)

@@ -365,6 +365,11 @@ class HifiGanGenerator:
         self.pair_upsample = os.environ.get("SRB_PAIR_UPSAMPLE", "1") != "0" and not tight
         self.fork = _Fork(packed.w_pre.device, 2)
         self.device = packed.w_pre.device
+        # One copy of every tensor of the unfused resblock chains: only the ACTIVATED tensor (what the next conv reads) is
+        # stored; the residual adds recover the raw value from it in the epilogue (srb_hifigan_conv_res_act: leaky_relu is
+        # invertible, and the recovered value is as accurate as a bf16 copy of the raw one).  These launches run at the
+        # HBM roofline, so a third less traffic is a third less time.  SRB_SINGLE_COPY=0 keeps both copies (A/B knob).
+        self.single_copy = os.environ.get("SRB_SINGLE_COPY", "1") != "0" and not tight and self.slope > 0
 
     def call(self, name: str, *args, **kw) -> None:
         nat.call(name, *args, tight=self.tight, **kw)
@@ -384,10 +389,15 @@ class HifiGanGenerator:
         for i, (k, s) in enumerate(zip(UPSAMPLE_KERNELS, UPSAMPLE_RATES)):
             rows = (rows - 1) * s - 2 * ((k - s) // 2) + k
             c //= 2
-            st = dict(rows=rows, c=c, u_raw=take((batch, rows, c)), out=take((batch, rows, c)))
-            if not (self.fuse_mrf and i in self.w.w_mrf):
+            fused = self.fuse_mrf and i in self.w.w_mrf
+            st = dict(rows=rows, c=c, out=take((batch, rows, c)))
+            if fused or not self.single_copy:
+                st["u_raw"] = take((batch, rows, c))
+            if not fused:
                 st.update(u_act=take((batch, rows, c)), t=[take((batch, rows, c)) for _ in range(3)],
-                          xr=[take((batch, rows, c)) for _ in range(3)], xa=[take((batch, rows, c)) for _ in range(3)])
+                          xa=[take((batch, rows, c)) for _ in range(3)])
+                if not self.single_copy:
+                    st["xr"] = [take((batch, rows, c)) for _ in range(3)]
             stages.append(st)
         ws["stages"] = stages
         ws["rows"] = rows
@@ -413,16 +423,19 @@ class HifiGanGenerator:
             st = ws["stages"][i]
             rows, c = st["rows"], st["c"]
             fused = self.fuse_mrf and i in w.w_mrf
+            single = self.single_copy and not fused
+            u_raw = None if single else P(st["u_raw"])
             # upsampler (HF:1472-1473): raw copy = residual of the three resblocks, activated copy = their input
+            # (single-copy form: the activated copy serves as both)
             if i in w.up_pair and self.pair_upsample:
                 # L_out = s L: all s output phases of an input row from one 3-tap conv (packing.upsampler_as_row_group_conv);
                 # (B, rows_in, s c) is the (B, rows, c) result.  FLOPs reported are the transposed conv's own.
                 wp, bp = w.up_pair[i]
                 self.call("srb_hifigan_conv", P(x_act), None, None, 1, _i32([3]), dil1, P(wp), P(bp), None, None, None,
-                         P(st["u_raw"]), None if fused else P(st["u_act"]), b, rows_in, c_in, s * c, 1.0, self.slope,
+                         u_raw, None if fused else P(st["u_act"]), b, rows_in, c_in, s * c, 1.0, self.slope,
                          flops=2.0 * b * rows_in * k * c_in * c)
             else:
-                self.call("srb_hifigan_upsample", P(x_act), P(w.w_up[i]), P(w.b_up[i]), P(st["u_raw"]),
+                self.call("srb_hifigan_upsample", P(x_act), P(w.w_up[i]), P(w.b_up[i]), u_raw,
                          None if fused else P(st["u_act"]), b, rows_in, c_in, c, k, s, self.slope,
                          flops=2.0 * b * rows_in * k * c_in * c)
             if fused:
@@ -434,9 +447,11 @@ class HifiGanGenerator:
                 continue
             res: List[Optional[torch.Tensor]] = [None, None, None]
 
-            def chain(j: int, rk: int, st=st, rows=rows, c=c, i=i) -> None:
+            res_slope = self.slope if single else 0.0
+
+            def chain(j: int, rk: int, st=st, rows=rows, c=c, i=i, single=single, res_slope=res_slope) -> None:
                 kk = _i32([rk])
-                xr, xa = st["u_raw"], st["u_act"]
+                xr, xa = (st["u_act"], st["u_act"]) if single else (st["u_raw"], st["u_act"])
                 for q, dil in enumerate(RESBLOCK_DILATIONS):
                     # conv1 with dilation (HF:1361-1363), output only needed activated
                     self.call("srb_hifigan_conv", P(xa), None, None, 1, kk, _i32([dil]), P(w.w_c1[i][j][q]),
@@ -444,10 +459,11 @@ class HifiGanGenerator:
                              flops=2.0 * b * rows * rk * c * c)
                     if q < 2 or self.tight:
                         # conv2 + residual (HF:1364-1366): raw (next residual) and activated (next conv1 input)
-                        self.call("srb_hifigan_conv", P(st["t"][j]), None, None, 1, kk, dil1, P(w.w_c2[i][j][q]),
-                                 P(w.b_c2[i][j][q]), P(xr), None, None, P(st["xr"][j]), P(st["xa"][j]) if q < 2 else None,
-                                 b, rows, c, c, 1.0, self.slope, flops=2.0 * b * rows * rk * c * c)
-                        xr, xa = st["xr"][j], st["xa"][j]
+                        self.call("srb_hifigan_conv_res_act", P(st["t"][j]), None, None, 1, kk, dil1, P(w.w_c2[i][j][q]),
+                                 P(w.b_c2[i][j][q]), P(xr), None, None, res_slope, None if single else P(st["xr"][j]),
+                                 P(st["xa"][j]) if q < 2 else None, b, rows, c, c, 1.0, self.slope,
+                                 flops=2.0 * b * rows * rk * c * c)
+                        xr, xa = (st["xa"][j], st["xa"][j]) if single else (st["xr"][j], st["xa"][j])
                 res[j] = xr
 
             # the three resblocks of a stage are independent until the MRF mean: three parallel graph branches
@@ -462,8 +478,8 @@ class HifiGanGenerator:
                 self.call("srb_hifigan_mean3", P(res[0]), P(res[1]), P(res[2]), P(st["out"]), b * rows, c, 1.0 / 3.0, slope_next)
                 x_act, rows_in, c_in = st["out"], rows, c
                 continue
-            self.call("srb_hifigan_conv", P(st["t"][0]), P(st["t"][1]), P(st["t"][2]), 3, _i32(list(RESBLOCK_KERNELS)),
-                     _i32([1, 1, 1]), P(w.w_tail[i]), P(w.b_tail[i]), P(res[0]), P(res[1]), P(res[2]), None, P(st["out"]),
+            self.call("srb_hifigan_conv_res_act", P(st["t"][0]), P(st["t"][1]), P(st["t"][2]), 3, _i32(list(RESBLOCK_KERNELS)),
+                     _i32([1, 1, 1]), P(w.w_tail[i]), P(w.b_tail[i]), P(res[0]), P(res[1]), P(res[2]), res_slope, None, P(st["out"]),
                      b, rows, c, c, 1.0 / 3.0, slope_next, flops=2.0 * b * rows * sum(RESBLOCK_KERNELS) * c * c)
             x_act, rows_in, c_in = st["out"], rows, c
         return x_act

@@ -180,6 +180,44 @@ def _conv_case(c_in, c_out, k, dil, batch=2, rows=300, with_res=True, seed=0):
     return max(e1, e2), BF16_TOL
 
 
+def _conv_res_act_case(c, k, rows=300, batch=2, seed=3, n_src=1):
+    """srb_hifigan_conv_res_act: residuals handed over as bf16(leaky_relu(r, 0.1)); the launch must add the RAW r (recovered
+    in the epilogue) and, with only the activated output requested, equal the two-copy form to one bf16 rounding -- for one
+    source (TMA epilogue, in place: the output overwrites the residual tensor, as the resblock chains do) and for the
+    three-source fused tail (register epilogue, three residuals)."""
+    gen = g(seed)
+    ks = [k] if n_src == 1 else [3, 7, 11]
+    xs = [bf(torch.randn(batch, rows, c, generator=gen)) for _ in ks]
+    ws = [bf(torch.randn(c, c, kk, generator=gen) / math.sqrt(c * kk * n_src)) for kk in ks]
+    bias = torch.randn(c, generator=gen)
+    raws = [torch.randn(batch, rows, c, generator=gen) * 2.0 for _ in ks]
+    acts = [bf(F.leaky_relu(r, 0.1)) for r in raws]                       # what the chain stores
+    recovered = [torch.where(a < 0, a * 10.0, a) for a in acts]           # what the epilogue must add
+    y = bias.double()[None, None, :].expand(batch, rows, c).clone()
+    for x, w, kk, r in zip(xs, ws, ks, recovered):
+        y = y + F.conv1d(x.transpose(1, 2).double(), w.double(), None, padding=(kk - 1) // 2).transpose(1, 2) + r.double()
+    y = y * (1.0 / n_src)
+    wp = torch.cat([packing.pack_conv_weight(w.to(DEV), packing.block_k_for(c)) for w in ws], dim=1).contiguous()
+    xd = [x.to(DEV).to(torch.bfloat16).contiguous() for x in xs]
+    rd = [a.to(DEV).to(torch.bfloat16).contiguous() for a in acts]
+    out = rd[0] if n_src == 1 else torch.full((batch, rows, c), float("nan"), dtype=torch.bfloat16, device=DEV)
+    nat.call("srb_hifigan_conv_res_act", P(xd[0]), P(xd[1]) if n_src == 3 else None, P(xd[2]) if n_src == 3 else None, n_src,
+             _i32(ks), _i32([1] * n_src), P(wp), P(bias.to(DEV)), P(rd[0]), P(rd[1]) if n_src == 3 else None,
+             P(rd[2]) if n_src == 3 else None, 0.1, None, P(out), batch, rows, c, c, 1.0 / n_src, 0.1)
+    torch.cuda.synchronize()
+    # the recovered residual itself is within one bf16 rounding of the raw one
+    assert max(rel_l2(rc, r) for rc, r in zip(recovered, raws)) < 3e-3
+    return rel_l2(out.float(), F.leaky_relu(y, 0.1)), BF16_TOL
+
+
+for _name, _args in (("conv_res_act_c64_k3", dict(c=64, k=3)), ("conv_res_act_c128_k7", dict(c=128, k=7)),
+                     ("conv_res_act_c256_k11", dict(c=256, k=11, rows=400)), ("conv_res_act_tail_c64", dict(c=64, k=0, n_src=3))):
+    def _fn(_args=_args):
+        return _conv_res_act_case(**_args)
+    _fn.__name__ = _name
+    CHECKS[_name] = _fn
+
+
 def _make_conv_check(name, *args, **kw):
     def fn():
         return _conv_case(*args, **kw)
