@@ -465,6 +465,8 @@ static int launch_convgemm(const ConvGemmDesc& d, cudaStream_t stream) {
     const int work = (d.group_tap_begin[1] - d.group_tap_begin[0]) * p.kchunks;   // K steps of a tile (first group)
     p.gen_lsu = (n_res >= 2 || (bn >= 128 && work > 16 && d.row_mul == 1)) ? 1 : 0;
     if (force && n_res < 2) p.gen_lsu = strcmp(force, "lsu") == 0;
+    // (two staging blocks for the BN = 64 conv2 launches were measured at the end of round 2 -- same-box A/B: k = 11 272.9 ->
+    // 268.8 us, k = 3 176.8 -> 174.7, step unchanged -- and not kept: their extra time over conv1 is not residual latency)
     p.gen_nbuf = bn >= 128 ? 2 : 1;
     p.res_bufs = p.gen_lsu ? -1 : p.gen_nbuf * (n_res + 1);
     void* outs[2] = {p.out1, p.out0};
