@@ -221,6 +221,15 @@ int srb_hifigan_conv_res_act(const void* x0, const void* x1, const void* x2, int
                              const void* res1, const void* res2, float res_slope, void* out_raw, void* out_act, int32_t batch,
                              int32_t rows, int32_t c_in, int32_t c_out, float scale, float slope, void* stream);
 
+/* One resblock pair in ONE launch for the C = 64 stage, single-copy form (HF:1359-1367):
+ *   out_act = leaky_relu( r + conv2_{k,1}( leaky_relu( conv1_{k,dilation}(x_act) + b1 ) ) + b2 ),  r = the raw value of x_act
+ * x_act (B, L, 64) bf16 = leaky_relu(x, slope) is both the conv input and the residual (recovered in the epilogue);
+ * out_act (B, L, 64) != x_act.  kernel 3 or 7 (the k = 11 resblock is tensor-bound unfused and keeps its two launches);
+ * w1 / w2 packed as for srb_hifigan_conv ([64][k * 64]).  Two passes over the tensors instead of five. */
+int srb_hifigan_pair_fused(const void* x_act, const void* w1_packed, const float* b1, const void* w2_packed, const float* b2,
+                           void* out_act, int32_t batch, int32_t rows, int32_t channels, int32_t kernel, int32_t dilation,
+                           float slope, void* stream);
+
 /* ConvTranspose1d (HF:1392-1402,1473) in polyphase form: for phase r < stride, output rows q*stride + r are a
  * 2-3 tap conv of the input.  x (B, L_in, c_in) bf16 (already leaky-relu'ed by its producer);
  * out rows L_out = (L_in-1)*stride - 2*pad + k; writes raw and lrelu(slope) copies. */

@@ -50,6 +50,7 @@ _PROTOTYPES = {
     "srb_cfm_ffn_out_norm": [_P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _P],
     "srb_cfm_pred_euler": [_P, _P, _F, _P, _P, _P, _P, _I, _F, _F, _F, _P, _I, _I, _P],
     "srb_hifigan_conv": [_P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _P],
+    "srb_hifigan_pair_fused": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
     "srb_hifigan_conv_res_act": [_P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _F, _P, _P, _I, _I, _I, _I, _F, _F, _P],
     "srb_hifigan_upsample": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P],
     "srb_hifigan_mrf_fused": [_P, _P, _P, _P, _I, _I, _I, _F, _F, _P],

@@ -7,7 +7,7 @@ set -e
 cd "$(dirname "$0")"
 NVCC=${NVCC:-nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -O2"
-SRCS="srb_convgemm srb_elementwise srb_attention_tc srb_mrf_fused"
+SRCS="srb_convgemm srb_elementwise srb_attention_tc srb_mrf_fused srb_pair_fused"
 mkdir -p ../../build
 
 compile() {   # <object dir> <extra flags...>

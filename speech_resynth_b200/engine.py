@@ -370,6 +370,13 @@ class HifiGanGenerator:
         # invertible, and the recovered value is as accurate as a bf16 copy of the raw one).  These launches run at the
         # HBM roofline, so a third less traffic is a third less time.  SRB_SINGLE_COPY=0 keeps both copies (A/B knob).
         self.single_copy = os.environ.get("SRB_SINGLE_COPY", "1") != "0" and not tight and self.slope > 0
+        # The first two (conv1, conv2) pairs of the k = 3 resblock of the C = 64 stage as ONE launch each
+        # (srb_hifigan_pair_fused: the conv1 output never leaves the SM; two tensor passes instead of five).  Needs the
+        # single-copy form.  Measured at config 2: 232-246 us per pair against 110 + 178 = 288 us unfused; the k = 7 pair
+        # is slower fused (410-424 us against 140 + 203 = 343: its 56 MMAs per tile run serially with the rest of the tile's
+        # shared-memory traffic) and keeps its two launches.  SRB_PAIR_FUSED=0: never, =2: k = 7 too (A/B knob).
+        pf = os.environ.get("SRB_PAIR_FUSED", "1")
+        self.pair_fused_kernels = () if (pf == "0" or not self.single_copy) else ((3, 7) if pf == "2" else (3,))
 
     def call(self, name: str, *args, **kw) -> None:
         nat.call(name, *args, tight=self.tight, **kw)
@@ -446,12 +453,27 @@ class HifiGanGenerator:
                 x_act, rows_in, c_in = st["out"], rows, c
                 continue
             res: List[Optional[torch.Tensor]] = [None, None, None]
+            srcs: List[torch.Tensor] = list(st["t"])       # the tail's conv inputs (the last conv1 output of each chain)
 
             res_slope = self.slope if single else 0.0
 
             def chain(j: int, rk: int, st=st, rows=rows, c=c, i=i, single=single, res_slope=res_slope) -> None:
                 kk = _i32([rk])
                 xr, xa = (st["u_act"], st["u_act"]) if single else (st["u_raw"], st["u_act"])
+                if single and c == 64 and rk in self.pair_fused_kernels:
+                    # pairs 0 and 1 fused: u_act -> xa[j] -> t[j]; then the last conv1 t[j] -> xa[j] (the tail's source) with
+                    # t[j] as the tail's residual
+                    bufs = (st["u_act"], st["xa"][j], st["t"][j])
+                    for q in range(2):
+                        self.call("srb_hifigan_pair_fused", P(bufs[q]), P(w.w_c1[i][j][q]), P(w.b_c1[i][j][q]), P(w.w_c2[i][j][q]),
+                                 P(w.b_c2[i][j][q]), P(bufs[q + 1]), b, rows, c, rk, RESBLOCK_DILATIONS[q], self.slope,
+                                 flops=4.0 * b * rows * rk * c * c)
+                    self.call("srb_hifigan_conv", P(st["t"][j]), None, None, 1, kk, _i32([RESBLOCK_DILATIONS[2]]),
+                             P(w.w_c1[i][j][2]), P(w.b_c1[i][j][2]), None, None, None, None, P(st["xa"][j]), b, rows, c, c, 1.0,
+                             self.slope, flops=2.0 * b * rows * rk * c * c)
+                    res[j] = st["t"][j]
+                    srcs[j] = st["xa"][j]
+                    return
                 for q, dil in enumerate(RESBLOCK_DILATIONS):
                     # conv1 with dilation (HF:1361-1363), output only needed activated
                     self.call("srb_hifigan_conv", P(xa), None, None, 1, kk, _i32([dil]), P(w.w_c1[i][j][q]),
@@ -478,7 +500,7 @@ class HifiGanGenerator:
                 self.call("srb_hifigan_mean3", P(res[0]), P(res[1]), P(res[2]), P(st["out"]), b * rows, c, 1.0 / 3.0, slope_next)
                 x_act, rows_in, c_in = st["out"], rows, c
                 continue
-            self.call("srb_hifigan_conv_res_act", P(st["t"][0]), P(st["t"][1]), P(st["t"][2]), 3, _i32(list(RESBLOCK_KERNELS)),
+            self.call("srb_hifigan_conv_res_act", P(srcs[0]), P(srcs[1]), P(srcs[2]), 3, _i32(list(RESBLOCK_KERNELS)),
                      _i32([1, 1, 1]), P(w.w_tail[i]), P(w.b_tail[i]), P(res[0]), P(res[1]), P(res[2]), res_slope, None, P(st["out"]),
                      b, rows, c, c, 1.0 / 3.0, slope_next, flops=2.0 * b * rows * sum(RESBLOCK_KERNELS) * c * c)
             x_act, rows_in, c_in = st["out"], rows, c

@@ -218,6 +218,48 @@ for _name, _args in (("conv_res_act_c64_k3", dict(c=64, k=3)), ("conv_res_act_c1
     CHECKS[_name] = _fn
 
 
+def _pair_fused_case(k, dil, rows=300, batch=2, seed=5):
+    """srb_hifigan_pair_fused (C = 64): conv1_{k,dil} -> leaky_relu -> conv2_{k,1} -> + residual -> leaky_relu in one launch,
+    input handed over activated (single-copy form).  Against a float64 reference that rounds t to bf16 where the kernel
+    does, and against the two-launch form (srb_hifigan_conv + srb_hifigan_conv_res_act) on the same operands."""
+    c = 64
+    gen = g(seed)
+    raw = torch.randn(batch, rows, c, generator=gen) * 1.5
+    xa = bf(F.leaky_relu(raw, 0.1))
+    rec = torch.where(xa < 0, xa * 10.0, xa)
+    w1 = bf(torch.randn(c, c, k, generator=gen) / math.sqrt(c * k))
+    w2 = bf(torch.randn(c, c, k, generator=gen) / math.sqrt(c * k))
+    b1, b2 = torch.randn(c, generator=gen) * 0.1, torch.randn(c, generator=gen) * 0.1
+    t = F.conv1d(xa.transpose(1, 2).double(), w1.double(), b1.double(), dilation=dil, padding=(k - 1) // 2 * dil)
+    t = bf(F.leaky_relu(t, 0.1).float()).double()
+    y = F.conv1d(t, w2.double(), b2.double(), padding=(k - 1) // 2).transpose(1, 2) + rec.double()
+    ref = F.leaky_relu(y, 0.1)
+    wp1 = packing.pack_conv_weight(w1.to(DEV), 64)
+    wp2 = packing.pack_conv_weight(w2.to(DEV), 64)
+    xd = xa.to(DEV).to(torch.bfloat16).contiguous()
+    out = torch.full((batch, rows, c), float("nan"), dtype=torch.bfloat16, device=DEV)
+    nat.call("srb_hifigan_pair_fused", P(xd), P(wp1), P(b1.to(DEV)), P(wp2), P(b2.to(DEV)), P(out), batch, rows, c, k, dil, 0.1)
+    # the two-launch form
+    td = torch.empty_like(out)
+    out2 = torch.empty_like(out)
+    nat.call("srb_hifigan_conv", P(xd), None, None, 1, _i32([k]), _i32([dil]), P(wp1), P(b1.to(DEV)), None, None, None, None,
+             P(td), batch, rows, c, c, 1.0, 0.1)
+    nat.call("srb_hifigan_conv_res_act", P(td), None, None, 1, _i32([k]), _i32([1]), P(wp2), P(b2.to(DEV)), P(xd), None, None, 0.1,
+             None, P(out2), batch, rows, c, c, 1.0, 0.1)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(out.float()).all()), "pair_fused left rows unwritten"
+    e_two = rel_l2(out.float(), out2.float().double())
+    assert e_two < 2e-3, f"pair_fused differs from the two-launch form: {e_two}"
+    return rel_l2(out.float(), ref), BF16_TOL
+
+
+for _k, _d, _rows, _b in ((3, 1, 300, 2), (3, 3, 126, 1), (3, 5, 1000, 3), (7, 1, 300, 2), (7, 3, 122, 1), (7, 5, 1000, 3), (3, 1, 5, 2)):
+    def _fn(_k=_k, _d=_d, _rows=_rows, _b=_b):
+        return _pair_fused_case(_k, _d, rows=_rows, batch=_b)
+    _fn.__name__ = f"pair_fused_c64_k{_k}_d{_d}_r{_rows}"
+    CHECKS[_fn.__name__] = _fn
+
+
 def _make_conv_check(name, *args, **kw):
     def fn():
         return _conv_case(*args, **kw)
