@@ -282,6 +282,7 @@ __global__ void __launch_bounds__(576, 1) pair_fused_kernel(const __grid_constan
         }
         int valid = (R < p.rows - r0 ? R : p.rows - r0) - quarter * 32;   // rows of this warp that exist and belong to the tile
         valid = valid < 0 ? 0 : (valid > 32 ? 32 : valid);
+        // (every thread storing its own row's 64 bytes instead of staging through shared memory: 248 / 238 us against 252 / 242)
         scatter_store<4>(ew, o, p.out + ((long long)b * p.rows + r0 + quarter * 32) * 64 + half * 32, 128, valid);
       }
     }
