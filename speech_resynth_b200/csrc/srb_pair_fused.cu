@@ -13,6 +13,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/srb.h"
@@ -30,6 +31,7 @@ struct PairParams {
   int batch, rows, tiles_per_b, total_tiles;
   int dil, box_rows;
   float slope, res_unact;
+  int debug;                // timing experiments only (SRB_PAIR_DEBUG): 1 = issue no MMAs, 2 = skip the output stores (wrong results)
 };
 
 template <int K>
@@ -174,7 +176,8 @@ __global__ void __launch_bounds__(576, 1) pair_fused_kernel(const __grid_constan
           const uint64_t adesc = umma_smem_desc<128>(s_box(sb) + static_cast<uint32_t>(j * p.dil) * 128u);
           const uint64_t wdesc = umma_smem_desc<128>(s_w1 + j * L::slab);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16_pred(1u, acc1(s), adesc + 2 * k, wdesc + 2 * k, IDESC, (j | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k)
+            if (!(p.debug & 1)) umma_bf16_pred(1u, acc1(s), adesc + 2 * k, wdesc + 2 * k, IDESC, (j | k) != 0 ? 1u : 0u);
         }
         umma_commit_pred(1u, a1_full(s));
       }
@@ -189,7 +192,8 @@ __global__ void __launch_bounds__(576, 1) pair_fused_kernel(const __grid_constan
           const uint64_t adesc = umma_smem_desc<128>(s_t(s) + static_cast<uint32_t>(j) * 128u);
           const uint64_t wdesc = umma_smem_desc<128>(s_w2 + j * L::slab);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16_pred(1u, acc2(s), adesc + 2 * k, wdesc + 2 * k, IDESC, (j | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k)
+            if (!(p.debug & 1)) umma_bf16_pred(1u, acc2(s), adesc + 2 * k, wdesc + 2 * k, IDESC, (j | k) != 0 ? 1u : 0u);
         }
         umma_commit_pred(1u, a2_full(s));
         umma_commit_pred(1u, t_empty(s));
@@ -283,7 +287,7 @@ __global__ void __launch_bounds__(576, 1) pair_fused_kernel(const __grid_constan
         int valid = (R < p.rows - r0 ? R : p.rows - r0) - quarter * 32;   // rows of this warp that exist and belong to the tile
         valid = valid < 0 ? 0 : (valid > 32 ? 32 : valid);
         // (every thread storing its own row's 64 bytes instead of staging through shared memory: 248 / 238 us against 252 / 242)
-        scatter_store<4>(ew, o, p.out + ((long long)b * p.rows + r0 + quarter * 32) * 64 + half * 32, 128, valid);
+        if (!(p.debug & 2)) scatter_store<4>(ew, o, p.out + ((long long)b * p.rows + r0 + quarter * 32) * 64 + half * 32, 128, valid);
       }
     }
   }
@@ -352,6 +356,10 @@ extern "C" int srb_hifigan_pair_fused(const void* x_act, const void* w1_packed, 
   p.dil = dilation;
   p.slope = slope;
   p.res_unact = 1.f / slope;
+  {
+    static const int dbg = [] { const char* e = getenv("SRB_PAIR_DEBUG"); return e ? atoi(e) : 0; }();
+    p.debug = dbg;
+  }
   const int h = (kernel - 1) / 2;
   {
     cuuint64_t dims[3] = {64, (cuuint64_t)rows, (cuuint64_t)batch};

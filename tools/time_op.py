@@ -49,6 +49,17 @@ if __name__ == "__main__":
         w = torch.randn(7 * 16, device=dev)
         wav = torch.empty(b, rows, device=dev)
         us = timed(lambda: nat.call("srb_hifigan_post", P(xa), P(w), 0.1, P(wav), b, rows, None))
+    elif what == "pair":
+        # srb_hifigan_pair_fused at the C = 64 stage's shape (SRB_PAIR_DEBUG=1: no MMAs, =2: no output stores -- timing only)
+        rows = 40020
+        k = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+        xa = torch.randn(b, rows, 64, device=dev).to(torch.bfloat16)
+        out = torch.empty_like(xa)
+        w1 = (torch.randn(64, k * 64, device=dev) * 0.05).to(torch.bfloat16)
+        w2 = (torch.randn(64, k * 64, device=dev) * 0.05).to(torch.bfloat16)
+        bias = torch.zeros(64, device=dev)
+        us = timed(lambda: nat.call("srb_hifigan_pair_fused", P(xa), P(w1), P(bias), P(w2), P(bias), P(out), b, rows, 64, k, 1, 0.1), reps=20)
+        what = f"pair k={k} SRB_PAIR_DEBUG={os.environ.get('SRB_PAIR_DEBUG', '0')}"
     else:
         raise SystemExit(f"unknown op {what}")
     print(f"{what} {os.environ.get('SRB_POSCONV_ROWS', '')}: {us:.1f} us (L2 flushed between launches)")
